@@ -1,0 +1,135 @@
+/* p5_b200.h — C-ABI of libp5b200.so, the B200 (sm_100a) engine for the OpenP5 T5 hot path.
+ *
+ * The reference (agiresearch/OpenP5) has no FFI layer: its hot path is the Python object protocol the runner
+ * uses on `model` / `optimizer`.  Each entry point below replaces one of those call sites;
+ * the citation after "replaces:" is the reference file:line (relative to the reference tree, `HF:` = the
+ * transformers package the reference imports).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; p5_last_error() returns the message of the
+ *     last failing call on this thread.
+ *   - all tensor pointers are DEVICE pointers unless the name ends in `_host`; they are borrowed for the
+ *     duration of the call.  Work is enqueued on the cudaStream_t given at p5_create (stream-ordered, no
+ *     internal threads).  One handle per process/GPU; a handle is not thread-safe.
+ *   - token ids / masks are int32 on this boundary (the Python wrapper converts the collator's int64).
+ *   - dtype codes: 0 = fp32, 1 = bf16.   major codes: 0 = K-major, 1 = MN-major.
+ */
+#ifndef P5_B200_H
+#define P5_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p5_engine* p5_handle;
+typedef struct p5_trie_s* p5_trie;
+
+/* Model / run configuration.  Field meaning follows HF T5Config as used by the reference
+ * (src/src_t5/main.py:176-184, HF:models/t5/configuration_t5.py). */
+typedef struct {
+    int32_t vocab_size;        /* after resize_token_embeddings(len(tokenizer)), main.py:193 */
+    int32_t d_model;
+    int32_t d_kv;              /* must be 64 */
+    int32_t d_ff;
+    int32_t num_layers;        /* encoder blocks */
+    int32_t num_decoder_layers;
+    int32_t num_heads;
+    int32_t rel_buckets;       /* relative_attention_num_buckets (32) */
+    int32_t rel_max_distance;  /* relative_attention_max_distance (128) */
+    int32_t ffn_gated_gelu;    /* 0 = DenseReluDense (t5-small/base/large), 1 = gated-GELU (v1.1) */
+    int32_t whole_word_rows;   /* 512, P5_T5.py:64-66 */
+    float   dropout;           /* dropout_rate */
+    float   ln_eps;            /* layer_norm_epsilon */
+    int32_t precision;         /* 0 = fp32 parity path (SIMT fp32), 1 = bf16 tensor-core path */
+    int32_t max_batch;         /* workspace sizing: largest B the handle will see */
+    int32_t max_enc_len;       /* largest Le (<= 512, Collator.py:13) */
+    int32_t max_dec_len;       /* largest Ld for training / max_length for generate */
+    int32_t max_beams;         /* largest num_beams for p5_generate (0 = no generate workspace) */
+    int32_t use_mn_major;      /* 1: dgrad/wgrad read forward tensors in place via MN-major UMMA descriptors */
+    int32_t reserved[7];
+} P5Config;
+
+const char* p5_last_error(void);
+int p5_version(void);
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+/* replaces: P5_T5.from_pretrained(...).to(device)  (main.py:184)  — parameters are created zeroed; the host
+ * fills them through p5_param_info pointers (state_dict protocol). */
+int p5_create(const P5Config* cfg, int device, void* cuda_stream, p5_handle* out);
+int p5_destroy(p5_handle h);
+
+/* replaces: model.named_parameters() / state_dict() (SingleRunner.py:196; DistributedRunner.py:155,169,193).
+ * Names are the HF T5 keys ("shared.weight", "encoder.block.0.layer.0.SelfAttention.q.weight", ...). */
+int p5_param_count(p5_handle h, int* n);
+int p5_param_info(p5_handle h, int i, const char** name, int* ndim, int64_t shape[2], float** data, float** grad);
+/* call after writing parameter data from the host side (refreshes the bf16 GEMM shadows) */
+int p5_params_changed(p5_handle h);
+
+/* ---- training step ---------------------------------------------------------------------------------- */
+/* replaces: model(input_ids=, whole_word_ids=, attention_mask=, labels=) (DistributedRunner.py:63-70; P5_T5.py:275-386).
+ * loss_tok [B*Ld] = un-reduced per-token CE (P5_T5.py:368-369); logits_or_null [B*Ld, vocab] fp32 if non-null.
+ * training != 0 enables dropout with the given seed. */
+int p5_forward(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask, const int32_t* whole_word_ids,
+               const int32_t* labels, int B, int Le, int Ld, float* loss_tok, float* logits_or_null, int training,
+               uint64_t seed);
+/* replaces: loss.backward() (DistributedRunner.py:80) given dL/dloss_tok [B*Ld]; accumulates into the grad buffers */
+int p5_backward(p5_handle h, const float* dloss_tok);
+/* fused form of DistributedRunner.py:72-80: loss = mean_b( sum_t loss_tok*m / max(sum_t m,1) ), m = (labels_mask != 0);
+ * runs forward + backward with that reduction; loss_out (device, 1 float) receives the scalar loss. */
+int p5_train_fwd_bwd(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask,
+                     const int32_t* whole_word_ids, const int32_t* labels, const int32_t* labels_mask, int B, int Le,
+                     int Ld, float* loss_out, uint64_t seed);
+/* replaces: torch.nn.utils.clip_grad_norm_ (DistributedRunner.py:81): out (device, 1 float) = global L2 norm */
+int p5_grad_norm(p5_handle h, float* out);
+int p5_grad_scale(p5_handle h, float s);
+/* replaces: model.zero_grad() (DistributedRunner.py:87) */
+int p5_zero_grad(p5_handle h);
+/* replaces: transformers(4.26).AdamW.step (SingleRunner.py:214): m,v update, eps outside bias correction,
+ * decoupled decay after the update.  clip > 0 folds clip_grad_norm_(clip) into the same pass using the norm
+ * computed on device (no host sync).  step is 1-based. */
+int p5_adamw_step(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float clip);
+
+/* ---- data-parallel gradient exchange (the DDP all-reduce the reference constructs, DistributedRunner.py:26) ---- */
+int p5_comm_unique_id(void* id128_host);                      /* 128-byte ncclUniqueId */
+int p5_comm_init(p5_handle h, const void* id128_host, int rank, int world);
+int p5_allreduce_grads(p5_handle h);                          /* mean over ranks */
+
+/* ---- constrained beam search ------------------------------------------------------------------------ */
+/* replaces: gt.Trie([...]) + prefix_allowed_tokens_fn (utils/generation_trie.py:7-97; DistributedRunner.py:344-351).
+ * paths_host: concatenated token paths (each starts with decoder_start 0), offsets_host[n_paths+1]. */
+int p5_trie_build(p5_handle h, const int32_t* paths_host, const int64_t* offsets_host, int n_paths, p5_trie* out);
+int p5_trie_free(p5_trie t);
+int p5_trie_stats(p5_trie t, int* n_nodes, int* n_edges, int* max_depth);
+/* device lookup used by the tests: for each prefix (host arrays) return allowed next tokens like Trie.get */
+int p5_trie_get(p5_trie t, const int32_t* prefix_host, int prefix_len, int32_t* out_tokens_host, int cap, int* n_out);
+
+/* replaces: model.generate(num_beams=K, num_return_sequences=R, max_length=T, prefix_allowed_tokens_fn=...)
+ * (DistributedRunner.py:361-371; HF:generation/utils.py:3076-3400).  seqs [B*R, max_len] int32 (pad 0),
+ * scores [B*R] fp32 = sum log-prob / generated_len^length_penalty, rows per user sorted by score desc.
+ * out_len_host receives the cropped output length (prompt + longest generated). */
+int p5_generate(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask, const int32_t* whole_word_ids,
+                int B, int Le, p5_trie trie, int num_beams, int num_return, int max_len, float length_penalty,
+                int32_t* seqs, float* scores, int* out_len_host);
+
+/* ---- op-level hooks (unit tests / micro-benchmarks of individual kernels) ------------------------------ */
+typedef struct {
+    int32_t backend;            /* 0 = SIMT fp32-accumulate kernel, 1 = tcgen05 kernel, 2 = auto */
+    int32_t M, N, K, nb1, nb2;
+    const void* A; int32_t a_dtype, a_major; int64_t lda, a_bs1, a_bs2;
+    const void* B; int32_t b_dtype, b_major; int64_t ldb, b_bs1, b_bs2;
+    void* C; int32_t c_dtype; int32_t pad0; int64_t ldc, c_bs1, c_bs2;
+    float alpha; int32_t flags;
+    const void* aux; int32_t aux_dtype; int32_t pad1;
+    const float* resid;
+    uint64_t seed; uint32_t site; float drop_p;
+    int32_t force_block_n; int32_t pad2;
+} P5GemmDesc;
+int p5_op_gemm(const P5GemmDesc* d, void* cuda_stream);
+int p5_launch_count(void);   /* kernels launched by this library since load */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P5_B200_H */

@@ -1,0 +1,199 @@
+// openp5_b200 — shared device/host helpers for the sm_100a hot path.
+// Everything in csrc/ is compiled with -gencode arch=compute_100a,code=sm_100a only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+namespace p5 {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// error handling: the C-ABI converts P5Error into a return code + p5_last_error() string
+// ---------------------------------------------------------------------------------------------
+struct P5Error : public std::runtime_error {
+    int code;
+    P5Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define P5_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            char _b[512];                                                                          \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                     __LINE__, cudaGetErrorString(_e));                                            \
+            throw ::p5::P5Error(2, _b);                                                            \
+        }                                                                                          \
+    } while (0)
+
+#define P5_CHECK(cond, msg)                                                               \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            char _b[512];                                                                 \
+            snprintf(_b, sizeof(_b), "%s (%s) at %s:%d", msg, #cond, __FILE__, __LINE__); \
+            throw ::p5::P5Error(1, _b);                                                   \
+        }                                                                                 \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------------
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+template <typename T> struct dtype_of;
+template <> struct dtype_of<float> { static constexpr int value = DT_F32; };
+template <> struct dtype_of<bf16> { static constexpr int value = DT_BF16; };
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float ld_as_f32(const void* p, int dt, int64_t i) {
+    return dt == DT_F32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+}
+__device__ __forceinline__ void st_from_f32(void* p, int dt, int64_t i, float v) {
+    if (dt == DT_F32) ((float*)p)[i] = v;
+    else ((bf16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout RNG. keep(seed, site, idx) is a pure function so the backward pass
+// regenerates the forward mask instead of storing it.  (Reference semantics: nn.Dropout(p) in
+// HF:models/t5/modeling_t5.py:94,125,331,375; bit-parity with torch's Philox stream is not
+// possible nor required — tests check keep-rate, scaling and fwd/bwd mask agreement.)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint32_t site, uint64_t idx) {
+    uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+    uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+    uint32_t h = mix32(lo ^ s0);
+    h = mix32(h + 0x9e3779b9U * (site + 1u) + hi * 0x85ebca6bU + s1);
+    return h;
+}
+// threshold = round(p * 2^32); keep iff hash >= threshold
+__host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thr) {
+    return drop_hash(seed, site, idx) >= thr;
+}
+static inline uint32_t drop_threshold(float p) {
+    double t = (double)p * 4294967296.0;
+    if (t <= 0) return 0u;
+    if (t >= 4294967295.0) return 4294967295u;
+    return (uint32_t)t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; `sh` must hold >= 32 floats; all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? sh[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? sh[lane] : -INFINITY;
+    r = warp_max(r);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM interface shared by the tcgen05 kernel (gemm_tc.cu) and the SIMT kernel (gemm_simt.cu)
+// ---------------------------------------------------------------------------------------------
+enum Major : int { MAJOR_K = 0, MAJOR_MN = 1 };
+
+// A logical [rows, K] operand (rows = M for A, N for B), optionally batched over (b1, b2).
+//   MAJOR_K : element (r, k) at ptr[r*ld + k]     (the reduction index is contiguous)
+//   MAJOR_MN: element (r, k) at ptr[k*ld + r]     (the row index is contiguous)
+struct GemmOperand {
+    const void* ptr = nullptr;
+    int dtype = DT_BF16;
+    int major = MAJOR_K;
+    int64_t ld = 0;
+    int64_t bs1 = 0, bs2 = 0;  // batch strides in elements
+};
+
+enum EpiFlags : int {
+    EPI_RELU = 1,        // v = max(v, 0)
+    EPI_MULPOS = 2,      // v = aux[idx] > 0 ? v : 0        (ReLU backward from the saved activation)
+    EPI_DROPOUT = 4,     // v = keep(seed, site, idx) ? v * inv_keep : 0
+    EPI_ADD_RESID = 8,   // v += resid_f32[idx]
+    EPI_ACCUM = 16,      // v += C_old[idx]                  (gradient accumulation, C must be fp32)
+};
+
+struct GemmEpilogue {
+    void* C = nullptr;          // output, logical [M, N] row-major, ldc
+    int c_dtype = DT_BF16;
+    int64_t ldc = 0;
+    int64_t cs1 = 0, cs2 = 0;   // batch strides (elements)
+    float alpha = 1.f;
+    int flags = 0;
+    const void* aux = nullptr;  // same layout (ldc, cs1, cs2) as C, dtype aux_dtype
+    int aux_dtype = DT_BF16;
+    const float* resid = nullptr;  // fp32, same layout as C
+    uint64_t seed = 0;
+    uint32_t site = 0;
+    uint32_t drop_thr = 0;
+    float inv_keep = 1.f;
+};
+
+struct GemmProblem {
+    int M = 0, N = 0, K = 0;
+    int nb1 = 1, nb2 = 1;
+    GemmOperand A, B;
+    GemmEpilogue epi;
+};
+
+// shared epilogue math: acc -> value to store; idx is the element offset within C (incl. batch)
+__device__ __forceinline__ float epilogue_apply(const GemmEpilogue& e, float acc, int64_t idx) {
+    float v = acc * e.alpha;
+    if (e.flags & EPI_RELU) v = fmaxf(v, 0.f);
+    if (e.flags & EPI_MULPOS) v = ld_as_f32(e.aux, e.aux_dtype, idx) > 0.f ? v : 0.f;
+    if (e.flags & EPI_DROPOUT) v = drop_keep(e.seed, e.site, (uint64_t)idx, e.drop_thr) ? v * e.inv_keep : 0.f;
+    if (e.flags & EPI_ADD_RESID) v += e.resid[idx];
+    if (e.flags & EPI_ACCUM) v += ((const float*)e.C)[idx];
+    return v;
+}
+
+// launchers (throw P5Error)
+void gemm_simt(const GemmProblem& p, cudaStream_t stream);
+bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major);
+void gemm_tc(const GemmProblem& p, cudaStream_t stream);
+void gemm_tc_clear_cache();
+int  gemm_tc_launch_count();
+
+}  // namespace p5

@@ -1,0 +1,564 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[b][M,N] = epilogue( A[b][M,K] * B[b][N,K]^T )
+//
+// This single kernel carries every dense contraction of the T5 block
+// (HF:models/t5/modeling_t5.py:277,298-299,338 q/k/v/o; :93-102 wi/wo; P5_T5.py:361 lm_head) and their
+// dgrad / wgrad forms.  bf16 operands, fp32 accumulation in tensor memory.
+//
+// Structure (persistent, warp specialised, one CTA per SM):
+//   warp 0   : TMA producer      cp.async.bulk.tensor.4d -> 128B-swizzled smem ring (STAGES deep)
+//   warp 1   : MMA issuer        one lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16
+//   warp 2   : TMEM allocator    2 accumulator stages x BLOCK_N fp32 columns
+//   warps 4-7: epilogue          tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue).
+//
+// Operands may be K-major (reduction index contiguous) or MN-major (row index contiguous); the latter lets
+// dgrad/wgrad read the forward tensors in place (no transposes): TMA loads [64k x 64mn] boxes and the smem
+// descriptor uses the MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) (uint128 units).
+#include "common.cuh"
+#include <unordered_map>
+#include <vector>
+#include <mutex>
+#include <string.h>
+
+namespace p5 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
+static constexpr int UMMA_K = 16;
+static constexpr int GEMM_THREADS = 256;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a mis-programmed pipeline traps after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+            printf("p5 gemm_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all previously issued MMAs arrives on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+struct TcParams {
+    int M, N, K;
+    int nb1, nb2;
+    int a_major, b_major;
+    GemmEpilogue epi;
+};
+
+template <int BLOCK_N>
+struct TcCfg {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// 8 consecutive output columns of one row: fused epilogue + (vectorised) store
+__device__ __forceinline__ void epi_store8(const GemmEpilogue& e, const float* acc, int64_t idx, int ncols_valid) {
+    const bool vec = (ncols_valid == 8) && ((idx & 7) == 0);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j] * e.alpha;
+    if (e.flags & EPI_RELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (e.flags & EPI_MULPOS) {
+        if (vec && e.aux_dtype == DT_BF16) {
+            uint4 a = *reinterpret_cast<const uint4*>((const bf16*)e.aux + idx);
+            const bf16* ab = reinterpret_cast<const bf16*>(&a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(ab[j]) > 0.f ? v[j] : 0.f;
+        } else {
+            for (int j = 0; j < ncols_valid; ++j) v[j] = ld_as_f32(e.aux, e.aux_dtype, idx + j) > 0.f ? v[j] : 0.f;
+        }
+    }
+    if (e.flags & EPI_DROPOUT) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = drop_keep(e.seed, e.site, (uint64_t)(idx + j), e.drop_thr) ? v[j] * e.inv_keep : 0.f;
+    }
+    if (e.flags & EPI_ADD_RESID) {
+        if (vec) {
+            float4 r0 = *reinterpret_cast<const float4*>(e.resid + idx);
+            float4 r1 = *reinterpret_cast<const float4*>(e.resid + idx + 4);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        } else {
+            for (int j = 0; j < ncols_valid; ++j) v[j] += e.resid[idx + j];
+        }
+    }
+    if (e.flags & EPI_ACCUM) {
+        const float* c = (const float*)e.C;
+        if (vec) {
+            float4 r0 = *reinterpret_cast<const float4*>(c + idx);
+            float4 r1 = *reinterpret_cast<const float4*>(c + idx + 4);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        } else {
+            for (int j = 0; j < ncols_valid; ++j) v[j] += c[idx + j];
+        }
+    }
+    if (e.c_dtype == DT_F32) {
+        float* c = (float*)e.C;
+        if (vec) {
+            *reinterpret_cast<float4*>(c + idx) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(c + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            for (int j = 0; j < ncols_valid; ++j) c[idx + j] = v[j];
+        }
+    } else {
+        bf16* c = (bf16*)e.C;
+        if (vec) {
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(c + idx) = o;
+        } else {
+            for (int j = 0; j < ncols_valid; ++j) c[idx + j] = __float2bfloat16_rn(v[j]);
+        }
+    }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcParams P) {
+    using Cfg = TcCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_holder_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (P.M + BLOCK_M - 1) / BLOCK_M;
+    const int n_tiles = (P.N + BLOCK_N - 1) / BLOCK_N;
+    const int k_blocks = (P.K + BLOCK_K - 1) / BLOCK_K;
+    const long long total_tiles = (long long)m_tiles * n_tiles * P.nb1 * P.nb2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n_blk = (int)(t % n_tiles);
+                const long long t2 = t / n_tiles;
+                const int m_blk = (int)(t2 % m_tiles);
+                const int b = (int)(t2 / m_tiles);
+                const int b1 = b % P.nb1, b2 = b / P.nb1;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    if (P.a_major == MAJOR_K) {
+                        tma_load_4d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M, b1, b2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / 64; ++c)
+                            tma_load_4d(sa + c * 8192, &tmA, full_bar(stage), m_blk * BLOCK_M + c * 64, kb * BLOCK_K,
+                                        b1, b2);
+                    }
+                    if (P.b_major == MAJOR_K) {
+                        tma_load_4d(sb, &tmB, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N, b1, b2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_N / 64; ++c)
+                            tma_load_4d(sb + c * 8192, &tmB, full_bar(stage), n_blk * BLOCK_N + c * 64, kb * BLOCK_K,
+                                        b1, b2);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+            // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.a_major & 1) << 15) |
+                                   ((uint32_t)(P.b_major & 1) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // K-major : advance 16 elements = 32 bytes inside the 128B swizzle row; SBO = 8 rows = 1024 B
+                        // MN-major: advance 16 k-rows   = 2048 bytes; LBO = next 64-wide MN chunk (8192 B); SBO = 1024 B
+                        const uint64_t da = (P.a_major == MAJOR_K) ? make_smem_desc(sa + k * 32, 16, 1024)
+                                                                   : make_smem_desc(sa + k * 2048, 8192, 1024);
+                        const uint64_t db = (P.b_major == MAJOR_K) ? make_smem_desc(sb + k * 32, 16, 1024)
+                                                                   : make_smem_desc(sb + k * 2048, 8192, 1024);
+                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp & 3;  // TMEM lane quarter owned by this warp
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n_blk = (int)(t % n_tiles);
+            const long long t2 = t / n_tiles;
+            const int m_blk = (int)(t2 % m_tiles);
+            const int b = (int)(t2 / m_tiles);
+            const int b1 = b % P.nb1, b2 = b / P.nb1;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + ew * 32 + lane;
+            const bool row_ok = row < P.M;
+            const int64_t row_off = (int64_t)b1 * P.epi.cs1 + (int64_t)b2 * P.epi.cs2 + (int64_t)row * P.epi.ldc;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == BLOCK_N / 32 - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                const int col0 = n_blk * BLOCK_N + c * 32;
+                if (row_ok && col0 < P.N) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = col0 + g * 8;
+                        int nv = P.N - col;
+                        if (nv > 0) {
+                            if (nv > 8) nv = 8;
+                            float a[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[j] = __uint_as_float(r[g * 8 + j]);
+                            epi_store8(P.epi, a, row_off + col, nv);
+                        }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        P5_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        P5_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+struct TmapKey {
+    const void* ptr;
+    uint64_t dims[4];
+    uint64_t strides[3];
+    uint32_t box[4];
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        size_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        return h;
+    }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mu;
+static int g_tc_launches = 0;
+
+void gemm_tc_clear_cache() {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    g_tmap_cache.clear();
+}
+int gemm_tc_launch_count() { return g_tc_launches; }
+
+static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, int nb2, int box_rows) {
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = op.ptr;
+    const uint64_t ld_b = (uint64_t)op.ld * 2;
+    if (op.major == MAJOR_K) {
+        key.dims[0] = (uint64_t)K; key.dims[1] = (uint64_t)rows;
+        key.box[0] = BLOCK_K; key.box[1] = (uint32_t)box_rows;
+    } else {
+        key.dims[0] = (uint64_t)rows; key.dims[1] = (uint64_t)K;
+        key.box[0] = 64; key.box[1] = BLOCK_K;
+    }
+    key.dims[2] = (uint64_t)nb1; key.dims[3] = (uint64_t)nb2;
+    key.box[2] = 1; key.box[3] = 1;
+    key.strides[0] = ld_b;
+    key.strides[1] = nb1 > 1 ? (uint64_t)op.bs1 * 2 : key.dims[1] * ld_b;
+    key.strides[2] = nb2 > 1 ? (uint64_t)op.bs2 * 2 : (nb1 > 1 ? (uint64_t)op.bs1 * 2 * nb1 : key.dims[1] * ld_b);
+    {
+        std::lock_guard<std::mutex> g(g_tmap_mu);
+        auto it = g_tmap_cache.find(key);
+        if (it != g_tmap_cache.end()) return it->second;
+    }
+    CUtensorMap m;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), key.dims,
+                                 key.strides, key.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[512];
+        snprintf(b, sizeof(b),
+                 "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] "
+                 "box=[%u,%u,%u,%u]",
+                 (int)r, op.ptr, (unsigned long long)key.dims[0], (unsigned long long)key.dims[1],
+                 (unsigned long long)key.dims[2], (unsigned long long)key.dims[3], (unsigned long long)key.strides[0],
+                 (unsigned long long)key.strides[1], (unsigned long long)key.strides[2], key.box[0], key.box[1],
+                 key.box[2], key.box[3]);
+        throw P5Error(3, b);
+    }
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    g_tmap_cache[key] = m;
+    return m;
+}
+
+static bool operand_ok(const GemmOperand& o, int nb1, int nb2, bool allow_mn) {
+    if (o.dtype != DT_BF16) return false;
+    if (o.major == MAJOR_MN && !allow_mn) return false;
+    if (((uintptr_t)o.ptr & 15) != 0) return false;
+    if (o.ld % 8 != 0 || o.ld <= 0) return false;
+    if (nb1 > 1 && (o.bs1 % 8 != 0 || o.bs1 <= 0)) return false;
+    if (nb2 > 1 && (o.bs2 % 8 != 0 || o.bs2 <= 0)) return false;
+    return true;
+}
+
+bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) return false;
+    if (!operand_ok(p.A, p.nb1, p.nb2, allow_mn_major)) return false;
+    if (!operand_ok(p.B, p.nb1, p.nb2, allow_mn_major)) return false;
+    // TMA zero-fills out-of-bounds boxes, so M, N, K need no padding; the inner (contiguous) extent must still
+    // cover whole 16-byte units for the tensor map
+    if (p.A.major == MAJOR_K && p.K % 8 != 0) return false;
+    if (p.B.major == MAJOR_K && p.K % 8 != 0) return false;
+    if (p.A.major == MAJOR_MN && p.M % 8 != 0) return false;
+    if (p.B.major == MAJOR_MN && p.N % 8 != 0) return false;
+    if ((p.epi.flags & EPI_ACCUM) && p.epi.c_dtype != DT_F32) return false;
+    return true;
+}
+
+static int g_num_sms = 0;
+static int g_force_block_n = 0;  // test hook
+void gemm_tc_force_block_n(int bn) { g_force_block_n = bn; }
+
+template <int BN>
+static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
+    using Cfg = TcCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        P5_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA = make_tmap(p.A, p.M, p.K, p.nb1, p.nb2, BLOCK_M);
+    CUtensorMap tmB = make_tmap(p.B, p.N, p.K, p.nb1, p.nb2, BN);
+    TcParams P;
+    P.M = p.M; P.N = p.N; P.K = p.K; P.nb1 = p.nb1; P.nb2 = p.nb2;
+    P.a_major = p.A.major; P.b_major = p.B.major;
+    P.epi = p.epi;
+    const long long tiles = (long long)cdiv(p.M, BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, P);
+    P5_CUDA(cudaGetLastError());
+    ++g_tc_launches;
+}
+
+void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
+    P5_CHECK(gemm_tc_supported(p, true), "gemm_tc: unsupported problem");
+    if (!g_num_sms) {
+        int dev = 0;
+        P5_CUDA(cudaGetDevice(&dev));
+        P5_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int bn = g_force_block_n;
+    if (!bn) {
+        const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
+        // largest tile that still gives every SM a tile; narrow outputs use a narrow tile
+        if (p.N > 128 && mt * cdiv(p.N, 256) >= g_num_sms) bn = 256;
+        else if (p.N > 64 && mt * cdiv(p.N, 128) >= g_num_sms) bn = 128;
+        else bn = 64;
+        if (p.N <= 64) bn = 64;
+    }
+    if (bn == 256) launch_tc<256>(p, stream);
+    else if (bn == 128) launch_tc<128>(p, stream);
+    else launch_tc<64>(p, stream);
+}
+
+}  // namespace p5
