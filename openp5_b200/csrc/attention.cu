@@ -1,0 +1,497 @@
+// Attention kernels (HF:models/t5/modeling_t5.py:253-344): scores are UNSCALED q.k, plus the shared relative
+// position bias and the additive finfo(fp32).min padding / causal mask, softmax in fp32, dropout on the
+// probabilities, then P.V.
+//
+//  * attn_simt_fwd / attn_simt_bwd : fused fp32 kernels (no S materialised).  They are the exact-arithmetic path
+//    of the parity mode and serve the decoder's short query blocks (Lq = Ld ~ 8, decode Lq = 1) in bf16 mode.
+//  * softmax_fwd / softmax_bwd     : row kernels between the batched tcgen05 GEMMs (S = QK^T, O = PV, dP = dO V^T,
+//    dQ/dK/dV) of the bf16 encoder path.
+#include "kernels.cuh"
+#include <float.h>
+
+namespace p5 {
+extern int g_launches;
+#define LAUNCHED() do { P5_CUDA(cudaGetLastError()); ++g_launches; } while (0)
+
+static constexpr int QB = 16;    // query rows per CTA (2 per warp)
+static constexpr int KT = 64;    // keys per smem tile
+static constexpr int DK = 64;    // d_kv
+#define MASK_MIN (-FLT_MAX)      // torch.finfo(torch.float32).min
+
+struct AttnDev {
+    int B, H, Lq, Lk;
+    const void *q, *k, *v;
+    int q_dt, k_dt, v_dt;
+    int64_t q_ld, q_bs, k_ld, k_bs, v_ld, v_bs;
+    const float* bias_rel; int bias_off, n_delta;
+    const int* key_mask;
+    int causal, q_pos_offset;
+    const int* row_map;
+    DropCfg drop;
+};
+
+__device__ __forceinline__ float score_bias(const AttnDev& a, int h, int kb, int i_pos, int j) {
+    float s = 0.f;
+    if (a.bias_rel) {
+        int di = j - i_pos + a.bias_off;
+        di = di < 0 ? 0 : (di >= a.n_delta ? a.n_delta - 1 : di);
+        s += a.bias_rel[h * a.n_delta + di];
+    }
+    float m = 0.f;
+    if (a.key_mask && a.key_mask[(int64_t)kb * a.Lk + j] == 0) m = MASK_MIN;
+    if (a.causal && j > i_pos) m = MASK_MIN;
+    return s + m;
+}
+
+// cooperative load of a [KT x 64] tile (rows = keys) into smem as fp32, zero beyond Lk
+__device__ __forceinline__ void load_kv_tile(float (*dst)[DK + 1], const void* base, int dt, int64_t ld, int64_t boff,
+                                             int h, int j0, int Lk) {
+    for (int e = threadIdx.x; e < KT * DK; e += blockDim.x) {
+        const int j = e >> 6, c = e & 63;
+        float v = 0.f;
+        if (j0 + j < Lk) v = ld_as_f32(base, dt, boff + (int64_t)(j0 + j) * ld + h * DK + c);
+        dst[j][c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, float* lse) {
+    extern __shared__ float smem[];
+    float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);                       // [QB][64]
+    float (*KVs)[DK + 1] = reinterpret_cast<float (*)[DK + 1]>(smem + QB * DK);    // [KT][65]
+    float* Ss = smem + QB * DK + KT * (DK + 1);                                     // [QB][Lk]
+    const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QB;
+    const int kb = a.row_map ? a.row_map[b] : b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Lk = a.Lk;
+
+    for (int e = threadIdx.x; e < QB * DK; e += blockDim.x) {
+        const int r = e >> 6, c = e & 63;
+        float v = 0.f;
+        if (i0 + r < a.Lq) v = ld_as_f32(a.q, a.q_dt, (int64_t)b * a.q_bs + (int64_t)(i0 + r) * a.q_ld + h * DK + c);
+        Qs[r][c] = v;
+    }
+    // ---- scores
+    for (int j0 = 0; j0 < Lk; j0 += KT) {
+        __syncthreads();
+        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)kb * a.k_bs, h, j0, Lk);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr;
+            const int i_pos = a.q_pos_offset + i0 + r;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int jl = lane + 32 * jj, j = j0 + jl;
+                if (j < Lk) {
+                    float s = 0.f;
+#pragma unroll 16
+                    for (int c = 0; c < DK; ++c) s = fmaf(Qs[r][c], KVs[jl][c], s);
+                    Ss[r * Lk + j] = s + score_bias(a, h, kb, i_pos, j);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- softmax (each warp owns its two rows; Ss rows are private to the warp)
+    float inv_sum[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = warp * 2 + rr;
+        float mx = -INFINITY;
+        for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, Ss[r * Lk + j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Lk; j += 32) {
+            const float p = __expf(Ss[r * Lk + j] - mx);
+            Ss[r * Lk + j] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        inv_sum[rr] = 1.f / sum;
+        const int i = i0 + r;
+        if (lse && lane == 0 && i < a.Lq) lse[((int64_t)b * a.H + h) * a.Lq + i] = mx + logf(sum);
+        for (int j = lane; j < Lk; j += 32) {
+            float p = Ss[r * Lk + j] * inv_sum[rr];
+            if (a.drop.thr) {
+                const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + i) * (uint64_t)Lk + j;
+                p = drop_keep(a.drop.seed, a.drop.site, idx, a.drop.thr) ? p * a.drop.inv_keep : 0.f;
+            }
+            Ss[r * Lk + j] = p;
+        }
+    }
+    // ---- O = P V
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int j0 = 0; j0 < Lk; j0 += KT) {
+        __syncthreads();
+        load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, (int64_t)kb * a.v_bs, h, j0, Lk);
+        __syncthreads();
+        const int jn = min(KT, Lk - j0);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr;
+            for (int j = 0; j < jn; ++j) {
+                const float p = Ss[r * Lk + j0 + j];
+                acc[rr][0] = fmaf(p, KVs[j][lane], acc[rr][0]);
+                acc[rr][1] = fmaf(p, KVs[j][lane + 32], acc[rr][1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = i0 + warp * 2 + rr;
+        if (i < a.Lq) {
+            const int64_t o = (int64_t)b * bs_o + (int64_t)i * ld_o + h * DK;
+            st_from_f32(O, o_dt, o + lane, acc[rr][0]);
+            st_from_f32(O, o_dt, o + lane + 32, acc[rr][1]);
+        }
+    }
+}
+
+static AttnDev to_dev(const AttnArgs& a) {
+    const int bias_off = a.bias_off, n_delta = a.n_delta;
+    AttnDev d;
+    d.B = a.B; d.H = a.H; d.Lq = a.Lq; d.Lk = a.Lk;
+    d.q = a.q.ptr; d.k = a.k.ptr; d.v = a.v.ptr;
+    d.q_dt = a.q.dtype; d.k_dt = a.k.dtype; d.v_dt = a.v.dtype;
+    d.q_ld = a.q.ld; d.q_bs = a.q.bs; d.k_ld = a.k.ld; d.k_bs = a.k.bs; d.v_ld = a.v.ld; d.v_bs = a.v.bs;
+    d.bias_rel = a.bias_rel; d.bias_off = bias_off; d.n_delta = n_delta;
+    d.key_mask = a.key_mask; d.causal = a.causal; d.q_pos_offset = a.q_pos_offset; d.row_map = a.row_map;
+    d.drop = a.drop;
+    return d;
+}
+
+static size_t fwd_smem(int Lk) { return (size_t)(QB * DK + KT * (DK + 1) + QB * Lk) * sizeof(float); }
+static size_t bwd_smem(int Lk, int n_delta) {
+    return (size_t)(2 * QB * DK + KT * (DK + 1) + QB * Lk + QB * KT + QB + n_delta) * sizeof(float);
+}
+
+void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
+    if (a.B <= 0 || a.Lq <= 0) return;
+    P5_CHECK(a.Lk >= 1 && a.Lk <= 2048, "attn_simt_fwd: Lk out of range");
+    static size_t max_set = 0;
+    const size_t sm = fwd_smem(a.Lk);
+    if (sm > max_set) {
+        P5_CUDA(cudaFuncSetAttribute(attn_simt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        max_set = sm;
+    }
+    AttnDev d = to_dev(a);
+    dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
+    attn_simt_fwd_kernel<<<grid, 256, sm, st>>>(d, O, o_dtype, ld_o, bs_o, lse);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward (recomputes P from the saved log-sum-exp)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t ld_o, int64_t bs_o,
+                     const float* __restrict__ lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV,
+                     int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel) {
+    extern __shared__ float smem[];
+    float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);
+    float (*dOs)[DK] = reinterpret_cast<float (*)[DK]>(smem + QB * DK);
+    float (*KVs)[DK + 1] = reinterpret_cast<float (*)[DK + 1]>(smem + 2 * QB * DK);
+    float* Ss = smem + 2 * QB * DK + KT * (DK + 1);         // [QB][Lk]  p, then ds
+    float* Pt = Ss + QB * a.Lk;                              // [QB][KT]  dropped p of the current tile
+    float* dlt = Pt + QB * KT;                               // [QB]
+    float* sdb = dlt + QB;                                   // [n_delta]
+    const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Lk = a.Lk;
+
+    for (int e = threadIdx.x; e < QB * DK; e += blockDim.x) {
+        const int r = e >> 6, c = e & 63;
+        float qv = 0.f, gv = 0.f;
+        if (i0 + r < a.Lq) {
+            qv = ld_as_f32(a.q, a.q_dt, (int64_t)b * a.q_bs + (int64_t)(i0 + r) * a.q_ld + h * DK + c);
+            gv = ld_as_f32(dO, o_dt, (int64_t)b * bs_o + (int64_t)(i0 + r) * ld_o + h * DK + c);
+        }
+        Qs[r][c] = qv;
+        dOs[r][c] = gv;
+    }
+    if (dbias_rel)
+        for (int e = threadIdx.x; e < a.n_delta; e += blockDim.x) sdb[e] = 0.f;
+    __syncthreads();
+    // delta_i = sum_c dO_ic * O_ic
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = warp * 2 + rr, i = i0 + r;
+        float dsum = 0.f;
+        if (i < a.Lq) {
+            const int64_t o = (int64_t)b * bs_o + (int64_t)i * ld_o + h * DK;
+            dsum = dOs[r][lane] * ld_as_f32(O, o_dt, o + lane) + dOs[r][lane + 32] * ld_as_f32(O, o_dt, o + lane + 32);
+        }
+        dsum = warp_sum(dsum);
+        if (lane == 0) dlt[r] = dsum;
+    }
+    // ---- recompute p_ij = exp(s_ij - lse_i)
+    for (int j0 = 0; j0 < Lk; j0 += KT) {
+        __syncthreads();
+        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)b * a.k_bs, h, j0, Lk);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr, i = i0 + r;
+            const int i_pos = a.q_pos_offset + i;
+            const float l = (i < a.Lq) ? lse[((int64_t)b * a.H + h) * a.Lq + i] : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int jl = lane + 32 * jj, j = j0 + jl;
+                if (j < Lk) {
+                    float s = 0.f;
+#pragma unroll 16
+                    for (int c = 0; c < DK; ++c) s = fmaf(Qs[r][c], KVs[jl][c], s);
+                    s += score_bias(a, h, b, i_pos, j);
+                    Ss[r * Lk + j] = (i < a.Lq) ? __expf(s - l) : 0.f;
+                }
+            }
+        }
+    }
+    // ---- dP, dS, dV
+    for (int j0 = 0; j0 < Lk; j0 += KT) {
+        __syncthreads();
+        load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, (int64_t)b * a.v_bs, h, j0, Lk);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr, i = i0 + r;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int jl = lane + 32 * jj, j = j0 + jl;
+                float pd = 0.f;
+                if (j < Lk && i < a.Lq) {
+                    float dpd = 0.f;
+#pragma unroll 16
+                    for (int c = 0; c < DK; ++c) dpd = fmaf(dOs[r][c], KVs[jl][c], dpd);
+                    const float p = Ss[r * Lk + j];
+                    float dp = dpd;
+                    pd = p;
+                    if (a.drop.thr) {
+                        const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + i) * (uint64_t)Lk + j;
+                        const bool keep = drop_keep(a.drop.seed, a.drop.site, idx, a.drop.thr);
+                        dp = keep ? dpd * a.drop.inv_keep : 0.f;
+                        pd = keep ? p * a.drop.inv_keep : 0.f;
+                    }
+                    const float ds = p * (dp - dlt[r]);
+                    Ss[r * Lk + j] = ds;
+                    if (dbias_rel) {
+                        int di = j - (a.q_pos_offset + i) + a.bias_off;
+                        di = di < 0 ? 0 : (di >= a.n_delta ? a.n_delta - 1 : di);
+                        atomicAdd(&sdb[di], ds);
+                    }
+                }
+                Pt[r * KT + jl] = pd;
+            }
+        }
+        __syncthreads();
+        // dV[j, c] += sum_r pd[r][j] * dO[r][c]
+        for (int e = threadIdx.x; e < KT * DK; e += blockDim.x) {
+            const int j = e >> 6, c = e & 63;
+            if (j0 + j < Lk) {
+                float v = 0.f;
+#pragma unroll
+                for (int r = 0; r < QB; ++r) v = fmaf(Pt[r * KT + j], dOs[r][c], v);
+                if (v != 0.f) atomicAdd(dV + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c, v);
+            }
+        }
+    }
+    // ---- dQ, dK
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int j0 = 0; j0 < Lk; j0 += KT) {
+        __syncthreads();
+        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)b * a.k_bs, h, j0, Lk);
+        __syncthreads();
+        const int jn = min(KT, Lk - j0);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr;
+            for (int j = 0; j < jn; ++j) {
+                const float ds = Ss[r * Lk + j0 + j];
+                acc[rr][0] = fmaf(ds, KVs[j][lane], acc[rr][0]);
+                acc[rr][1] = fmaf(ds, KVs[j][lane + 32], acc[rr][1]);
+            }
+        }
+        for (int e = threadIdx.x; e < KT * DK; e += blockDim.x) {
+            const int j = e >> 6, c = e & 63;
+            if (j0 + j < Lk) {
+                float v = 0.f;
+#pragma unroll
+                for (int r = 0; r < QB; ++r) v = fmaf(Ss[r * Lk + j0 + j], Qs[r][c], v);
+                if (v != 0.f) atomicAdd(dK + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c, v);
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = i0 + warp * 2 + rr;
+        if (i < a.Lq) {
+            const int64_t o = (int64_t)b * bs_dq + (int64_t)i * ld_dq + h * DK;
+            dQ[o + lane] = acc[rr][0];
+            dQ[o + lane + 32] = acc[rr][1];
+        }
+    }
+    if (dbias_rel) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < a.n_delta; e += blockDim.x) {
+            const float v = sdb[e];
+            if (v != 0.f) atomicAdd(dbias_rel + h * a.n_delta + e, v);
+        }
+    }
+}
+
+void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype, int64_t ld_o, int64_t bs_o,
+                   const float* lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV, int64_t ld_dkv,
+                   int64_t bs_dkv, float* dbias_rel, cudaStream_t st) {
+    if (a.B <= 0 || a.Lq <= 0) return;
+    P5_CHECK(a.Lk >= 1 && a.Lk <= 1024, "attn_simt_bwd: Lk out of range");
+    P5_CHECK(a.row_map == nullptr, "attn_simt_bwd: row_map is inference-only");
+    static size_t max_set = 0;
+    const size_t sm = bwd_smem(a.Lk, a.n_delta);
+    if (sm > max_set) {
+        P5_CUDA(cudaFuncSetAttribute(attn_simt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        max_set = sm;
+    }
+    AttnDev d = to_dev(a);
+    dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
+    attn_simt_bwd_kernel<<<grid, 256, sm, st>>>(d, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv,
+                                                bs_dkv, dbias_rel);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// materialised softmax between the batched tensor-core GEMMs.  One CTA per (b, h); each warp walks rows.
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int SM_MAXK = 16;  // Lk <= 512
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ bias_rel, const int* __restrict__ key_mask,
+                   T* __restrict__ P_save, T* __restrict__ Pd, int H, int Lq, int Lk, int causal, DropCfg drop) {
+    const int bh = blockIdx.x, b = bh / H, h = bh % H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_delta = Lq + Lk - 1;
+    for (int i = blockIdx.y * nw + warp; i < Lq; i += nw * gridDim.y) {
+        const int64_t row = ((int64_t)bh * Lq + i) * Lk;
+        float v[SM_MAXK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < SM_MAXK; ++k) {
+            const int j = lane + 32 * k;
+            v[k] = -INFINITY;
+            if (j < Lk) {
+                float s = S[row + j];
+                if (bias_rel) s += bias_rel[h * n_delta + (j - i + Lq - 1)];
+                float m = 0.f;
+                if (key_mask && key_mask[b * Lk + j] == 0) m = MASK_MIN;
+                if (causal && j > i) m = MASK_MIN;
+                v[k] = s + m;
+                mx = fmaxf(mx, v[k]);
+            }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < SM_MAXK; ++k) {
+            const int j = lane + 32 * k;
+            if (j < Lk) { v[k] = __expf(v[k] - mx); sum += v[k]; }
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < SM_MAXK; ++k) {
+            const int j = lane + 32 * k;
+            if (j < Lk) {
+                const float p = v[k] * inv;
+                P_save[row + j] = from_f32<T>(p);
+                if (drop.thr) {
+                    const float pd = drop_keep(drop.seed, drop.site, (uint64_t)(row + j), drop.thr) ? p * drop.inv_keep : 0.f;
+                    Pd[row + j] = from_f32<T>(pd);
+                }
+            }
+        }
+    }
+}
+
+void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, void* P_save, void* Pd, int dtype, int B,
+                 int H, int Lq, int Lk, int causal, DropCfg drop, cudaStream_t st) {
+    if (B <= 0) return;
+    P5_CHECK(Lk <= 32 * SM_MAXK, "softmax_fwd: Lk > 512");
+    P5_CHECK(!drop.thr || Pd != nullptr, "softmax_fwd: dropout needs a Pd buffer");
+    dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
+    if (dtype == DT_F32)
+        softmax_fwd_kernel<float><<<grid, 256, 0, st>>>(S, bias_rel, key_mask, (float*)P_save, (float*)Pd, H, Lq, Lk, causal, drop);
+    else
+        softmax_fwd_kernel<bf16><<<grid, 256, 0, st>>>(S, bias_rel, key_mask, (bf16*)P_save, (bf16*)Pd, H, Lq, Lk, causal, drop);
+    LAUNCHED();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __restrict__ dS, T* __restrict__ Pd_out,
+                   float* __restrict__ dbias_rel, int H, int Lq, int Lk, DropCfg drop) {
+    extern __shared__ float sdb[];  // [n_delta]
+    const int bh = blockIdx.x, h = bh % H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_delta = Lq + Lk - 1;
+    if (dbias_rel) {
+        for (int e = threadIdx.x; e < n_delta; e += blockDim.x) sdb[e] = 0.f;
+        __syncthreads();
+    }
+    for (int i = blockIdx.y * nw + warp; i < Lq; i += nw * gridDim.y) {
+        const int64_t row = ((int64_t)bh * Lq + i) * Lk;
+        float p[SM_MAXK], dp[SM_MAXK];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < SM_MAXK; ++k) {
+            const int j = lane + 32 * k;
+            p[k] = 0.f; dp[k] = 0.f;
+            if (j < Lk) {
+                p[k] = to_f32(P[row + j]);
+                float g = dPd[row + j];
+                if (drop.thr) {
+                    const bool keep = drop_keep(drop.seed, drop.site, (uint64_t)(row + j), drop.thr);
+                    g = keep ? g * drop.inv_keep : 0.f;
+                    if (Pd_out) Pd_out[row + j] = from_f32<T>(keep ? p[k] * drop.inv_keep : 0.f);
+                }
+                dp[k] = g;
+                dot += g * p[k];
+            }
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int k = 0; k < SM_MAXK; ++k) {
+            const int j = lane + 32 * k;
+            if (j < Lk) {
+                const float ds = p[k] * (dp[k] - dot);
+                dS[row + j] = from_f32<T>(ds);
+                if (dbias_rel) atomicAdd(&sdb[j - i + Lq - 1], ds);
+            }
+        }
+    }
+    if (dbias_rel) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_delta; e += blockDim.x) {
+            const float v = sdb[e];
+            if (v != 0.f) atomicAdd(dbias_rel + h * n_delta + e, v);
+        }
+    }
+}
+
+void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
+                 int Lq, int Lk, DropCfg drop, cudaStream_t st) {
+    if (B <= 0) return;
+    P5_CHECK(Lk <= 32 * SM_MAXK, "softmax_bwd: Lk > 512");
+    dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
+    const size_t sm = (size_t)(Lq + Lk) * sizeof(float);
+    if (dtype == DT_F32)
+        softmax_bwd_kernel<float><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop);
+    else
+        softmax_bwd_kernel<bf16><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop);
+    LAUNCHED();
+}
+
+}  // namespace p5

@@ -1,0 +1,568 @@
+// Trie-constrained beam search on device.
+//
+// Replaces, for `model.generate(num_beams=K, num_return_sequences=R, prefix_allowed_tokens_fn=trie)`
+// (ref src/src_t5/runner/DistributedRunner.py:344-371):
+//   * utils/generation_trie.py:7-97      nested-dict Trie + per-beam Python callback  ->  CSR trie in HBM, each
+//                                         running beam carries its trie NODE (no prefix re-walk, no D2H sync)
+//   * HF:generation/logits_process.py:1532-1549 (-inf mask over V) -> only the children of the node are scored
+//   * HF:generation/utils.py:3231-3378   _beam_search step: log_softmax, + running score, top-2K over K*V,
+//                                         running/finished split, length-normalised finished scores, early-stop
+//                                         heuristic, KV-cache reorder -> index indirection (no KV copies)
+//   * P5_T5.py:543-578                    encoder states repeated xK  -> cross-K/V stored once per USER
+// Semantics mirror transformers 5.5 `_beam_search` (early_stopping=False, do_sample=False); ties are broken by
+// lowest flat index (beam * V + token).  The whole search is enqueued without host synchronisation: the step
+// count is the trie depth, and finished users are frozen by the same `-1e9` gating HF uses.
+#include "engine.h"
+#include <map>
+#include <vector>
+#include <float.h>
+
+namespace p5 {
+#define LAUNCHED() do { P5_CUDA(cudaGetLastError()); ++g_launches; } while (0)
+static constexpr float NEG_BIG = -1.0e9f;   // HF:generation/utils.py:3200-3201
+
+// ------------------------------------------------------------------------------------------------------------
+// trie
+// ------------------------------------------------------------------------------------------------------------
+struct Trie {
+    int device = 0;
+    int n_nodes = 0, n_edges = 0, max_depth = 0, max_fanout = 0;
+    std::vector<int> h_off, h_tok, h_node;
+    int *d_off = nullptr, *d_tok = nullptr, *d_node = nullptr;
+};
+
+int trie_build(Engine* e, const int32_t* paths, const int64_t* offsets, int n_paths, Trie** out) {
+    P5_CHECK(paths && offsets && n_paths > 0, "trie_build: empty path set");
+    std::vector<std::map<int, int>> nodes(1);
+    int max_depth = 0;
+    for (int i = 0; i < n_paths; ++i) {
+        int cur = 0;
+        const int64_t n = offsets[i + 1] - offsets[i];
+        if ((int)n > max_depth) max_depth = (int)n;
+        for (int64_t j = offsets[i]; j < offsets[i + 1]; ++j) {
+            const int t = paths[j];
+            auto it = nodes[cur].find(t);
+            if (it == nodes[cur].end()) {
+                nodes.push_back({});
+                const int id = (int)nodes.size() - 1;
+                nodes[cur][t] = id;
+                cur = id;
+            } else {
+                cur = it->second;
+            }
+        }
+    }
+    Trie* t = new Trie();
+    t->device = e->device;
+    t->n_nodes = (int)nodes.size();
+    t->max_depth = max_depth;
+    t->h_off.resize(t->n_nodes + 1);
+    int edges = 0;
+    for (int i = 0; i < t->n_nodes; ++i) {
+        t->h_off[i] = edges;
+        edges += (int)nodes[i].size();
+        if ((int)nodes[i].size() > t->max_fanout) t->max_fanout = (int)nodes[i].size();
+    }
+    t->h_off[t->n_nodes] = edges;
+    t->n_edges = edges;
+    t->h_tok.resize(edges > 0 ? edges : 1);
+    t->h_node.resize(edges > 0 ? edges : 1);
+    for (int i = 0; i < t->n_nodes; ++i) {
+        int k = t->h_off[i];
+        for (auto& kv : nodes[i]) { t->h_tok[k] = kv.first; t->h_node[k] = kv.second; ++k; }
+    }
+    P5_CUDA(cudaSetDevice(e->device));
+    P5_CUDA(cudaMalloc(&t->d_off, (t->n_nodes + 1) * sizeof(int)));
+    P5_CUDA(cudaMalloc(&t->d_tok, t->h_tok.size() * sizeof(int)));
+    P5_CUDA(cudaMalloc(&t->d_node, t->h_node.size() * sizeof(int)));
+    P5_CUDA(cudaMemcpy(t->d_off, t->h_off.data(), (t->n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    P5_CUDA(cudaMemcpy(t->d_tok, t->h_tok.data(), t->h_tok.size() * sizeof(int), cudaMemcpyHostToDevice));
+    P5_CUDA(cudaMemcpy(t->d_node, t->h_node.data(), t->h_node.size() * sizeof(int), cudaMemcpyHostToDevice));
+    *out = t;
+    return 0;
+}
+void trie_free(Trie* t) {
+    cudaSetDevice(t->device);
+    cudaFree(t->d_off); cudaFree(t->d_tok); cudaFree(t->d_node);
+    delete t;
+}
+void trie_stats(Trie* t, int* n_nodes, int* n_edges, int* max_depth) {
+    if (n_nodes) *n_nodes = t->n_nodes;
+    if (n_edges) *n_edges = t->n_edges;
+    if (max_depth) *max_depth = t->max_depth;
+}
+
+__device__ __forceinline__ int trie_child(const int* off, const int* tok, const int* node, int n, int t) {
+    if (n < 0) return -1;
+    int lo = off[n], hi = off[n + 1] - 1;
+    while (lo <= hi) {   // children are sorted by token
+        const int mid = (lo + hi) >> 1;
+        const int v = tok[mid];
+        if (v == t) return node[mid];
+        if (v < t) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+// walks `prefix` from the root on the DEVICE copy and lists the children (Trie.get of the reference)
+__global__ void trie_get_kernel(const int* off, const int* tok, const int* node, const int* prefix, int n, int* out,
+                                int cap, int* n_out) {
+    int cur = 0;
+    for (int i = 0; i < n && cur >= 0; ++i) cur = trie_child(off, tok, node, cur, prefix[i]);
+    int cnt = 0;
+    if (cur >= 0)
+        for (int k = off[cur]; k < off[cur + 1]; ++k) { if (cnt < cap) out[cnt] = tok[k]; ++cnt; }
+    *n_out = cnt;
+}
+int trie_get(Trie* t, const int32_t* prefix, int prefix_len, int32_t* out, int cap) {
+    P5_CUDA(cudaSetDevice(t->device));
+    int *d_pre = nullptr, *d_out = nullptr, *d_n = nullptr;
+    P5_CUDA(cudaMalloc(&d_pre, (prefix_len + 1) * sizeof(int)));
+    P5_CUDA(cudaMalloc(&d_out, (cap + 1) * sizeof(int)));
+    P5_CUDA(cudaMalloc(&d_n, sizeof(int)));
+    if (prefix_len) P5_CUDA(cudaMemcpy(d_pre, prefix, prefix_len * sizeof(int), cudaMemcpyHostToDevice));
+    trie_get_kernel<<<1, 1>>>(t->d_off, t->d_tok, t->d_node, d_pre, prefix_len, d_out, cap, d_n);
+    P5_CUDA(cudaGetLastError());
+    int n = 0;
+    P5_CUDA(cudaMemcpy(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n > 0) P5_CUDA(cudaMemcpy(out, d_out, (n < cap ? n : cap) * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_pre); cudaFree(d_out); cudaFree(d_n);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// generate workspace
+// ------------------------------------------------------------------------------------------------------------
+struct GenWs {
+    int Rm = 0, Tm = 0, Km = 0, Bm = 0;
+    float* y = nullptr;
+    void *n = nullptr, *qkv = nullptr, *ctx = nullptr, *cq = nullptr, *h = nullptr, *z = nullptr;
+    std::vector<void*> Kc, Vc;
+    float *logits = nullptr, *rowmax = nullptr, *logsum = nullptr;
+    int* seq[2] = {nullptr, nullptr};      // running sequences [R, T]
+    int* fin_seq[2] = {nullptr, nullptr};  // finished sequences [R, T]
+    int* src[2] = {nullptr, nullptr};      // KV-cache row indirection [R, T]
+    int* node[2] = {nullptr, nullptr};     // trie node of each running beam
+    float* run_score[2] = {nullptr, nullptr};
+    float* fin_score[2] = {nullptr, nullptr};
+    int* is_fin[2] = {nullptr, nullptr};
+    int* gen_len[2] = {nullptr, nullptr};
+    int *cur_tok = nullptr, *unsat = nullptr, *out_len = nullptr;
+    float* cand_lp = nullptr; int *cand_beam = nullptr, *cand_tok = nullptr;
+    float* scr_score = nullptr; int* scr_flat = nullptr; int scr_cap = 0;
+    std::vector<void*> allocs;
+};
+void free_gen_ws(GenWs* g) {
+    for (void* p : g->allocs) cudaFree(p);
+    delete g;
+}
+static GenWs* get_gen_ws(Engine* e, int R, int T, int K, int B, int cand_cap) {
+    GenWs* g = e->gen;
+    if (g && g->Rm >= R && g->Tm >= T && g->Km >= K && g->Bm >= B && g->scr_cap >= cand_cap) return g;
+    if (g) { P5_CUDA(cudaStreamSynchronize(e->st)); free_gen_ws(g); e->gen = nullptr; }
+    g = new GenWs();
+    auto al = [&](size_t bytes) { void* p = nullptr; P5_CUDA(cudaMalloc(&p, bytes ? bytes : 256)); g->allocs.push_back(p); return p; };
+    const size_t es = e->esz();
+    const int A = e->A, d = e->d, ff = e->ff;
+    g->Rm = R; g->Tm = T; g->Km = K; g->Bm = B; g->scr_cap = cand_cap;
+    g->y = (float*)al((size_t)R * d * 4);
+    g->n = al((size_t)R * d * es); g->qkv = al((size_t)R * 3 * A * es); g->ctx = al((size_t)R * A * es);
+    g->cq = al((size_t)R * A * es); g->h = al((size_t)R * ff * es);
+    if (e->gated) g->z = al((size_t)R * 2 * ff * es);
+    g->Kc.resize(e->ND); g->Vc.resize(e->ND);
+    for (int l = 0; l < e->ND; ++l) { g->Kc[l] = al((size_t)R * T * A * es); g->Vc[l] = al((size_t)R * T * A * es); }
+    g->logits = (float*)al((size_t)R * e->Vpad * 4);
+    g->rowmax = (float*)al((size_t)R * 4); g->logsum = (float*)al((size_t)R * 4);
+    for (int i = 0; i < 2; ++i) {
+        g->seq[i] = (int*)al((size_t)R * T * 4); g->fin_seq[i] = (int*)al((size_t)R * T * 4);
+        g->src[i] = (int*)al((size_t)R * T * 4); g->node[i] = (int*)al((size_t)R * 4);
+        g->run_score[i] = (float*)al((size_t)R * 4); g->fin_score[i] = (float*)al((size_t)R * 4);
+        g->is_fin[i] = (int*)al((size_t)R * 4); g->gen_len[i] = (int*)al((size_t)R * 4);
+    }
+    g->cur_tok = (int*)al((size_t)R * 4); g->unsat = (int*)al((size_t)B * 4); g->out_len = (int*)al(16);
+    g->cand_lp = (float*)al((size_t)B * 2 * K * 4); g->cand_beam = (int*)al((size_t)B * 2 * K * 4);
+    g->cand_tok = (int*)al((size_t)B * 2 * K * 4);
+    g->scr_score = (float*)al((size_t)B * cand_cap * 4); g->scr_flat = (int*)al((size_t)B * cand_cap * 4);
+    e->gen = g;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gen_init_kernel(int* seq, int* fin_seq, int* src, int* node, float* run_score, float* fin_score,
+                                int* is_fin, int* gen_len, int* cur_tok, int* unsat, int B, int K, int T, int root_child) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B * K) return;
+    for (int t = 0; t < T; ++t) { seq[r * T + t] = 0; fin_seq[r * T + t] = 0; src[r * T + t] = r; }
+    node[r] = root_child;                        // node reached by the decoder-start token 0
+    run_score[r] = (r % K == 0) ? 0.f : NEG_BIG; // only beam 0 is live at the first step
+    fin_score[r] = NEG_BIG;
+    is_fin[r] = 0; gen_len[r] = 0; cur_tok[r] = 0;
+    if (r % K == 0) unsat[r / K] = 1;
+}
+
+// decode self-attention for ONE new position per row, with KV append and row indirection.
+// grid (H, R), 64 threads.  K/V cache layout [R, T, A].
+template <typename T>
+__global__ void __launch_bounds__(64)
+decode_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ Kc, T* __restrict__ Vc, const int* __restrict__ src,
+                        const float* __restrict__ bias_rel, int n_delta, int bias_off, T* __restrict__ ctx, int A, int Tm,
+                        int pos) {
+    extern __shared__ float sm[];
+    float* q = sm;            // [64]
+    float* p = sm + 64;       // [pos+1]
+    const int h = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
+    const T* row = qkv + (int64_t)r * 3 * A + h * 64;
+    q[c] = to_f32(row[c]);
+    const T kc = row[A + c], vc = row[2 * A + c];
+    Kc[((int64_t)r * Tm + pos) * A + h * 64 + c] = kc;
+    Vc[((int64_t)r * Tm + pos) * A + h * 64 + c] = vc;
+    __syncthreads();
+    for (int j = c; j <= pos; j += 64) {
+        const T* kp = (j == pos) ? (row + A) : (Kc + ((int64_t)src[r * Tm + j] * Tm + j) * A + h * 64);
+        float s = 0.f;
+#pragma unroll 16
+        for (int k = 0; k < 64; ++k) s = fmaf(q[k], to_f32(kp[k]), s);
+        int di = j - pos + bias_off;
+        di = di < 0 ? 0 : (di >= n_delta ? n_delta - 1 : di);
+        p[j] = s + bias_rel[h * n_delta + di];
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = 0; j <= pos; ++j) mx = fmaxf(mx, p[j]);
+    float sum = 0.f;
+    for (int j = 0; j <= pos; ++j) sum += __expf(p[j] - mx);
+    const float inv = 1.f / sum;
+    float acc = 0.f;
+    for (int j = 0; j <= pos; ++j) {
+        const float w = __expf(p[j] - mx) * inv;
+        const float v = (j == pos) ? to_f32(vc) : to_f32(Vc[((int64_t)src[r * Tm + j] * Tm + j) * A + h * 64 + c]);
+        acc = fmaf(w, v, acc);
+    }
+    ctx[(int64_t)r * A + h * 64 + c] = from_f32<T>(acc);
+}
+
+// row-wise max and log(sum(exp(x - max))) over the vocabulary (torch log_softmax = (x - max) - logsum)
+__global__ void __launch_bounds__(256)
+rows_logsumexp_kernel(const float* __restrict__ logits, int64_t ld, int V, float* __restrict__ rowmax,
+                      float* __restrict__ logsum) {
+    __shared__ float sh[32];
+    const int r = blockIdx.x;
+    const float* l = logits + (int64_t)r * ld;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, l[c]);
+    mx = block_max(mx, sh);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(l[c] - mx);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) { rowmax[r] = mx; logsum[r] = logf(s); }
+}
+
+// per user: score the trie children of every running beam and keep the best 2K (score desc, flat index asc)
+__global__ void __launch_bounds__(256)
+topk_candidates_kernel(const float* __restrict__ logits, int64_t ld, int V, const float* __restrict__ rowmax,
+                       const float* __restrict__ logsum, const float* __restrict__ run_score,
+                       const int* __restrict__ node, const int* __restrict__ t_off, const int* __restrict__ t_tok,
+                       int K, float* __restrict__ scr_score, int* __restrict__ scr_flat, int scr_cap,
+                       float* __restrict__ cand_lp, int* __restrict__ cand_beam, int* __restrict__ cand_tok) {
+    __shared__ int s_count;
+    __shared__ float s_best[8];
+    __shared__ int s_besti[8], s_bestf[8];
+    const int b = blockIdx.x;
+    float* sc = scr_score + (int64_t)b * scr_cap;
+    int* fl = scr_flat + (int64_t)b * scr_cap;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        const int r = b * K + k;
+        const int nd = node[r];
+        if (nd < 0) continue;
+        const int e0 = t_off[nd], e1 = t_off[nd + 1];
+        __shared__ int s_base;
+        if (threadIdx.x == 0) { s_base = s_count; s_count += e1 - e0; }
+        __syncthreads();
+        const int base = s_base;
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int tok = t_tok[e];
+            const int slot = base + (e - e0);
+            if (slot < scr_cap && tok >= 0 && tok < V) {
+                const float lp = (logits[(int64_t)r * ld + tok] - rowmax[r]) - logsum[r];
+                sc[slot] = lp + run_score[r];
+                fl[slot] = k * V + tok;
+            } else if (slot < scr_cap) {
+                sc[slot] = -INFINITY; fl[slot] = 0x7fffffff;
+            }
+        }
+        __syncthreads();
+    }
+    const int n = min(s_count, scr_cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sel = 0; sel < 2 * K; ++sel) {
+        float best = -INFINITY; int bi = -1, bf = 0x7fffffff;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float v = sc[i]; const int f = fl[i];
+            if (v > best || (v == best && v > -INFINITY && f < bf)) { best = v; bi = i; bf = f; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+            if (ov > best || (ov == best && ov > -INFINITY && of < bf)) { best = ov; bi = oi; bf = of; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_besti[warp] = bi; s_bestf[warp] = bf; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bb = -INFINITY; int ii = -1, ff = 0x7fffffff;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+                if (s_best[w] > bb || (s_best[w] == bb && bb > -INFINITY && s_bestf[w] < ff)) { bb = s_best[w]; ii = s_besti[w]; ff = s_bestf[w]; }
+            const int o = b * 2 * K + sel;
+            if (ii >= 0 && bb > -INFINITY) {
+                cand_lp[o] = bb; cand_beam[o] = ff / V; cand_tok[o] = ff % V;
+                sc[ii] = -INFINITY;
+            } else {   // fewer than 2K continuations: HF's remaining top-k slots hold -inf entries
+                cand_lp[o] = -INFINITY; cand_beam[o] = 0; cand_tok[o] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// per user: HF:generation/utils.py:2999-3073 (running beams, finished beams) + :2876-2921 (early stop heuristic)
+__global__ void __launch_bounds__(128)
+beam_update_kernel(const float* __restrict__ cand_lp, const int* __restrict__ cand_beam, const int* __restrict__ cand_tok,
+                   const int* __restrict__ seq_in, int* __restrict__ seq_out, const int* __restrict__ fin_in,
+                   int* __restrict__ fin_out, const int* __restrict__ src_in, int* __restrict__ src_out,
+                   const int* __restrict__ node_in, int* __restrict__ node_out, float* __restrict__ run_out,
+                   const float* __restrict__ fscore_in, float* __restrict__ fscore_out, const int* __restrict__ isfin_in,
+                   int* __restrict__ isfin_out, const int* __restrict__ glen_in, int* __restrict__ glen_out,
+                   int* __restrict__ cur_tok, int* __restrict__ unsat, const int* __restrict__ t_off,
+                   const int* __restrict__ t_tok, const int* __restrict__ t_node, int K, int T, int cur_len, int max_len,
+                   int eos, float denom_fin, float denom_next) {
+    extern __shared__ int smi[];
+    int* run_sel = smi;              // [K]   candidate index chosen for running slot k
+    int* fin_sel = smi + K;          // [K]   merged index chosen for finished slot k
+    const int b = blockIdx.x;
+    const float* lp = cand_lp + b * 2 * K;
+    const int* cb = cand_beam + b * 2 * K;
+    const int* ct = cand_tok + b * 2 * K;
+    if (threadIdx.x == 0) {
+        const bool at_max = (cur_len + 1 >= max_len);
+        const bool us = unsat[b] != 0;
+        float runv[128], finv[192];
+        bool used[192];
+        // ---- running beams: top-K of lp + hits * -1e9 (stable: lowest index first)
+        for (int c = 0; c < 2 * K; ++c) {
+            const bool hit = (ct[c] == eos) || at_max;
+            runv[c] = lp[c] + (hit ? NEG_BIG : -0.0f);
+            used[c] = false;
+        }
+        for (int k = 0; k < K; ++k) {
+            int bi = -1;
+            for (int c = 0; c < 2 * K; ++c)
+                if (!used[c] && (bi < 0 || runv[c] > runv[bi])) bi = c;
+            used[bi] = true;
+            run_sel[k] = bi;
+            run_out[b * K + k] = runv[bi];
+        }
+        // ---- finished beams: merge [old finished (K), new candidates (2K)]
+        for (int k = 0; k < K; ++k) finv[k] = fscore_in[b * K + k];
+        for (int c = 0; c < 2 * K; ++c) {
+            const bool hit = (ct[c] == eos) || at_max;
+            float v = lp[c] / denom_fin;
+            v += us ? -0.0f : NEG_BIG;
+            v += (hit && c < K) ? -0.0f : NEG_BIG;
+            finv[K + c] = v;
+        }
+        for (int m = 0; m < 3 * K; ++m) used[m] = false;
+        float min_fs = INFINITY;
+        bool all_fin = true;
+        for (int k = 0; k < K; ++k) {
+            int bi = -1;
+            for (int m = 0; m < 3 * K; ++m)
+                if (!used[m] && (bi < 0 || finv[m] > finv[bi])) bi = m;
+            used[bi] = true;
+            fin_sel[k] = bi;
+            fscore_out[b * K + k] = finv[bi];
+            int fin, gl;
+            if (bi < K) { fin = isfin_in[b * K + bi]; gl = glen_in[b * K + bi]; }
+            else {
+                const int c = bi - K;
+                const bool hit = (ct[c] == eos) || at_max;
+                fin = (hit && c < K) ? 1 : 0;
+                gl = cur_len;   // cur_len + 1 - prompt_len(=1)
+            }
+            isfin_out[b * K + k] = fin; glen_out[b * K + k] = gl;
+            min_fs = fminf(min_fs, finv[bi]);
+            all_fin = all_fin && fin;
+        }
+        // ---- early-stop heuristic with cur_len already incremented
+        const float best_running = run_out[b * K] / denom_next;
+        bool any = false;
+        for (int k = 0; k < K; ++k) {
+            const float worst = isfin_out[b * K + k] ? min_fs : NEG_BIG;
+            if (best_running > worst) any = true;
+        }
+        unsat[b] = (us && any) ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- materialise the selected rows (all threads)
+    for (int k = 0; k < K; ++k) {
+        const int c = run_sel[k];
+        const int parent = b * K + cb[c];
+        const int r = b * K + k;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            int v = seq_in[parent * T + t];
+            if (t == cur_len) v = ct[c];
+            seq_out[r * T + t] = v;
+            int s = src_in[parent * T + t];
+            if (t >= cur_len) s = r;
+            src_out[r * T + t] = s;
+        }
+        if (threadIdx.x == 0) {
+            cur_tok[r] = ct[c];
+            node_out[r] = (lp[c] > -INFINITY) ? trie_child(t_off, t_tok, t_node, node_in[parent], ct[c]) : -1;
+        }
+        const int m = fin_sel[k];
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            int v;
+            if (m < K) v = fin_in[(b * K + m) * T + t];
+            else {
+                const int c2 = m - K;
+                v = seq_in[(b * K + cb[c2]) * T + t];
+                if (t == cur_len) v = ct[c2];
+            }
+            fin_out[r * T + t] = v;
+        }
+    }
+}
+
+__global__ void gen_finalize_kernel(const int* __restrict__ fin_seq, const float* __restrict__ fin_score,
+                                    const int* __restrict__ is_fin, const int* __restrict__ gen_len, int B, int K, int R,
+                                    int T, int max_len, int32_t* __restrict__ seqs, float* __restrict__ scores,
+                                    int* __restrict__ out_len) {
+    __shared__ int s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * R; i += blockDim.x) {
+        const int b = i / R, k = i % R;
+        const int r = b * K + k;
+        scores[i] = fin_score[r];
+        for (int t = 0; t < max_len; ++t) seqs[(int64_t)i * max_len + t] = fin_seq[r * T + t];
+        if (is_fin[r]) atomicMax(&s_max, gen_len[r]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out_len[0] = 1 + s_max;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------------------
+void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t* ww, int B, int Le_user, Trie* trie,
+              int K, int Rret, int max_len, float length_penalty, int32_t* seqs, float* scores, int* out_len_host) {
+    P5_CHECK(K >= 1 && K <= 64, "num_beams must be in [1, 64]");
+    P5_CHECK(Rret >= 1 && Rret <= K, "num_return_sequences must be in [1, num_beams]");
+    P5_CHECK(max_len >= 2 && max_len <= 256, "max_length must be in [2, 256]");
+    P5_CHECK(ids && mask, "null input");
+    P5_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->st;
+    const int dt = e->dt, d = e->d, A = e->A, H = e->H, ff = e->ff, V = e->V, Vpad = e->Vpad;
+    const int R = B * K, T = max_len;
+    // root child reached by the decoder start token (all reference paths start with 0)
+    int root_child = -1;
+    for (int k = trie->h_off[0]; k < trie->h_off[1]; ++k)
+        if (trie->h_tok[k] == 0) root_child = trie->h_node[k];
+    P5_CHECK(root_child >= 0, "trie paths must start with the decoder start token 0");
+    const int cand_cap = K * (trie->max_fanout > 0 ? trie->max_fanout : 1);
+    GenWs* g = get_gen_ws(e, R, T, K, B, cand_cap);
+
+    // ---- encoder once per user (eval mode) + cross K/V once per user
+    e->set_geometry(B, Le_user, 1);
+    e->training = false; e->seed = 0;
+    if (e->shadow_stale) e->refresh_shadow();
+    e->load_inputs(ids, mask, ww, nullptr);
+    e->encoder_forward();
+    e->have_fwd = false;   // training activations are not valid for backward any more
+    const int Le = e->Le;
+    DropCfg none;
+    for (int l = 0; l < e->ND; ++l)
+        e->linear_fwd(e->enc_out, d, e->dec[l].ca.k, 2 * A, d, (int)e->Me, e->ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
+    e->build_bias(false, T);   // decoder relative bias for positions 0..T-1: [H, 2T-1], offset T-1
+    const int n_delta = 2 * T - 1, bias_off = T - 1;
+
+    gen_init_kernel<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(g->seq[0], g->fin_seq[0], g->src[0], g->node[0], g->run_score[0],
+                                                           g->fin_score[0], g->is_fin[0], g->gen_len[0], g->cur_tok, g->unsat,
+                                                           B, K, T, root_child);
+    LAUNCHED();
+    const int n_steps = std::min(max_len - 1, trie->max_depth - 1);
+    int cur = 0;
+    const float hs = 1.f / sqrtf((float)d);
+    for (int step = 0; step < n_steps; ++step) {
+        const int cur_len = step + 1, pos = step;
+        // ---- one decoder step over R rows
+        embed_fwd(e->P + e->off_shared, nullptr, g->cur_tok, nullptr, g->y, R, d, V, e->cfg.whole_word_rows, none, st);
+        for (int l = 0; l < e->ND; ++l) {
+            const DecLayerOff& w = e->dec[l];
+            rmsnorm_fwd(g->y, e->P + w.ln0, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
+            e->linear_fwd(g->n, d, w.sa.q, 3 * A, d, R, g->qkv, dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
+            const size_t sm = (64 + pos + 1) * sizeof(float);
+            if (dt == DT_F32)
+                decode_self_attn_kernel<float><<<dim3(H, R), 64, sm, st>>>((const float*)g->qkv, (float*)g->Kc[l], (float*)g->Vc[l],
+                                                                         g->src[cur], e->bias_dec, n_delta, bias_off,
+                                                                         (float*)g->ctx, A, T, pos);
+            else
+                decode_self_attn_kernel<bf16><<<dim3(H, R), 64, sm, st>>>((const bf16*)g->qkv, (bf16*)g->Kc[l], (bf16*)g->Vc[l],
+                                                                        g->src[cur], e->bias_dec, n_delta, bias_off,
+                                                                        (bf16*)g->ctx, A, T, pos);
+            LAUNCHED();
+            e->linear_fwd(g->ctx, A, w.sa.o, d, A, R, g->y, DT_F32, d, EPI_ADD_RESID, 1.f, nullptr, g->y, none);
+            rmsnorm_fwd(g->y, e->P + w.ln1, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
+            e->linear_fwd(g->n, d, w.ca.q, A, d, R, g->cq, dt, A, 0, 1.f, nullptr, nullptr, none);
+            AttnArgs a;   // the K beams of a user are the query rows against that user's cross K/V
+            a.B = B; a.H = H; a.Lq = K; a.Lk = Le;
+            a.q = {g->cq, dt, A, (int64_t)K * A};
+            a.k = {e->ckv[l], dt, 2 * A, (int64_t)Le * 2 * A};
+            a.v = {(const char*)e->ckv[l] + (size_t)A * e->esz(), dt, 2 * A, (int64_t)Le * 2 * A};
+            a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0; a.key_mask = e->mask_e; a.causal = 0; a.q_pos_offset = 0;
+            a.row_map = nullptr;
+            attn_simt_fwd(a, g->ctx, dt, A, (int64_t)K * A, nullptr, st);
+            e->linear_fwd(g->ctx, A, w.ca.o, d, A, R, g->y, DT_F32, d, EPI_ADD_RESID, 1.f, nullptr, g->y, none);
+            rmsnorm_fwd(g->y, e->P + w.ln2, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
+            if (!e->gated) {
+                e->linear_fwd(g->n, d, w.ff.wi, ff, d, R, g->h, dt, ff, EPI_RELU, 1.f, nullptr, nullptr, none);
+            } else {
+                e->linear_fwd(g->n, d, w.ff.wi, 2 * ff, d, R, g->z, dt, 2 * ff, 0, 1.f, nullptr, nullptr, none);
+                gated_gelu_fwd(g->z, g->h, dt, R, ff, none, st);
+            }
+            e->linear_fwd(g->h, ff, w.ff.wo, d, ff, R, g->y, DT_F32, d, EPI_ADD_RESID, 1.f, nullptr, g->y, none);
+        }
+        rmsnorm_fwd(g->y, e->P + e->off_dec_final, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
+        e->linear_fwd(g->n, d, e->off_shared, V, d, R, g->logits, DT_F32, Vpad, 0, hs, nullptr, nullptr, none);
+        // ---- log-softmax normaliser, constrained top-2K, beam bookkeeping
+        rows_logsumexp_kernel<<<R, 256, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum);
+        LAUNCHED();
+        topk_candidates_kernel<<<B, 256, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum, g->run_score[cur], g->node[cur],
+                                                 trie->d_off, trie->d_tok, K, g->scr_score, g->scr_flat, g->scr_cap,
+                                                 g->cand_lp, g->cand_beam, g->cand_tok);
+        LAUNCHED();
+        const int nxt = cur ^ 1;
+        const float denom_fin = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
+        const float denom_next = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
+        beam_update_kernel<<<B, 128, 2 * K * sizeof(int), st>>>(
+            g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
+            g->src[nxt], g->node[cur], g->node[nxt], g->run_score[nxt], g->fin_score[cur], g->fin_score[nxt], g->is_fin[cur],
+            g->is_fin[nxt], g->gen_len[cur], g->gen_len[nxt], g->cur_tok, g->unsat, trie->d_off, trie->d_tok, trie->d_node, K,
+            T, cur_len, max_len, 1 /*eos*/, denom_fin, denom_next);
+        LAUNCHED();
+        cur = nxt;
+    }
+    gen_finalize_kernel<<<1, 256, 0, st>>>(g->fin_seq[cur], g->fin_score[cur], g->is_fin[cur], g->gen_len[cur], B, K, Rret, T,
+                                          max_len, seqs, scores, g->out_len);
+    LAUNCHED();
+    if (out_len_host) {
+        P5_CUDA(cudaMemcpyAsync(out_len_host, g->out_len, sizeof(int), cudaMemcpyDeviceToHost, st));
+        P5_CUDA(cudaStreamSynchronize(st));
+    }
+}
+
+}  // namespace p5

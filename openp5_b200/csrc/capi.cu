@@ -1,8 +1,7 @@
 // extern "C" boundary of libp5b200.so — see include/p5_b200.h for the contract of every entry point.
-#include "common.cuh"
 #include "engine.h"
-#include "../../include/p5_b200.h"
 #include <string>
+#include <dlfcn.h>
 
 using namespace p5;
 
@@ -10,23 +9,196 @@ static thread_local std::string g_last_error;
 namespace p5 { int g_launches = 0; }
 
 #define P5_API_BEGIN try {
-#define P5_API_END                                        \
-    }                                                     \
-    catch (const P5Error& e) {                            \
-        g_last_error = e.what();                          \
-        return e.code ? e.code : 1;                       \
-    }                                                     \
-    catch (const std::exception& e) {                     \
+#define P5_API_END                                            \
+    }                                                         \
+    catch (const P5Error& e) {                                \
+        g_last_error = e.what();                              \
+        return e.code ? e.code : 1;                           \
+    }                                                         \
+    catch (const std::exception& e) {                         \
         g_last_error = std::string("exception: ") + e.what(); \
-        return 99;                                        \
-    }                                                     \
+        return 99;                                            \
+    }                                                         \
     return 0;
+
+static Engine* E(p5_handle h) {
+    P5_CHECK(h != nullptr, "null engine handle");
+    return reinterpret_cast<Engine*>(h);
+}
+
+namespace p5 {
+// beam.cu
+int trie_build(Engine* e, const int32_t* paths, const int64_t* offsets, int n_paths, Trie** out);
+void trie_free(Trie* t);
+void trie_stats(Trie* t, int* n_nodes, int* n_edges, int* max_depth);
+int trie_get(Trie* t, const int32_t* prefix, int prefix_len, int32_t* out, int cap);
+void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t* ww, int B, int Le, Trie* trie,
+              int K, int R, int max_len, float length_penalty, int32_t* seqs, float* scores, int* out_len);
+// comm.cu
+void comm_unique_id(void* id128);
+void comm_init(Engine* e, const void* id128, int rank, int world);
+void comm_allreduce_grads(Engine* e);
+void comm_destroy(Engine* e);
+}
 
 extern "C" {
 
 const char* p5_last_error(void) { return g_last_error.c_str(); }
 int p5_version(void) { return 100; }
 int p5_launch_count(void) { return p5::g_launches + gemm_tc_launch_count(); }
+
+int p5_create(const P5Config* cfg, int device, void* cuda_stream, p5_handle* out) {
+    P5_API_BEGIN
+    P5_CHECK(cfg && out, "null argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        throw P5Error(4, "p5_create: no CUDA device available — the B200 engine has no CPU fallback");
+    P5_CHECK(device >= 0 && device < ndev, "invalid device index");
+    *out = reinterpret_cast<p5_handle>(new Engine(*cfg, device, (cudaStream_t)cuda_stream));
+    P5_API_END
+}
+int p5_destroy(p5_handle h) {
+    P5_API_BEGIN
+    if (h) {
+        comm_destroy(E(h));
+        delete E(h);
+    }
+    P5_API_END
+}
+int p5_param_count(p5_handle h, int* n) {
+    P5_API_BEGIN
+    *n = (int)E(h)->params.size();
+    P5_API_END
+}
+int p5_param_info(p5_handle h, int i, const char** name, int* ndim, int64_t shape[2], float** data, float** grad) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CHECK(i >= 0 && i < (int)e->params.size(), "parameter index out of range");
+    const ParamInfo& p = e->params[i];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = p.ndim;
+    if (shape) { shape[0] = p.shape[0]; shape[1] = p.shape[1]; }
+    if (data) *data = e->P + p.off;
+    if (grad) *grad = e->G + p.off;
+    P5_API_END
+}
+int p5_params_changed(p5_handle h) {
+    P5_API_BEGIN
+    E(h)->shadow_stale = true;
+    P5_API_END
+}
+int p5_forward(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask, const int32_t* whole_word_ids,
+               const int32_t* labels, int B, int Le, int Ld, float* loss_tok, float* logits_or_null, int training,
+               uint64_t seed) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CHECK(input_ids && attention_mask && labels, "null input");
+    e->forward(input_ids, attention_mask, whole_word_ids, labels, B, Le, Ld, training != 0, seed);
+    if (loss_tok)
+        P5_CUDA(cudaMemcpyAsync(loss_tok, e->loss_tok, (size_t)B * Ld * 4, cudaMemcpyDeviceToDevice, e->st));
+    if (logits_or_null)
+        P5_CUDA(cudaMemcpy2DAsync(logits_or_null, (size_t)e->V * 4, e->logits, (size_t)e->Vpad * 4, (size_t)e->V * 4,
+                                  (size_t)B * Ld, cudaMemcpyDeviceToDevice, e->st));
+    P5_API_END
+}
+int p5_backward(p5_handle h, const float* dloss_tok) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CHECK(dloss_tok != nullptr, "null dloss");
+    P5_CUDA(cudaMemcpyAsync(e->dloss, dloss_tok, (size_t)e->Md * 4, cudaMemcpyDeviceToDevice, e->st));
+    e->backward();
+    P5_API_END
+}
+int p5_train_fwd_bwd(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask,
+                     const int32_t* whole_word_ids, const int32_t* labels, const int32_t* labels_mask, int B, int Le,
+                     int Ld, float* loss_out, uint64_t seed) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CHECK(input_ids && attention_mask && labels && labels_mask, "null input");
+    e->forward(input_ids, attention_mask, whole_word_ids, labels, B, Le, Ld, true, seed);
+    P5_CUDA(cudaMemcpyAsync(e->lmask, labels_mask, (size_t)B * Ld * 4, cudaMemcpyDeviceToDevice, e->st));
+    runner_loss_fwd_bwd(e->loss_tok, e->lmask, B, Ld, e->loss_scalar, e->dloss, e->st);
+    if (loss_out) P5_CUDA(cudaMemcpyAsync(loss_out, e->loss_scalar, 4, cudaMemcpyDeviceToDevice, e->st));
+    e->backward();
+    P5_API_END
+}
+int p5_grad_norm(p5_handle h, float* out) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    e->grad_norm();
+    if (out) P5_CUDA(cudaMemcpyAsync(out, e->norm_out, 4, cudaMemcpyDeviceToDevice, e->st));
+    P5_API_END
+}
+int p5_grad_scale(p5_handle h, float s) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    scale_f32(e->G, e->n_flat, s, e->st);
+    e->norm_valid = false;
+    P5_API_END
+}
+int p5_zero_grad(p5_handle h) {
+    P5_API_BEGIN
+    E(h)->zero_grad();
+    P5_API_END
+}
+int p5_adamw_step(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float clip) {
+    P5_API_BEGIN
+    P5_CHECK(step >= 1, "AdamW step is 1-based");
+    E(h)->adamw(lr, beta1, beta2, eps, weight_decay, step, clip);
+    P5_API_END
+}
+
+int p5_comm_unique_id(void* id128_host) {
+    P5_API_BEGIN
+    comm_unique_id(id128_host);
+    P5_API_END
+}
+int p5_comm_init(p5_handle h, const void* id128_host, int rank, int world) {
+    P5_API_BEGIN
+    comm_init(E(h), id128_host, rank, world);
+    P5_API_END
+}
+int p5_allreduce_grads(p5_handle h) {
+    P5_API_BEGIN
+    comm_allreduce_grads(E(h));
+    P5_API_END
+}
+
+int p5_trie_build(p5_handle h, const int32_t* paths_host, const int64_t* offsets_host, int n_paths, p5_trie* out) {
+    P5_API_BEGIN
+    Trie* t = nullptr;
+    trie_build(E(h), paths_host, offsets_host, n_paths, &t);
+    *out = reinterpret_cast<p5_trie>(t);
+    P5_API_END
+}
+int p5_trie_free(p5_trie t) {
+    P5_API_BEGIN
+    if (t) trie_free(reinterpret_cast<Trie*>(t));
+    P5_API_END
+}
+int p5_trie_stats(p5_trie t, int* n_nodes, int* n_edges, int* max_depth) {
+    P5_API_BEGIN
+    P5_CHECK(t != nullptr, "null trie");
+    trie_stats(reinterpret_cast<Trie*>(t), n_nodes, n_edges, max_depth);
+    P5_API_END
+}
+int p5_trie_get(p5_trie t, const int32_t* prefix_host, int prefix_len, int32_t* out_tokens_host, int cap, int* n_out) {
+    P5_API_BEGIN
+    P5_CHECK(t != nullptr, "null trie");
+    *n_out = trie_get(reinterpret_cast<Trie*>(t), prefix_host, prefix_len, out_tokens_host, cap);
+    P5_API_END
+}
+int p5_generate(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask, const int32_t* whole_word_ids,
+                int B, int Le, p5_trie trie, int num_beams, int num_return, int max_len, float length_penalty,
+                int32_t* seqs, float* scores, int* out_len_host) {
+    P5_API_BEGIN
+    P5_CHECK(trie != nullptr, "null trie");
+    generate(E(h), input_ids, attention_mask, whole_word_ids, B, Le, reinterpret_cast<Trie*>(trie), num_beams,
+             num_return, max_len, length_penalty, seqs, scores, out_len_host);
+    P5_API_END
+}
 
 int p5_op_gemm(const P5GemmDesc* d, void* cuda_stream) {
     P5_API_BEGIN
@@ -42,6 +214,7 @@ int p5_op_gemm(const P5GemmDesc* d, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (d->backend == 0) {
         gemm_simt(p, st);
+        ++p5::g_launches;
     } else if (d->backend == 1) {
         gemm_tc_force_block_n(d->force_block_n);
         gemm_tc(p, st);

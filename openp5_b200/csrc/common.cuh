@@ -153,6 +153,7 @@ enum EpiFlags : int {
     EPI_DROPOUT = 4,     // v = keep(seed, site, idx) ? v * inv_keep : 0
     EPI_ADD_RESID = 8,   // v += resid_f32[idx]
     EPI_ACCUM = 16,      // v += C_old[idx]                  (gradient accumulation, C must be fp32)
+    EPI_ATOMIC = 32,     // atomicAdd(C[idx], v)             (split-K weight gradients; C must be fp32)
 };
 
 struct GemmEpilogue {

@@ -1,0 +1,624 @@
+// engine.cu — parameter layout, workspace, and the forward / backward pass of the P5 T5 model on one B200.
+//
+// Reference path restated here (what the kernels are wired to compute):
+//   encoder  : ref src/src_t5/model/P5_T5.py:74-204  (JointEncoder: token + whole-word embedding, shared position
+//              bias + padding mask built once, T5 blocks, final RMSNorm + dropout)
+//   decoder  : HF:models/t5/modeling_t5.py:637-793 via P5_T5.py:338-350 (causal self-attention, NO decoder pad mask,
+//              cross-attention with zero position bias + encoder pad mask)
+//   head/loss: P5_T5.py:352-369 (hidden * d_model^-0.5, tied lm_head, un-reduced CE)
+// Data layout in HBM: token-major row-major activations [B*L, features]; the residual stream is fp32, GEMM
+// operands are `dt` (bf16 on the tensor-core path, fp32 on the parity path); heads are column slices of width 64.
+#include "engine.h"
+#include <math.h>
+#include <string.h>
+
+namespace p5 {
+
+static inline void* poff(const void* p, int64_t elems, int dt) {
+    return (void*)((const char*)p + elems * (int64_t)dtype_size(dt));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// construction
+// ------------------------------------------------------------------------------------------------------------
+void* Engine::dalloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 256;
+    P5_CUDA(cudaMalloc(&p, bytes));
+    P5_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+    allocs.push_back(p);
+    return p;
+}
+
+Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device(dev), st(stream) {
+    P5_CHECK(c.d_kv == 64, "d_kv must be 64");
+    P5_CHECK(c.d_model % 32 == 0 && c.d_model <= 1024, "d_model must be a multiple of 32 and <= 1024");
+    P5_CHECK(c.d_ff % 8 == 0, "d_ff must be a multiple of 8");
+    P5_CHECK(c.max_enc_len >= 1 && c.max_enc_len <= 512, "max_enc_len must be in [1, 512] (Collator.py:13)");
+    P5_CHECK(c.max_batch >= 1 && c.max_dec_len >= 1, "max_batch / max_dec_len");
+    P5_CUDA(cudaSetDevice(dev));
+    dt = c.precision == 0 ? DT_F32 : DT_BF16;
+    mn = c.use_mn_major != 0;
+    d = c.d_model; H = c.num_heads; A = H * 64; ff = c.d_ff; V = c.vocab_size; Vpad = (int)round_up(V, 64);
+    NE = c.num_layers; ND = c.num_decoder_layers; gated = c.ffn_gated_gelu != 0; p_drop = c.dropout;
+
+    // ---- parameter table (HF state_dict names); q,k,v / cross k,v / wi_0,wi_1 are adjacent so
+    //      that each group is ONE GEMM weight
+    int64_t off = 0;
+    auto add = [&](const std::string& name, int64_t r, int64_t cdim) {
+        ParamInfo pi;
+        pi.name = name; pi.ndim = cdim > 0 ? 2 : 1; pi.shape[0] = r; pi.shape[1] = cdim > 0 ? cdim : 0;
+        pi.numel = cdim > 0 ? r * cdim : r;
+        pi.off = off;
+        off += round_up(pi.numel, 64);
+        params.push_back(pi);
+        return pi.off;
+    };
+    auto add_attn = [&](const std::string& pre, AttnOff& a) {
+        a.q = add(pre + ".q.weight", A, d);
+        a.k = add(pre + ".k.weight", A, d);
+        a.v = add(pre + ".v.weight", A, d);
+        a.o = add(pre + ".o.weight", d, A);
+    };
+    auto add_ffn = [&](const std::string& pre, FfnOff& f) {
+        if (gated) {
+            f.wi = add(pre + ".DenseReluDense.wi_0.weight", ff, d);
+            f.wi1 = add(pre + ".DenseReluDense.wi_1.weight", ff, d);
+        } else {
+            f.wi = add(pre + ".DenseReluDense.wi.weight", ff, d);
+            f.wi1 = -1;
+        }
+        f.wo = add(pre + ".DenseReluDense.wo.weight", d, ff);
+    };
+    off_shared = add("shared.weight", V, d);
+    off_ww = add("encoder.whole_word_embeddings.weight", c.whole_word_rows, d);
+    enc.resize(NE);
+    for (int i = 0; i < NE; ++i) {
+        const std::string b = "encoder.block." + std::to_string(i) + ".layer";
+        add_attn(b + ".0.SelfAttention", enc[i].sa);
+        if (i == 0) off_enc_rel = add(b + ".0.SelfAttention.relative_attention_bias.weight", c.rel_buckets, H);
+        enc[i].ln0 = add(b + ".0.layer_norm.weight", d, 0);
+        add_ffn(b + ".1", enc[i].ff);
+        enc[i].ln1 = add(b + ".1.layer_norm.weight", d, 0);
+    }
+    off_enc_final = add("encoder.final_layer_norm.weight", d, 0);
+    dec.resize(ND);
+    for (int i = 0; i < ND; ++i) {
+        const std::string b = "decoder.block." + std::to_string(i) + ".layer";
+        add_attn(b + ".0.SelfAttention", dec[i].sa);
+        if (i == 0) off_dec_rel = add(b + ".0.SelfAttention.relative_attention_bias.weight", c.rel_buckets, H);
+        dec[i].ln0 = add(b + ".0.layer_norm.weight", d, 0);
+        add_attn(b + ".1.EncDecAttention", dec[i].ca);
+        dec[i].ln1 = add(b + ".1.layer_norm.weight", d, 0);
+        add_ffn(b + ".2", dec[i].ff);
+        dec[i].ln2 = add(b + ".2.layer_norm.weight", d, 0);
+    }
+    off_dec_final = add("decoder.final_layer_norm.weight", d, 0);
+    n_flat = off;
+    P = dalloc_t<float>(n_flat);
+    G = dalloc_t<float>(n_flat);
+    M1 = dalloc_t<float>(n_flat);
+    V2 = dalloc_t<float>(n_flat);
+    if (dt == DT_BF16) P16 = dalloc_t<bf16>(n_flat);
+
+    // ---- workspace
+    Bm = c.max_batch; Lem = (int)round_up(c.max_enc_len, 8); Ldm = c.max_dec_len;
+    const int64_t Mem = (int64_t)Bm * Lem, Mdm = (int64_t)Bm * Ldm, Mx = Mem > Mdm ? Mem : Mdm;
+    const size_t e = esz();
+    ids_e = dalloc_t<int>(Mem); mask_e = dalloc_t<int>(Mem); ww_e = dalloc_t<int>(Mem);
+    labels = dalloc_t<int>(Mdm); dec_ids = dalloc_t<int>(Mdm); lmask = dalloc_t<int>(Mdm);
+    const bool tc_attn = dt == DT_BF16;
+    xe.resize(2 * NE + 1); rstd_e.resize(2 * NE + 1); ne.resize(2 * NE);
+    for (auto& p : xe) p = dalloc_t<float>(Mem * d);
+    for (auto& p : rstd_e) p = dalloc_t<float>(Mem);
+    for (auto& p : ne) p = dalloc(Mem * d * e);
+    enc_out = dalloc(Mem * d * e);
+    qkv_e.resize(NE); ctx_e.resize(NE); h_e.resize(NE); z_e.assign(NE, nullptr); P_e.assign(NE, nullptr);
+    lse_e.assign(NE, nullptr);
+    const int64_t SS = (int64_t)Bm * H * Lem * Lem;
+    for (int i = 0; i < NE; ++i) {
+        qkv_e[i] = dalloc(Mem * 3 * A * e);
+        ctx_e[i] = dalloc(Mem * A * e);
+        h_e[i] = dalloc(Mem * ff * e);
+        if (gated) z_e[i] = dalloc(Mem * 2 * ff * e);
+        if (tc_attn) P_e[i] = dalloc(SS * e);
+        else lse_e[i] = dalloc_t<float>((int64_t)Bm * H * Lem);
+    }
+    if (tc_attn) {
+        S_scr = dalloc_t<float>(SS);
+        Pd_scr = dalloc(SS * e);
+        dS_scr = dalloc(SS * e);
+    }
+    yd.resize(3 * ND + 1); rstd_d.resize(3 * ND + 1); nd.resize(3 * ND);
+    for (auto& p : yd) p = dalloc_t<float>(Mdm * d);
+    for (auto& p : rstd_d) p = dalloc_t<float>(Mdm);
+    for (auto& p : nd) p = dalloc(Mdm * d * e);
+    dec_out = dalloc(Mdm * d * e);
+    sqkv.resize(ND); sctx.resize(ND); cq.resize(ND); ckv.resize(ND); cctx.resize(ND); h_d.resize(ND);
+    z_d.assign(ND, nullptr); slse.resize(ND); clse.resize(ND);
+    for (int i = 0; i < ND; ++i) {
+        sqkv[i] = dalloc(Mdm * 3 * A * e);
+        sctx[i] = dalloc(Mdm * A * e);
+        cq[i] = dalloc(Mdm * A * e);
+        ckv[i] = dalloc(Mem * 2 * A * e);
+        cctx[i] = dalloc(Mdm * A * e);
+        h_d[i] = dalloc(Mdm * ff * e);
+        if (gated) z_d[i] = dalloc(Mdm * 2 * ff * e);
+        slse[i] = dalloc_t<float>((int64_t)Bm * H * Ldm);
+        clse[i] = dalloc_t<float>((int64_t)Bm * H * Ldm);
+    }
+    logits = dalloc_t<float>(Mdm * Vpad);
+    lse_ce = dalloc_t<float>(Mdm); loss_tok = dalloc_t<float>(Mdm); dloss = dalloc_t<float>(Mdm);
+    loss_scalar = dalloc_t<float>(4);
+    dlogits = dalloc(Mdm * Vpad * e);
+    dx_a = dalloc_t<float>(Mx * d);
+    d_encout = dalloc_t<float>(Mem * d);
+    g_ff = dalloc(Mx * (gated ? 3 : 1) * ff * e);
+    g_d = dalloc(Mx * d * e); g_d2 = dalloc(Mx * d * e);
+    g_qkv = dalloc(Mx * 3 * A * e); g_ctx = dalloc(Mx * A * e); g_ckv = dalloc(Mem * 2 * A * e);
+    f_qkv = dalloc_t<float>((tc_attn ? Mdm : Mx) * 3 * A);
+    f_ckv = dalloc_t<float>(Mem * 2 * A);
+    bias_enc = dalloc_t<float>((int64_t)H * (2 * Lem)); dbias_enc = dalloc_t<float>((int64_t)H * (2 * Lem));
+    const int Ldb = Ldm > 256 ? Ldm : 256;   // generate() builds the decoder table for max_length <= 256 positions
+    bias_dec = dalloc_t<float>((int64_t)H * (2 * Ldb)); dbias_dec = dalloc_t<float>((int64_t)H * (2 * Ldb));
+    lut_enc = dalloc_t<int>(2 * Lem); lut_dec = dalloc_t<int>(2 * Ldb);
+    norm_partial = dalloc_t<float>(1024); norm_out = dalloc_t<float>(4);
+    P5_CUDA(cudaStreamSynchronize(st));
+}
+
+void free_gen_ws(struct GenWs* g);
+
+Engine::~Engine() {
+    cudaSetDevice(device);
+    cudaStreamSynchronize(st);
+    if (gen) free_gen_ws(gen);
+    for (void* p : allocs) cudaFree(p);
+    gemm_tc_clear_cache();
+}
+
+DropCfg Engine::drop(uint32_t kind, int layer) const {
+    DropCfg c;
+    if (training && p_drop > 0.f) {
+        c.seed = seed; c.site = kind * 64u + (uint32_t)layer; c.thr = drop_threshold(p_drop);
+        c.inv_keep = 1.f / (1.f - p_drop);
+    }
+    return c;
+}
+
+void Engine::refresh_shadow() {
+    if (dt == DT_BF16) cast_f32_to(P, P16, DT_BF16, n_flat, st);
+    shadow_stale = false;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GEMM helpers
+// ------------------------------------------------------------------------------------------------------------
+void Engine::gemm(GemmProblem& p) {
+    if (dt == DT_BF16 && gemm_tc_supported(p, mn)) gemm_tc(p, st);
+    else { gemm_simt(p, st); ++g_launches; }
+}
+
+// Y[M,N] = epi( X[M,K] * W[N,K]^T )
+void Engine::linear_fwd(const void* X, int64_t ldx, int64_t w_off, int N, int K, int M, void* Y, int y_dtype,
+                        int64_t ldy, int flags, float alpha, const void* aux, const float* resid, DropCfg dc) {
+    GemmProblem p;
+    p.M = M; p.N = N; p.K = K;
+    p.A.ptr = X; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = ldx;
+    p.B.ptr = W(w_off); p.B.dtype = dt; p.B.major = MAJOR_K; p.B.ld = K;
+    p.epi.C = Y; p.epi.c_dtype = y_dtype; p.epi.ldc = ldy; p.epi.alpha = alpha; p.epi.flags = flags;
+    p.epi.aux = aux; p.epi.aux_dtype = dt; p.epi.resid = resid;
+    if (dc.thr == 0) p.epi.flags &= ~EPI_DROPOUT;
+    p.epi.seed = dc.seed; p.epi.site = dc.site; p.epi.drop_thr = dc.thr; p.epi.inv_keep = dc.inv_keep;
+    gemm(p);
+}
+
+// dX[M,K] = epi( dY[M,N] * W[N,K] )      (B operand = W read in place as MN-major)
+void Engine::linear_dgrad(const void* dY, int64_t lddy, int64_t w_off, int N, int K, int M, void* dX, int dx_dtype,
+                          int64_t lddx, int flags, float alpha, const void* aux, bool accum_f32) {
+    GemmProblem p;
+    p.M = M; p.N = K; p.K = N;
+    p.A.ptr = dY; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = lddy;
+    p.B.ptr = W(w_off); p.B.dtype = dt; p.B.major = MAJOR_MN; p.B.ld = K;
+    p.epi.C = dX; p.epi.c_dtype = dx_dtype; p.epi.ldc = lddx; p.epi.alpha = alpha; p.epi.flags = flags;
+    p.epi.aux = aux; p.epi.aux_dtype = dt;
+    if (accum_f32) p.epi.flags |= EPI_ACCUM;
+    gemm(p);
+}
+
+// G[w_off : N x K] += alpha * dY[M,N]^T * X[M,K]     (both operands read in place as MN-major, split-K over M)
+void Engine::linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t w_off, int N, int K, int M,
+                          float alpha) {
+    GemmProblem p;
+    p.M = N; p.N = K; p.K = M;
+    int splits = 1;
+    {
+        const int64_t tiles = cdiv(N, 128) * cdiv(K, 128);
+        int want = (int)(296 / (tiles > 0 ? tiles : 1));
+        if (want > 32) want = 32;
+        while (want > 1 && !(M % want == 0 && M / want >= 128)) --want;
+        splits = want < 1 ? 1 : want;
+    }
+    const int Ks = M / splits;
+    p.K = Ks; p.nb1 = splits;
+    p.A.ptr = dY; p.A.dtype = dt; p.A.major = MAJOR_MN; p.A.ld = lddy; p.A.bs1 = (int64_t)Ks * lddy;
+    p.B.ptr = X; p.B.dtype = dt; p.B.major = MAJOR_MN; p.B.ld = ldx; p.B.bs1 = (int64_t)Ks * ldx;
+    p.epi.C = G + w_off; p.epi.c_dtype = DT_F32; p.epi.ldc = K; p.epi.cs1 = 0; p.epi.alpha = alpha;
+    p.epi.flags = EPI_ATOMIC;
+    gemm(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// inputs
+// ------------------------------------------------------------------------------------------------------------
+__global__ void shift_right_kernel(const int* __restrict__ labels, int* __restrict__ dec_ids, int B, int Ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Ld) return;
+    const int t = i % Ld;
+    int v = t == 0 ? 0 : labels[i - 1];
+    if (v == -100) v = 0;
+    dec_ids[i] = v;
+}
+
+void Engine::set_geometry(int B_, int Le_user_, int Ld_) {
+    P5_CHECK(B_ >= 1 && B_ <= Bm, "batch exceeds max_batch");
+    P5_CHECK(Le_user_ >= 1 && round_up(Le_user_, 8) <= Lem, "encoder length exceeds max_enc_len");
+    P5_CHECK(Ld_ >= 1 && Ld_ <= Ldm, "decoder length exceeds max_dec_len");
+    B = B_; Le_user = Le_user_; Le = (int)round_up(Le_user_, 8); Ld = Ld_;
+    Me = (int64_t)B * Le; Md = (int64_t)B * Ld;
+}
+
+void Engine::load_inputs(const int32_t* ids, const int32_t* mask, const int32_t* ww, const int32_t* lab) {
+    const size_t wbytes = (size_t)Le_user * 4, pitch = (size_t)Le * 4;
+    if (Le != Le_user) {
+        P5_CUDA(cudaMemsetAsync(ids_e, 0, Me * 4, st));
+        P5_CUDA(cudaMemsetAsync(mask_e, 0, Me * 4, st));
+        P5_CUDA(cudaMemsetAsync(ww_e, 0, Me * 4, st));
+    }
+    P5_CUDA(cudaMemcpy2DAsync(ids_e, pitch, ids, wbytes, wbytes, B, cudaMemcpyDeviceToDevice, st));
+    P5_CUDA(cudaMemcpy2DAsync(mask_e, pitch, mask, wbytes, wbytes, B, cudaMemcpyDeviceToDevice, st));
+    if (ww) P5_CUDA(cudaMemcpy2DAsync(ww_e, pitch, ww, wbytes, wbytes, B, cudaMemcpyDeviceToDevice, st));
+    else P5_CUDA(cudaMemsetAsync(ww_e, 0xff, Me * 4, st));  // -1 = no whole-word embedding
+    if (lab) {
+        P5_CUDA(cudaMemcpyAsync(labels, lab, Md * 4, cudaMemcpyDeviceToDevice, st));
+        shift_right_kernel<<<(unsigned)cdiv(Md, 256), 256, 0, st>>>(labels, dec_ids, B, Ld);
+        P5_CUDA(cudaGetLastError());
+        ++g_launches;
+    }
+}
+
+// relative_position_bucket (HF:modeling_t5.py:189-235) for every delta = key_pos - query_pos in [-(L-1), L-1]
+static int rel_bucket(int rel, bool bidirectional, int num_buckets, int max_distance) {
+    int b = 0, n = num_buckets;
+    if (bidirectional) {
+        n /= 2;
+        if (rel > 0) b += n;
+        rel = rel < 0 ? -rel : rel;
+    } else {
+        rel = rel < 0 ? -rel : 0;
+    }
+    const int max_exact = n / 2;
+    if (rel < max_exact) return b + rel;
+    // fp32 arithmetic as torch does it; +1e-5 guards the exact-integer cases (rel = max_exact * 2^k)
+    const float v = logf((float)rel / (float)max_exact) / (float)log((double)max_distance / max_exact) * (float)(n - max_exact);
+    int l = max_exact + (int)(v + 1e-5f);
+    if (l > n - 1) l = n - 1;
+    return b + l;
+}
+
+void Engine::build_bias(bool encoder, int L) {
+    int& cur = encoder ? lut_enc_L : lut_dec_L;
+    int* lut = encoder ? lut_enc : lut_dec;
+    const int n_delta = 2 * L - 1;
+    if (cur != L) {
+        std::vector<int> h(n_delta);
+        for (int i = 0; i < n_delta; ++i) h[i] = rel_bucket(i - (L - 1), encoder, cfg.rel_buckets, cfg.rel_max_distance);
+        // pageable source: the call returns once the data is staged, so `h` may go out of scope
+        P5_CUDA(cudaMemcpyAsync(lut, h.data(), n_delta * sizeof(int), cudaMemcpyHostToDevice, st));
+        cur = L;
+    }
+    relbias_build(P + (encoder ? off_enc_rel : off_dec_rel), lut, encoder ? bias_enc : bias_dec, H, n_delta, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// feed-forward sub-layer (HF:modeling_t5.py:84-150):  x_out = x + drop( Wo * drop(act(Wi * n)) )
+// ------------------------------------------------------------------------------------------------------------
+void Engine::ffn_fwd(const void* n, int64_t M, const FfnOff& w, void* z, void* h, const float* x_resid, float* x_out,
+                     uint32_t kind_act, uint32_t kind_wo, int layer) {
+    DropCfg none;
+    if (!gated) {
+        linear_fwd(n, d, w.wi, ff, d, (int)M, h, dt, ff, EPI_RELU | EPI_DROPOUT, 1.f, nullptr, nullptr, drop(kind_act, layer));
+    } else {
+        linear_fwd(n, d, w.wi, 2 * ff, d, (int)M, z, dt, 2 * ff, 0, 1.f, nullptr, nullptr, none);
+        gated_gelu_fwd(z, h, dt, (int)M, ff, drop(kind_act, layer), st);
+    }
+    linear_fwd(h, ff, w.wo, d, ff, (int)M, x_out, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, x_resid,
+               drop(kind_wo, layer));
+}
+
+// in: dx_out = dL/dx_out (fp32).  out: dn_out (dt) = dL/dn; weight grads accumulated.
+void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void* n, const void* z, const void* h,
+                     void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer) {
+    drop_cast(dx_out, g_d, dt, M * d, drop(kind_wo, layer), st);
+    linear_wgrad(g_d, d, h, ff, w.wo, d, ff, (int)M, 1.f);
+    if (!gated) {
+        const DropCfg da = drop(kind_act, layer);
+        linear_dgrad(g_d, d, w.wo, d, ff, (int)M, g_ff, dt, ff, EPI_MULPOS, da.inv_keep, h, false);
+        linear_wgrad(g_ff, ff, n, d, w.wi, ff, d, (int)M, 1.f);
+        linear_dgrad(g_ff, ff, w.wi, ff, d, (int)M, dn_out, dt, d, 0, 1.f, nullptr, false);
+    } else {
+        void* dh = poff(g_ff, (int64_t)M * 2 * ff, dt);   // g_ff = [dz (M x 2ff) | dh (M x ff)]
+        linear_dgrad(g_d, d, w.wo, d, ff, (int)M, dh, dt, ff, 0, 1.f, nullptr, false);
+        gated_gelu_bwd(z, dh, g_ff, dt, (int)M, ff, drop(kind_act, layer), st);
+        linear_wgrad(g_ff, 2 * ff, n, d, w.wi, 2 * ff, d, (int)M, 1.f);
+        linear_dgrad(g_ff, 2 * ff, w.wi, 2 * ff, d, (int)M, dn_out, dt, d, 0, 1.f, nullptr, false);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// encoder self-attention
+// ------------------------------------------------------------------------------------------------------------
+void Engine::enc_attention_fwd(int l) {
+    const int64_t SS1 = (int64_t)Le * Le;
+    if (dt == DT_BF16) {
+        GemmProblem p;   // S = Q K^T   (unscaled, HF:modeling_t5.py:308)
+        p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;
+        p.A.ptr = qkv_e[l]; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = 3 * A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * 3 * A;
+        p.B = p.A; p.B.ptr = poff(qkv_e[l], A, dt);
+        p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
+        gemm(p);
+        const DropCfg dc = drop(S_ENC_P, l);
+        softmax_fwd(S_scr, bias_enc, mask_e, P_e[l], Pd_scr, dt, B, H, Le, Le, 0, dc, st);
+        GemmProblem q;   // ctx = Pd V
+        q.M = Le; q.N = 64; q.K = Le; q.nb1 = H; q.nb2 = B;
+        q.A.ptr = dc.thr ? Pd_scr : P_e[l]; q.A.dtype = dt; q.A.major = MAJOR_K; q.A.ld = Le; q.A.bs1 = SS1; q.A.bs2 = SS1 * H;
+        q.B.ptr = poff(qkv_e[l], 2 * A, dt); q.B.dtype = dt; q.B.major = MAJOR_MN; q.B.ld = 3 * A; q.B.bs1 = 64;
+        q.B.bs2 = (int64_t)Le * 3 * A;
+        q.epi.C = ctx_e[l]; q.epi.c_dtype = dt; q.epi.ldc = A; q.epi.cs1 = 64; q.epi.cs2 = (int64_t)Le * A;
+        gemm(q);
+    } else {
+        AttnArgs a;
+        a.B = B; a.H = H; a.Lq = Le; a.Lk = Le;
+        a.q = {qkv_e[l], dt, 3 * A, (int64_t)Le * 3 * A};
+        a.k = {poff(qkv_e[l], A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.v = {poff(qkv_e[l], 2 * A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.bias_rel = bias_enc; a.bias_off = Le - 1; a.n_delta = 2 * Le - 1;
+        a.key_mask = mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = drop(S_ENC_P, l);
+        attn_simt_fwd(a, ctx_e[l], dt, A, (int64_t)Le * A, lse_e[l], st);
+    }
+}
+
+void Engine::enc_attention_bwd(int l, const void* dctx, void* dqkv) {
+    const int64_t SS1 = (int64_t)Le * Le;
+    const DropCfg dc = drop(S_ENC_P, l);
+    if (dt == DT_BF16) {
+        GemmProblem p;   // dPd = dctx V^T
+        p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;
+        p.A.ptr = dctx; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * A;
+        p.B.ptr = poff(qkv_e[l], 2 * A, dt); p.B.dtype = dt; p.B.major = MAJOR_K; p.B.ld = 3 * A; p.B.bs1 = 64;
+        p.B.bs2 = (int64_t)Le * 3 * A;
+        p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
+        gemm(p);
+        softmax_bwd(S_scr, P_e[l], dS_scr, dc.thr ? Pd_scr : nullptr, dt, dbias_enc, B, H, Le, Le, dc, st);
+        const void* Pd = dc.thr ? Pd_scr : P_e[l];
+        GemmProblem v;   // dV[j,c] = sum_i Pd[i,j] dctx[i,c]
+        v.M = Le; v.N = 64; v.K = Le; v.nb1 = H; v.nb2 = B;
+        v.A.ptr = Pd; v.A.dtype = dt; v.A.major = MAJOR_MN; v.A.ld = Le; v.A.bs1 = SS1; v.A.bs2 = SS1 * H;
+        v.B.ptr = dctx; v.B.dtype = dt; v.B.major = MAJOR_MN; v.B.ld = A; v.B.bs1 = 64; v.B.bs2 = (int64_t)Le * A;
+        v.epi.C = poff(dqkv, 2 * A, dt); v.epi.c_dtype = dt; v.epi.ldc = 3 * A; v.epi.cs1 = 64; v.epi.cs2 = (int64_t)Le * 3 * A;
+        gemm(v);
+        GemmProblem q;   // dQ[i,c] = sum_j dS[i,j] K[j,c]
+        q.M = Le; q.N = 64; q.K = Le; q.nb1 = H; q.nb2 = B;
+        q.A.ptr = dS_scr; q.A.dtype = dt; q.A.major = MAJOR_K; q.A.ld = Le; q.A.bs1 = SS1; q.A.bs2 = SS1 * H;
+        q.B.ptr = poff(qkv_e[l], A, dt); q.B.dtype = dt; q.B.major = MAJOR_MN; q.B.ld = 3 * A; q.B.bs1 = 64;
+        q.B.bs2 = (int64_t)Le * 3 * A;
+        q.epi.C = dqkv; q.epi.c_dtype = dt; q.epi.ldc = 3 * A; q.epi.cs1 = 64; q.epi.cs2 = (int64_t)Le * 3 * A;
+        gemm(q);
+        GemmProblem k;   // dK[j,c] = sum_i dS[i,j] Q[i,c]
+        k.M = Le; k.N = 64; k.K = Le; k.nb1 = H; k.nb2 = B;
+        k.A.ptr = dS_scr; k.A.dtype = dt; k.A.major = MAJOR_MN; k.A.ld = Le; k.A.bs1 = SS1; k.A.bs2 = SS1 * H;
+        k.B.ptr = qkv_e[l]; k.B.dtype = dt; k.B.major = MAJOR_MN; k.B.ld = 3 * A; k.B.bs1 = 64; k.B.bs2 = (int64_t)Le * 3 * A;
+        k.epi.C = poff(dqkv, A, dt); k.epi.c_dtype = dt; k.epi.ldc = 3 * A; k.epi.cs1 = 64; k.epi.cs2 = (int64_t)Le * 3 * A;
+        gemm(k);
+    } else {
+        // fp32 parity path: dqkv IS the fp32 scratch
+        P5_CUDA(cudaMemsetAsync(dqkv, 0, Me * 3 * A * sizeof(float), st));
+        AttnArgs a;
+        a.B = B; a.H = H; a.Lq = Le; a.Lk = Le;
+        a.q = {qkv_e[l], dt, 3 * A, (int64_t)Le * 3 * A};
+        a.k = {poff(qkv_e[l], A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.v = {poff(qkv_e[l], 2 * A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.bias_rel = bias_enc; a.bias_off = Le - 1; a.n_delta = 2 * Le - 1;
+        a.key_mask = mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
+        float* f = (float*)dqkv;
+        attn_simt_bwd(a, ctx_e[l], dctx, dt, A, (int64_t)Le * A, lse_e[l], f, 3 * A, (int64_t)Le * 3 * A, f + A,
+                      f + 2 * A, 3 * A, (int64_t)Le * 3 * A, dbias_enc, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+void Engine::encoder_forward() {
+    build_bias(true, Le);
+    embed_fwd(P + off_shared, P + off_ww, ids_e, ww_e, xe[0], (int)Me, d, V, cfg.whole_word_rows, drop(S_EMB_E, 0), st);
+    DropCfg none;
+    for (int l = 0; l < NE; ++l) {
+        const EncLayerOff& w = enc[l];
+        float *x_in = xe[2 * l], *x_mid = xe[2 * l + 1], *x_out = xe[2 * l + 2];
+        rmsnorm_fwd(x_in, P + w.ln0, ne[2 * l], dt, rstd_e[2 * l], (int)Me, d, cfg.ln_eps, none, st);
+        linear_fwd(ne[2 * l], d, w.sa.q, 3 * A, d, (int)Me, qkv_e[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
+        enc_attention_fwd(l);
+        linear_fwd(ctx_e[l], A, w.sa.o, d, A, (int)Me, x_mid, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, x_in,
+                   drop(S_ENC_O, l));
+        rmsnorm_fwd(x_mid, P + w.ln1, ne[2 * l + 1], dt, rstd_e[2 * l + 1], (int)Me, d, cfg.ln_eps, none, st);
+        ffn_fwd(ne[2 * l + 1], Me, w.ff, z_e[l], h_e[l], x_mid, x_out, S_ENC_ACT, S_ENC_WO, l);
+    }
+    rmsnorm_fwd(xe[2 * NE], P + off_enc_final, enc_out, dt, rstd_e[2 * NE], (int)Me, d, cfg.ln_eps, drop(S_ENC_FINAL, 0), st);
+}
+
+static AttnArgs dec_self_args(Engine& e, int l, DropCfg dc) {
+    AttnArgs a;
+    const int A = e.A, Ld = e.Ld;
+    a.B = e.B; a.H = e.H; a.Lq = Ld; a.Lk = Ld;
+    a.q = {e.sqkv[l], e.dt, 3 * A, (int64_t)Ld * 3 * A};
+    a.k = {poff(e.sqkv[l], A, e.dt), e.dt, 3 * A, (int64_t)Ld * 3 * A};
+    a.v = {poff(e.sqkv[l], 2 * A, e.dt), e.dt, 3 * A, (int64_t)Ld * 3 * A};
+    a.bias_rel = e.bias_dec; a.bias_off = Ld - 1; a.n_delta = 2 * Ld - 1;
+    a.key_mask = nullptr; a.causal = 1; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
+    return a;
+}
+static AttnArgs dec_cross_args(Engine& e, int l, DropCfg dc) {
+    AttnArgs a;
+    const int A = e.A, Ld = e.Ld, Le = e.Le;
+    a.B = e.B; a.H = e.H; a.Lq = Ld; a.Lk = Le;
+    a.q = {e.cq[l], e.dt, A, (int64_t)Ld * A};
+    a.k = {e.ckv[l], e.dt, 2 * A, (int64_t)Le * 2 * A};
+    a.v = {poff(e.ckv[l], A, e.dt), e.dt, 2 * A, (int64_t)Le * 2 * A};
+    a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0;   // cross-attention position bias is zero (HF:...:317-322)
+    a.key_mask = e.mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
+    return a;
+}
+
+void Engine::decoder_forward() {
+    build_bias(false, Ld);
+    embed_fwd(P + off_shared, nullptr, dec_ids, nullptr, yd[0], (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
+    DropCfg none;
+    for (int l = 0; l < ND; ++l) {
+        const DecLayerOff& w = dec[l];
+        float *y0 = yd[3 * l], *y1 = yd[3 * l + 1], *y2 = yd[3 * l + 2], *y3 = yd[3 * l + 3];
+        rmsnorm_fwd(y0, P + w.ln0, nd[3 * l], dt, rstd_d[3 * l], (int)Md, d, cfg.ln_eps, none, st);
+        linear_fwd(nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, sqkv[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
+        attn_simt_fwd(dec_self_args(*this, l, drop(S_DEC_SP, l)), sctx[l], dt, A, (int64_t)Ld * A, slse[l], st);
+        linear_fwd(sctx[l], A, w.sa.o, d, A, (int)Md, y1, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, y0,
+                   drop(S_DEC_SO, l));
+        rmsnorm_fwd(y1, P + w.ln1, nd[3 * l + 1], dt, rstd_d[3 * l + 1], (int)Md, d, cfg.ln_eps, none, st);
+        linear_fwd(nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, cq[l], dt, A, 0, 1.f, nullptr, nullptr, none);
+        linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Me, ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
+        attn_simt_fwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], dt, A, (int64_t)Ld * A, clse[l], st);
+        linear_fwd(cctx[l], A, w.ca.o, d, A, (int)Md, y2, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, y1,
+                   drop(S_DEC_CO, l));
+        rmsnorm_fwd(y2, P + w.ln2, nd[3 * l + 2], dt, rstd_d[3 * l + 2], (int)Md, d, cfg.ln_eps, none, st);
+        ffn_fwd(nd[3 * l + 2], Md, w.ff, z_d[l], h_d[l], y2, y3, S_DEC_ACT, S_DEC_WO, l);
+    }
+    rmsnorm_fwd(yd[3 * ND], P + off_dec_final, dec_out, dt, rstd_d[3 * ND], (int)Md, d, cfg.ln_eps, drop(S_DEC_FINAL, 0), st);
+}
+
+void Engine::head_forward() {
+    DropCfg none;
+    // logits = (h * d_model^-0.5) * shared^T   (P5_T5.py:357-361)
+    linear_fwd(dec_out, d, off_shared, V, d, (int)Md, logits, DT_F32, Vpad, 0, 1.f / sqrtf((float)d), nullptr, nullptr, none);
+    ce_fwd(logits, Vpad, labels, loss_tok, lse_ce, (int)Md, V, st);
+}
+
+void Engine::forward(const int32_t* ids, const int32_t* mask, const int32_t* ww, const int32_t* lab, int B_, int Le_,
+                     int Ld_, bool train, uint64_t seed_) {
+    P5_CUDA(cudaSetDevice(device));
+    set_geometry(B_, Le_, Ld_);
+    training = train; seed = seed_;
+    if (shadow_stale) refresh_shadow();
+    load_inputs(ids, mask, ww, lab);
+    encoder_forward();
+    decoder_forward();
+    head_forward();
+    have_fwd = true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward (consumes this->dloss = dL/dloss_tok)
+// ------------------------------------------------------------------------------------------------------------
+void Engine::backward() {
+    P5_CHECK(have_fwd, "p5_backward called without a preceding p5_forward");
+    P5_CUDA(cudaSetDevice(device));
+    norm_valid = false;
+    const float hs = 1.f / sqrtf((float)d);
+    auto as_T = [&](float* src, void* dst, int64_t n) -> void* {
+        if (dt == DT_F32) return (void*)src;
+        cast_f32_to(src, dst, dt, n, st);
+        return dst;
+    };
+    // ---- head
+    ce_bwd(logits, Vpad, lse_ce, labels, dloss, dlogits, dt, (int)Md, V, Vpad, st);
+    linear_wgrad(dlogits, Vpad, dec_out, d, off_shared, V, d, (int)Md, hs);
+    linear_dgrad(dlogits, Vpad, off_shared, V, d, (int)Md, g_d2, dt, d, 0, hs, nullptr, false);
+    float* dy = dx_a;
+    rmsnorm_bwd(g_d2, dt, yd[3 * ND], rstd_d[3 * ND], P + off_dec_final, nullptr, dy, G + off_dec_final, (int)Md, d,
+                drop(S_DEC_FINAL, 0), st);
+    P5_CUDA(cudaMemsetAsync(d_encout, 0, Me * d * sizeof(float), st));
+    P5_CUDA(cudaMemsetAsync(dbias_dec, 0, (size_t)H * (2 * Ld) * sizeof(float), st));
+    DropCfg none;
+    // ---- decoder blocks
+    for (int l = ND - 1; l >= 0; --l) {
+        const DecLayerOff& w = dec[l];
+        float *y0 = yd[3 * l], *y1 = yd[3 * l + 1], *y2 = yd[3 * l + 2];
+        ffn_bwd(dy, Md, w.ff, nd[3 * l + 2], z_d[l], h_d[l], g_d2, S_DEC_ACT, S_DEC_WO, l);
+        rmsnorm_bwd(g_d2, dt, y2, rstd_d[3 * l + 2], P + w.ln2, dy, dy, G + w.ln2, (int)Md, d, none, st);
+        // cross attention
+        drop_cast(dy, g_d, dt, Md * d, drop(S_DEC_CO, l), st);
+        linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f);
+        linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        P5_CUDA(cudaMemsetAsync(f_ckv, 0, Me * 2 * A * sizeof(float), st));
+        attn_simt_bwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], g_ctx, dt, A, (int64_t)Ld * A, clse[l], f_qkv, A,
+                      (int64_t)Ld * A, f_ckv, f_ckv + A, 2 * A, (int64_t)Le * 2 * A, nullptr, st);
+        void* gq = as_T(f_qkv, g_qkv, Md * A);
+        void* gkv = as_T(f_ckv, g_ckv, Me * 2 * A);
+        linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Me, 1.f);
+        linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Me, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
+        linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f);
+        linear_dgrad(gq, A, w.ca.q, A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
+        rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st);
+        // self attention
+        drop_cast(dy, g_d, dt, Md * d, drop(S_DEC_SO, l), st);
+        linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f);
+        linear_dgrad(g_d, d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
+        attn_simt_bwd(dec_self_args(*this, l, drop(S_DEC_SP, l)), sctx[l], g_ctx, dt, A, (int64_t)Ld * A, slse[l], f_qkv,
+                      3 * A, (int64_t)Ld * 3 * A, f_qkv + A, f_qkv + 2 * A, 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
+        void* gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
+        linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f);
+        linear_dgrad(gqkv, 3 * A, w.sa.q, 3 * A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
+        rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st);
+    }
+    embed_bwd(dy, dec_ids, nullptr, G + off_shared, nullptr, (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
+    relbias_scatter_grad(dbias_dec, lut_dec, G + off_dec_rel, H, 2 * Ld - 1, st);
+
+    // ---- encoder
+    float* dx = dx_a;
+    rmsnorm_bwd(d_encout, DT_F32, xe[2 * NE], rstd_e[2 * NE], P + off_enc_final, nullptr, dx, G + off_enc_final, (int)Me, d,
+                drop(S_ENC_FINAL, 0), st);
+    P5_CUDA(cudaMemsetAsync(dbias_enc, 0, (size_t)H * (2 * Le) * sizeof(float), st));
+    for (int l = NE - 1; l >= 0; --l) {
+        const EncLayerOff& w = enc[l];
+        float *x_in = xe[2 * l], *x_mid = xe[2 * l + 1];
+        ffn_bwd(dx, Me, w.ff, ne[2 * l + 1], z_e[l], h_e[l], g_d2, S_ENC_ACT, S_ENC_WO, l);
+        rmsnorm_bwd(g_d2, dt, x_mid, rstd_e[2 * l + 1], P + w.ln1, dx, dx, G + w.ln1, (int)Me, d, none, st);
+        drop_cast(dx, g_d, dt, Me * d, drop(S_ENC_O, l), st);
+        linear_wgrad(g_d, d, ctx_e[l], A, w.sa.o, d, A, (int)Me, 1.f);
+        linear_dgrad(g_d, d, w.sa.o, d, A, (int)Me, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        void* dqkv = dt == DT_F32 ? (void*)f_qkv : g_qkv;
+        enc_attention_bwd(l, g_ctx, dqkv);
+        linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Me, 1.f);
+        linear_dgrad(dqkv, 3 * A, w.sa.q, 3 * A, d, (int)Me, g_d2, dt, d, 0, 1.f, nullptr, false);
+        rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Me, d, none, st);
+    }
+    embed_bwd(dx, ids_e, ww_e, G + off_shared, G + off_ww, (int)Me, d, V, cfg.whole_word_rows, drop(S_EMB_E, 0), st);
+    relbias_scatter_grad(dbias_enc, lut_enc, G + off_enc_rel, H, 2 * Le - 1, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// optimiser
+// ------------------------------------------------------------------------------------------------------------
+void Engine::grad_norm() {
+    sumsq_norm(G, n_flat, norm_partial, norm_out, st);
+    norm_valid = true;
+}
+void Engine::zero_grad() {
+    P5_CUDA(cudaMemsetAsync(G, 0, n_flat * sizeof(float), st));
+    norm_valid = false;
+}
+void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip) {
+    if (clip > 0.f && !norm_valid) grad_norm();
+    adamw_flat(P, G, M1, V2, P16, n_flat, lr, b1, b2, eps, wd, step, clip, clip > 0.f ? norm_out : nullptr, 1.f, st);
+    shadow_stale = false;
+}
+
+}  // namespace p5

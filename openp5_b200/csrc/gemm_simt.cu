@@ -68,7 +68,8 @@ gemm_simt_kernel(int M, int N, int K, int nb1, const TA* __restrict__ A, int64_t
             if (gn >= N) continue;
             int64_t idx = boff + (int64_t)gm * epi.ldc + gn;
             float v = epilogue_apply(epi, acc[i][j], idx);
-            st_from_f32(epi.C, epi.c_dtype, idx, v);
+            if (epi.flags & EPI_ATOMIC) atomicAdd((float*)epi.C + idx, v);
+            else st_from_f32(epi.C, epi.c_dtype, idx, v);
         }
     }
 }

@@ -199,7 +199,10 @@ __device__ __forceinline__ void epi_store8(const GemmEpilogue& e, const float* a
             for (int j = 0; j < ncols_valid; ++j) v[j] += c[idx + j];
         }
     }
-    if (e.c_dtype == DT_F32) {
+    if (e.flags & EPI_ATOMIC) {
+        float* c = (float*)e.C;
+        for (int j = 0; j < ncols_valid; ++j) atomicAdd(c + idx + j, v[j]);
+    } else if (e.c_dtype == DT_F32) {
         float* c = (float*)e.C;
         if (vec) {
             *reinterpret_cast<float4*>(c + idx) = make_float4(v[0], v[1], v[2], v[3]);
@@ -505,13 +508,8 @@ bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return false;
     if (!operand_ok(p.A, p.nb1, p.nb2, allow_mn_major)) return false;
     if (!operand_ok(p.B, p.nb1, p.nb2, allow_mn_major)) return false;
-    // TMA zero-fills out-of-bounds boxes, so M, N, K need no padding; the inner (contiguous) extent must still
-    // cover whole 16-byte units for the tensor map
-    if (p.A.major == MAJOR_K && p.K % 8 != 0) return false;
-    if (p.B.major == MAJOR_K && p.K % 8 != 0) return false;
-    if (p.A.major == MAJOR_MN && p.M % 8 != 0) return false;
-    if (p.B.major == MAJOR_MN && p.N % 8 != 0) return false;
-    if ((p.epi.flags & EPI_ACCUM) && p.epi.c_dtype != DT_F32) return false;
+    // TMA zero-fills out-of-bounds boxes, so M, N, K need no padding or alignment (only ld / base address do)
+    if ((p.epi.flags & (EPI_ACCUM | EPI_ATOMIC)) && p.epi.c_dtype != DT_F32) return false;
     return true;
 }
 

@@ -1,0 +1,469 @@
+// HBM-bound kernels of the T5 block: embedding gather, RMSNorm fwd/bwd, dropout-cast, gated-GELU, cross-entropy,
+// runner loss, relative-position-bias tables.  Coalesced / vectorised; statistics in fp32.
+#include "kernels.cuh"
+
+namespace p5 {
+extern int g_launches;
+#define LAUNCHED() do { P5_CUDA(cudaGetLastError()); ++g_launches; } while (0)
+
+// ---- small vector helpers ------------------------------------------------------------------------------------
+template <int VEC> __device__ __forceinline__ void ldv(const float* p, float* v) {
+    if constexpr (VEC == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else v[0] = p[0];
+}
+template <int VEC> __device__ __forceinline__ void ldv(const bf16* p, float* v) {
+    if constexpr (VEC == 4) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+        float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else v[0] = __bfloat162float(p[0]);
+}
+template <int VEC> __device__ __forceinline__ void stv(float* p, const float* v) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else p[0] = v[0];
+}
+template <int VEC> __device__ __forceinline__ void stv(bf16* p, const float* v) {
+    if constexpr (VEC == 4) {
+        uint2 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+        h[0] = __floats2bfloat162_rn(v[0], v[1]);
+        h[1] = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = t;
+    } else p[0] = __float2bfloat16_rn(v[0]);
+}
+
+// =================================================================================================================
+// embeddings
+// =================================================================================================================
+template <int VEC>
+__global__ void embed_fwd_kernel(const float* __restrict__ E, const float* __restrict__ W, const int* __restrict__ ids,
+                                 const int* __restrict__ ww, float* __restrict__ x, int M, int d, int vocab,
+                                 int ww_rows, DropCfg drop) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    int id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    int w = ww ? ww[row] : -1;
+    if (w >= ww_rows) w = ww_rows - 1;
+    const float* e = E + (int64_t)id * d;
+    const float* wr = (w >= 0) ? W + (int64_t)w * d : nullptr;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC], u[VEC];
+        ldv<VEC>(e + c, v);
+        if (wr) {
+            ldv<VEC>(wr + c, u);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] += u[j];
+        }
+        if (drop.thr) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                v[j] = drop_keep(drop.seed, drop.site, (uint64_t)row * d + c + j, drop.thr) ? v[j] * drop.inv_keep : 0.f;
+        }
+        stv<VEC>(x + (int64_t)row * d + c, v);
+    }
+}
+
+void embed_fwd(const float* E, const float* Wword, const int* ids, const int* ww, float* x, int M, int d, int vocab,
+               int ww_rows, DropCfg drop, cudaStream_t st) {
+    if (M <= 0) return;
+    const int rows_per_block = 8;
+    dim3 grid((unsigned)cdiv(M, rows_per_block));
+    if (d % 128 == 0)
+        embed_fwd_kernel<4><<<grid, rows_per_block * 32, 0, st>>>(E, Wword, ids, ww, x, M, d, vocab, ww_rows, drop);
+    else
+        embed_fwd_kernel<1><<<grid, rows_per_block * 32, 0, st>>>(E, Wword, ids, ww, x, M, d, vocab, ww_rows, drop);
+    LAUNCHED();
+}
+
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ ids, const int* __restrict__ ww,
+                                 float* __restrict__ dE, float* __restrict__ dW, int M, int d, int vocab, int ww_rows,
+                                 DropCfg drop) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    int id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    int w = ww ? ww[row] : -1;
+    if (w >= ww_rows) w = ww_rows - 1;
+    for (int c = lane; c < d; c += 32) {
+        float g = dx[(int64_t)row * d + c];
+        if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)row * d + c, drop.thr) ? g * drop.inv_keep : 0.f;
+        if (g != 0.f) {
+            atomicAdd(dE + (int64_t)id * d + c, g);
+            if (w >= 0) atomicAdd(dW + (int64_t)w * d + c, g);
+        }
+    }
+}
+
+void embed_bwd(const float* dx, const int* ids, const int* ww, float* dE, float* dWword, int M, int d, int vocab,
+               int ww_rows, DropCfg drop, cudaStream_t st) {
+    if (M <= 0) return;
+    embed_bwd_kernel<<<(unsigned)cdiv(M, 8), 256, 0, st>>>(dx, ids, ww, dE, dWword, M, d, vocab, ww_rows, drop);
+    LAUNCHED();
+}
+
+// =================================================================================================================
+// RMSNorm
+// =================================================================================================================
+template <typename T, int VEC>
+__global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ n,
+                                   float* __restrict__ rstd, int M, int d, float eps, DropCfg drop) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (int64_t)row * d;
+    float ss = 0.f;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC];
+        ldv<VEC>(xr + c, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) ss += v[j] * v[j];
+    }
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss / (float)d + eps);
+    if (rstd && lane == 0) rstd[row] = r;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC], g[VEC];
+        ldv<VEC>(xr + c, v);
+        ldv<VEC>(w + c, g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            v[j] = g[j] * (v[j] * r);
+            if (drop.thr)
+                v[j] = drop_keep(drop.seed, drop.site, (uint64_t)row * d + c + j, drop.thr) ? v[j] * drop.inv_keep : 0.f;
+        }
+        stv<VEC>(n + (int64_t)row * d + c, v);
+    }
+}
+
+void rmsnorm_fwd(const float* x, const float* w, void* n, int n_dtype, float* rstd, int M, int d, float eps,
+                 DropCfg drop, cudaStream_t st) {
+    if (M <= 0) return;
+    dim3 grid((unsigned)cdiv(M, 8));
+    const bool v4 = d % 128 == 0;
+    if (n_dtype == DT_F32) {
+        if (v4) rmsnorm_fwd_kernel<float, 4><<<grid, 256, 0, st>>>(x, w, (float*)n, rstd, M, d, eps, drop);
+        else rmsnorm_fwd_kernel<float, 1><<<grid, 256, 0, st>>>(x, w, (float*)n, rstd, M, d, eps, drop);
+    } else {
+        if (v4) rmsnorm_fwd_kernel<bf16, 4><<<grid, 256, 0, st>>>(x, w, (bf16*)n, rstd, M, d, eps, drop);
+        else rmsnorm_fwd_kernel<bf16, 1><<<grid, 256, 0, st>>>(x, w, (bf16*)n, rstd, M, d, eps, drop);
+    }
+    LAUNCHED();
+}
+
+// One CTA = 8 warps handles RB rows; each warp owns rows (warp, warp+8, ...).  dw partials are reduced through
+// shared memory and flushed with one atomicAdd per column per CTA.
+static constexpr int RMS_BWD_ROWS = 32;
+template <typename T>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const T* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ rstd,
+                   const float* __restrict__ w, const float* dres, float* dx,   // dres may alias dx (in-place)
+                   float* __restrict__ dw, int M, int d, DropCfg drop) {
+    extern __shared__ float sdw[];  // [d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) sdw[c] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * RMS_BWD_ROWS;
+    float acc[32];  // per-lane dw partials for columns lane + 32*k (d <= 1024)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    for (int rr = warp; rr < RMS_BWD_ROWS; rr += 8) {
+        const int row = r0 + rr;
+        if (row >= M) break;
+        const float* xr = x + (int64_t)row * d;
+        const T* dr = dn + (int64_t)row * d;
+        const float r = rstd[row];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d) {
+                float g = to_f32(dr[c]);
+                if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)row * d + c, drop.thr) ? g * drop.inv_keep : 0.f;
+                const float xh = xr[c] * r;
+                dot += g * w[c] * xh;
+                acc[k] += g * xh;
+            }
+        }
+        dot = warp_sum(dot) / (float)d;
+        for (int c = lane; c < d; c += 32) {
+            float g = to_f32(dr[c]);
+            if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)row * d + c, drop.thr) ? g * drop.inv_keep : 0.f;
+            const float xh = xr[c] * r;
+            float v = r * (g * w[c] - xh * dot);
+            if (dres) v += dres[(int64_t)row * d + c];
+            dx[(int64_t)row * d + c] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int c = lane + 32 * k;
+        if (c < d && acc[k] != 0.f) atomicAdd(&sdw[c], acc[k]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float v = sdw[c];
+        if (v != 0.f) atomicAdd(dw + c, v);
+    }
+}
+
+void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd, const float* w, const float* dres,
+                 float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st) {
+    if (M <= 0) return;
+    dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
+    const size_t sm = (size_t)d * sizeof(float);
+    if (dn_dtype == DT_F32)
+        rmsnorm_bwd_kernel<float><<<grid, 256, sm, st>>>((const float*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
+    else
+        rmsnorm_bwd_kernel<bf16><<<grid, 256, sm, st>>>((const bf16*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
+    LAUNCHED();
+}
+
+// =================================================================================================================
+// casts / dropout-cast
+// =================================================================================================================
+template <typename T>
+__global__ void drop_cast_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t n, DropCfg drop) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float v[4];
+            ldv<4>(in + i, v);
+            if (drop.thr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = drop_keep(drop.seed, drop.site, (uint64_t)(i + j), drop.thr) ? v[j] * drop.inv_keep : 0.f;
+            }
+            stv<4>(out + i, v);
+        } else {
+            for (int64_t k = i; k < n; ++k) {
+                float v = in[k];
+                if (drop.thr) v = drop_keep(drop.seed, drop.site, (uint64_t)k, drop.thr) ? v * drop.inv_keep : 0.f;
+                out[k] = from_f32<T>(v);
+            }
+        }
+    }
+}
+static inline unsigned ew_grid(int64_t n, int per_thread) {
+    int64_t b = cdiv(n, (int64_t)256 * per_thread);
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+void drop_cast(const float* in, void* out, int out_dtype, int64_t n, DropCfg drop, cudaStream_t st) {
+    if (n <= 0) return;
+    if (out_dtype == DT_F32) drop_cast_kernel<float><<<ew_grid(n, 4), 256, 0, st>>>(in, (float*)out, n, drop);
+    else drop_cast_kernel<bf16><<<ew_grid(n, 4), 256, 0, st>>>(in, (bf16*)out, n, drop);
+    LAUNCHED();
+}
+void cast_f32_to(const float* in, void* out, int out_dtype, int64_t n, cudaStream_t st) {
+    DropCfg none;
+    drop_cast(in, out, out_dtype, n, none, st);
+}
+__global__ void cast_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(in[i]);
+}
+void cast_to_f32(const void* in, int in_dtype, float* out, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    if (in_dtype == DT_F32) {
+        P5_CUDA(cudaMemcpyAsync(out, in, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        return;
+    }
+    cast_to_f32_kernel<<<ew_grid(n, 1), 256, 0, st>>>((const bf16*)in, out, n);
+    LAUNCHED();
+}
+template <typename T>
+__global__ void cast_block_kernel(const float* __restrict__ in, int64_t ld_in, T* __restrict__ out, int64_t ld_out,
+                                  int rows, int cols) {
+    const int64_t n = (int64_t)rows * cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        out[(int64_t)r * ld_out + c] = from_f32<T>(in[(int64_t)r * ld_in + c]);
+    }
+}
+void cast_block_f32_to(const float* in, int64_t ld_in, void* out, int out_dtype, int64_t ld_out, int rows, int cols,
+                       cudaStream_t st) {
+    const int64_t n = (int64_t)rows * cols;
+    if (n <= 0) return;
+    if (out_dtype == DT_F32) cast_block_kernel<float><<<ew_grid(n, 1), 256, 0, st>>>(in, ld_in, (float*)out, ld_out, rows, cols);
+    else cast_block_kernel<bf16><<<ew_grid(n, 1), 256, 0, st>>>(in, ld_in, (bf16*)out, ld_out, rows, cols);
+    LAUNCHED();
+}
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
+void add_f32(float* dst, const float* src, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    add_f32_kernel<<<ew_grid(n, 1), 256, 0, st>>>(dst, src, n);
+    LAUNCHED();
+}
+
+// =================================================================================================================
+// gated GELU (T5 v1.1 FFN)
+// =================================================================================================================
+__device__ __forceinline__ float gelu_new_f(float x) {
+    const float k = 0.7978845608028654f;  // sqrt(2/pi)
+    return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float gelu_new_grad(float x) {
+    const float k = 0.7978845608028654f;
+    const float u = k * (x + 0.044715f * x * x * x);
+    const float t = tanhf(u);
+    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * 0.044715f * x * x);
+}
+template <typename T>
+__global__ void gated_gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ h, int M, int ff, DropCfg drop) {
+    const int64_t n = (int64_t)M * ff;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t r = i / ff, c = i % ff;
+        float v = gelu_new_f(to_f32(z[r * 2 * ff + c])) * to_f32(z[r * 2 * ff + ff + c]);
+        if (drop.thr) v = drop_keep(drop.seed, drop.site, (uint64_t)i, drop.thr) ? v * drop.inv_keep : 0.f;
+        h[i] = from_f32<T>(v);
+    }
+}
+template <typename T>
+__global__ void gated_gelu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, T* __restrict__ dz, int M,
+                                      int ff, DropCfg drop) {
+    const int64_t n = (int64_t)M * ff;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t r = i / ff, c = i % ff;
+        float g = to_f32(dh[i]);
+        if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)i, drop.thr) ? g * drop.inv_keep : 0.f;
+        const float z0 = to_f32(z[r * 2 * ff + c]), z1 = to_f32(z[r * 2 * ff + ff + c]);
+        dz[r * 2 * ff + c] = from_f32<T>(g * z1 * gelu_new_grad(z0));
+        dz[r * 2 * ff + ff + c] = from_f32<T>(g * gelu_new_f(z0));
+    }
+}
+void gated_gelu_fwd(const void* z, void* h, int dtype, int M, int ff, DropCfg drop, cudaStream_t st) {
+    const int64_t n = (int64_t)M * ff;
+    if (n <= 0) return;
+    if (dtype == DT_F32) gated_gelu_fwd_kernel<float><<<ew_grid(n, 1), 256, 0, st>>>((const float*)z, (float*)h, M, ff, drop);
+    else gated_gelu_fwd_kernel<bf16><<<ew_grid(n, 1), 256, 0, st>>>((const bf16*)z, (bf16*)h, M, ff, drop);
+    LAUNCHED();
+}
+void gated_gelu_bwd(const void* z, const void* dh, void* dz, int dtype, int M, int ff, DropCfg drop, cudaStream_t st) {
+    const int64_t n = (int64_t)M * ff;
+    if (n <= 0) return;
+    if (dtype == DT_F32)
+        gated_gelu_bwd_kernel<float><<<ew_grid(n, 1), 256, 0, st>>>((const float*)z, (const float*)dh, (float*)dz, M, ff, drop);
+    else
+        gated_gelu_bwd_kernel<bf16><<<ew_grid(n, 1), 256, 0, st>>>((const bf16*)z, (const bf16*)dh, (bf16*)dz, M, ff, drop);
+    LAUNCHED();
+}
+
+// =================================================================================================================
+// cross entropy over the item-token vocabulary (one CTA per decoder position)
+// =================================================================================================================
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int* __restrict__ labels, float* __restrict__ loss,
+              float* __restrict__ lse, int V) {
+    __shared__ float sh[32];
+    const int row = blockIdx.x;
+    const float* l = logits + (int64_t)row * ld;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, l[c]);
+    mx = block_max(mx, sh);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) s += __expf(l[c] - mx);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        const float z = mx + logf(s);
+        lse[row] = z;
+        const int y = labels[row];
+        loss[row] = (y >= 0 && y < V) ? z - l[y] : 0.f;  // ignore_index = -100 (never produced by the collator)
+    }
+}
+void ce_fwd(const float* logits, int64_t ld, const int* labels, float* loss_tok, float* lse, int M, int V,
+            cudaStream_t st) {
+    if (M <= 0) return;
+    ce_fwd_kernel<<<M, 256, 0, st>>>(logits, ld, labels, loss_tok, lse, V);
+    LAUNCHED();
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restrict__ lse,
+              const int* __restrict__ labels, const float* __restrict__ dloss, T* __restrict__ dlogits, int V,
+              int Vpad) {
+    const int row = blockIdx.x;
+    const float* l = logits + (int64_t)row * ld;
+    T* o = dlogits + (int64_t)row * Vpad;
+    const int y = labels[row];
+    const float g = (y >= 0 && y < V) ? dloss[row] : 0.f;
+    const float z = lse[row];
+    for (int c = threadIdx.x; c < Vpad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < V) v = g * (__expf(l[c] - z) - (c == y ? 1.f : 0.f));
+        o[c] = from_f32<T>(v);
+    }
+}
+void ce_bwd(const float* logits, int64_t ld, const float* lse, const int* labels, const float* dloss, void* dlogits,
+            int d_dtype, int M, int V, int Vpad, cudaStream_t st) {
+    if (M <= 0) return;
+    if (d_dtype == DT_F32) ce_bwd_kernel<float><<<M, 256, 0, st>>>(logits, ld, lse, labels, dloss, (float*)dlogits, V, Vpad);
+    else ce_bwd_kernel<bf16><<<M, 256, 0, st>>>(logits, ld, lse, labels, dloss, (bf16*)dlogits, V, Vpad);
+    LAUNCHED();
+}
+
+// one block; B*Ld is small (<= 64K)
+__global__ void runner_loss_kernel(const float* __restrict__ loss_tok, const int* __restrict__ mask, int B, int Ld,
+                                   float* __restrict__ loss_out, float* __restrict__ dloss) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float s = 0.f, cnt = 0.f;
+        for (int t = 0; t < Ld; ++t) {
+            const float m = mask[b * Ld + t] != 0 ? 1.f : 0.f;
+            s += loss_tok[b * Ld + t] * m;
+            cnt += m;
+        }
+        const float den = fmaxf(cnt, 1.f);
+        acc += s / den;
+        if (dloss)
+            for (int t = 0; t < Ld; ++t) dloss[b * Ld + t] = (mask[b * Ld + t] != 0 ? 1.f : 0.f) / den / (float)B;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) loss_out[0] = acc / (float)B;
+}
+void runner_loss_fwd_bwd(const float* loss_tok, const int* labels_mask, int B, int Ld, float* loss_out,
+                         float* dloss_tok, cudaStream_t st) {
+    runner_loss_kernel<<<1, 256, 0, st>>>(loss_tok, labels_mask, B, Ld, loss_out, dloss_tok);
+    LAUNCHED();
+}
+
+// =================================================================================================================
+// relative position bias tables
+// =================================================================================================================
+__global__ void relbias_build_kernel(const float* __restrict__ table, const int* __restrict__ lut,
+                                     float* __restrict__ bias_rel, int H, int n_delta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * n_delta) return;
+    const int h = i / n_delta, dlt = i % n_delta;
+    bias_rel[i] = table[lut[dlt] * H + h];
+}
+void relbias_build(const float* table, const int* bucket_lut, float* bias_rel, int H, int n_delta, cudaStream_t st) {
+    relbias_build_kernel<<<(unsigned)cdiv(H * n_delta, 256), 256, 0, st>>>(table, bucket_lut, bias_rel, H, n_delta);
+    LAUNCHED();
+}
+__global__ void relbias_scatter_kernel(const float* __restrict__ dbias_rel, const int* __restrict__ lut,
+                                       float* __restrict__ dtable, int H, int n_delta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * n_delta) return;
+    const int h = i / n_delta, dlt = i % n_delta;
+    const float g = dbias_rel[i];
+    if (g != 0.f) atomicAdd(dtable + lut[dlt] * H + h, g);
+}
+void relbias_scatter_grad(const float* dbias_rel, const int* bucket_lut, float* dtable, int H, int n_delta,
+                          cudaStream_t st) {
+    relbias_scatter_kernel<<<(unsigned)cdiv(H * n_delta, 256), 256, 0, st>>>(dbias_rel, bucket_lut, dtable, H, n_delta);
+    LAUNCHED();
+}
+
+}  // namespace p5

@@ -1,0 +1,98 @@
+// kernels.cuh — launchers of the HBM-bound (non-GEMM) kernels of the T5 hot path.  Implementations: kernels.cu,
+// attention.cu, optim.cu, beam.cu.  All launchers enqueue on `st` and throw P5Error on launch failure.
+#pragma once
+#include "common.cuh"
+
+namespace p5 {
+
+struct DropCfg {
+    uint64_t seed = 0;
+    uint32_t site = 0;
+    uint32_t thr = 0;       // 0 = dropout off
+    float inv_keep = 1.f;
+};
+
+// ---- embeddings (ref P5_T5.py:94-100,125; HF T5Stack embed + dropout) --------------------------------------
+void embed_fwd(const float* E, const float* Wword, const int* ids, const int* ww, float* x, int M, int d, int vocab,
+               int ww_rows, DropCfg drop, cudaStream_t st);
+void embed_bwd(const float* dx, const int* ids, const int* ww, float* dE, float* dWword, int M, int d, int vocab,
+               int ww_rows, DropCfg drop, cudaStream_t st);
+
+// ---- RMSNorm (HF:modeling_t5.py:55-70) -----------------------------------------------------------------------
+// n = drop( w * x * rsqrt(mean(x^2)+eps) ), rstd saved for backward (rstd may be null in inference)
+void rmsnorm_fwd(const float* x, const float* w, void* n, int n_dtype, float* rstd, int M, int d, float eps,
+                 DropCfg drop, cudaStream_t st);
+// dx = (dres ? dres : 0) + d/dx[ rmsnorm ](mask(dn));  dw += sum_rows(mask(dn) * xhat)   (atomic)
+void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd, const float* w, const float* dres,
+                 float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st);
+
+// out = drop(in) cast to out_dtype (backward of the `x + drop(y)` sites: the mask is regenerated, never stored)
+void drop_cast(const float* in, void* out, int out_dtype, int64_t n, DropCfg drop, cudaStream_t st);
+void cast_f32_to(const float* in, void* out, int out_dtype, int64_t n, cudaStream_t st);
+void cast_to_f32(const void* in, int in_dtype, float* out, int64_t n, cudaStream_t st);
+// out[r, c] (dtype) = in_f32[r, c] for a [rows, cols] block with leading dims
+void cast_block_f32_to(const float* in, int64_t ld_in, void* out, int out_dtype, int64_t ld_out, int rows, int cols,
+                       cudaStream_t st);
+void add_f32(float* dst, const float* src, int64_t n, cudaStream_t st);
+
+// gated-GELU (HF:modeling_t5.py:106-132): z = [z0 | z1] per row (ld = 2*ff); h = drop(gelu_new(z0) * z1)
+void gated_gelu_fwd(const void* z, void* h, int dtype, int M, int ff, DropCfg drop, cudaStream_t st);
+void gated_gelu_bwd(const void* z, const void* dh, void* dz, int dtype, int M, int ff, DropCfg drop, cudaStream_t st);
+
+// ---- LM head loss (ref P5_T5.py:364-369) ------------------------------------------------------------------------
+void ce_fwd(const float* logits, int64_t ld, const int* labels, float* loss_tok, float* lse, int M, int V,
+            cudaStream_t st);
+// dlogits[m, :] = dloss[m] * (softmax(logits[m]) - onehot(label)); columns [V, Vpad) are written as zero
+void ce_bwd(const float* logits, int64_t ld, const float* lse, const int* labels, const float* dloss, void* dlogits,
+            int d_dtype, int M, int V, int Vpad, cudaStream_t st);
+// runner loss (ref DistributedRunner.py:72-77): loss = mean_b( sum_t l*m / max(sum_t m, 1) ); also d loss / d l
+void runner_loss_fwd_bwd(const float* loss_tok, const int* labels_mask, int B, int Ld, float* loss_out,
+                         float* dloss_tok, cudaStream_t st);
+
+// ---- relative position bias (HF:modeling_t5.py:189-251) ---------------------------------------------------------
+// bias_rel[h, delta + (Lq-1)] = table[bucket_lut[delta + (Lq-1)], h] for delta = j - i in [-(Lq-1), Lk-1]
+void relbias_build(const float* table, const int* bucket_lut, float* bias_rel, int H, int n_delta, cudaStream_t st);
+void relbias_scatter_grad(const float* dbias_rel, const int* bucket_lut, float* dtable, int H, int n_delta,
+                          cudaStream_t st);
+
+// ---- attention --------------------------------------------------------------------------------------------------
+// Q, K, V are strided views: element (b, pos, h, c) at ptr[b*bs + pos*ld + h*64 + c].  d_kv = 64.
+struct AttnView {
+    const void* ptr; int dtype; int64_t ld; int64_t bs;
+};
+struct AttnArgs {
+    int B, H, Lq, Lk;
+    AttnView q, k, v;
+    const float* bias_rel;   // [H, n_delta] or null (cross-attention: zero bias); entry (j - i_pos) + bias_off
+    int bias_off, n_delta;
+    const int* key_mask;     // [B, Lk] (1 = keep) or null
+    int causal;              // 1: key j > query i is masked (decoder self-attention); q_pos_offset shifts i
+    int q_pos_offset;        // position of query row 0 (decode step with KV cache)
+    const int* row_map;      // optional [B] indirection for K/V/mask batch index (beam -> user), null = identity
+    DropCfg drop;
+};
+// fused SIMT attention (fp32 math): O[b, i, h*64 + c] (ld_o) and LSE[b, h, i]
+void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st);
+// backward: dQ/dK/dV written as fp32 with the same (ld, bs) geometry given by dq/dk/dv views (fp32); dK/dV atomics
+// => caller zeroes dK/dV first.  dbias_rel [H, Lq+Lk-1] accumulated atomically if non-null.
+void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype, int64_t ld_o, int64_t bs_o,
+                   const float* lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV, int64_t ld_dkv,
+                   int64_t bs_dkv, float* dbias_rel, cudaStream_t st);
+
+// materialised softmax for the tensor-core attention path: S fp32 [B,H,Lq,Lk]
+//   P  = softmax(S + bias + mask)             -> P_save (dtype)           (needed by backward)
+//   Pd = drop(P)                              -> Pd (dtype, may alias P_save when dropout is off)
+void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, void* P_save, void* Pd, int dtype, int B,
+                 int H, int Lq, int Lk, int causal, DropCfg drop, cudaStream_t st);
+//   dP_in = gradient wrt Pd (fp32); dS = P * (mask(dP) - rowsum(mask(dP) * P)) -> dS (dtype);  Pd regenerated
+void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
+                 int Lq, int Lk, DropCfg drop, cudaStream_t st);
+
+// ---- optimiser (optim.cu) ---------------------------------------------------------------------------------------
+void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
+void scale_f32(float* g, int64_t n, float s, cudaStream_t st);
+// transformers-4.26 AdamW on the flat parameter buffer; clip_norm_ptr (device) optional
+void adamw_flat(float* p, const float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
+                float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st);
+
+}  // namespace p5

@@ -1,0 +1,193 @@
+"""GPU bring-up check of the whole engine against the CPU oracle (each case in its own process).
+Run under gpurun:  python tools/gpu_check_model.py > gpurun_out/model_check.log 2>&1
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fused_fp32_tiny", "adamw_fp32_tiny",
+         "gen_fp32_tiny", "gen_bf16_tiny", "fwd_fp32_small", "bwd_fp32_small", "bwd_bf16_small", "gated_fp32_tiny",
+         "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256"]
+
+
+def setup(case):
+    import torch
+    from oracle import p5_oracle as po
+    if "base" in case:
+        cfg = po.t5_cfg("t5-base", vocab_size=32100, num_layers=2, num_decoder_layers=2)
+        B, Le, Ld, n_items = 8, 256, 8, 200
+    elif "small" in case:
+        cfg = po.t5_cfg("t5-small", vocab_size=2100, num_layers=2, num_decoder_layers=2)
+        B, Le, Ld, n_items = 4, 64, 8, 300
+    else:
+        cfg = po.t5_cfg("t5-tiny", vocab_size=1200)
+        B, Le, Ld, n_items = 3, 21, 8, 60
+    if "gated" in case:
+        cfg.ffn_gated_gelu = True
+    w = po.init_weights(cfg, seed=1)
+    items = po.synth_items(n_items, seed=3)
+    batch = po.synth_batch(B, Le, Ld, cfg.vocab_size, items, seed=5)
+    return po, cfg, w, items, batch
+
+
+def make_model(cfg, w, precision, dropout=0.0, **kw):
+    from openp5_b200.model import P5B200
+    m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, precision=precision, dropout=dropout, max_batch=8,
+               max_enc_len=256, max_dec_len=16, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
+               num_decoder_layers=cfg.num_decoder_layers, num_heads=cfg.num_heads, ffn_gated_gelu=cfg.ffn_gated_gelu, **kw)
+    m.load_state_dict(w, strict=True)
+    return m
+
+
+def relerr(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def run_case(case):
+    import torch
+    po, cfg, w, items, (ids, attn, ww, labels, oattn) = setup(case)
+    prec = "bf16" if "bf16" in case else "fp32"
+    tol = 6e-2 if prec == "bf16" else 2e-4
+    dev = "cuda"
+    res = dict(name=case)
+    if case.startswith("fwd"):
+        m = make_model(cfg, w, prec).eval()
+        with torch.no_grad():
+            out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev))
+        lt_o, lg_o = po.forward(w, cfg, ids, ww, attn, labels)
+        res["logits_rel"] = relerr(out["logits"].cpu(), lg_o)
+        res["loss_rel"] = relerr(out["loss"].cpu(), lt_o)
+        res["ok"] = res["logits_rel"] < tol and res["loss_rel"] < tol
+    elif case.startswith("bwd") or case.startswith("gated") or case.startswith("fused"):
+        m = make_model(cfg, w, prec).eval()   # eval => dropout off; gradients still flow
+        l_o, lt_o, lg_o, g_o = po.loss_and_grads(w, cfg, ids, ww, attn, labels, oattn)
+        m.zero_grad()
+        if case.startswith("fused"):
+            import ctypes as C
+            from openp5_b200 import _lib
+            i32 = lambda t: t.to(dev).to(torch.int32).contiguous()
+            a = [i32(t) for t in (ids, attn, ww, labels, oattn)]
+            loss = torch.empty(1, device=dev)
+            m.training = False
+            m.cfg.dropout = 0.0
+            _lib.check(m.lib.p5_train_fwd_bwd(m.handle, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
+                                              a[4].data_ptr(), ids.shape[0], ids.shape[1], labels.shape[1], loss.data_ptr(),
+                                              C.c_uint64(1)))
+            loss = loss[0]
+        else:
+            out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev))
+            B, Ld = labels.shape
+            lm = (oattn.to(dev) != 0).float()
+            loss = ((out["loss"].view(B, Ld) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
+            loss.backward()
+        torch.cuda.synchronize()
+        res["loss"] = loss.item()
+        res["loss_ref"] = l_o.item()
+        worst, worst_name = 0.0, ""
+        bad = []
+        for k, p in m.named_parameters():
+            g = p.grad.cpu()
+            e = ((g - g_o[k]).abs().max() / g_o[k].abs().max().clamp_min(1e-9)).item()
+            if e > worst:
+                worst, worst_name = e, k
+            if e > tol * (3 if prec == "bf16" else 5):
+                bad.append((k, round(e, 5)))
+        res["worst_grad_rel"] = worst
+        res["worst_grad_name"] = worst_name
+        res["bad"] = bad[:8]
+        res["n_bad"] = len(bad)
+        res["ok"] = abs(res["loss"] - res["loss_ref"]) < tol * abs(res["loss_ref"]) and not bad
+    elif case.startswith("adamw"):
+        m = make_model(cfg, w, prec).eval()
+        wo = {k: v.clone() for k, v in w.items()}
+        mo = {k: torch.zeros_like(v) for k, v in w.items()}
+        vo = {k: torch.zeros_like(v) for k, v in w.items()}
+        losses = []
+        for step in range(1, 4):
+            lr = 1e-3
+            l_o, _, _, g = po.loss_and_grads(wo, cfg, ids, ww, attn, labels, oattn)
+            po.clip_grad_norm(g, 1.0)
+            for k in wo:
+                po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, lr, eps=1e-6, weight_decay=0.01)
+            m.training = False
+            loss = m.train_step(ids.to(dev), ww.to(dev), attn.to(dev), labels.to(dev), oattn.to(dev), lr=lr, clip=1.0, step=step)
+            losses.append((loss.item(), l_o.item()))
+        worst = max(relerr(p.detach().cpu(), wo[k]) for k, p in m.named_parameters())
+        res["losses"] = losses
+        res["worst_param_rel"] = worst
+        res["ok"] = worst < 1e-3 and all(abs(a - b) < 1e-3 * abs(b) for a, b in losses)
+    elif case.startswith("gen"):
+        m = make_model(cfg, w, prec).eval()
+        K = 5 if "tiny" in case else 10
+        trie_o = po.Trie(items)
+        t0 = time.time()
+        s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, trie_o, K, K, 20)
+        res["oracle_s"] = time.time() - t0
+        trie = m.build_trie(items)
+        res["trie"] = trie.stats()
+        res["trie_get_ok"] = sorted(trie.get(items[0][:6])) == sorted(trie_o.get(items[0][:6]))
+        out = m.generate(input_ids=ids.to(dev), attention_mask=attn.to(dev), whole_word_ids=ww.to(dev), max_length=20,
+                         trie=trie, num_beams=K, num_return_sequences=K)
+        s, sc = out["sequences"].cpu(), out["sequences_scores"].cpu()
+        res["shape"] = [list(s.shape), list(s_o.shape)]
+        same = s.shape == s_o.shape and bool((s == s_o).all())
+        res["seq_equal"] = same
+        res["score_err"] = (sc - sc_o).abs().max().item()
+        if not same and s.shape == s_o.shape:
+            res["rows_equal_frac"] = (s == s_o).all(dim=1).float().mean().item()
+            res["top1_equal_frac"] = (s.view(ids.shape[0], K, -1)[:, 0] == s_o.view(ids.shape[0], K, -1)[:, 0]).all(dim=1).float().mean().item()
+        if prec == "fp32":
+            res["ok"] = same and res["score_err"] < 1e-4 and res["trie_get_ok"]
+        else:
+            res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
+    elif case.startswith("dropout"):
+        m = make_model(cfg, w, prec, dropout=0.1).train()
+        a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+        m.zero_grad()
+        out1 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])
+        l1 = out1["loss"].detach().clone()
+        out1["loss"].mean().backward()
+        g1 = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        finite = all(torch.isfinite(g).all().item() for g in g1.values())
+        m._step_seed -= 1            # same seed -> identical masks -> identical loss
+        with torch.no_grad():
+            l2 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["loss"]
+        l3 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["loss"].detach()
+        m.eval()
+        with torch.no_grad():
+            l_eval = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["loss"]
+        res["same_seed_equal"] = bool((l1 == l2).all())
+        res["diff_seed_differs"] = bool((l1 != l3).any())
+        res["train_vs_eval_rel"] = relerr(l1, l_eval)
+        res["finite"] = finite
+        res["ok"] = finite and res["same_seed_equal"] and res["diff_seed_differs"] and 0.0 < res["train_vs_eval_rel"] < 0.8
+    return res
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--case":
+        try:
+            print("RESULT " + json.dumps(run_case(sys.argv[2])))
+        except Exception as e:  # noqa
+            import traceback
+            print("RESULT " + json.dumps(dict(name=sys.argv[2], ok=False, error=repr(e)[:500], tb=traceback.format_exc()[-900:])))
+        sys.exit(0)
+    cases = sys.argv[1:] or CASES
+    results = []
+    for c in cases:
+        try:
+            p = subprocess.run([sys.executable, __file__, "--case", c], capture_output=True, text=True, timeout=300)
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            if line:
+                results.append(json.loads(line[-1][7:]))
+            else:
+                results.append(dict(name=c, ok=False, rc=p.returncode, stdout=p.stdout[-800:], stderr=p.stderr[-1500:]))
+        except subprocess.TimeoutExpired:
+            results.append(dict(name=c, ok=False, error="timeout"))
+        print(json.dumps(results[-1]), flush=True)
+    print("SUMMARY passed %d / %d" % (sum(1 for r in results if r.get("ok")), len(results)))
