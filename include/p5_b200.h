@@ -128,6 +128,10 @@ typedef struct {
 } P5GemmDesc;
 int p5_op_gemm(const P5GemmDesc* d, void* cuda_stream);
 int p5_launch_count(void);   /* kernels launched by this library since load */
+/* per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg): enable, run steps, read a JSON summary
+ * {"bn256": {"launches", "ms", "flops"}, "bn128": ..., "bn64": ...} (algorithmic FLOPs = 2*M*N*K per launch) */
+int p5_prof_enable(int on);
+int p5_prof_summary(char* json_out, int cap);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ DECLARED_SYMBOLS = [
     "p5_params_changed", "p5_forward", "p5_backward", "p5_train_fwd_bwd", "p5_grad_norm", "p5_grad_scale",
     "p5_zero_grad", "p5_adamw_step", "p5_comm_unique_id", "p5_comm_init", "p5_allreduce_grads",
     "p5_trie_build", "p5_trie_free", "p5_trie_stats", "p5_trie_get", "p5_generate", "p5_op_gemm",
-    "p5_launch_count",
+    "p5_launch_count", "p5_prof_enable", "p5_prof_summary",
 ]
 
 _lib = None
@@ -97,6 +97,8 @@ def load():
     sig("p5_generate", vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp,
         C.POINTER(C.c_int))
     sig("p5_op_gemm", C.POINTER(P5GemmDesc), vp)
+    sig("p5_prof_enable", C.c_int)
+    sig("p5_prof_summary", C.c_char_p, C.c_int)
     lib.p5_version.restype = C.c_int
     lib.p5_launch_count.restype = C.c_int
     _lib = lib

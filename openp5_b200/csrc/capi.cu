@@ -27,6 +27,8 @@ static Engine* E(p5_handle h) {
 }
 
 namespace p5 {
+void gemm_tc_prof_enable(bool on);
+std::string gemm_tc_prof_summary();
 // beam.cu
 int trie_build(Engine* e, const int32_t* paths, const int64_t* offsets, int n_paths, Trie** out);
 void trie_free(Trie* t);
@@ -197,6 +199,19 @@ int p5_generate(p5_handle h, const int32_t* input_ids, const int32_t* attention_
     P5_CHECK(trie != nullptr, "null trie");
     generate(E(h), input_ids, attention_mask, whole_word_ids, B, Le, reinterpret_cast<Trie*>(trie), num_beams,
              num_return, max_len, length_penalty, seqs, scores, out_len_host);
+    P5_API_END
+}
+
+int p5_prof_enable(int on) {
+    P5_API_BEGIN
+    gemm_tc_prof_enable(on != 0);
+    P5_API_END
+}
+int p5_prof_summary(char* json_out, int cap) {
+    P5_API_BEGIN
+    P5_CHECK(json_out && cap > 0, "null buffer");
+    const std::string s = gemm_tc_prof_summary();
+    snprintf(json_out, (size_t)cap, "%s", s.c_str());
     P5_API_END
 }
 

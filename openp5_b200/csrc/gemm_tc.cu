@@ -515,6 +515,37 @@ bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major) {
 
 static int g_num_sms = 0;
 static int g_force_block_n = 0;  // test hook
+
+// ---- optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream around every
+//      tcgen05 GEMM launch, with the algorithmic FLOPs of the problem
+struct ProfRec { cudaEvent_t e0, e1; double flops; int bn; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+void gemm_tc_prof_enable(bool on) {
+    g_prof_on = on;
+    if (on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        g_prof.clear();
+    }
+}
+// returns JSON: per BLOCK_N class {launches, ms, flops}; synchronises the device
+std::string gemm_tc_prof_summary() {
+    cudaDeviceSynchronize();
+    double ms[3] = {0, 0, 0}, fl[3] = {0, 0, 0};
+    long n[3] = {0, 0, 0};
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
+        const int c = r.bn == 256 ? 0 : (r.bn == 128 ? 1 : 2);
+        ms[c] += t; fl[c] += r.flops; n[c] += 1;
+    }
+    char b[512];
+    snprintf(b, sizeof(b),
+             "{\"bn256\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e}, \"bn128\": {\"launches\": %ld, \"ms\": %.6f, "
+             "\"flops\": %.6e}, \"bn64\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e}}",
+             n[0], ms[0], fl[0], n[1], ms[1], fl[1], n[2], ms[2], fl[2]);
+    return std::string(b);
+}
 void gemm_tc_force_block_n(int bn) { g_force_block_n = bn; }
 
 template <int BN>
@@ -533,8 +564,15 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     P.epi = p.epi;
     const long long tiles = (long long)cdiv(p.M, BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    ProfRec rec;
+    if (g_prof_on) {
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+        rec.flops = 2.0 * p.M * p.N * (double)p.K * p.nb1 * p.nb2; rec.bn = BN;
+        cudaEventRecord(rec.e0, stream);
+    }
     gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, P);
     P5_CUDA(cudaGetLastError());
+    if (g_prof_on) { cudaEventRecord(rec.e1, stream); g_prof.push_back(rec); }
     ++g_tc_launches;
 }
 

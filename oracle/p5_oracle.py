@@ -495,49 +495,7 @@ def calculate_whole_word_ids(tokens: Sequence[str]) -> List[int]:
 
 
 # ----------------------------------------------------------------------------------------------------
-# synthetic ML-1M-shaped data — shared by tests and bench.py so both arms see the same inputs
+# synthetic ML-1M-shaped data: the generators live in openp5_b200/synth.py (pure torch-CPU, no
+# engine dependency) so that bench.py, the tests and this oracle all see identical token ids
 # ----------------------------------------------------------------------------------------------------
-DIGIT_BASE = 1000        # 100-token "digit" sub-vocabulary [DIGIT_BASE, DIGIT_BASE+100)
-ITEM_PREFIX = [300, 301, 302, 303]  # fixed 4-token "{dataset} item_" prefix
-
-
-def synth_items(n_items: int, seed: int = 2023, min_digits: int = 3, max_digits: int = 3) -> List[List[int]]:
-    """n unique trie paths [0, p1..p4, d1..dn, 1] with digit tokens from the digit sub-vocabulary.
-    Default depth is uniform (3 digit tokens): with ragged depths a running beam can end in EOS while others
-    continue, and transformers 5.5 raises on the resulting empty allowed-token list (4.26 produced an all -inf
-    row) — ragged tries are exercised with on_empty="neg_inf" only."""
-    g = torch.Generator().manual_seed(seed)
-    seen, out = set(), []
-    while len(out) < n_items:
-        nd = int(torch.randint(min_digits, max_digits + 1, (1,), generator=g))
-        digs = tuple(int(x) + DIGIT_BASE for x in torch.randint(0, 100, (nd,), generator=g))
-        if digs in seen:
-            continue
-        seen.add(digs)
-        out.append([0] + ITEM_PREFIX + list(digs) + [1])
-    return out
-
-
-def synth_batch(B: int, Le: int, Ld: int, vocab: int, items: Optional[List[List[int]]] = None, seed: int = 2023):
-    """(input_ids, attention_mask, whole_word_ids, labels, output_attention), all int64 [B, L]."""
-    g = torch.Generator().manual_seed(seed)
-    ids = torch.randint(2, vocab, (B, Le), generator=g)
-    lens = torch.randint(max(1, Le // 2), Le + 1, (B,), generator=g)
-    lens[0] = Le  # pad-to-longest: at least one full row
-    pos = torch.arange(Le)[None, :]
-    ids = torch.where(pos < lens[:, None], ids, torch.zeros_like(ids))
-    ids[torch.arange(B), lens - 1] = 1
-    attn = (ids != 0).long()
-    new_word = (torch.rand(B, Le, generator=g) < 0.4).long()
-    new_word[:, 0] = 1
-    ww = torch.cumsum(new_word, dim=1).clamp(max=511) * attn
-    ww[torch.arange(B), lens - 1] = 0
-    labels = torch.zeros(B, Ld, dtype=torch.long)
-    if items is None:
-        items = synth_items(max(B, 64), seed)
-    pick = torch.randint(0, len(items), (B,), generator=g)
-    for b in range(B):
-        path = items[int(pick[b])][1:][:Ld]
-        labels[b, : len(path)] = torch.tensor(path)
-    out_attn = (labels != 0).long()
-    return ids, attn, ww, labels, out_attn
+from openp5_b200.synth import DIGIT_BASE, ITEM_PREFIX, synth_items, synth_batch  # noqa: E402,F401
