@@ -82,6 +82,7 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int r = warp * 2 + rr;
+            if (i0 + r >= a.Lq) continue;          // rows past Lq (short decoder blocks) do no work
             const int i_pos = a.q_pos_offset + i0 + r;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -101,6 +102,7 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         const int r = warp * 2 + rr;
+        if (i0 + r >= a.Lq) continue;
         float mx = -INFINITY;
         for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, Ss[r * Lk + j]);
         mx = warp_max(mx);
@@ -133,6 +135,7 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int r = warp * 2 + rr;
+            if (i0 + r >= a.Lq) continue;
             for (int j = 0; j < jn; ++j) {
                 const float p = Ss[r * Lk + j0 + j];
                 acc[rr][0] = fmaf(p, KVs[j][lane], acc[rr][0]);
@@ -190,7 +193,7 @@ void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_
 __global__ void __launch_bounds__(256)
 attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t ld_o, int64_t bs_o,
                      const float* __restrict__ lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV,
-                     int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel) {
+                     int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, int atomic_kv) {
     extern __shared__ float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);
     float (*dOs)[DK] = reinterpret_cast<float (*)[DK]>(smem + QB * DK);
@@ -241,13 +244,14 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int jl = lane + 32 * jj, j = j0 + jl;
-                if (j < Lk) {
+                if (j < Lk && i >= a.Lq) Ss[r * Lk + j] = 0.f;
+                if (j < Lk && i < a.Lq) {
                     float s = 0.f;
 #pragma unroll 16
                     for (int c = 0; c < DK; ++c) s = fmaf(Qs[r][c], KVs[jl][c], s);
                     s += score_bias(a, h, b, i_pos, j);
                     Ss[r * Lk + j] = (i < a.Lq) ? __expf(s - l) : 0.f;
-                }
+                } 
             }
         }
     }
@@ -295,7 +299,9 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
                 float v = 0.f;
 #pragma unroll
                 for (int r = 0; r < QB; ++r) v = fmaf(Pt[r * KT + j], dOs[r][c], v);
-                if (v != 0.f) atomicAdd(dV + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c, v);
+                float* dst = dV + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
+                if (!atomic_kv) *dst = v;           // one q-block per (b, h): this CTA owns the element
+                else if (v != 0.f) atomicAdd(dst, v);
             }
         }
     }
@@ -321,7 +327,9 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
                 float v = 0.f;
 #pragma unroll
                 for (int r = 0; r < QB; ++r) v = fmaf(Ss[r * Lk + j0 + j], Qs[r][c], v);
-                if (v != 0.f) atomicAdd(dK + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c, v);
+                float* dst = dK + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
+                if (!atomic_kv) *dst = v;
+                else if (v != 0.f) atomicAdd(dst, v);
             }
         }
     }
@@ -357,59 +365,85 @@ void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype
     }
     AttnDev d = to_dev(a);
     dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
+    // with a single q-block per (b, h) every dK/dV element has exactly one producer: plain stores, no memset needed
     attn_simt_bwd_kernel<<<grid, 256, sm, st>>>(d, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv,
-                                                bs_dkv, dbias_rel);
+                                                bs_dkv, dbias_rel, grid.x > 1 ? 1 : 0);
     LAUNCHED();
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// materialised softmax between the batched tensor-core GEMMs.  One CTA per (b, h); each warp walks rows.
+// materialised softmax between the batched tensor-core GEMMs.  One CTA per (b, h) [x row slice]; each warp walks
+// rows; each lane owns adjacent column PAIRS (8-byte loads of S / dP, 4-byte bf16x2 stores), Lk even and <= 512.
+// Dropout uses one counter hash per pair (16 bits per element), regenerated identically in backward.
 // ------------------------------------------------------------------------------------------------------------
-static constexpr int SM_MAXK = 16;  // Lk <= 512
+static constexpr int SM_MAXP = 8;  // pairs per lane: Lk <= 512
+
+__device__ __forceinline__ void drop_pair(const DropCfg& d, uint64_t pair_idx, bool& k0, bool& k1) {
+    const uint32_t h = drop_hash(d.seed, d.site, pair_idx);
+    const uint32_t t16 = d.thr >> 16;
+    k0 = (h & 0xffffu) >= t16;
+    k1 = (h >> 16) >= t16;
+}
+template <typename T> __device__ __forceinline__ void st_pair(T* p, float a, float b);
+template <> __device__ __forceinline__ void st_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void st_pair<bf16>(bf16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+template <typename T> __device__ __forceinline__ float2 ld_pair(const T* p);
+template <> __device__ __forceinline__ float2 ld_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld_pair<bf16>(const bf16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ bias_rel, const int* __restrict__ key_mask,
                    T* __restrict__ P_save, T* __restrict__ Pd, int H, int Lq, int Lk, int causal, DropCfg drop) {
+    extern __shared__ float sh_mask[];   // [Lk] additive key mask of this batch row (0 or finfo.min)
     const int bh = blockIdx.x, b = bh / H, h = bh % H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n_delta = Lq + Lk - 1;
+    for (int j = threadIdx.x; j < Lk; j += blockDim.x) sh_mask[j] = (key_mask && key_mask[b * Lk + j] == 0) ? MASK_MIN : 0.f;
+    __syncthreads();
+    const float* brow = bias_rel ? bias_rel + h * n_delta : nullptr;
     for (int i = blockIdx.y * nw + warp; i < Lq; i += nw * gridDim.y) {
         const int64_t row = ((int64_t)bh * Lq + i) * Lk;
-        float v[SM_MAXK];
+        float v[SM_MAXP][2];
         float mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < SM_MAXK; ++k) {
-            const int j = lane + 32 * k;
-            v[k] = -INFINITY;
+        for (int k = 0; k < SM_MAXP; ++k) {
+            const int j = 2 * (lane + 32 * k);
+            v[k][0] = v[k][1] = -INFINITY;
             if (j < Lk) {
-                float s = S[row + j];
-                if (bias_rel) s += bias_rel[h * n_delta + (j - i + Lq - 1)];
-                float m = 0.f;
-                if (key_mask && key_mask[b * Lk + j] == 0) m = MASK_MIN;
-                if (causal && j > i) m = MASK_MIN;
-                v[k] = s + m;
-                mx = fmaxf(mx, v[k]);
+                const float2 s = *reinterpret_cast<const float2*>(S + row + j);
+                const float2 m = *reinterpret_cast<const float2*>(sh_mask + j);
+                float a0 = s.x, a1 = s.y;
+                if (brow) { a0 += brow[j - i + Lq - 1]; a1 += brow[j + 1 - i + Lq - 1]; }
+                float m0 = m.x, m1 = m.y;
+                if (causal) { if (j > i) m0 = MASK_MIN; if (j + 1 > i) m1 = MASK_MIN; }
+                v[k][0] = a0 + m0; v[k][1] = a1 + m1;
+                mx = fmaxf(mx, fmaxf(v[k][0], v[k][1]));
             }
         }
         mx = warp_max(mx);
         float sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < SM_MAXK; ++k) {
-            const int j = lane + 32 * k;
-            if (j < Lk) { v[k] = __expf(v[k] - mx); sum += v[k]; }
+        for (int k = 0; k < SM_MAXP; ++k) {
+            const int j = 2 * (lane + 32 * k);
+            if (j < Lk) { v[k][0] = __expf(v[k][0] - mx); v[k][1] = __expf(v[k][1] - mx); sum += v[k][0] + v[k][1]; }
         }
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
 #pragma unroll
-        for (int k = 0; k < SM_MAXK; ++k) {
-            const int j = lane + 32 * k;
+        for (int k = 0; k < SM_MAXP; ++k) {
+            const int j = 2 * (lane + 32 * k);
             if (j < Lk) {
-                const float p = v[k] * inv;
-                P_save[row + j] = from_f32<T>(p);
+                const float p0 = v[k][0] * inv, p1 = v[k][1] * inv;
+                st_pair<T>(P_save + row + j, p0, p1);
                 if (drop.thr) {
-                    const float pd = drop_keep(drop.seed, drop.site, (uint64_t)(row + j), drop.thr) ? p * drop.inv_keep : 0.f;
-                    Pd[row + j] = from_f32<T>(pd);
+                    bool k0, k1;
+                    drop_pair(drop, (uint64_t)(row + j) >> 1, k0, k1);
+                    st_pair<T>(Pd + row + j, k0 ? p0 * drop.inv_keep : 0.f, k1 ? p1 * drop.inv_keep : 0.f);
                 }
             }
         }
@@ -419,13 +453,14 @@ softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ bias_r
 void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, void* P_save, void* Pd, int dtype, int B,
                  int H, int Lq, int Lk, int causal, DropCfg drop, cudaStream_t st) {
     if (B <= 0) return;
-    P5_CHECK(Lk <= 32 * SM_MAXK, "softmax_fwd: Lk > 512");
+    P5_CHECK(Lk <= 64 * SM_MAXP && (Lk % 2) == 0, "softmax_fwd: Lk must be even and <= 512");
     P5_CHECK(!drop.thr || Pd != nullptr, "softmax_fwd: dropout needs a Pd buffer");
     dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
+    const size_t sm = (size_t)Lk * sizeof(float);
     if (dtype == DT_F32)
-        softmax_fwd_kernel<float><<<grid, 256, 0, st>>>(S, bias_rel, key_mask, (float*)P_save, (float*)Pd, H, Lq, Lk, causal, drop);
+        softmax_fwd_kernel<float><<<grid, 256, sm, st>>>(S, bias_rel, key_mask, (float*)P_save, (float*)Pd, H, Lq, Lk, causal, drop);
     else
-        softmax_fwd_kernel<bf16><<<grid, 256, 0, st>>>(S, bias_rel, key_mask, (bf16*)P_save, (bf16*)Pd, H, Lq, Lk, causal, drop);
+        softmax_fwd_kernel<bf16><<<grid, 256, sm, st>>>(S, bias_rel, key_mask, (bf16*)P_save, (bf16*)Pd, H, Lq, Lk, causal, drop);
     LAUNCHED();
 }
 
@@ -443,32 +478,35 @@ softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __
     }
     for (int i = blockIdx.y * nw + warp; i < Lq; i += nw * gridDim.y) {
         const int64_t row = ((int64_t)bh * Lq + i) * Lk;
-        float p[SM_MAXK], dp[SM_MAXK];
+        float p[SM_MAXP][2], dp[SM_MAXP][2];
         float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < SM_MAXK; ++k) {
-            const int j = lane + 32 * k;
-            p[k] = 0.f; dp[k] = 0.f;
+        for (int k = 0; k < SM_MAXP; ++k) {
+            const int j = 2 * (lane + 32 * k);
+            p[k][0] = p[k][1] = dp[k][0] = dp[k][1] = 0.f;
             if (j < Lk) {
-                p[k] = to_f32(P[row + j]);
-                float g = dPd[row + j];
+                const float2 pp = ld_pair<T>(P + row + j);
+                const float2 g = *reinterpret_cast<const float2*>(dPd + row + j);
+                float g0 = g.x, g1 = g.y;
                 if (drop.thr) {
-                    const bool keep = drop_keep(drop.seed, drop.site, (uint64_t)(row + j), drop.thr);
-                    g = keep ? g * drop.inv_keep : 0.f;
-                    if (Pd_out) Pd_out[row + j] = from_f32<T>(keep ? p[k] * drop.inv_keep : 0.f);
+                    bool k0, k1;
+                    drop_pair(drop, (uint64_t)(row + j) >> 1, k0, k1);
+                    g0 = k0 ? g0 * drop.inv_keep : 0.f;
+                    g1 = k1 ? g1 * drop.inv_keep : 0.f;
+                    if (Pd_out) st_pair<T>(Pd_out + row + j, k0 ? pp.x * drop.inv_keep : 0.f, k1 ? pp.y * drop.inv_keep : 0.f);
                 }
-                dp[k] = g;
-                dot += g * p[k];
+                p[k][0] = pp.x; p[k][1] = pp.y; dp[k][0] = g0; dp[k][1] = g1;
+                dot += g0 * pp.x + g1 * pp.y;
             }
         }
         dot = warp_sum(dot);
 #pragma unroll
-        for (int k = 0; k < SM_MAXK; ++k) {
-            const int j = lane + 32 * k;
+        for (int k = 0; k < SM_MAXP; ++k) {
+            const int j = 2 * (lane + 32 * k);
             if (j < Lk) {
-                const float ds = p[k] * (dp[k] - dot);
-                dS[row + j] = from_f32<T>(ds);
-                if (dbias_rel) atomicAdd(&sdb[j - i + Lq - 1], ds);
+                const float d0 = p[k][0] * (dp[k][0] - dot), d1 = p[k][1] * (dp[k][1] - dot);
+                st_pair<T>(dS + row + j, d0, d1);
+                if (dbias_rel) { atomicAdd(&sdb[j - i + Lq - 1], d0); atomicAdd(&sdb[j + 1 - i + Lq - 1], d1); }
             }
         }
     }
@@ -484,7 +522,7 @@ softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
                  int Lq, int Lk, DropCfg drop, cudaStream_t st) {
     if (B <= 0) return;
-    P5_CHECK(Lk <= 32 * SM_MAXK, "softmax_bwd: Lk > 512");
+    P5_CHECK(Lk <= 64 * SM_MAXP && (Lk % 2) == 0, "softmax_bwd: Lk must be even and <= 512");
     dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     const size_t sm = (size_t)(Lq + Lk) * sizeof(float);
     if (dtype == DT_F32)

@@ -122,7 +122,9 @@ int p5_train_fwd_bwd(p5_handle h, const int32_t* input_ids, const int32_t* atten
     P5_CUDA(cudaMemcpyAsync(e->lmask, labels_mask, (size_t)B * Ld * 4, cudaMemcpyDeviceToDevice, e->st));
     runner_loss_fwd_bwd(e->loss_tok, e->lmask, B, Ld, e->loss_scalar, e->dloss, e->st);
     if (loss_out) P5_CUDA(cudaMemcpyAsync(loss_out, e->loss_scalar, 4, cudaMemcpyDeviceToDevice, e->st));
+    e->overlap_comm = e->world > 1 && e->nccl_comm != nullptr;
     e->backward();
+    e->overlap_comm = false;
     P5_API_END
 }
 int p5_grad_norm(p5_handle h, float* out) {

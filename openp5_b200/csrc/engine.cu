@@ -14,6 +14,8 @@
 
 namespace p5 {
 
+void comm_allreduce_range(Engine* e, int64_t off, int64_t n);   // comm.cu (no-op without a communicator)
+
 static inline void* poff(const void* p, int64_t elems, int dt) {
     return (void*)((const char*)p + elems * (int64_t)dtype_size(dt));
 }
@@ -421,7 +423,7 @@ void Engine::enc_attention_bwd(int l, const void* dctx, void* dqkv) {
         gemm(k);
     } else {
         // fp32 parity path: dqkv IS the fp32 scratch
-        P5_CUDA(cudaMemsetAsync(dqkv, 0, Me * 3 * A * sizeof(float), st));
+        if (attn_bwd_needs_zero(Le)) P5_CUDA(cudaMemsetAsync(dqkv, 0, Me * 3 * A * sizeof(float), st));
         AttnArgs a;
         a.B = B; a.H = H; a.Lq = Le; a.Lk = Le;
         a.q = {qkv_e[l], dt, 3 * A, (int64_t)Le * 3 * A};
@@ -556,7 +558,7 @@ void Engine::backward() {
         drop_cast(dy, g_d, dt, Md * d, drop(S_DEC_CO, l), st);
         linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        P5_CUDA(cudaMemsetAsync(f_ckv, 0, Me * 2 * A * sizeof(float), st));
+        if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Me * 2 * A * sizeof(float), st));
         attn_simt_bwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], g_ctx, dt, A, (int64_t)Ld * A, clse[l], f_qkv, A,
                       (int64_t)Ld * A, f_ckv, f_ckv + A, 2 * A, (int64_t)Le * 2 * A, nullptr, st);
         void* gq = as_T(f_qkv, g_qkv, Md * A);
@@ -570,7 +572,7 @@ void Engine::backward() {
         drop_cast(dy, g_d, dt, Md * d, drop(S_DEC_SO, l), st);
         linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
+        if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
         attn_simt_bwd(dec_self_args(*this, l, drop(S_DEC_SP, l)), sctx[l], g_ctx, dt, A, (int64_t)Ld * A, slse[l], f_qkv,
                       3 * A, (int64_t)Ld * 3 * A, f_qkv + A, f_qkv + 2 * A, 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
         void* gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
@@ -580,6 +582,8 @@ void Engine::backward() {
     }
     embed_bwd(dy, dec_ids, nullptr, G + off_shared, nullptr, (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
     relbias_scatter_grad(dbias_dec, lut_dec, G + off_dec_rel, H, 2 * Ld - 1, st);
+    // every decoder gradient is final: hand the range to NCCL while the encoder backward runs
+    if (overlap_comm && ND > 0) comm_allreduce_range(this, dec[0].sa.q, n_flat - dec[0].sa.q);
 
     // ---- encoder
     float* dx = dx_a;
@@ -599,6 +603,11 @@ void Engine::backward() {
         linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Me, 1.f);
         linear_dgrad(dqkv, 3 * A, w.sa.q, 3 * A, d, (int)Me, g_d2, dt, d, 0, 1.f, nullptr, false);
         rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Me, d, none, st);
+        // block l >= 1 is final (block 0 also holds the shared relative bias, reduced with the embeddings at the end)
+        if (overlap_comm && l >= 1) {
+            const int64_t hi = (l + 1 < NE) ? enc[l + 1].sa.q : (ND > 0 ? dec[0].sa.q : n_flat);
+            comm_allreduce_range(this, w.sa.q, hi - w.sa.q);
+        }
     }
     embed_bwd(dx, ids_e, ww_e, G + off_shared, G + off_ww, (int)Me, d, V, cfg.whole_word_rows, drop(S_EMB_E, 0), st);
     relbias_scatter_grad(dbias_enc, lut_enc, G + off_enc_rel, H, 2 * Le - 1, st);

@@ -100,6 +100,7 @@ struct Engine {
     // comm
     void* nccl_comm = nullptr;
     int world = 1, rank = 0;
+    bool overlap_comm = false;   // set for the fused train step: ranges are all-reduced as backward completes them
 
     // ---- generate workspace (beam.cu) ----
     struct GenWs* gen = nullptr;

@@ -19,6 +19,7 @@
 #include <vector>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace p5 {
 
@@ -150,7 +151,9 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_STRIDE = 66;                       // floats per staged row (64 + 2 pad: conflict-free 8-byte accesses)
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_STRIDE * 4;   // one 32x64 fp32 tile per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 // 8 consecutive output columns of one row: fused epilogue + (vectorised) store
@@ -224,7 +227,58 @@ __device__ __forceinline__ void epi_store8(const GemmEpilogue& e, const float* a
     }
 }
 
-template <int BLOCK_N>
+// 2 consecutive output columns of one row (the staged epilogue: lanes own adjacent column pairs, so every warp-wide
+// access below is one contiguous 128-byte (bf16) or 256-byte (fp32) row segment)
+// EPI >= 0: the flag set (bits 0-5) and the output dtype (bit 6 = fp32) are compile-time constants, so each
+// specialisation is straight-line code (the runtime-flag form made the epilogue instruction-fetch bound);
+// EPI = -1 keeps the generic runtime form for uncommon combinations.
+static constexpr int EPI_OUT_F32 = 64;
+template <int EPI>
+__device__ __forceinline__ void epi_store2(const GemmEpilogue& e, float a0, float a1, int64_t idx, bool two) {
+    const int flags = EPI >= 0 ? (EPI & 63) : e.flags;
+    const bool out_f32 = EPI >= 0 ? ((EPI & EPI_OUT_F32) != 0) : (e.c_dtype == DT_F32);
+    const bool vec = two && ((idx & 1) == 0);
+    float v0 = a0 * e.alpha, v1 = a1 * e.alpha;
+    if (flags & EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+    if (flags & EPI_MULPOS) {
+        if (vec && e.aux_dtype == DT_BF16) {
+            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>((const bf16*)e.aux + idx);
+            const float2 f = __bfloat1622float2(a);
+            v0 = f.x > 0.f ? v0 : 0.f; v1 = f.y > 0.f ? v1 : 0.f;
+        } else {
+            v0 = ld_as_f32(e.aux, e.aux_dtype, idx) > 0.f ? v0 : 0.f;
+            if (two) v1 = ld_as_f32(e.aux, e.aux_dtype, idx + 1) > 0.f ? v1 : 0.f;
+        }
+    }
+    if (flags & EPI_DROPOUT) {
+        v0 = drop_keep(e.seed, e.site, (uint64_t)idx, e.drop_thr) ? v0 * e.inv_keep : 0.f;
+        v1 = drop_keep(e.seed, e.site, (uint64_t)(idx + 1), e.drop_thr) ? v1 * e.inv_keep : 0.f;
+    }
+    if (flags & EPI_ADD_RESID) {
+        if (vec) { const float2 r = *reinterpret_cast<const float2*>(e.resid + idx); v0 += r.x; v1 += r.y; }
+        else { v0 += e.resid[idx]; if (two) v1 += e.resid[idx + 1]; }
+    }
+    if (flags & EPI_ACCUM) {
+        const float* c = (const float*)e.C;
+        if (vec) { const float2 r = *reinterpret_cast<const float2*>(c + idx); v0 += r.x; v1 += r.y; }
+        else { v0 += c[idx]; if (two) v1 += c[idx + 1]; }
+    }
+    if (flags & EPI_ATOMIC) {
+        float* c = (float*)e.C;
+        atomicAdd(c + idx, v0);
+        if (two) atomicAdd(c + idx + 1, v1);
+    } else if (out_f32) {
+        float* c = (float*)e.C;
+        if (vec) *reinterpret_cast<float2*>(c + idx) = make_float2(v0, v1);
+        else { c[idx] = v0; if (two) c[idx + 1] = v1; }
+    } else {
+        bf16* c = (bf16*)e.C;
+        if (vec) *reinterpret_cast<__nv_bfloat162*>(c + idx) = __floats2bfloat162_rn(v0, v1);
+        else { c[idx] = __float2bfloat16_rn(v0); if (two) c[idx + 1] = __float2bfloat16_rn(v1); }
+    }
+}
+
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
@@ -239,6 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 4);
+    float* epi_stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
     volatile uint32_t* tmem_holder_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
 
@@ -367,6 +422,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = row < P.M;
             const int64_t row_off = (int64_t)b1 * P.epi.cs1 + (int64_t)b2 * P.epi.cs2 + (int64_t)row * P.epi.ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            if constexpr (EPI != -2) {
+                // TMEM -> registers (thread = row) -> per-warp smem tile -> registers (lane = column pair) -> global:
+                // every global access of the fused epilogue (aux / residual / C) is a contiguous row segment
+                float* tile = epi_stage + ew * (32 * Cfg::EPI_STRIDE);
+                const int64_t boff = (int64_t)b1 * P.epi.cs1 + (int64_t)b2 * P.epi.cs2;
+                const int row0 = m_blk * BLOCK_M + ew * 32;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 64; ++c) {
+                    uint32_t r[64];
+                    tmem_ld32(taddr + c * 64, r);
+                    tmem_ld32(taddr + c * 64 + 32, r + 32);
+                    tmem_ld_wait();
+                    if (c == BLOCK_N / 64 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    float* myrow = tile + lane * Cfg::EPI_STRIDE;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        *reinterpret_cast<float2*>(myrow + 2 * j) = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    __syncwarp();
+                    const int col = n_blk * BLOCK_N + c * 64 + 2 * lane;
+                    if (col < P.N) {
+                        const bool two = col + 1 < P.N;
+                        const int nrows = min(32, P.M - row0);
+#pragma unroll 4
+                        for (int rr = 0; rr < nrows; ++rr) {
+                            const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
+                            epi_store2<EPI>(P.epi, v.x, v.y, boff + (int64_t)(row0 + rr) * P.epi.ldc + col, two);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t r[32];
@@ -548,12 +640,15 @@ std::string gemm_tc_prof_summary() {
 }
 void gemm_tc_force_block_n(int bn) { g_force_block_n = bn; }
 
-template <int BN>
+static int g_epi_mode = -1;   // -1: read P5_GEMM_EPI; 0 = direct register->global generic epilogue, 1 = staged generic, 2 = staged specialised
+void gemm_tc_set_epilogue(int mode) { g_epi_mode = mode; }
+
+template <int BN, int EPI>
 static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     using Cfg = TcCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        P5_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        P5_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     CUtensorMap tmA = make_tmap(p.A, p.M, p.K, p.nb1, p.nb2, BLOCK_M);
@@ -570,10 +665,17 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
         rec.flops = 2.0 * p.M * p.N * (double)p.K * p.nb1 * p.nb2; rec.bn = BN;
         cudaEventRecord(rec.e0, stream);
     }
-    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, P);
+    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, P);
     P5_CUDA(cudaGetLastError());
     if (g_prof_on) { cudaEventRecord(rec.e1, stream); g_prof.push_back(rec); }
     ++g_tc_launches;
+}
+
+template <int EPI>
+static void launch_bn(int bn, const GemmProblem& p, cudaStream_t stream) {
+    if (bn == 256) launch_tc<256, EPI>(p, stream);
+    else if (bn == 128) launch_tc<128, EPI>(p, stream);
+    else launch_tc<64, EPI>(p, stream);
 }
 
 void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
@@ -592,9 +694,26 @@ void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         else bn = 64;
         if (p.N <= 64) bn = 64;
     }
-    if (bn == 256) launch_tc<256>(p, stream);
-    else if (bn == 128) launch_tc<128>(p, stream);
-    else launch_tc<64>(p, stream);
+    if (g_epi_mode < 0) {
+        const char* e = getenv("P5_GEMM_EPI");
+        g_epi_mode = (e && strcmp(e, "direct") == 0) ? 0 : ((e && strcmp(e, "generic") == 0) ? 1 : 2);
+    }
+    if (g_epi_mode == 0) { launch_bn<-2>(bn, p, stream); return; }
+    if (g_epi_mode == 1) { launch_bn<-1>(bn, p, stream); return; }
+    // compile-time specialisations of the flag sets the engine uses; anything else takes the generic kernel
+    const int key = (p.epi.flags & 63) | (p.epi.c_dtype == DT_F32 ? EPI_OUT_F32 : 0);
+    switch (key) {
+        case 0: launch_bn<0>(bn, p, stream); break;
+        case EPI_OUT_F32: launch_bn<EPI_OUT_F32>(bn, p, stream); break;
+        case EPI_RELU: launch_bn<EPI_RELU>(bn, p, stream); break;
+        case EPI_RELU | EPI_DROPOUT: launch_bn<(EPI_RELU | EPI_DROPOUT)>(bn, p, stream); break;
+        case EPI_ADD_RESID | EPI_OUT_F32: launch_bn<(EPI_ADD_RESID | EPI_OUT_F32)>(bn, p, stream); break;
+        case EPI_ADD_RESID | EPI_DROPOUT | EPI_OUT_F32: launch_bn<(EPI_ADD_RESID | EPI_DROPOUT | EPI_OUT_F32)>(bn, p, stream); break;
+        case EPI_MULPOS: launch_bn<EPI_MULPOS>(bn, p, stream); break;
+        case EPI_ACCUM | EPI_OUT_F32: launch_bn<(EPI_ACCUM | EPI_OUT_F32)>(bn, p, stream); break;
+        case EPI_ATOMIC | EPI_OUT_F32: launch_bn<(EPI_ATOMIC | EPI_OUT_F32)>(bn, p, stream); break;
+        default: launch_bn<-1>(bn, p, stream); break;
+    }
 }
 
 }  // namespace p5

@@ -210,9 +210,97 @@ rmsnorm_bwd_kernel(const T* __restrict__ dn, const float* __restrict__ x, const 
     }
 }
 
+// vectorised form for d = NV * 128: each lane owns NV float4 column groups, the whole row lives in registers
+// (x, dn, dres are each read exactly once: 2+4+4 B in, 4 B out per element), dw partials stay in registers per warp
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ rstd,
+                       const float* __restrict__ w, const float* dres, float* dx, float* __restrict__ dw, int M,
+                       DropCfg drop) {
+    constexpr int d = NV * 128;
+    __shared__ float sdw[d];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < d; c += 256) sdw[c] = 0.f;
+    __syncthreads();
+    float wv[NV][4], acc[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        ldv<4>(w + 4 * (lane + 32 * k), wv[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+    }
+    const int r0 = blockIdx.x * RMS_BWD_ROWS;
+    for (int rr = warp; rr < RMS_BWD_ROWS; rr += 8) {
+        const int row = r0 + rr;
+        if (row >= M) break;
+        const int64_t base = (int64_t)row * d;
+        float xv[NV][4], gv[NV][4], rv[NV][4];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = 4 * (lane + 32 * k);
+            ldv<4>(x + base + c, xv[k]);
+            ldv<4>(dn + base + c, gv[k]);
+            if (dres) ldv<4>(dres + base + c, rv[k]);
+        }
+        const float r = rstd[row];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = 4 * (lane + 32 * k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float g = gv[k][j];
+                if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)(base + c + j), drop.thr) ? g * drop.inv_keep : 0.f;
+                gv[k][j] = g;
+                xv[k][j] *= r;                  // xhat
+                dot += g * wv[k][j] * xv[k][j];
+                acc[k][j] += g * xv[k][j];
+            }
+        }
+        dot = warp_sum(dot) * (1.f / (float)d);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = 4 * (lane + 32 * k);
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o[j] = r * (gv[k][j] * wv[k][j] - xv[k][j] * dot);
+                if (dres) o[j] += rv[k][j];
+            }
+            stv<4>(dx + base + c, o);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&sdw[4 * (lane + 32 * k) + j], acc[k][j]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        const float v = sdw[c];
+        if (v != 0.f) atomicAdd(dw + c, v);
+    }
+}
+
+template <typename T>
+static bool launch_rms_bwd_vec(const void* dn, const float* x, const float* rstd, const float* w, const float* dres,
+                               float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st) {
+    dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
+    switch (d) {
+        case 512: rmsnorm_bwd_vec_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop); return true;
+        case 768: rmsnorm_bwd_vec_kernel<T, 6><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop); return true;
+        case 1024: rmsnorm_bwd_vec_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop); return true;
+        default: return false;
+    }
+}
+
 void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd, const float* w, const float* dres,
                  float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st) {
     if (M <= 0) return;
+    if (dn_dtype == DT_F32 ? launch_rms_bwd_vec<float>(dn, x, rstd, w, dres, dx, dw, M, d, drop, st)
+                           : launch_rms_bwd_vec<bf16>(dn, x, rstd, w, dres, dx, dw, M, d, drop, st)) {
+        LAUNCHED();
+        return;
+    }
     dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
     const size_t sm = (size_t)d * sizeof(float);
     if (dn_dtype == DT_F32)
