@@ -11,6 +11,7 @@
 #include "engine.h"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace p5 {
 
@@ -361,6 +362,11 @@ void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void
 // ------------------------------------------------------------------------------------------------------------
 void Engine::enc_attention_fwd(int l) {
     const int64_t SS1 = (int64_t)Le * Le;
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("P5_ATTN"); fused = (e && strcmp(e, "unfused") == 0) ? 0 : 1; }
+    if (dt == DT_BF16 && fused &&
+        fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, P_e[l], ctx_e[l], A, drop(S_ENC_P, l), st))
+        return;
     if (dt == DT_BF16) {
         GemmProblem p;   // S = Q K^T   (unscaled, HF:modeling_t5.py:308)
         p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;

@@ -1,0 +1,384 @@
+// Fused encoder self-attention forward on tcgen05 (bf16 operands, fp32 softmax): S = Q K^T is never written to HBM.
+//   HF:models/t5/modeling_t5.py:308-334 — scores (unscaled) + shared relative position bias + additive padding mask,
+//   softmax in fp32, dropout on the probabilities, P V.
+//
+// One persistent CTA per SM walks (batch, head) pairs; K and V of the pair ([Lk, 64] each, Lk <= 512) are loaded once
+// into 128B-swizzled smem by TMA and reused by every 128-row query tile.
+//   warp 0    : TMA producer (K, V per pair; Q per tile)
+//   warp 1    : MMA issuer.  pass 1: S_blk = Q K_blk^T (128x128x64) per 128-key block -> TMEM (double buffered)
+//               pass 2: S_blk again, then O += P_blk V_blk (128x64x128) with P_blk read from smem
+//   warp 2    : TMEM allocator (2 x 128 columns S + 64 columns O)
+//   warps 4-7 : softmax.  thread = query row.  pass 1: row max / sum (online over blocks);
+//               pass 2: p = exp(s - m) / l -> P_save (bf16, for the backward), dropout -> bf16 -> swizzled smem A tile
+// Two passes over the key blocks (QK^T is recomputed: K = 64, cheap) make the written P exactly normalised and avoid
+// rescaling the O accumulator in TMEM.
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+#include <float.h>
+
+namespace p5 {
+extern int g_launches;
+#define MASK_MIN (-FLT_MAX)
+
+static constexpr int FA_THREADS = 256;
+static constexpr int QT = 128;      // query rows per tile
+static constexpr int KB = 128;      // keys per block
+
+struct FaParams {
+    int B, H, Lq, Lk, nkb, nqt, nq_buf;
+    const float* bias_rel;   // [H, Lq + Lk - 1]
+    const int* key_mask;     // [B, Lk]
+    bf16* P_save;            // [B, H, Lq, Lk] normalised probabilities (un-dropped)
+    bf16* ctx;               // [B*Lq, ld_ctx]
+    int64_t ld_ctx;
+    uint32_t sK, sV, sQ, sP, sBias, sMask, sBar;   // smem offsets from the 1024-aligned base
+    DropCfg drop;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sK = base + P.sK, sV = base + P.sV, sQ = base + P.sQ, sP = base + P.sP, bar = base + P.sBar;
+    float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
+    float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
+    // barriers (8 bytes each)
+    const uint32_t kv_full = bar, kv_empty = bar + 8;
+    auto q_full = [&](int i) { return bar + 16 + 8 * i; };
+    auto q_empty = [&](int i) { return bar + 32 + 8 * i; };
+    auto s_full = [&](int i) { return bar + 48 + 8 * i; };
+    auto s_empty = [&](int i) { return bar + 64 + 8 * i; };
+    auto p_full = [&](int i) { return bar + 80 + 8 * i; };
+    auto p_empty = [&](int i) { return bar + 96 + 8 * i; };
+    const uint32_t o_full = bar + 112, o_empty = bar + 120, bm_full = bar + 128, bm_empty = bar + 136;
+    const uint32_t tmem_holder = bar + 144;
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 144);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_pairs = P.B * P.H;
+    const int Lk = P.Lk, Lq = P.Lq, nkb = P.nkb, nqt = P.nqt;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); }
+    if (warp == 1 && lane == 0) {
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1);
+            mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4);
+            mbar_init(p_full(i), 4); mbar_init(p_empty(i), 1);
+        }
+        mbar_init(o_full, 1); mbar_init(o_empty, 4);
+        mbar_init(bm_full, 1); mbar_init(bm_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder_ptr;
+    const uint32_t tS[2] = {tmem, tmem + 128};
+    const uint32_t tO = tmem + 256;
+
+    if (warp == 0) {
+        // ========================= TMA producer =========================
+        if (lane == 0) {
+            uint32_t kv_ph = 0, q_ph[2] = {0, 0};
+            int qb = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const int b = pair / P.H, h = pair % P.H;
+                mbar_wait(kv_empty, kv_ph ^ 1);
+                mbar_expect_tx(kv_full, (uint32_t)(2 * nkb * KB * 128));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_4d(sK + kb * (KB * 128), &tmK, kv_full, 0, kb * KB, h, b);
+                    tma_load_4d(sV + kb * (KB * 128), &tmV, kv_full, 0, kb * KB, h, b);
+                }
+                kv_ph ^= 1;
+                for (int qt = 0; qt < nqt; ++qt) {
+                    mbar_wait(q_empty(qb), q_ph[qb] ^ 1);
+                    mbar_expect_tx(q_full(qb), QT * 128);
+                    tma_load_4d(sQ + qb * (QT * 128), &tmQ, q_full(qb), 0, qt * QT, h, b);
+                    q_ph[qb] ^= 1;
+                    qb = (qb + 1) % P.nq_buf;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ========================= MMA issuer =========================
+        if (lane == 0) {
+            // S: M=128, N=128, A (Q) K-major, B (K) K-major.   PV: M=128, N=64, A (P) K-major, B (V) MN-major.
+            const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                                     ((uint32_t)(128 >> 4) << 24);
+            uint32_t kv_ph = 0, q_ph[2] = {0, 0}, se_ph[2] = {0, 0}, pf_ph[2] = {0, 0}, oe_ph = 0;
+            int qb = 0, sb = 0, pb = 0;
+            auto issue_s = [&](int kb, uint32_t q_addr) {
+                mbar_wait(s_empty(sb), se_ph[sb] ^ 1);
+                se_ph[sb] ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tS[sb], make_smem_desc(q_addr + k * 32, 16, 1024),
+                              make_smem_desc(sK + kb * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
+                umma_commit(s_full(sb));
+                sb ^= 1;
+            };
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                mbar_wait(kv_full, kv_ph);
+                kv_ph ^= 1;
+                for (int qt = 0; qt < nqt; ++qt) {
+                    mbar_wait(q_full(qb), q_ph[qb]);
+                    q_ph[qb] ^= 1;
+                    tc_fence_after();
+                    const uint32_t q_addr = sQ + qb * (QT * 128);
+                    // pass 1: statistics
+                    for (int kb = 0; kb < nkb; ++kb) issue_s(kb, q_addr);
+                    // pass 2: probabilities and O
+                    mbar_wait(o_empty, oe_ph ^ 1);     // the previous tile's O has been read out
+                    oe_ph ^= 1;
+                    issue_s(0, q_addr);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (kb + 1 < nkb) issue_s(kb + 1, q_addr);
+                        else umma_commit(q_empty(qb));   // all QK^T of this tile issued: Q slot may be refilled once they retire
+                        mbar_wait(p_full(pb), pf_ph[pb]);
+                        pf_ph[pb] ^= 1;
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < KB / 16; ++k) {
+                            const uint64_t da = make_smem_desc(sP + pb * (QT * KB * 2) + (k >> 2) * (QT * 128) + (k & 3) * 32, 16, 1024);
+                            const uint64_t db = make_smem_desc(sV + kb * (KB * 128) + k * 2048, 8192, 1024);
+                            umma_bf16(tO, da, db, idesc_o, (kb | k) != 0);
+                        }
+                        umma_commit(p_empty(pb));
+                        pb ^= 1;
+                    }
+                    umma_commit(o_full);
+                    qb = (qb + 1) % P.nq_buf;
+                }
+                umma_commit(kv_empty);   // K/V of this pair may be overwritten once every MMA above has retired
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ========================= bias / mask tables per (batch, head) =========================
+        uint32_t bm_ph = 0;
+        const int n_delta = Lq + Lk - 1;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const int b = pair / P.H, h = pair % P.H;
+            mbar_wait(bm_empty, bm_ph ^ 1);
+            // entries past n_delta are only touched for padded keys (masked with -inf): keep them finite
+            for (int e = lane; e < Lq + nkb * KB; e += 32)
+                bias_s[e] = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] : 0.f;
+            for (int j = lane; j < nkb * KB; j += 32)
+                mask_s[j] = (j < Lk && (!P.key_mask || P.key_mask[b * Lk + j] != 0)) ? 0.f : (j < Lk ? MASK_MIN : -INFINITY);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bm_full);
+            bm_ph ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ========================= softmax warps =========================
+        const int sw = warp & 3;
+        const int r = sw * 32 + lane;                     // row of the query tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
+        uint32_t sf_ph[2] = {0, 0}, pe_ph[2] = {0, 0}, of_ph = 0, bm_ph = 0;
+        int sb = 0, pb = 0;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const int b = pair / P.H, h = pair % P.H;
+            mbar_wait(bm_full, bm_ph);
+            bm_ph ^= 1;
+            for (int qt = 0; qt < nqt; ++qt) {
+                const int i = qt * QT + r;                // query position
+                const bool row_ok = i < Lq;
+                const float* brow = bias_s + (Lq - 1 - i);   // bias for key j is brow[j]
+                // ---------------- pass 1: m = max_j s_ij, l = sum_j exp(s_ij - m)
+                float m = -INFINITY, l = 0.f;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(s_full(sb), sf_ph[sb]);
+                    sf_ph[sb] ^= 1;
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < KB / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tS[sb] + lane_off + c * 32, v);
+                        tmem_ld_wait();
+                        const int j0 = kb * KB + c * 32;
+                        float cm = -INFINITY;
+                        float s[32];
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            s[t] = __uint_as_float(v[t]) + (row_ok ? brow[j0 + t] : 0.f) + mask_s[j0 + t];
+                            cm = fmaxf(cm, s[t]);
+                        }
+                        const float mn = fmaxf(m, cm);
+                        if (mn > -INFINITY) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int t = 0; t < 32; ++t) acc += __expf(s[t] - mn);
+                            l = l * __expf(m - mn) + acc;
+                            m = mn;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty(sb));
+                    sb ^= 1;
+                }
+                const float inv_l = 1.f / l;
+                // ---------------- pass 2: P, dropout, smem A tile
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(s_full(sb), sf_ph[sb]);
+                    sf_ph[sb] ^= 1;
+                    tc_fence_after();
+                    mbar_wait(p_empty(pb), pe_ph[pb] ^ 1);   // the MMA that read this P buffer has retired
+                    pe_ph[pb] ^= 1;
+                    const uint32_t p_tile = sP + pb * (QT * KB * 2);
+#pragma unroll 1
+                    for (int c = 0; c < KB / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tS[sb] + lane_off + c * 32, v);
+                        tmem_ld_wait();
+                        const int j0 = kb * KB + c * 32;
+                        const int64_t grow = (((int64_t)b * P.H + h) * Lq + i) * Lk;
+                        uint32_t pk[16], pd[16];
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const int j = j0 + 2 * t;
+                            const float s0 = __uint_as_float(v[2 * t]) + (row_ok ? brow[j] : 0.f) + mask_s[j];
+                            const float s1 = __uint_as_float(v[2 * t + 1]) + (row_ok ? brow[j + 1] : 0.f) + mask_s[j + 1];
+                            const float p0 = __expf(s0 - m) * inv_l, p1 = __expf(s1 - m) * inv_l;
+                            pk[t] = pack_bf16x2(p0, p1);
+                            if (P.drop.thr) {
+                                const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(grow + j) >> 1);
+                                const uint32_t t16 = P.drop.thr >> 16;
+                                pd[t] = pack_bf16x2((hsh & 0xffffu) >= t16 ? p0 * P.drop.inv_keep : 0.f,
+                                                    (hsh >> 16) >= t16 ? p1 * P.drop.inv_keep : 0.f);
+                            } else {
+                                pd[t] = pk[t];
+                            }
+                        }
+                        // global P_save (normalised, un-dropped): 64 contiguous bytes of this row
+                        if (row_ok && P.P_save) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int j = j0 + 8 * q;
+                                if (j + 8 <= Lk) {
+                                    *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                } else {
+                                    for (int t = 0; t < 4; ++t)
+                                        if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[4 * q + t];
+                                }
+                            }
+                        }
+                        // smem A tile, K-major SWIZZLE_128B: chunk (64 keys) -> [128 rows][128 B], 16-byte units XOR (row & 7)
+                        {
+                            const int kk = c * 32;                               // key offset inside the 128-key block
+                            const uint32_t chunk = p_tile + (kk >> 6) * (QT * 128) + r * 128;
+                            const int u0 = (kk & 63) >> 3;                         // first 16-byte unit (8 keys each)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t addr = chunk + (uint32_t)(((u0 + q) ^ (r & 7)) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[4 * q]), "r"(pd[4 * q + 1]),
+                                             "r"(pd[4 * q + 2]), "r"(pd[4 * q + 3]) : "memory");
+                            }
+                        }
+                    }
+                    // S buffer free; P tile complete: make the generic-proxy smem writes visible to the tensor core
+                    tc_fence_before();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(s_empty(sb)); mbar_arrive(p_full(pb)); }
+                    sb ^= 1;
+                    pb ^= 1;
+                }
+                // ---------------- O -> ctx
+                mbar_wait(o_full, of_ph);
+                of_ph ^= 1;
+                tc_fence_after();
+                {
+                    uint32_t o[64];
+                    tmem_ld32(tO + lane_off, o);
+                    tmem_ld32(tO + lane_off + 32, o + 32);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_empty);
+                    if (row_ok) {
+                        bf16* dst = P.ctx + ((int64_t)b * Lq + i) * P.ld_ctx + h * 64;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            uint4 w;
+                            w.x = pack_bf16x2(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1]));
+                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3]));
+                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5]));
+                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7]));
+                            *reinterpret_cast<uint4*>(dst + 8 * q) = w;
+                        }
+                    }
+                }
+            }
+            // bias/mask tables of this pair no longer needed
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bm_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// qkv: [B*L, 3A] bf16 (q | k | v column blocks, heads 64 wide).  Returns false if the shape is not supported.
+bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
+               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st) {
+    if (L > 512 || L % 8 != 0 || ld_qkv % 8 != 0) return false;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        P5_CUDA(cudaGetDevice(&dev));
+        P5_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    FaParams P;
+    P.B = B; P.H = H; P.Lq = L; P.Lk = L;
+    P.nkb = (int)cdiv(L, KB); P.nqt = (int)cdiv(L, QT);
+    const uint32_t kv_bytes = (uint32_t)P.nkb * KB * 128;
+    P.nq_buf = (kv_bytes <= 48 * 1024) ? 2 : 1;
+    P.sK = 0; P.sV = kv_bytes; P.sQ = 2 * kv_bytes; P.sP = P.sQ + P.nq_buf * QT * 128;
+    P.sBias = P.sP + 2 * QT * KB * 2;
+    P.sMask = P.sBias + (uint32_t)round_up((L + P.nkb * KB) * 4, 16);
+    P.sBar = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
+    const size_t smem = P.sBar + 256 + 1024;
+    P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
+    P.bias_rel = bias_rel; P.key_mask = key_mask; P.P_save = (bf16*)P_save; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
+    P.drop = drop;
+    static size_t max_set = 0;
+    if (smem > max_set) {
+        P5_CUDA(cudaFuncSetAttribute(fattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = smem;
+    }
+    // 4-D views (c, pos, h, b): row stride ld_qkv, head stride 64 elements, batch stride L*ld_qkv
+    const uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)ld_qkv * 2, 128, (uint64_t)L * ld_qkv * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    const bf16* base = (const bf16*)qkv;
+    CUtensorMap tmQ = tmap_bf16_4d(base, dims, strides, box);
+    CUtensorMap tmK = tmap_bf16_4d(base + A, dims, strides, box);
+    CUtensorMap tmV = tmap_bf16_4d(base + 2 * A, dims, strides, box);
+    const int n_pairs = B * H;
+    const int grid = n_pairs < num_sms ? n_pairs : num_sms;
+    fattn_fwd_kernel<<<grid, FA_THREADS, smem, st>>>(tmQ, tmK, tmV, P);
+    P5_CUDA(cudaGetLastError());
+    ++g_launches;
+    return true;
+}
+
+}  // namespace p5

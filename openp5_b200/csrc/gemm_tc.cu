@@ -15,6 +15,7 @@
 // dgrad/wgrad read the forward tensors in place (no transposes): TMA loads [64k x 64mn] boxes and the smem
 // descriptor uses the MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) (uint128 units).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <unordered_map>
 #include <vector>
 #include <mutex>
@@ -30,118 +31,13 @@ static constexpr int GEMM_THREADS = 256;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 // ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Bounded wait: a mis-programmed pipeline traps after ~4 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-            printf("p5 gemm_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                   threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-        "%6}], [%2];" ::"r"(dst),
-        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// completion of all previously issued MMAs arrives on the mbarrier (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 struct TcParams {
     int M, N, K;
     int nb1, nb2;
     int a_major, b_major;
+    int dbg;   // perf-debug only (P5_GEMM_DBG): 1 = no global stores, 2 = no smem staging either, 4 = no TMEM loads
     GemmEpilogue epi;
 };
 
@@ -265,8 +161,12 @@ __device__ __forceinline__ void epi_store2(const GemmEpilogue& e, float a0, floa
     }
     if (flags & EPI_ATOMIC) {
         float* c = (float*)e.C;
-        atomicAdd(c + idx, v0);
-        if (two) atomicAdd(c + idx + 1, v1);
+        if (vec) {   // one 8-byte vector reduction instead of two scalar atomics (sm_90+)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(c + idx), "f"(v0), "f"(v1) : "memory");
+        } else {
+            atomicAdd(c + idx, v0);
+            if (two) atomicAdd(c + idx + 1, v1);
+        }
     } else if (out_f32) {
         float* c = (float*)e.C;
         if (vec) *reinterpret_cast<float2*>(c + idx) = make_float2(v0, v1);
@@ -431,13 +331,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 64; ++c) {
                     uint32_t r[64];
-                    tmem_ld32(taddr + c * 64, r);
-                    tmem_ld32(taddr + c * 64 + 32, r + 32);
-                    tmem_ld_wait();
+                    if (!(P.dbg & 4)) {
+                        tmem_ld32(taddr + c * 64, r);
+                        tmem_ld32(taddr + c * 64 + 32, r + 32);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) r[j] = j;
+                    }
                     if (c == BLOCK_N / 64 - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    if (P.dbg & 2) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) x ^= r[j];
+                        if (x == 0x12345u) P.epi.alpha == 0.f ? (void)0 : (void)atomicAdd((int*)P.epi.C, 1);
+                        continue;
                     }
                     float* myrow = tile + lane * Cfg::EPI_STRIDE;
 #pragma unroll
@@ -448,10 +360,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (col < P.N) {
                         const bool two = col + 1 < P.N;
                         const int nrows = min(32, P.M - row0);
+                        if (P.dbg & 1) {
+                            float acc2 = 0.f;
+                            for (int rr = 0; rr < nrows; ++rr) {
+                                const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
+                                acc2 += v.x + v.y;
+                            }
+                            if (acc2 == 1.2345e30f) ((float*)P.epi.C)[0] = acc2;
+                        } else {
 #pragma unroll 4
-                        for (int rr = 0; rr < nrows; ++rr) {
-                            const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
-                            epi_store2<EPI>(P.epi, v.x, v.y, boff + (int64_t)(row0 + rr) * P.epi.ldc + col, two);
+                            for (int rr = 0; rr < nrows; ++rr) {
+                                const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
+                                epi_store2<EPI>(P.epi, v.x, v.y, boff + (int64_t)(row0 + rr) * P.epi.ldc + col, two);
+                            }
                         }
                     }
                     __syncwarp();
@@ -542,23 +463,13 @@ void gemm_tc_clear_cache() {
 }
 int gemm_tc_launch_count() { return g_tc_launches; }
 
-static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, int nb2, int box_rows) {
+// cached 4-D bf16 SWIZZLE_128B tensor map (dims innermost first, strides in bytes for dims 1..3)
+CUtensorMap tmap_bf16_4d(const void* ptr, const uint64_t dims[4], const uint64_t strides[3], const uint32_t box[4]) {
     TmapKey key;
     memset(&key, 0, sizeof(key));
-    key.ptr = op.ptr;
-    const uint64_t ld_b = (uint64_t)op.ld * 2;
-    if (op.major == MAJOR_K) {
-        key.dims[0] = (uint64_t)K; key.dims[1] = (uint64_t)rows;
-        key.box[0] = BLOCK_K; key.box[1] = (uint32_t)box_rows;
-    } else {
-        key.dims[0] = (uint64_t)rows; key.dims[1] = (uint64_t)K;
-        key.box[0] = 64; key.box[1] = BLOCK_K;
-    }
-    key.dims[2] = (uint64_t)nb1; key.dims[3] = (uint64_t)nb2;
-    key.box[2] = 1; key.box[3] = 1;
-    key.strides[0] = ld_b;
-    key.strides[1] = nb1 > 1 ? (uint64_t)op.bs1 * 2 : key.dims[1] * ld_b;
-    key.strides[2] = nb2 > 1 ? (uint64_t)op.bs2 * 2 : (nb1 > 1 ? (uint64_t)op.bs1 * 2 * nb1 : key.dims[1] * ld_b);
+    key.ptr = ptr;
+    for (int i = 0; i < 4; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+    for (int i = 0; i < 3; ++i) key.strides[i] = strides[i];
     {
         std::lock_guard<std::mutex> g(g_tmap_mu);
         auto it = g_tmap_cache.find(key);
@@ -566,7 +477,7 @@ static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, in
     }
     CUtensorMap m;
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), key.dims,
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), key.dims,
                                  key.strides, key.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -575,7 +486,7 @@ static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, in
         snprintf(b, sizeof(b),
                  "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] "
                  "box=[%u,%u,%u,%u]",
-                 (int)r, op.ptr, (unsigned long long)key.dims[0], (unsigned long long)key.dims[1],
+                 (int)r, ptr, (unsigned long long)key.dims[0], (unsigned long long)key.dims[1],
                  (unsigned long long)key.dims[2], (unsigned long long)key.dims[3], (unsigned long long)key.strides[0],
                  (unsigned long long)key.strides[1], (unsigned long long)key.strides[2], key.box[0], key.box[1],
                  key.box[2], key.box[3]);
@@ -584,6 +495,25 @@ static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, in
     std::lock_guard<std::mutex> g(g_tmap_mu);
     g_tmap_cache[key] = m;
     return m;
+}
+
+static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, int nb2, int box_rows) {
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    const uint64_t ld_b = (uint64_t)op.ld * 2;
+    if (op.major == MAJOR_K) {
+        dims[0] = (uint64_t)K; dims[1] = (uint64_t)rows;
+        box[0] = BLOCK_K; box[1] = (uint32_t)box_rows;
+    } else {
+        dims[0] = (uint64_t)rows; dims[1] = (uint64_t)K;
+        box[0] = 64; box[1] = BLOCK_K;
+    }
+    dims[2] = (uint64_t)nb1; dims[3] = (uint64_t)nb2;
+    box[2] = 1; box[3] = 1;
+    strides[0] = ld_b;
+    strides[1] = nb1 > 1 ? (uint64_t)op.bs1 * 2 : dims[1] * ld_b;
+    strides[2] = nb2 > 1 ? (uint64_t)op.bs2 * 2 : (nb1 > 1 ? (uint64_t)op.bs1 * 2 * nb1 : dims[1] * ld_b);
+    return tmap_bf16_4d(op.ptr, dims, strides, box);
 }
 
 static bool operand_ok(const GemmOperand& o, int nb1, int nb2, bool allow_mn) {
@@ -657,6 +587,9 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     P.M = p.M; P.N = p.N; P.K = p.K; P.nb1 = p.nb1; P.nb2 = p.nb2;
     P.a_major = p.A.major; P.b_major = p.B.major;
     P.epi = p.epi;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("P5_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    P.dbg = dbg;
     const long long tiles = (long long)cdiv(p.M, BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     ProfRec rec;

@@ -90,6 +90,11 @@ void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, voi
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
                  int Lq, int Lk, DropCfg drop, cudaStream_t st);
 
+// fused tcgen05 encoder self-attention forward (fattn.cu): qkv [B*L, 3A] bf16 -> ctx [B*L, A] bf16 (+ P_save bf16
+// [B,H,L,L] normalised un-dropped probabilities for the backward).  Returns false when the shape is unsupported.
+bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
+               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st);
+
 // ---- optimiser (optim.cu) ---------------------------------------------------------------------------------------
 void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
 void scale_f32(float* g, int64_t n, float s, cudaStream_t st);
