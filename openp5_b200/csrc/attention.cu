@@ -43,14 +43,35 @@ __device__ __forceinline__ float score_bias(const AttnDev& a, int h, int kb, int
     return s + m;
 }
 
-// cooperative load of a [KT x 64] tile (rows = keys) into smem as fp32, zero beyond Lk
+// cooperative load of a [KT x 64] tile (rows = keys) into smem as fp32, zero beyond Lk.  16-byte global loads
+// (8 bf16 / 4 fp32 per thread per request); the views are 16-byte aligned (ld, bs, h*64 multiples of 8 elements).
 __device__ __forceinline__ void load_kv_tile(float (*dst)[DK + 1], const void* base, int dt, int64_t ld, int64_t boff,
                                              int h, int j0, int Lk) {
-    for (int e = threadIdx.x; e < KT * DK; e += blockDim.x) {
-        const int j = e >> 6, c = e & 63;
-        float v = 0.f;
-        if (j0 + j < Lk) v = ld_as_f32(base, dt, boff + (int64_t)(j0 + j) * ld + h * DK + c);
-        dst[j][c] = v;
+    if (dt == DT_BF16) {
+        const bf16* p = (const bf16*)base;
+        for (int e = threadIdx.x; e < KT * DK / 8; e += blockDim.x) {
+            const int j = e >> 3, c = (e & 7) * 8;
+            float v[8];
+            if (j0 + j < Lk) {
+                const uint4 t = *reinterpret_cast<const uint4*>(p + boff + (int64_t)(j0 + j) * ld + h * DK + c);
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hh[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[j][c + q] = v[q];
+        }
+    } else {
+        const float* p = (const float*)base;
+        for (int e = threadIdx.x; e < KT * DK / 4; e += blockDim.x) {
+            const int j = e >> 4, c = (e & 15) * 4;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + j < Lk) t = *reinterpret_cast<const float4*>(p + boff + (int64_t)(j0 + j) * ld + h * DK + c);
+            dst[j][c] = t.x; dst[j][c + 1] = t.y; dst[j][c + 2] = t.z; dst[j][c + 3] = t.w;
+        }
     }
 }
 

@@ -8,7 +8,8 @@
 //   warp 1    : MMA issuer.  pass 1: S_blk = Q K_blk^T (128x128x64) per 128-key block -> TMEM (double buffered)
 //               pass 2: S_blk again, then O += P_blk V_blk (128x64x128) with P_blk read from smem
 //   warp 2    : TMEM allocator (2 x 128 columns S + 64 columns O)
-//   warps 4-7 : softmax.  thread = query row.  pass 1: row max / sum (online over blocks);
+//   warps 4-11: softmax, two warpgroups.  thread = (query row, half of the 128 key columns of a block).
+//               pass 1: row max / sum (online over blocks; the two halves are combined through smem);
 //               pass 2: p = exp(s - m) / l -> P_save (bf16, for the backward), dropout -> bf16 -> swizzled smem A tile
 // Two passes over the key blocks (QK^T is recomputed: K = 64, cheap) make the written P exactly normalised and avoid
 // rescaling the O accumulator in TMEM.
@@ -20,7 +21,7 @@ namespace p5 {
 extern int g_launches;
 #define MASK_MIN (-FLT_MAX)
 
-static constexpr int FA_THREADS = 256;
+static constexpr int FA_THREADS = 384;   // 4 control warps + 2 softmax warpgroups (each owns half of the key columns)
 static constexpr int QT = 128;      // query rows per tile
 static constexpr int KB = 128;      // keys per block
 
@@ -31,7 +32,7 @@ struct FaParams {
     bf16* P_save;            // [B, H, Lq, Lk] normalised probabilities (un-dropped)
     bf16* ctx;               // [B*Lq, ld_ctx]
     int64_t ld_ctx;
-    uint32_t sK, sV, sQ, sP, sBias, sMask, sBar;   // smem offsets from the 1024-aligned base
+    uint32_t sK, sV, sQ, sP, sBias, sMask, sStat, sBar;   // smem offsets from the 1024-aligned base
     DropCfg drop;
 };
 
@@ -49,6 +50,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t sK = base + P.sK, sV = base + P.sV, sQ = base + P.sQ, sP = base + P.sP, bar = base + P.sBar;
     float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
     float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
+    float2* stat_s = reinterpret_cast<float2*>(gbase + P.sStat);   // [2][128] (m, l) per warpgroup and row
     // barriers (8 bytes each)
     const uint32_t kv_full = bar, kv_empty = bar + 8;
     auto q_full = [&](int i) { return bar + 16 + 8 * i; };
@@ -70,11 +72,11 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1);
-            mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4);
-            mbar_init(p_full(i), 4); mbar_init(p_empty(i), 1);
+            mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8);
+            mbar_init(p_full(i), 8); mbar_init(p_empty(i), 1);
         }
-        mbar_init(o_full, 1); mbar_init(o_empty, 4);
-        mbar_init(bm_full, 1); mbar_init(bm_empty, 4);
+        mbar_init(o_full, 1); mbar_init(o_empty, 8);
+        mbar_init(bm_full, 1); mbar_init(bm_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -184,6 +186,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ========================= softmax warps =========================
+        const int wg = (warp - 4) >> 2;                   // warpgroup: key columns [wg*64, wg*64+64) of every block
         const int sw = warp & 3;
         const int r = sw * 32 + lane;                     // row of the query tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
@@ -196,24 +199,25 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int qt = 0; qt < nqt; ++qt) {
                 const int i = qt * QT + r;                // query position
                 const bool row_ok = i < Lq;
-                const float* brow = bias_s + (Lq - 1 - i);   // bias for key j is brow[j]
-                // ---------------- pass 1: m = max_j s_ij, l = sum_j exp(s_ij - m)
+                const float* brow = bias_s + (row_ok ? (Lq - 1 - i) : 0);   // bias for key j is brow[j]
+                const int64_t grow = (((int64_t)b * P.H + h) * Lq + i) * Lk;
+                // ---------------- pass 1: m = max_j s_ij, l = sum_j exp(s_ij - m) over this warpgroup's columns
                 float m = -INFINITY, l = 0.f;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(s_full(sb), sf_ph[sb]);
                     sf_ph[sb] ^= 1;
                     tc_fence_after();
-#pragma unroll 1
-                    for (int c = 0; c < KB / 32; ++c) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
                         uint32_t v[32];
-                        tmem_ld32(tS[sb] + lane_off + c * 32, v);
+                        tmem_ld32(tS[sb] + lane_off + wg * 64 + c * 32, v);
                         tmem_ld_wait();
-                        const int j0 = kb * KB + c * 32;
+                        const int j0 = kb * KB + wg * 64 + c * 32;
                         float cm = -INFINITY;
                         float s[32];
 #pragma unroll
                         for (int t = 0; t < 32; ++t) {
-                            s[t] = __uint_as_float(v[t]) + (row_ok ? brow[j0 + t] : 0.f) + mask_s[j0 + t];
+                            s[t] = __uint_as_float(v[t]) + brow[j0 + t] + mask_s[j0 + t];
                             cm = fmaxf(cm, s[t]);
                         }
                         const float mn = fmaxf(m, cm);
@@ -230,6 +234,17 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     if (lane == 0) mbar_arrive(s_empty(sb));
                     sb ^= 1;
                 }
+                // combine the two column halves of the row
+                stat_s[wg * QT + r] = make_float2(m, l);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    const float2 o = stat_s[(wg ^ 1) * QT + r];
+                    const float mm = fmaxf(m, o.x);
+                    float ll = 0.f;
+                    if (m > -INFINITY) ll += l * __expf(m - mm);
+                    if (o.x > -INFINITY) ll += o.y * __expf(o.x - mm);
+                    m = mm; l = ll;
+                }
                 const float inv_l = 1.f / l;
                 // ---------------- pass 2: P, dropout, smem A tile
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -238,20 +253,19 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     tc_fence_after();
                     mbar_wait(p_empty(pb), pe_ph[pb] ^ 1);   // the MMA that read this P buffer has retired
                     pe_ph[pb] ^= 1;
-                    const uint32_t p_tile = sP + pb * (QT * KB * 2);
-#pragma unroll 1
-                    for (int c = 0; c < KB / 32; ++c) {
+                    const uint32_t p_chunk = sP + pb * (QT * KB * 2) + wg * (QT * 128) + r * 128;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
                         uint32_t v[32];
-                        tmem_ld32(tS[sb] + lane_off + c * 32, v);
+                        tmem_ld32(tS[sb] + lane_off + wg * 64 + c * 32, v);
                         tmem_ld_wait();
-                        const int j0 = kb * KB + c * 32;
-                        const int64_t grow = (((int64_t)b * P.H + h) * Lq + i) * Lk;
+                        const int j0 = kb * KB + wg * 64 + c * 32;
                         uint32_t pk[16], pd[16];
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
                             const int j = j0 + 2 * t;
-                            const float s0 = __uint_as_float(v[2 * t]) + (row_ok ? brow[j] : 0.f) + mask_s[j];
-                            const float s1 = __uint_as_float(v[2 * t + 1]) + (row_ok ? brow[j + 1] : 0.f) + mask_s[j + 1];
+                            const float s0 = __uint_as_float(v[2 * t]) + brow[j] + mask_s[j];
+                            const float s1 = __uint_as_float(v[2 * t + 1]) + brow[j + 1] + mask_s[j + 1];
                             const float p0 = __expf(s0 - m) * inv_l, p1 = __expf(s1 - m) * inv_l;
                             pk[t] = pack_bf16x2(p0, p1);
                             if (P.drop.thr) {
@@ -276,17 +290,13 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                 }
                             }
                         }
-                        // smem A tile, K-major SWIZZLE_128B: chunk (64 keys) -> [128 rows][128 B], 16-byte units XOR (row & 7)
-                        {
-                            const int kk = c * 32;                               // key offset inside the 128-key block
-                            const uint32_t chunk = p_tile + (kk >> 6) * (QT * 128) + r * 128;
-                            const int u0 = (kk & 63) >> 3;                         // first 16-byte unit (8 keys each)
+                        // smem A tile, K-major SWIZZLE_128B: this warpgroup's 64-key chunk = [128 rows][128 B],
+                        // 16-byte units XOR (row & 7)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t addr = chunk + (uint32_t)(((u0 + q) ^ (r & 7)) << 4);
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[4 * q]), "r"(pd[4 * q + 1]),
-                                             "r"(pd[4 * q + 2]), "r"(pd[4 * q + 3]) : "memory");
-                            }
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t addr = p_chunk + (uint32_t)(((c * 4 + q) ^ (r & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[4 * q]), "r"(pd[4 * q + 1]),
+                                         "r"(pd[4 * q + 2]), "r"(pd[4 * q + 3]) : "memory");
                         }
                     }
                     // S buffer free; P tile complete: make the generic-proxy smem writes visible to the tensor core
@@ -297,22 +307,21 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     sb ^= 1;
                     pb ^= 1;
                 }
-                // ---------------- O -> ctx
+                // ---------------- O -> ctx (this warpgroup writes 32 of the 64 head columns)
                 mbar_wait(o_full, of_ph);
                 of_ph ^= 1;
                 tc_fence_after();
                 {
-                    uint32_t o[64];
-                    tmem_ld32(tO + lane_off, o);
-                    tmem_ld32(tO + lane_off + 32, o + 32);
+                    uint32_t o[32];
+                    tmem_ld32(tO + lane_off + wg * 32, o);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_empty);
                     if (row_ok) {
-                        bf16* dst = P.ctx + ((int64_t)b * Lq + i) * P.ld_ctx + h * 64;
+                        bf16* dst = P.ctx + ((int64_t)b * Lq + i) * P.ld_ctx + h * 64 + wg * 32;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
+                        for (int q = 0; q < 4; ++q) {
                             uint4 w;
                             w.x = pack_bf16x2(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1]));
                             w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3]));
@@ -355,7 +364,8 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.sK = 0; P.sV = kv_bytes; P.sQ = 2 * kv_bytes; P.sP = P.sQ + P.nq_buf * QT * 128;
     P.sBias = P.sP + 2 * QT * KB * 2;
     P.sMask = P.sBias + (uint32_t)round_up((L + P.nkb * KB) * 4, 16);
-    P.sBar = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
+    P.sStat = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
+    P.sBar = P.sStat + 2 * QT * 8;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
     P.bias_rel = bias_rel; P.key_mask = key_mask; P.P_save = (bf16*)P_save; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;

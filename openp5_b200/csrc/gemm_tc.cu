@@ -328,8 +328,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float* tile = epi_stage + ew * (32 * Cfg::EPI_STRIDE);
                 const int64_t boff = (int64_t)b1 * P.epi.cs1 + (int64_t)b2 * P.epi.cs2;
                 const int row0 = m_blk * BLOCK_M + ew * 32;
+                // inputs of the fused epilogue (ReLU-mask operand, fp32 residual, fp32 accumulate target) are PREFETCHED
+                // into registers for all 32 rows of a chunk before the TMEM load: 32 independent 128-byte loads in
+                // flight per warp instead of one dependent load per row (4 epilogue warps cannot hide DRAM latency)
+                constexpr int F = EPI >= 0 ? (EPI & 63) : 0;
+                constexpr bool PF_AUX = (F & EPI_MULPOS) != 0, PF_RES = (F & EPI_ADD_RESID) != 0, PF_ACC = (F & EPI_ACCUM) != 0;
+                constexpr bool PF = PF_AUX || PF_RES || PF_ACC;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 64; ++c) {
+                    const int col = n_blk * BLOCK_N + c * 64 + 2 * lane;
+                    const bool col_ok = col < P.N, two = col + 1 < P.N;
+                    const int nrows = min(32, P.M - row0);
+                    const int64_t idx0 = boff + (int64_t)row0 * P.epi.ldc + col;
+                    const bool fast = PF && col_ok && two && (((idx0 | P.epi.ldc) & 1) == 0) && (!PF_AUX || P.epi.aux_dtype == DT_BF16);
+                    uint32_t pa[PF_AUX ? 32 : 1];
+                    float2 pr[PF_RES ? 32 : 1], pc[PF_ACC ? 32 : 1];
+                    if (fast) {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            if (rr < nrows) {
+                                const int64_t idx = idx0 + (int64_t)rr * P.epi.ldc;
+                                if constexpr (PF_AUX) pa[rr] = *reinterpret_cast<const uint32_t*>((const bf16*)P.epi.aux + idx);
+                                if constexpr (PF_RES) pr[rr] = *reinterpret_cast<const float2*>(P.epi.resid + idx);
+                                if constexpr (PF_ACC) pc[rr] = *reinterpret_cast<const float2*>((const float*)P.epi.C + idx);
+                            }
+                        }
+                    }
                     uint32_t r[64];
                     if (!(P.dbg & 4)) {
                         tmem_ld32(taddr + c * 64, r);
@@ -356,10 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j)
                         *reinterpret_cast<float2*>(myrow + 2 * j) = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                     __syncwarp();
-                    const int col = n_blk * BLOCK_N + c * 64 + 2 * lane;
-                    if (col < P.N) {
-                        const bool two = col + 1 < P.N;
-                        const int nrows = min(32, P.M - row0);
+                    if (col_ok) {
                         if (P.dbg & 1) {
                             float acc2 = 0.f;
                             for (int rr = 0; rr < nrows; ++rr) {
@@ -367,6 +388,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 acc2 += v.x + v.y;
                             }
                             if (acc2 == 1.2345e30f) ((float*)P.epi.C)[0] = acc2;
+                        } else if (fast) {
+                            const GemmEpilogue& e = P.epi;
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) {
+                                if (rr < nrows) {
+                                    const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
+                                    const int64_t idx = idx0 + (int64_t)rr * e.ldc;
+                                    float v0 = v.x * e.alpha, v1 = v.y * e.alpha;
+                                    if constexpr ((F & EPI_RELU) != 0) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                                    if constexpr (PF_AUX) {
+                                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pa[rr]));
+                                        v0 = f.x > 0.f ? v0 : 0.f; v1 = f.y > 0.f ? v1 : 0.f;
+                                    }
+                                    if constexpr ((F & EPI_DROPOUT) != 0) {
+                                        v0 = drop_keep(e.seed, e.site, (uint64_t)idx, e.drop_thr) ? v0 * e.inv_keep : 0.f;
+                                        v1 = drop_keep(e.seed, e.site, (uint64_t)(idx + 1), e.drop_thr) ? v1 * e.inv_keep : 0.f;
+                                    }
+                                    if constexpr (PF_RES) { v0 += pr[rr].x; v1 += pr[rr].y; }
+                                    if constexpr (PF_ACC) { v0 += pc[rr].x; v1 += pc[rr].y; }
+                                    if constexpr ((EPI & EPI_OUT_F32) != 0)
+                                        *reinterpret_cast<float2*>((float*)e.C + idx) = make_float2(v0, v1);
+                                    else
+                                        *reinterpret_cast<__nv_bfloat162*>((bf16*)e.C + idx) = __floats2bfloat162_rn(v0, v1);
+                                }
+                            }
                         } else {
 #pragma unroll 4
                             for (int rr = 0; rr < nrows; ++rr) {
