@@ -16,6 +16,7 @@ extern int g_launches;
 static constexpr int QB = 16;    // query rows per CTA (2 per warp)
 static constexpr int KT = 64;    // keys per smem tile
 static constexpr int DK = 64;    // d_kv
+static constexpr int KS = DK + 4;  // smem row stride of K/V tiles: 16-byte aligned rows, conflict-free LDS.128 across keys
 #define MASK_MIN (-FLT_MAX)      // torch.finfo(torch.float32).min
 
 struct AttnDev {
@@ -43,9 +44,21 @@ __device__ __forceinline__ float score_bias(const AttnDev& a, int h, int kb, int
     return s + m;
 }
 
+// 64-wide dot product of two smem rows with 128-bit shared loads (a: broadcast row, b: per-lane row)
+__device__ __forceinline__ float dot64(const float* a, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < DK; c += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(a + c);
+        const float4 y = *reinterpret_cast<const float4*>(b + c);
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    return s;
+}
+
 // cooperative load of a [KT x 64] tile (rows = keys) into smem as fp32, zero beyond Lk.  16-byte global loads
 // (8 bf16 / 4 fp32 per thread per request); the views are 16-byte aligned (ld, bs, h*64 multiples of 8 elements).
-__device__ __forceinline__ void load_kv_tile(float (*dst)[DK + 1], const void* base, int dt, int64_t ld, int64_t boff,
+__device__ __forceinline__ void load_kv_tile(float (*dst)[KS], const void* base, int dt, int64_t ld, int64_t boff,
                                              int h, int j0, int Lk) {
     if (dt == DT_BF16) {
         const bf16* p = (const bf16*)base;
@@ -80,10 +93,10 @@ __device__ __forceinline__ void load_kv_tile(float (*dst)[DK + 1], const void* b
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, float* lse) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);                       // [QB][64]
-    float (*KVs)[DK + 1] = reinterpret_cast<float (*)[DK + 1]>(smem + QB * DK);    // [KT][65]
-    float* Ss = smem + QB * DK + KT * (DK + 1);                                     // [QB][Lk]
+    float (*KVs)[KS] = reinterpret_cast<float (*)[KS]>(smem + QB * DK);    // [KT][65]
+    float* Ss = smem + QB * DK + KT * (KS);                                     // [QB][Lk]
     const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QB;
     const int kb = a.row_map ? a.row_map[b] : b;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,9 +122,7 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
             for (int jj = 0; jj < 2; ++jj) {
                 const int jl = lane + 32 * jj, j = j0 + jl;
                 if (j < Lk) {
-                    float s = 0.f;
-#pragma unroll 16
-                    for (int c = 0; c < DK; ++c) s = fmaf(Qs[r][c], KVs[jl][c], s);
+                    const float s = dot64(Qs[r], KVs[jl]);
                     Ss[r * Lk + j] = s + score_bias(a, h, kb, i_pos, j);
                 }
             }
@@ -188,9 +199,9 @@ static AttnDev to_dev(const AttnArgs& a) {
     return d;
 }
 
-static size_t fwd_smem(int Lk) { return (size_t)(QB * DK + KT * (DK + 1) + QB * Lk) * sizeof(float); }
+static size_t fwd_smem(int Lk) { return (size_t)(QB * DK + KT * (KS) + QB * Lk) * sizeof(float); }
 static size_t bwd_smem(int Lk, int n_delta) {
-    return (size_t)(2 * QB * DK + KT * (DK + 1) + QB * Lk + QB * KT + QB + n_delta) * sizeof(float);
+    return (size_t)(2 * QB * DK + KT * (KS) + QB * Lk + QB * KT + QB + n_delta) * sizeof(float);
 }
 
 void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
@@ -215,11 +226,11 @@ __global__ void __launch_bounds__(256)
 attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t ld_o, int64_t bs_o,
                      const float* __restrict__ lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV,
                      int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, int atomic_kv) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);
     float (*dOs)[DK] = reinterpret_cast<float (*)[DK]>(smem + QB * DK);
-    float (*KVs)[DK + 1] = reinterpret_cast<float (*)[DK + 1]>(smem + 2 * QB * DK);
-    float* Ss = smem + 2 * QB * DK + KT * (DK + 1);         // [QB][Lk]  p, then ds
+    float (*KVs)[KS] = reinterpret_cast<float (*)[KS]>(smem + 2 * QB * DK);
+    float* Ss = smem + 2 * QB * DK + KT * (KS);         // [QB][Lk]  p, then ds
     float* Pt = Ss + QB * a.Lk;                              // [QB][KT]  dropped p of the current tile
     float* dlt = Pt + QB * KT;                               // [QB]
     float* sdb = dlt + QB;                                   // [n_delta]
@@ -267,9 +278,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
                 const int jl = lane + 32 * jj, j = j0 + jl;
                 if (j < Lk && i >= a.Lq) Ss[r * Lk + j] = 0.f;
                 if (j < Lk && i < a.Lq) {
-                    float s = 0.f;
-#pragma unroll 16
-                    for (int c = 0; c < DK; ++c) s = fmaf(Qs[r][c], KVs[jl][c], s);
+                    float s = dot64(Qs[r], KVs[jl]);
                     s += score_bias(a, h, b, i_pos, j);
                     Ss[r * Lk + j] = (i < a.Lq) ? __expf(s - l) : 0.f;
                 } 
@@ -289,9 +298,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
                 const int jl = lane + 32 * jj, j = j0 + jl;
                 float pd = 0.f;
                 if (j < Lk && i < a.Lq) {
-                    float dpd = 0.f;
-#pragma unroll 16
-                    for (int c = 0; c < DK; ++c) dpd = fmaf(dOs[r][c], KVs[jl][c], dpd);
+                    const float dpd = dot64(dOs[r], KVs[jl]);
                     const float p = Ss[r * Lk + j];
                     float dp = dpd;
                     pd = p;
@@ -400,10 +407,7 @@ void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype
 static constexpr int SM_MAXP = 8;  // pairs per lane: Lk <= 512
 
 __device__ __forceinline__ void drop_pair(const DropCfg& d, uint64_t pair_idx, bool& k0, bool& k1) {
-    const uint32_t h = drop_hash(d.seed, d.site, pair_idx);
-    const uint32_t t16 = d.thr >> 16;
-    k0 = (h & 0xffffu) >= t16;
-    k1 = (h >> 16) >= t16;
+    drop_keep2(d.seed, d.site, pair_idx << 1, d.thr, k0, k1);
 }
 template <typename T> __device__ __forceinline__ void st_pair(T* p, float a, float b);
 template <> __device__ __forceinline__ void st_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }

@@ -85,9 +85,18 @@ __host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint32_t s
     h = mix32(h + 0x9e3779b9U * (site + 1u) + hi * 0x85ebca6bU + s1);
     return h;
 }
-// threshold = round(p * 2^32); keep iff hash >= threshold
+// One 32-bit hash serves an aligned PAIR of elements (2k, 2k+1): the low 16 bits decide the even element, the high
+// 16 bits the odd one (keep iff bits >= thr16, thr16 = round(p * 2^16)).  Kernels that own both elements of a pair
+// (GEMM epilogue, softmax, dropout-cast) hash once per pair; element-wise kernels call drop_keep and get the same mask.
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thr) {
-    return drop_hash(seed, site, idx) >= thr;
+    const uint32_t h = drop_hash(seed, site, idx >> 1);
+    return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= (thr >> 16);
+}
+__host__ __device__ __forceinline__ void drop_keep2(uint64_t seed, uint32_t site, uint64_t even_idx, uint32_t thr, bool& k0,
+                                                    bool& k1) {
+    const uint32_t h = drop_hash(seed, site, even_idx >> 1);
+    k0 = (h & 0xffffu) >= (thr >> 16);
+    k1 = (h >> 16) >= (thr >> 16);
 }
 static inline uint32_t drop_threshold(float p) {
     double t = (double)p * 4294967296.0;

@@ -340,10 +340,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const bool col_ok = col < P.N, two = col + 1 < P.N;
                     const int nrows = min(32, P.M - row0);
                     const int64_t idx0 = boff + (int64_t)row0 * P.epi.ldc + col;
-                    const bool fast = PF && col_ok && two && (((idx0 | P.epi.ldc) & 1) == 0) && (!PF_AUX || P.epi.aux_dtype == DT_BF16);
+                    // fast path (every specialised epilogue): whole column pair in range and 4/8-byte aligned -> hoisted
+                    // address arithmetic, straight-line fully unrolled row loop
+                    const bool fast = (EPI >= 0) && col_ok && two && (((idx0 | P.epi.ldc) & 1) == 0) &&
+                                      (!PF_AUX || P.epi.aux_dtype == DT_BF16);
                     uint32_t pa[PF_AUX ? 32 : 1];
                     float2 pr[PF_RES ? 32 : 1], pc[PF_ACC ? 32 : 1];
-                    if (fast) {
+                    if (PF && fast) {
 #pragma unroll
                         for (int rr = 0; rr < 32; ++rr) {
                             if (rr < nrows) {
@@ -390,27 +393,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (acc2 == 1.2345e30f) ((float*)P.epi.C)[0] = acc2;
                         } else if (fast) {
                             const GemmEpilogue& e = P.epi;
+                            const float alpha = e.alpha;
+                            const float* trow = tile + 2 * lane;
+                            const int64_t ldc = e.ldc;
+                            char* cptr = (char*)e.C + idx0 * ((EPI & EPI_OUT_F32) ? 4 : 2);
+                            const int64_t cstep = ldc * ((EPI & EPI_OUT_F32) ? 4 : 2);
 #pragma unroll
                             for (int rr = 0; rr < 32; ++rr) {
                                 if (rr < nrows) {
-                                    const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
-                                    const int64_t idx = idx0 + (int64_t)rr * e.ldc;
-                                    float v0 = v.x * e.alpha, v1 = v.y * e.alpha;
+                                    const float2 v = *reinterpret_cast<const float2*>(trow + rr * Cfg::EPI_STRIDE);
+                                    float v0 = v.x * alpha, v1 = v.y * alpha;
                                     if constexpr ((F & EPI_RELU) != 0) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                                     if constexpr (PF_AUX) {
                                         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pa[rr]));
                                         v0 = f.x > 0.f ? v0 : 0.f; v1 = f.y > 0.f ? v1 : 0.f;
                                     }
                                     if constexpr ((F & EPI_DROPOUT) != 0) {
-                                        v0 = drop_keep(e.seed, e.site, (uint64_t)idx, e.drop_thr) ? v0 * e.inv_keep : 0.f;
-                                        v1 = drop_keep(e.seed, e.site, (uint64_t)(idx + 1), e.drop_thr) ? v1 * e.inv_keep : 0.f;
+                                        bool k0, k1;   // idx is even on the fast path: one hash for the pair
+                                        drop_keep2(e.seed, e.site, (uint64_t)(idx0 + (int64_t)rr * ldc), e.drop_thr, k0, k1);
+                                        v0 = k0 ? v0 * e.inv_keep : 0.f;
+                                        v1 = k1 ? v1 * e.inv_keep : 0.f;
                                     }
                                     if constexpr (PF_RES) { v0 += pr[rr].x; v1 += pr[rr].y; }
                                     if constexpr (PF_ACC) { v0 += pc[rr].x; v1 += pc[rr].y; }
-                                    if constexpr ((EPI & EPI_OUT_F32) != 0)
-                                        *reinterpret_cast<float2*>((float*)e.C + idx) = make_float2(v0, v1);
+                                    char* dst = cptr + rr * cstep;
+                                    if constexpr ((F & EPI_ATOMIC) != 0)
+                                        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v0), "f"(v1) : "memory");
+                                    else if constexpr ((EPI & EPI_OUT_F32) != 0)
+                                        *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
                                     else
-                                        *reinterpret_cast<__nv_bfloat162*>((bf16*)e.C + idx) = __floats2bfloat162_rn(v0, v1);
+                                        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v0, v1);
                                 }
                             }
                         } else {

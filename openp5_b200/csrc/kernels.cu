@@ -321,9 +321,11 @@ __global__ void drop_cast_kernel(const float* __restrict__ in, T* __restrict__ o
             float v[4];
             ldv<4>(in + i, v);
             if (drop.thr) {
+                bool k[4];
+                drop_keep2(drop.seed, drop.site, (uint64_t)i, drop.thr, k[0], k[1]);
+                drop_keep2(drop.seed, drop.site, (uint64_t)i + 2, drop.thr, k[2], k[3]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    v[j] = drop_keep(drop.seed, drop.site, (uint64_t)(i + j), drop.thr) ? v[j] * drop.inv_keep : 0.f;
+                for (int j = 0; j < 4; ++j) v[j] = k[j] ? v[j] * drop.inv_keep : 0.f;
             }
             stv<4>(out + i, v);
         } else {

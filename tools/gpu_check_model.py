@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 
 CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fused_fp32_tiny", "adamw_fp32_tiny",
          "gen_fp32_tiny", "gen_bf16_tiny", "fwd_fp32_small", "bwd_fp32_small", "bwd_bf16_small", "gated_fp32_tiny",
-         "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256"]
+         "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256", "bwd_bf16_small_le512", "bwd_fp32_small_le300"]
 
 
 def setup(case):
@@ -21,6 +21,9 @@ def setup(case):
     if "base" in case:
         cfg = po.t5_cfg("t5-base", vocab_size=32100, num_layers=2, num_decoder_layers=2)
         B, Le, Ld, n_items = 8, 256, 8, 200
+    elif "le512" in case or "le300" in case:
+        cfg = po.t5_cfg("t5-small", vocab_size=2100, num_layers=1, num_decoder_layers=1)
+        B, Le, Ld, n_items = 2, (512 if "le512" in case else 300), 8, 300
     elif "small" in case:
         cfg = po.t5_cfg("t5-small", vocab_size=2100, num_layers=2, num_decoder_layers=2)
         B, Le, Ld, n_items = 4, 64, 8, 300
@@ -38,7 +41,7 @@ def setup(case):
 def make_model(cfg, w, precision, dropout=0.0, **kw):
     from openp5_b200.model import P5B200
     m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, precision=precision, dropout=dropout, max_batch=8,
-               max_enc_len=256, max_dec_len=16, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
+               max_enc_len=512, max_dec_len=16, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
                num_decoder_layers=cfg.num_decoder_layers, num_heads=cfg.num_heads, ffn_gated_gelu=cfg.ffn_gated_gelu, **kw)
     m.load_state_dict(w, strict=True)
     return m
