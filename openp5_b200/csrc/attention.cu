@@ -237,6 +237,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Lk = a.Lk;
+    const int nvalid = min(QB, a.Lq - i0);     // query rows of this block that exist
 
     for (int e = threadIdx.x; e < QB * DK; e += blockDim.x) {
         const int r = e >> 6, c = e & 63;
@@ -320,16 +321,19 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
             }
         }
         __syncthreads();
-        // dV[j, c] += sum_r pd[r][j] * dO[r][c]
-        for (int e = threadIdx.x; e < KT * DK; e += blockDim.x) {
-            const int j = e >> 6, c = e & 63;
+        // dV[j, c..c+3] += sum_r pd[r][j] * dO[r][c..c+3]   (valid rows only; one LDS + one LDS.128 per 4 FMAs)
+        for (int e = threadIdx.x; e < KT * DK / 4; e += blockDim.x) {
+            const int j = e >> 4, c = (e & 15) * 4;
             if (j0 + j < Lk) {
-                float v = 0.f;
-#pragma unroll
-                for (int r = 0; r < QB; ++r) v = fmaf(Pt[r * KT + j], dOs[r][c], v);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < nvalid; ++r) {
+                    const float p = Pt[r * KT + j];
+                    const float4 g = *reinterpret_cast<const float4*>(&dOs[r][c]);
+                    v.x = fmaf(p, g.x, v.x); v.y = fmaf(p, g.y, v.y); v.z = fmaf(p, g.z, v.z); v.w = fmaf(p, g.w, v.w);
+                }
                 float* dst = dV + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
-                if (!atomic_kv) *dst = v;           // one q-block per (b, h): this CTA owns the element
-                else if (v != 0.f) atomicAdd(dst, v);
+                if (!atomic_kv) *reinterpret_cast<float4*>(dst) = v;   // one q-block per (b, h): this CTA owns the element
+                else { atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w); }
             }
         }
     }
@@ -343,21 +347,25 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int r = warp * 2 + rr;
+            if (r >= nvalid) continue;
             for (int j = 0; j < jn; ++j) {
                 const float ds = Ss[r * Lk + j0 + j];
                 acc[rr][0] = fmaf(ds, KVs[j][lane], acc[rr][0]);
                 acc[rr][1] = fmaf(ds, KVs[j][lane + 32], acc[rr][1]);
             }
         }
-        for (int e = threadIdx.x; e < KT * DK; e += blockDim.x) {
-            const int j = e >> 6, c = e & 63;
+        for (int e = threadIdx.x; e < KT * DK / 4; e += blockDim.x) {
+            const int j = e >> 4, c = (e & 15) * 4;
             if (j0 + j < Lk) {
-                float v = 0.f;
-#pragma unroll
-                for (int r = 0; r < QB; ++r) v = fmaf(Ss[r * Lk + j0 + j], Qs[r][c], v);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < nvalid; ++r) {
+                    const float ds = Ss[r * Lk + j0 + j];
+                    const float4 q = *reinterpret_cast<const float4*>(&Qs[r][c]);
+                    v.x = fmaf(ds, q.x, v.x); v.y = fmaf(ds, q.y, v.y); v.z = fmaf(ds, q.z, v.z); v.w = fmaf(ds, q.w, v.w);
+                }
                 float* dst = dK + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
-                if (!atomic_kv) *dst = v;
-                else if (v != 0.f) atomicAdd(dst, v);
+                if (!atomic_kv) *reinterpret_cast<float4*>(dst) = v;
+                else { atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w); }
             }
         }
     }

@@ -184,6 +184,7 @@ struct GemmEpilogue {
 struct GemmProblem {
     int M = 0, N = 0, K = 0;
     int nb1 = 1, nb2 = 1;
+    int prefer_bn = 0;   // tcgen05 path: 0 = heuristic, else force BLOCK_N (256 / 128 / 64)
     GemmOperand A, B;
     GemmEpilogue epi;
 };

@@ -233,14 +233,20 @@ void Engine::linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t l
                           float alpha) {
     GemmProblem p;
     p.M = N; p.N = K; p.K = M;
+    // split-K over the token dimension with 128 x 256 tiles: pick the split count (a divisor of M, >= 256 rows per
+    // split) that minimises  rounds(tiles * splits / #SM) * (k-blocks per split + fixed tile overhead)
     int splits = 1;
     {
-        const int64_t tiles = cdiv(N, 128) * cdiv(K, 128);
-        int want = (int)(296 / (tiles > 0 ? tiles : 1));
-        if (want > 32) want = 32;
-        while (want > 1 && !(M % want == 0 && M / want >= 128)) --want;
-        splits = want < 1 ? 1 : want;
+        const int64_t t256 = cdiv(N, 128) * cdiv(K, 256);
+        double best = 1e30;
+        for (int s = 1; s <= 32; s *= 2) {
+            if (M % s != 0 || M / s < 256) break;
+            const double rounds = (double)cdiv(t256 * s, 148);
+            const double cost = rounds * ((double)(M / s) / 64.0 + 16.0);
+            if (cost < best) { best = cost; splits = s; }
+        }
     }
+    p.prefer_bn = K > 128 ? 256 : (K > 64 ? 128 : 64);
     const int Ks = M / splits;
     p.K = Ks; p.nb1 = splits;
     p.A.ptr = dY; p.A.dtype = dt; p.A.major = MAJOR_MN; p.A.ld = lddy; p.A.bs1 = (int64_t)Ks * lddy;
@@ -341,7 +347,7 @@ void Engine::ffn_fwd(const void* n, int64_t M, const FfnOff& w, void* z, void* h
 // in: dx_out = dL/dx_out (fp32).  out: dn_out (dt) = dL/dn; weight grads accumulated.
 void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void* n, const void* z, const void* h,
                      void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer) {
-    drop_cast(dx_out, g_d, dt, M * d, drop(kind_wo, layer), st);
+    // g_d = dropout-cast(dx_out) was already produced by the rmsnorm_bwd that computed dx_out
     linear_wgrad(g_d, d, h, ff, w.wo, d, ff, (int)M, 1.f);
     if (!gated) {
         const DropCfg da = drop(kind_act, layer);
@@ -550,7 +556,7 @@ void Engine::backward() {
     linear_dgrad(dlogits, Vpad, off_shared, V, d, (int)Md, g_d2, dt, d, 0, hs, nullptr, false);
     float* dy = dx_a;
     rmsnorm_bwd(g_d2, dt, yd[3 * ND], rstd_d[3 * ND], P + off_dec_final, nullptr, dy, G + off_dec_final, (int)Md, d,
-                drop(S_DEC_FINAL, 0), st);
+                drop(S_DEC_FINAL, 0), st, g_d, dt, drop(S_DEC_WO, ND - 1));
     P5_CUDA(cudaMemsetAsync(d_encout, 0, Me * d * sizeof(float), st));
     P5_CUDA(cudaMemsetAsync(dbias_dec, 0, (size_t)H * (2 * Ld) * sizeof(float), st));
     DropCfg none;
@@ -559,9 +565,9 @@ void Engine::backward() {
         const DecLayerOff& w = dec[l];
         float *y0 = yd[3 * l], *y1 = yd[3 * l + 1], *y2 = yd[3 * l + 2];
         ffn_bwd(dy, Md, w.ff, nd[3 * l + 2], z_d[l], h_d[l], g_d2, S_DEC_ACT, S_DEC_WO, l);
-        rmsnorm_bwd(g_d2, dt, y2, rstd_d[3 * l + 2], P + w.ln2, dy, dy, G + w.ln2, (int)Md, d, none, st);
-        // cross attention
-        drop_cast(dy, g_d, dt, Md * d, drop(S_DEC_CO, l), st);
+        rmsnorm_bwd(g_d2, dt, y2, rstd_d[3 * l + 2], P + w.ln2, dy, dy, G + w.ln2, (int)Md, d, none, st, g_d, dt,
+                    drop(S_DEC_CO, l));
+        // cross attention (g_d = dropout-cast(dy))
         linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
         if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Me * 2 * A * sizeof(float), st));
@@ -573,9 +579,9 @@ void Engine::backward() {
         linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Me, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
         linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f);
         linear_dgrad(gq, A, w.ca.q, A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
-        rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st);
-        // self attention
-        drop_cast(dy, g_d, dt, Md * d, drop(S_DEC_SO, l), st);
+        rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st, g_d, dt,
+                    drop(S_DEC_SO, l));
+        // self attention (g_d = dropout-cast(dy))
         linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
         if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
@@ -584,7 +590,8 @@ void Engine::backward() {
         void* gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
         linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f);
         linear_dgrad(gqkv, 3 * A, w.sa.q, 3 * A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
-        rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st);
+        rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st, l > 0 ? g_d : nullptr, dt,
+                    drop(S_DEC_WO, l > 0 ? l - 1 : 0));
     }
     embed_bwd(dy, dec_ids, nullptr, G + off_shared, nullptr, (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
     relbias_scatter_grad(dbias_dec, lut_dec, G + off_dec_rel, H, 2 * Ld - 1, st);
@@ -594,21 +601,22 @@ void Engine::backward() {
     // ---- encoder
     float* dx = dx_a;
     rmsnorm_bwd(d_encout, DT_F32, xe[2 * NE], rstd_e[2 * NE], P + off_enc_final, nullptr, dx, G + off_enc_final, (int)Me, d,
-                drop(S_ENC_FINAL, 0), st);
+                drop(S_ENC_FINAL, 0), st, g_d, dt, drop(S_ENC_WO, NE - 1));
     P5_CUDA(cudaMemsetAsync(dbias_enc, 0, (size_t)H * (2 * Le) * sizeof(float), st));
     for (int l = NE - 1; l >= 0; --l) {
         const EncLayerOff& w = enc[l];
         float *x_in = xe[2 * l], *x_mid = xe[2 * l + 1];
         ffn_bwd(dx, Me, w.ff, ne[2 * l + 1], z_e[l], h_e[l], g_d2, S_ENC_ACT, S_ENC_WO, l);
-        rmsnorm_bwd(g_d2, dt, x_mid, rstd_e[2 * l + 1], P + w.ln1, dx, dx, G + w.ln1, (int)Me, d, none, st);
-        drop_cast(dx, g_d, dt, Me * d, drop(S_ENC_O, l), st);
+        rmsnorm_bwd(g_d2, dt, x_mid, rstd_e[2 * l + 1], P + w.ln1, dx, dx, G + w.ln1, (int)Me, d, none, st, g_d, dt,
+                    drop(S_ENC_O, l));
         linear_wgrad(g_d, d, ctx_e[l], A, w.sa.o, d, A, (int)Me, 1.f);
         linear_dgrad(g_d, d, w.sa.o, d, A, (int)Me, g_ctx, dt, A, 0, 1.f, nullptr, false);
         void* dqkv = dt == DT_F32 ? (void*)f_qkv : g_qkv;
         enc_attention_bwd(l, g_ctx, dqkv);
         linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Me, 1.f);
         linear_dgrad(dqkv, 3 * A, w.sa.q, 3 * A, d, (int)Me, g_d2, dt, d, 0, 1.f, nullptr, false);
-        rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Me, d, none, st);
+        rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Me, d, none, st, l > 0 ? g_d : nullptr, dt,
+                    drop(S_ENC_WO, l > 0 ? l - 1 : 0));
         // block l >= 1 is final (block 0 also holds the shared relative bias, reduced with the embeddings at the end)
         if (overlap_comm && l >= 1) {
             const int64_t hi = (l + 1 < NE) ? enc[l + 1].sa.q : (ND > 0 ? dec[0].sa.q : n_flat);

@@ -342,19 +342,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int64_t idx0 = boff + (int64_t)row0 * P.epi.ldc + col;
                     // fast path (every specialised epilogue): whole column pair in range and 4/8-byte aligned -> hoisted
                     // address arithmetic, straight-line fully unrolled row loop
-                    const bool fast = (EPI >= 0) && col_ok && two && (((idx0 | P.epi.ldc) & 1) == 0) &&
+                    // (full 32-row tiles only, so that the unrolled row loop is branch-free and the rows interleave)
+                    const bool fast = (EPI >= 0) && col_ok && two && nrows == 32 && (((idx0 | P.epi.ldc) & 1) == 0) &&
                                       (!PF_AUX || P.epi.aux_dtype == DT_BF16);
                     uint32_t pa[PF_AUX ? 32 : 1];
                     float2 pr[PF_RES ? 32 : 1], pc[PF_ACC ? 32 : 1];
                     if (PF && fast) {
 #pragma unroll
                         for (int rr = 0; rr < 32; ++rr) {
-                            if (rr < nrows) {
-                                const int64_t idx = idx0 + (int64_t)rr * P.epi.ldc;
-                                if constexpr (PF_AUX) pa[rr] = *reinterpret_cast<const uint32_t*>((const bf16*)P.epi.aux + idx);
-                                if constexpr (PF_RES) pr[rr] = *reinterpret_cast<const float2*>(P.epi.resid + idx);
-                                if constexpr (PF_ACC) pc[rr] = *reinterpret_cast<const float2*>((const float*)P.epi.C + idx);
-                            }
+                            const int64_t idx = idx0 + (int64_t)rr * P.epi.ldc;
+                            if constexpr (PF_AUX) pa[rr] = *reinterpret_cast<const uint32_t*>((const bf16*)P.epi.aux + idx);
+                            if constexpr (PF_RES) pr[rr] = *reinterpret_cast<const float2*>(P.epi.resid + idx);
+                            if constexpr (PF_ACC) pc[rr] = *reinterpret_cast<const float2*>((const float*)P.epi.C + idx);
                         }
                     }
                     uint32_t r[64];
@@ -398,32 +397,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int64_t ldc = e.ldc;
                             char* cptr = (char*)e.C + idx0 * ((EPI & EPI_OUT_F32) ? 4 : 2);
                             const int64_t cstep = ldc * ((EPI & EPI_OUT_F32) ? 4 : 2);
+                            const uint64_t seed = e.seed;
+                            const uint32_t site = e.site, thr = e.drop_thr;
+                            const float inv_keep = e.inv_keep;
 #pragma unroll
                             for (int rr = 0; rr < 32; ++rr) {
-                                if (rr < nrows) {
-                                    const float2 v = *reinterpret_cast<const float2*>(trow + rr * Cfg::EPI_STRIDE);
-                                    float v0 = v.x * alpha, v1 = v.y * alpha;
-                                    if constexpr ((F & EPI_RELU) != 0) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                                    if constexpr (PF_AUX) {
-                                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pa[rr]));
-                                        v0 = f.x > 0.f ? v0 : 0.f; v1 = f.y > 0.f ? v1 : 0.f;
-                                    }
-                                    if constexpr ((F & EPI_DROPOUT) != 0) {
-                                        bool k0, k1;   // idx is even on the fast path: one hash for the pair
-                                        drop_keep2(e.seed, e.site, (uint64_t)(idx0 + (int64_t)rr * ldc), e.drop_thr, k0, k1);
-                                        v0 = k0 ? v0 * e.inv_keep : 0.f;
-                                        v1 = k1 ? v1 * e.inv_keep : 0.f;
-                                    }
-                                    if constexpr (PF_RES) { v0 += pr[rr].x; v1 += pr[rr].y; }
-                                    if constexpr (PF_ACC) { v0 += pc[rr].x; v1 += pc[rr].y; }
-                                    char* dst = cptr + rr * cstep;
-                                    if constexpr ((F & EPI_ATOMIC) != 0)
-                                        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v0), "f"(v1) : "memory");
-                                    else if constexpr ((EPI & EPI_OUT_F32) != 0)
-                                        *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
-                                    else
-                                        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v0, v1);
+                                const float2 v = *reinterpret_cast<const float2*>(trow + rr * Cfg::EPI_STRIDE);
+                                float v0 = v.x * alpha, v1 = v.y * alpha;
+                                if constexpr ((F & EPI_RELU) != 0) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                                if constexpr (PF_AUX) {
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pa[rr]));
+                                    v0 = f.x > 0.f ? v0 : 0.f; v1 = f.y > 0.f ? v1 : 0.f;
                                 }
+                                if constexpr ((F & EPI_DROPOUT) != 0) {
+                                    bool k0, k1;   // idx is even on the fast path: one hash for the pair
+                                    drop_keep2(seed, site, (uint64_t)(idx0 + (int64_t)rr * ldc), thr, k0, k1);
+                                    v0 = k0 ? v0 * inv_keep : 0.f;
+                                    v1 = k1 ? v1 * inv_keep : 0.f;
+                                }
+                                if constexpr (PF_RES) { v0 += pr[rr].x; v1 += pr[rr].y; }
+                                if constexpr (PF_ACC) { v0 += pc[rr].x; v1 += pc[rr].y; }
+                                char* dst = cptr + rr * cstep;
+                                if constexpr ((F & EPI_ATOMIC) != 0)
+                                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v0), "f"(v1) : "memory");
+                                else if constexpr ((EPI & EPI_OUT_F32) != 0)
+                                    *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                                else
+                                    *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v0, v1);
                             }
                         } else {
 #pragma unroll 4
@@ -676,7 +676,7 @@ void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         P5_CUDA(cudaGetDevice(&dev));
         P5_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    int bn = g_force_block_n;
+    int bn = g_force_block_n ? g_force_block_n : p.prefer_bn;
     if (!bn) {
         const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
         // largest tile that still gives every SM a tile; narrow outputs use a narrow tile

@@ -216,7 +216,7 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ rstd,
                        const float* __restrict__ w, const float* dres, float* dx, float* __restrict__ dw, int M,
-                       DropCfg drop) {
+                       DropCfg drop, bf16* __restrict__ dx_cast, DropCfg cast_drop) {
     constexpr int d = NV * 128;
     __shared__ float sdw[d];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -268,6 +268,16 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
                 if (dres) o[j] += rv[k][j];
             }
             stv<4>(dx + base + c, o);
+            if (dx_cast) {   // bf16 copy of dx with the NEXT backward op's dropout mask applied (saves a drop_cast pass)
+                if (cast_drop.thr) {
+                    bool kk[4];
+                    drop_keep2(cast_drop.seed, cast_drop.site, (uint64_t)(base + c), cast_drop.thr, kk[0], kk[1]);
+                    drop_keep2(cast_drop.seed, cast_drop.site, (uint64_t)(base + c) + 2, cast_drop.thr, kk[2], kk[3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = kk[j] ? o[j] * cast_drop.inv_keep : 0.f;
+                }
+                stv<4>(dx_cast + base + c, o);
+            }
         }
     }
 #pragma unroll
@@ -283,22 +293,26 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
 
 template <typename T>
 static bool launch_rms_bwd_vec(const void* dn, const float* x, const float* rstd, const float* w, const float* dres,
-                               float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st) {
+                               float* dx, float* dw, int M, int d, DropCfg drop, bf16* dx_cast, DropCfg cast_drop,
+                               cudaStream_t st) {
     dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
     switch (d) {
-        case 512: rmsnorm_bwd_vec_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop); return true;
-        case 768: rmsnorm_bwd_vec_kernel<T, 6><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop); return true;
-        case 1024: rmsnorm_bwd_vec_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop); return true;
+        case 512: rmsnorm_bwd_vec_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
+        case 768: rmsnorm_bwd_vec_kernel<T, 6><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
+        case 1024: rmsnorm_bwd_vec_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
         default: return false;
     }
 }
 
 void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd, const float* w, const float* dres,
-                 float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st) {
+                 float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st, void* dx_cast, int cast_dtype,
+                 DropCfg cast_drop) {
     if (M <= 0) return;
-    if (dn_dtype == DT_F32 ? launch_rms_bwd_vec<float>(dn, x, rstd, w, dres, dx, dw, M, d, drop, st)
-                           : launch_rms_bwd_vec<bf16>(dn, x, rstd, w, dres, dx, dw, M, d, drop, st)) {
+    bf16* fused_cast = (dx_cast && cast_dtype == DT_BF16 && (d == 512 || d == 768 || d == 1024)) ? (bf16*)dx_cast : nullptr;
+    if (dn_dtype == DT_F32 ? launch_rms_bwd_vec<float>(dn, x, rstd, w, dres, dx, dw, M, d, drop, fused_cast, cast_drop, st)
+                           : launch_rms_bwd_vec<bf16>(dn, x, rstd, w, dres, dx, dw, M, d, drop, fused_cast, cast_drop, st)) {
         LAUNCHED();
+        if (dx_cast && !fused_cast) drop_cast(dx, dx_cast, cast_dtype, (int64_t)M * d, cast_drop, st);
         return;
     }
     dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
@@ -308,6 +322,7 @@ void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd
     else
         rmsnorm_bwd_kernel<bf16><<<grid, 256, sm, st>>>((const bf16*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
     LAUNCHED();
+    if (dx_cast) drop_cast(dx, dx_cast, cast_dtype, (int64_t)M * d, cast_drop, st);
 }
 
 // =================================================================================================================

@@ -23,8 +23,10 @@ void embed_bwd(const float* dx, const int* ids, const int* ww, float* dE, float*
 void rmsnorm_fwd(const float* x, const float* w, void* n, int n_dtype, float* rstd, int M, int d, float eps,
                  DropCfg drop, cudaStream_t st);
 // dx = (dres ? dres : 0) + d/dx[ rmsnorm ](mask(dn));  dw += sum_rows(mask(dn) * xhat)   (atomic)
+// optional dx_cast: cast_dtype copy of dx with `cast_drop` applied = the dropout-cast the NEXT backward op needs
 void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd, const float* w, const float* dres,
-                 float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st);
+                 float* dx, float* dw, int M, int d, DropCfg drop, cudaStream_t st, void* dx_cast = nullptr,
+                 int cast_dtype = DT_BF16, DropCfg cast_drop = DropCfg());
 
 // out = drop(in) cast to out_dtype (backward of the `x + drop(y)` sites: the mask is regenerated, never stored)
 void drop_cast(const float* in, void* out, int out_dtype, int64_t n, DropCfg drop, cudaStream_t st);
