@@ -13,7 +13,7 @@ namespace p5 {
 extern int g_launches;
 #define LAUNCHED() do { P5_CUDA(cudaGetLastError()); ++g_launches; } while (0)
 
-static constexpr int QB = 16;    // query rows per CTA (2 per warp)
+// query rows per CTA = 8 warps x RPW rows per warp (RPW = 1 for short decoder blocks, 2 default, 4 for beam rows)
 static constexpr int KT = 64;    // keys per smem tile
 static constexpr int DK = 64;    // d_kv
 static constexpr int KS = DK + 4;  // smem row stride of K/V tiles: 16-byte aligned rows, conflict-free LDS.128 across keys
@@ -91,8 +91,10 @@ __device__ __forceinline__ void load_kv_tile(float (*dst)[KS], const void* base,
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
+template <int RPW>
 __global__ void __launch_bounds__(256)
 attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, float* lse) {
+    constexpr int QB = 8 * RPW;
     extern __shared__ __align__(16) float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);                       // [QB][64]
     float (*KVs)[KS] = reinterpret_cast<float (*)[KS]>(smem + QB * DK);    // [KT][65]
@@ -114,8 +116,8 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
         load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)kb * a.k_bs, h, j0, Lk);
         __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = warp * 2 + rr;
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp * RPW + rr;
             if (i0 + r >= a.Lq) continue;          // rows past Lq (short decoder blocks) do no work
             const int i_pos = a.q_pos_offset + i0 + r;
 #pragma unroll
@@ -130,10 +132,10 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
     }
     __syncwarp();
     // ---- softmax (each warp owns its two rows; Ss rows are private to the warp)
-    float inv_sum[2];
+    float inv_sum[RPW];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int r = warp * 2 + rr;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int r = warp * RPW + rr;
         if (i0 + r >= a.Lq) continue;
         float mx = -INFINITY;
         for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, Ss[r * Lk + j]);
@@ -158,15 +160,17 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
         }
     }
     // ---- O = P V
-    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float acc[RPW][2];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) acc[rr][0] = acc[rr][1] = 0.f;
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
         load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, (int64_t)kb * a.v_bs, h, j0, Lk);
         __syncthreads();
         const int jn = min(KT, Lk - j0);
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = warp * 2 + rr;
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp * RPW + rr;
             if (i0 + r >= a.Lq) continue;
             for (int j = 0; j < jn; ++j) {
                 const float p = Ss[r * Lk + j0 + j];
@@ -176,8 +180,8 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
         }
     }
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int i = i0 + warp * 2 + rr;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int i = i0 + warp * RPW + rr;
         if (i < a.Lq) {
             const int64_t o = (int64_t)b * bs_o + (int64_t)i * ld_o + h * DK;
             st_from_f32(O, o_dt, o + lane, acc[rr][0]);
@@ -199,33 +203,46 @@ static AttnDev to_dev(const AttnArgs& a) {
     return d;
 }
 
-static size_t fwd_smem(int Lk) { return (size_t)(QB * DK + KT * (KS) + QB * Lk) * sizeof(float); }
-static size_t bwd_smem(int Lk, int n_delta) {
+static size_t fwd_smem(int QB, int Lk) { return (size_t)(QB * DK + KT * (KS) + QB * Lk) * sizeof(float); }
+static size_t bwd_smem(int QB, int Lk, int n_delta) {
     return (size_t)(2 * QB * DK + KT * (KS) + QB * Lk + QB * KT + QB + n_delta) * sizeof(float);
 }
+static int pick_rpw(int Lq) { return Lq <= 8 ? 1 : ((Lq > 16 && Lq <= 32) ? 4 : 2); }
 
-void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
-    if (a.B <= 0 || a.Lq <= 0) return;
-    P5_CHECK(a.Lk >= 1 && a.Lk <= 2048, "attn_simt_fwd: Lk out of range");
+template <int RPW>
+static void launch_attn_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
+    constexpr int QB = 8 * RPW;
     static size_t max_set = 0;
-    const size_t sm = fwd_smem(a.Lk);
+    const size_t sm = fwd_smem(QB, a.Lk);
     if (sm > max_set) {
-        P5_CUDA(cudaFuncSetAttribute(attn_simt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        P5_CUDA(cudaFuncSetAttribute(attn_simt_fwd_kernel<RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         max_set = sm;
     }
     AttnDev d = to_dev(a);
     dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
-    attn_simt_fwd_kernel<<<grid, 256, sm, st>>>(d, O, o_dtype, ld_o, bs_o, lse);
+    attn_simt_fwd_kernel<RPW><<<grid, 256, sm, st>>>(d, O, o_dtype, ld_o, bs_o, lse);
     LAUNCHED();
+}
+
+void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
+    if (a.B <= 0 || a.Lq <= 0) return;
+    P5_CHECK(a.Lk >= 1 && a.Lk <= 1024, "attn_simt_fwd: Lk out of range");
+    switch (pick_rpw(a.Lq)) {
+        case 1: launch_attn_fwd<1>(a, O, o_dtype, ld_o, bs_o, lse, st); break;
+        case 4: launch_attn_fwd<4>(a, O, o_dtype, ld_o, bs_o, lse, st); break;
+        default: launch_attn_fwd<2>(a, O, o_dtype, ld_o, bs_o, lse, st); break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // backward (recomputes P from the saved log-sum-exp)
 // ------------------------------------------------------------------------------------------------------------
+template <int RPW>
 __global__ void __launch_bounds__(256)
 attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t ld_o, int64_t bs_o,
                      const float* __restrict__ lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV,
                      int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, int atomic_kv) {
+    constexpr int QB = 8 * RPW;
     extern __shared__ __align__(16) float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);
     float (*dOs)[DK] = reinterpret_cast<float (*)[DK]>(smem + QB * DK);
@@ -254,8 +271,8 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     __syncthreads();
     // delta_i = sum_c dO_ic * O_ic
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int r = warp * 2 + rr, i = i0 + r;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int r = warp * RPW + rr, i = i0 + r;
         float dsum = 0.f;
         if (i < a.Lq) {
             const int64_t o = (int64_t)b * bs_o + (int64_t)i * ld_o + h * DK;
@@ -270,8 +287,8 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
         load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)b * a.k_bs, h, j0, Lk);
         __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = warp * 2 + rr, i = i0 + r;
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp * RPW + rr, i = i0 + r;
             const int i_pos = a.q_pos_offset + i;
             const float l = (i < a.Lq) ? lse[((int64_t)b * a.H + h) * a.Lq + i] : 0.f;
 #pragma unroll
@@ -292,8 +309,8 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
         load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, (int64_t)b * a.v_bs, h, j0, Lk);
         __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = warp * 2 + rr, i = i0 + r;
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp * RPW + rr, i = i0 + r;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int jl = lane + 32 * jj, j = j0 + jl;
@@ -338,15 +355,17 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
         }
     }
     // ---- dQ, dK
-    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float acc[RPW][2];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) acc[rr][0] = acc[rr][1] = 0.f;
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
         load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)b * a.k_bs, h, j0, Lk);
         __syncthreads();
         const int jn = min(KT, Lk - j0);
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = warp * 2 + rr;
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp * RPW + rr;
             if (r >= nvalid) continue;
             for (int j = 0; j < jn; ++j) {
                 const float ds = Ss[r * Lk + j0 + j];
@@ -370,8 +389,8 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
         }
     }
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int i = i0 + warp * 2 + rr;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int i = i0 + warp * RPW + rr;
         if (i < a.Lq) {
             const int64_t o = (int64_t)b * bs_dq + (int64_t)i * ld_dq + h * DK;
             dQ[o + lane] = acc[rr][0];
@@ -387,24 +406,35 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     }
 }
 
+template <int RPW>
+static void launch_attn_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype, int64_t ld_o, int64_t bs_o,
+                            const float* lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV, int64_t ld_dkv,
+                            int64_t bs_dkv, float* dbias_rel, cudaStream_t st) {
+    constexpr int QB = 8 * RPW;
+    static size_t max_set = 0;
+    const size_t sm = bwd_smem(QB, a.Lk, a.n_delta);
+    if (sm > max_set) {
+        P5_CUDA(cudaFuncSetAttribute(attn_simt_bwd_kernel<RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        max_set = sm;
+    }
+    AttnDev d = to_dev(a);
+    dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
+    // with a single q-block per (b, h) every dK/dV element has exactly one producer: plain stores, no memset needed
+    attn_simt_bwd_kernel<RPW><<<grid, 256, sm, st>>>(d, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv,
+                                                     bs_dkv, dbias_rel, grid.x > 1 ? 1 : 0);
+    LAUNCHED();
+}
+
 void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype, int64_t ld_o, int64_t bs_o,
                    const float* lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV, int64_t ld_dkv,
                    int64_t bs_dkv, float* dbias_rel, cudaStream_t st) {
     if (a.B <= 0 || a.Lq <= 0) return;
     P5_CHECK(a.Lk >= 1 && a.Lk <= 1024, "attn_simt_bwd: Lk out of range");
     P5_CHECK(a.row_map == nullptr, "attn_simt_bwd: row_map is inference-only");
-    static size_t max_set = 0;
-    const size_t sm = bwd_smem(a.Lk, a.n_delta);
-    if (sm > max_set) {
-        P5_CUDA(cudaFuncSetAttribute(attn_simt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        max_set = sm;
-    }
-    AttnDev d = to_dev(a);
-    dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
-    // with a single q-block per (b, h) every dK/dV element has exactly one producer: plain stores, no memset needed
-    attn_simt_bwd_kernel<<<grid, 256, sm, st>>>(d, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv,
-                                                bs_dkv, dbias_rel, grid.x > 1 ? 1 : 0);
-    LAUNCHED();
+    if (pick_rpw(a.Lq) == 1)
+        launch_attn_bwd<1>(a, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv, bs_dkv, dbias_rel, st);
+    else
+        launch_attn_bwd<2>(a, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv, bs_dkv, dbias_rel, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------

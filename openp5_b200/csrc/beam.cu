@@ -243,19 +243,31 @@ decode_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ Kc, T* __rest
 }
 
 // row-wise max and log(sum(exp(x - max))) over the vocabulary (torch log_softmax = (x - max) - logsum)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 rows_logsumexp_kernel(const float* __restrict__ logits, int64_t ld, int V, float* __restrict__ rowmax,
                       float* __restrict__ logsum) {
     __shared__ float sh[32];
     const int r = blockIdx.x;
     const float* l = logits + (int64_t)r * ld;
-    float mx = -INFINITY;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, l[c]);
-    mx = block_max(mx, sh);
-    float s = 0.f;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(l[c] - mx);
+    // single pass: per-thread online (max, sum) over float4 chunks, then a block combine
+    float mx = -INFINITY, s = 0.f;
+    const int V4 = V >> 2;
+    const float4* l4 = reinterpret_cast<const float4*>(l);
+    for (int c = threadIdx.x; c < V4; c += blockDim.x) {
+        const float4 v = l4[c];
+        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (m4 > mx) { s *= __expf(mx - m4); mx = m4; }
+        s += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+    }
+    for (int c = (V4 << 2) + threadIdx.x; c < V; c += blockDim.x) {
+        const float v = l[c];
+        if (v > mx) { s *= __expf(mx - v); mx = v; }
+        s += __expf(v - mx);
+    }
+    const float bm = block_max(mx, sh);
+    s = (mx > -INFINITY) ? s * __expf(mx - bm) : 0.f;
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) { rowmax[r] = mx; logsum[r] = logf(s); }
+    if (threadIdx.x == 0) { rowmax[r] = bm; logsum[r] = logf(s); }
 }
 
 // per user: score the trie children of every running beam and keep the best 2K (score desc, flat index asc)
@@ -342,10 +354,17 @@ beam_update_kernel(const float* __restrict__ cand_lp, const int* __restrict__ ca
     extern __shared__ int smi[];
     int* run_sel = smi;              // [K]   candidate index chosen for running slot k
     int* fin_sel = smi + K;          // [K]   merged index chosen for finished slot k
+    float* s_lp = reinterpret_cast<float*>(smi + 2 * K);   // [2K] candidates staged in smem (the selection is serial)
+    int* s_cb = smi + 4 * K;
+    int* s_ct = smi + 6 * K;
     const int b = blockIdx.x;
-    const float* lp = cand_lp + b * 2 * K;
-    const int* cb = cand_beam + b * 2 * K;
-    const int* ct = cand_tok + b * 2 * K;
+    for (int c = threadIdx.x; c < 2 * K; c += blockDim.x) {
+        s_lp[c] = cand_lp[b * 2 * K + c]; s_cb[c] = cand_beam[b * 2 * K + c]; s_ct[c] = cand_tok[b * 2 * K + c];
+    }
+    __syncthreads();
+    const float* lp = s_lp;
+    const int* cb = s_cb;
+    const int* ct = s_ct;
     if (threadIdx.x == 0) {
         const bool at_max = (cur_len + 1 >= max_len);
         const bool us = unsat[b] != 0;
@@ -494,6 +513,24 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
                                                            g->fin_score[0], g->is_fin[0], g->gen_len[0], g->cur_tok, g->unsat,
                                                            B, K, T, root_child);
     LAUNCHED();
+    // y += X * W^T for the decode rows.  No dropout at inference, so the residual add can be a split-K atomic
+    // accumulation straight into the fp32 residual stream: R ~ 400 rows give only 48 output tiles, splitting the
+    // reduction spreads each projection over >= 140 CTAs instead of streaming K serially in 48.
+    auto resid_gemm = [&](const void* X, int64_t ldx, int64_t w_off, int N, int K) {
+        GemmProblem p;
+        p.M = R; p.N = N;
+        const int kb = (int)cdiv(K, 64);
+        const int64_t tiles = cdiv(R, 128) * cdiv(N, 64);
+        int splits = 1;
+        for (int s2 = 1; s2 <= kb; ++s2)
+            if (kb % s2 == 0 && (K % 64 == 0)) { splits = s2; if (tiles * s2 >= 140) break; }
+        const int Ks = K / splits;
+        p.K = Ks; p.nb1 = splits; p.prefer_bn = 64;
+        p.A.ptr = X; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = ldx; p.A.bs1 = Ks;
+        p.B.ptr = e->W(w_off); p.B.dtype = dt; p.B.major = MAJOR_K; p.B.ld = K; p.B.bs1 = Ks;
+        p.epi.C = g->y; p.epi.c_dtype = DT_F32; p.epi.ldc = d; p.epi.cs1 = 0; p.epi.alpha = 1.f; p.epi.flags = EPI_ATOMIC;
+        e->gemm(p);
+    };
     const int n_steps = std::min(max_len - 1, trie->max_depth - 1);
     int cur = 0;
     const float hs = 1.f / sqrtf((float)d);
@@ -515,7 +552,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
                                                                         g->src[cur], e->bias_dec, n_delta, bias_off,
                                                                         (bf16*)g->ctx, A, T, pos);
             LAUNCHED();
-            e->linear_fwd(g->ctx, A, w.sa.o, d, A, R, g->y, DT_F32, d, EPI_ADD_RESID, 1.f, nullptr, g->y, none);
+            resid_gemm(g->ctx, A, w.sa.o, d, A);
             rmsnorm_fwd(g->y, e->P + w.ln1, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
             e->linear_fwd(g->n, d, w.ca.q, A, d, R, g->cq, dt, A, 0, 1.f, nullptr, nullptr, none);
             AttnArgs a;   // the K beams of a user are the query rows against that user's cross K/V
@@ -526,7 +563,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
             a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0; a.key_mask = e->mask_e; a.causal = 0; a.q_pos_offset = 0;
             a.row_map = nullptr;
             attn_simt_fwd(a, g->ctx, dt, A, (int64_t)K * A, nullptr, st);
-            e->linear_fwd(g->ctx, A, w.ca.o, d, A, R, g->y, DT_F32, d, EPI_ADD_RESID, 1.f, nullptr, g->y, none);
+            resid_gemm(g->ctx, A, w.ca.o, d, A);
             rmsnorm_fwd(g->y, e->P + w.ln2, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
             if (!e->gated) {
                 e->linear_fwd(g->n, d, w.ff.wi, ff, d, R, g->h, dt, ff, EPI_RELU, 1.f, nullptr, nullptr, none);
@@ -534,12 +571,12 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
                 e->linear_fwd(g->n, d, w.ff.wi, 2 * ff, d, R, g->z, dt, 2 * ff, 0, 1.f, nullptr, nullptr, none);
                 gated_gelu_fwd(g->z, g->h, dt, R, ff, none, st);
             }
-            e->linear_fwd(g->h, ff, w.ff.wo, d, ff, R, g->y, DT_F32, d, EPI_ADD_RESID, 1.f, nullptr, g->y, none);
+            resid_gemm(g->h, ff, w.ff.wo, d, ff);
         }
         rmsnorm_fwd(g->y, e->P + e->off_dec_final, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
         e->linear_fwd(g->n, d, e->off_shared, V, d, R, g->logits, DT_F32, Vpad, 0, hs, nullptr, nullptr, none);
         // ---- log-softmax normaliser, constrained top-2K, beam bookkeeping
-        rows_logsumexp_kernel<<<R, 256, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum);
+        rows_logsumexp_kernel<<<R, 512, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum);
         LAUNCHED();
         topk_candidates_kernel<<<B, 256, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum, g->run_score[cur], g->node[cur],
                                                  trie->d_off, trie->d_tok, K, g->scr_score, g->scr_flat, g->scr_cap,
@@ -548,7 +585,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         const int nxt = cur ^ 1;
         const float denom_fin = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
         const float denom_next = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
-        beam_update_kernel<<<B, 128, 2 * K * sizeof(int), st>>>(
+        beam_update_kernel<<<B, 128, 8 * K * sizeof(int), st>>>(
             g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
             g->src[nxt], g->node[cur], g->node[nxt], g->run_score[nxt], g->fin_score[cur], g->fin_score[nxt], g->is_fin[cur],
             g->is_fin[nxt], g->gen_len[cur], g->gen_len[nxt], g->cur_tok, g->unsat, trie->d_off, trie->d_tok, trie->d_node, K,

@@ -78,7 +78,7 @@ void attn_simt_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_o, int64_
 // backward: dQ/dK/dV written as fp32 with the (ld, bs) geometry given.  When Lq > 16 (several q-blocks per (b,h))
 // dK/dV are accumulated with atomics and the caller zeroes them first (attn_bwd_needs_zero); otherwise they are
 // plain stores.  dbias_rel [H, n_delta] accumulated atomically if non-null.
-static inline bool attn_bwd_needs_zero(int Lq) { return Lq > 16; }
+static inline bool attn_bwd_needs_zero(int Lq) { return Lq > 8; }   // one q-block: Lq <= 8 (1 row/warp) — else zero first
 void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype, int64_t ld_o, int64_t bs_o,
                    const float* lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV, int64_t ld_dkv,
                    int64_t bs_dkv, float* dbias_rel, cudaStream_t st);
