@@ -286,6 +286,14 @@ def run_b200(args):
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
     h2d = sum(x.numel() * x.element_size() for x in pinned[0])
 
+    # data-parallel sanity: after identical all-reduced updates every replica must hold the same weights
+    dp_diff = None
+    if world > 1:
+        probe = torch.stack([p.detach().double().sum() for _, p in list(model.named_parameters())[:40]])
+        gathered = [torch.zeros_like(probe) for _ in range(world)]
+        dist.all_gather(gathered, probe)
+        dp_diff = max(float((g - gathered[0]).abs().max() / gathered[0].abs().max().clamp_min(1e-30)) for g in gathered)
+
     out = None
     if rank == 0:
         pk = peaks()
@@ -376,6 +384,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "eval": eval_out,
             "final_loss": final_loss,
+            "dp_replica_max_rel_diff": dp_diff,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

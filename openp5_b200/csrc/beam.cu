@@ -365,64 +365,99 @@ beam_update_kernel(const float* __restrict__ cand_lp, const int* __restrict__ ca
     const float* lp = s_lp;
     const int* cb = s_cb;
     const int* ct = s_ct;
-    if (threadIdx.x == 0) {
+    // selection is done by warp 0: candidates live in registers (index c = lane + 32*q), every pick is a warp argmax
+    // with ties broken by the lowest index (the order torch.topk yields on distinct values; SURVEY §7 tie-break)
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         const bool at_max = (cur_len + 1 >= max_len);
         const bool us = unsat[b] != 0;
-        float runv[128], finv[192];
-        bool used[192];
-        // ---- running beams: top-K of lp + hits * -1e9 (stable: lowest index first)
-        for (int c = 0; c < 2 * K; ++c) {
-            const bool hit = (ct[c] == eos) || at_max;
-            runv[c] = lp[c] + (hit ? NEG_BIG : -0.0f);
-            used[c] = false;
-        }
-        for (int k = 0; k < K; ++k) {
-            int bi = -1;
-            for (int c = 0; c < 2 * K; ++c)
-                if (!used[c] && (bi < 0 || runv[c] > runv[bi])) bi = c;
-            used[bi] = true;
-            run_sel[k] = bi;
-            run_out[b * K + k] = runv[bi];
-        }
-        // ---- finished beams: merge [old finished (K), new candidates (2K)]
-        for (int k = 0; k < K; ++k) finv[k] = fscore_in[b * K + k];
-        for (int c = 0; c < 2 * K; ++c) {
-            const bool hit = (ct[c] == eos) || at_max;
-            float v = lp[c] / denom_fin;
-            v += us ? -0.0f : NEG_BIG;
-            v += (hit && c < K) ? -0.0f : NEG_BIG;
-            finv[K + c] = v;
-        }
-        for (int m = 0; m < 3 * K; ++m) used[m] = false;
-        float min_fs = INFINITY;
-        bool all_fin = true;
-        for (int k = 0; k < K; ++k) {
-            int bi = -1;
-            for (int m = 0; m < 3 * K; ++m)
-                if (!used[m] && (bi < 0 || finv[m] > finv[bi])) bi = m;
-            used[bi] = true;
-            fin_sel[k] = bi;
-            fscore_out[b * K + k] = finv[bi];
-            int fin, gl;
-            if (bi < K) { fin = isfin_in[b * K + bi]; gl = glen_in[b * K + bi]; }
-            else {
-                const int c = bi - K;
-                const bool hit = (ct[c] == eos) || at_max;
-                fin = (hit && c < K) ? 1 : 0;
-                gl = cur_len;   // cur_len + 1 - prompt_len(=1)
+        auto warp_argmax = [&](float v, int idx, float& bv, int& bi) {
+            bv = v; bi = idx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
             }
-            isfin_out[b * K + k] = fin; glen_out[b * K + k] = gl;
-            min_fs = fminf(min_fs, finv[bi]);
-            all_fin = all_fin && fin;
+        };
+        // ---- running beams: top-K of lp + hits * -1e9
+        float rv[4]; bool ru[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            ru[q] = c >= 2 * K;                     // slots past 2K never compete
+            rv[q] = 0.f;
+            if (c < 2 * K) {
+                const bool hit = (ct[c] == eos) || at_max;
+                rv[q] = lp[c] + (hit ? NEG_BIG : -0.0f);
+            }
         }
-        // ---- early-stop heuristic with cur_len already incremented
-        const float best_running = run_out[b * K] / denom_next;
-        bool any = false;
         for (int k = 0; k < K; ++k) {
-            const float worst = isfin_out[b * K + k] ? min_fs : NEG_BIG;
-            if (best_running > worst) any = true;
+            float lv = 0.f; int li = -1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (!ru[q] && (li < 0 || rv[q] > lv)) { lv = rv[q]; li = lane + 32 * q; }
+            float bv; int bi;
+            warp_argmax(lv, li, bv, bi);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (lane + 32 * q == bi) ru[q] = true;
+            if (lane == 0) { run_sel[k] = bi; run_out[b * K + k] = bv; }
         }
-        unsat[b] = (us && any) ? 1 : 0;
+        // ---- finished beams: merge [old finished (K), new candidates (2K)] -> index m = lane + 32*q, q < 6
+        float fv[6]; bool fu[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int m = lane + 32 * q;
+            fu[q] = m >= 3 * K;
+            fv[q] = 0.f;
+            if (m < K) fv[q] = fscore_in[b * K + m];
+            else if (m < 3 * K) {
+                const int c = m - K;
+                const bool hit = (ct[c] == eos) || at_max;
+                float v = lp[c] / denom_fin;
+                v += us ? -0.0f : NEG_BIG;
+                v += (hit && c < K) ? -0.0f : NEG_BIG;
+                fv[q] = v;
+            }
+        }
+        float min_fs = INFINITY;
+        int all_fin_bits = 0;   // unused; finished flags are re-read below
+        for (int k = 0; k < K; ++k) {
+            float lv = 0.f; int li = -1;
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                if (!fu[q] && (li < 0 || fv[q] > lv)) { lv = fv[q]; li = lane + 32 * q; }
+            float bv; int bi;
+            warp_argmax(lv, li, bv, bi);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) if (lane + 32 * q == bi) fu[q] = true;
+            if (lane == 0) {
+                fin_sel[k] = bi;
+                fscore_out[b * K + k] = bv;
+                int fin, gl;
+                if (bi < K) { fin = isfin_in[b * K + bi]; gl = glen_in[b * K + bi]; }
+                else {
+                    const int c = bi - K;
+                    const bool hit = (ct[c] == eos) || at_max;
+                    fin = (hit && c < K) ? 1 : 0;
+                    gl = cur_len;   // cur_len + 1 - prompt_len(=1)
+                }
+                isfin_out[b * K + k] = fin; glen_out[b * K + k] = gl;
+            }
+            min_fs = fminf(min_fs, bv);
+        }
+        (void)all_fin_bits;
+        __syncwarp();
+        // ---- early-stop heuristic with cur_len already incremented
+        if (lane == 0) {
+            const float best_running = run_out[b * K] / denom_next;
+            bool any = false;
+            for (int k = 0; k < K; ++k) {
+                const float worst = isfin_out[b * K + k] ? min_fs : NEG_BIG;
+                if (best_running > worst) any = true;
+            }
+            unsat[b] = (us && any) ? 1 : 0;
+        }
     }
     __syncthreads();
     // ---- materialise the selected rows (all threads)

@@ -412,7 +412,8 @@ void Engine::enc_attention_bwd(int l, const void* dctx, void* dqkv) {
         p.B.bs2 = (int64_t)Le * 3 * A;
         p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
         gemm(p);
-        softmax_bwd(S_scr, P_e[l], dS_scr, dc.thr ? Pd_scr : nullptr, dt, dbias_enc, B, H, Le, Le, dc, st);
+        softmax_bwd(S_scr, P_e[l], dS_scr, dc.thr ? Pd_scr : nullptr, dt, nullptr, B, H, Le, Le, dc, st);
+        relbias_diag_sum(dS_scr, dt, dbias_enc, B, H, Le, Le, st);
         const void* Pd = dc.thr ? Pd_scr : P_e[l];
         GemmProblem v;   // dV[j,c] = sum_i Pd[i,j] dctx[i,c]
         v.M = Le; v.N = 64; v.K = Le; v.nb1 = H; v.nb2 = B;

@@ -97,6 +97,9 @@ void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dt
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
                void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st);
 
+// dbias_rel[h, j - i + Lq - 1] += sum_{b,i} dS[b,h,i,j]   (dS [B,H,Lq,Lk], register accumulation per diagonal)
+void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H, int Lq, int Lk, cudaStream_t st);
+
 // ---- optimiser (optim.cu) ---------------------------------------------------------------------------------------
 void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
 void scale_f32(float* g, int64_t n, float s, cudaStream_t st);
