@@ -73,6 +73,11 @@ int p5_params_changed(p5_handle h);
 int p5_forward(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask, const int32_t* whole_word_ids,
                const int32_t* labels, int B, int Le, int Ld, float* loss_tok, float* logits_or_null, int training,
                uint64_t seed);
+/* Optional, applies to the NEXT p5_forward / p5_train_fwd_bwd only: number of valid (right-padded) encoder tokens of
+ * each sequence = attention_mask.sum(1) of the collator batch (Collator.py:8-34 pads to the longest; HF computes the
+ * padded positions and masks them).  With the lengths known on the host the engine drops the padding: every
+ * token-wise encoder kernel runs on sum(lens) rows instead of B*Le.  Results at valid positions are unchanged. */
+int p5_set_enc_lengths(p5_handle h, const int32_t* lens_host, int B);
 /* replaces: loss.backward() (DistributedRunner.py:80) given dL/dloss_tok [B*Ld]; accumulates into the grad buffers */
 int p5_backward(p5_handle h, const float* dloss_tok);
 /* fused form of DistributedRunner.py:72-80: loss = mean_b( sum_t loss_tok*m / max(sum_t m,1) ), m = (labels_mask != 0);

@@ -28,6 +28,7 @@ struct AttnDev {
     const int* key_mask;
     int causal, q_pos_offset;
     const int* row_map;
+    const int* kv_off; const int* kv_len;
     DropCfg drop;
 };
 
@@ -102,7 +103,9 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
     const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QB;
     const int kb = a.row_map ? a.row_map[b] : b;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Lk = a.Lk;
+    const int Lk = a.kv_len ? a.kv_len[kb] : a.Lk;                                   // packed K/V: per-batch key count
+    const int64_t k_boff = a.kv_off ? (int64_t)a.kv_off[kb] * a.k_ld : (int64_t)kb * a.k_bs;
+    const int64_t v_boff = a.kv_off ? (int64_t)a.kv_off[kb] * a.v_ld : (int64_t)kb * a.v_bs;
 
     for (int e = threadIdx.x; e < QB * DK; e += blockDim.x) {
         const int r = e >> 6, c = e & 63;
@@ -113,7 +116,7 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
     // ---- scores
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
-        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)kb * a.k_bs, h, j0, Lk);
+        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, k_boff, h, j0, Lk);
         __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
@@ -165,7 +168,7 @@ attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, f
     for (int rr = 0; rr < RPW; ++rr) acc[rr][0] = acc[rr][1] = 0.f;
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
-        load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, (int64_t)kb * a.v_bs, h, j0, Lk);
+        load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, v_boff, h, j0, Lk);
         __syncthreads();
         const int jn = min(KT, Lk - j0);
 #pragma unroll
@@ -199,6 +202,7 @@ static AttnDev to_dev(const AttnArgs& a) {
     d.q_ld = a.q.ld; d.q_bs = a.q.bs; d.k_ld = a.k.ld; d.k_bs = a.k.bs; d.v_ld = a.v.ld; d.v_bs = a.v.bs;
     d.bias_rel = a.bias_rel; d.bias_off = bias_off; d.n_delta = n_delta;
     d.key_mask = a.key_mask; d.causal = a.causal; d.q_pos_offset = a.q_pos_offset; d.row_map = a.row_map;
+    d.kv_off = a.kv_off; d.kv_len = a.kv_len;
     d.drop = a.drop;
     return d;
 }
@@ -253,7 +257,10 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     float* sdb = dlt + QB;                                   // [n_delta]
     const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Lk = a.Lk;
+    const int Lk = a.kv_len ? a.kv_len[b] : a.Lk;
+    const int64_t k_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.k_ld : (int64_t)b * a.k_bs;
+    const int64_t v_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.v_ld : (int64_t)b * a.v_bs;
+    const int64_t dkv_boff = a.kv_off ? (int64_t)a.kv_off[b] * ld_dkv : (int64_t)b * bs_dkv;
     const int nvalid = min(QB, a.Lq - i0);     // query rows of this block that exist
 
     for (int e = threadIdx.x; e < QB * DK; e += blockDim.x) {
@@ -284,7 +291,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     // ---- recompute p_ij = exp(s_ij - lse_i)
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
-        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)b * a.k_bs, h, j0, Lk);
+        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, k_boff, h, j0, Lk);
         __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
@@ -306,7 +313,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     // ---- dP, dS, dV
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
-        load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, (int64_t)b * a.v_bs, h, j0, Lk);
+        load_kv_tile(KVs, a.v, a.v_dt, a.v_ld, v_boff, h, j0, Lk);
         __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
@@ -348,7 +355,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
                     const float4 g = *reinterpret_cast<const float4*>(&dOs[r][c]);
                     v.x = fmaf(p, g.x, v.x); v.y = fmaf(p, g.y, v.y); v.z = fmaf(p, g.z, v.z); v.w = fmaf(p, g.w, v.w);
                 }
-                float* dst = dV + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
+                float* dst = dV + dkv_boff + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
                 if (!atomic_kv) *reinterpret_cast<float4*>(dst) = v;   // one q-block per (b, h): this CTA owns the element
                 else { atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w); }
             }
@@ -360,7 +367,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
     for (int rr = 0; rr < RPW; ++rr) acc[rr][0] = acc[rr][1] = 0.f;
     for (int j0 = 0; j0 < Lk; j0 += KT) {
         __syncthreads();
-        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, (int64_t)b * a.k_bs, h, j0, Lk);
+        load_kv_tile(KVs, a.k, a.k_dt, a.k_ld, k_boff, h, j0, Lk);
         __syncthreads();
         const int jn = min(KT, Lk - j0);
 #pragma unroll
@@ -382,7 +389,7 @@ attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t
                     const float4 q = *reinterpret_cast<const float4*>(&Qs[r][c]);
                     v.x = fmaf(ds, q.x, v.x); v.y = fmaf(ds, q.y, v.y); v.z = fmaf(ds, q.z, v.z); v.w = fmaf(ds, q.w, v.w);
                 }
-                float* dst = dK + (int64_t)b * bs_dkv + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
+                float* dst = dK + dkv_boff + (int64_t)(j0 + j) * ld_dkv + h * DK + c;
                 if (!atomic_kv) *reinterpret_cast<float4*>(dst) = v;
                 else { atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w); }
             }
@@ -530,9 +537,12 @@ void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, voi
 template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __restrict__ dS, T* __restrict__ Pd_out,
-                   float* __restrict__ dbias_rel, int H, int Lq, int Lk, DropCfg drop) {
+                   float* __restrict__ dbias_rel, int H, int Lq, int Lk, DropCfg drop, const int* __restrict__ lens) {
     extern __shared__ float sdb[];  // [n_delta]
     const int bh = blockIdx.x, h = bh % H;
+    // packed training: only the first len rows / columns of this (b, h) hold probabilities; everything else is
+    // written as exact zeros so that the dV / dQ / dK GEMMs over the padded geometry stay clean
+    const int len = lens ? lens[bh / H] : max(Lq, Lk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n_delta = Lq + Lk - 1;
     if (dbias_rel) {
@@ -548,18 +558,26 @@ softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __
             const int j = 2 * (lane + 32 * k);
             p[k][0] = p[k][1] = dp[k][0] = dp[k][1] = 0.f;
             if (j < Lk) {
-                const float2 pp = ld_pair<T>(P + row + j);
-                const float2 g = *reinterpret_cast<const float2*>(dPd + row + j);
-                float g0 = g.x, g1 = g.y;
-                if (drop.thr) {
-                    bool k0, k1;
-                    drop_pair(drop, (uint64_t)(row + j) >> 1, k0, k1);
-                    g0 = k0 ? g0 * drop.inv_keep : 0.f;
-                    g1 = k1 ? g1 * drop.inv_keep : 0.f;
-                    if (Pd_out) st_pair<T>(Pd_out + row + j, k0 ? pp.x * drop.inv_keep : 0.f, k1 ? pp.y * drop.inv_keep : 0.f);
+                if (i < len && j < len) {
+                    float2 pp = ld_pair<T>(P + row + j);
+                    if (j + 1 >= len) pp.y = 0.f;             // pair straddling the sequence end
+                    const float2 g = *reinterpret_cast<const float2*>(dPd + row + j);
+                    float g0 = g.x, g1 = g.y;
+                    if (drop.thr) {
+                        bool k0, k1;
+                        drop_pair(drop, (uint64_t)(row + j) >> 1, k0, k1);
+                        g0 = k0 ? g0 * drop.inv_keep : 0.f;
+                        g1 = k1 ? g1 * drop.inv_keep : 0.f;
+                        if (Pd_out) st_pair<T>(Pd_out + row + j, k0 ? pp.x * drop.inv_keep : 0.f, k1 ? pp.y * drop.inv_keep : 0.f);
+                    } else if (Pd_out) {
+                        st_pair<T>(Pd_out + row + j, pp.x, pp.y);   // packed, no dropout: clean copy of P
+                    }
+                    if (pp.y == 0.f) g1 = 0.f;
+                    p[k][0] = pp.x; p[k][1] = pp.y; dp[k][0] = g0; dp[k][1] = g1;
+                    dot += g0 * pp.x + g1 * pp.y;
+                } else if (Pd_out) {
+                    st_pair<T>(Pd_out + row + j, 0.f, 0.f);   // outside the sequence: exact zeros
                 }
-                p[k][0] = pp.x; p[k][1] = pp.y; dp[k][0] = g0; dp[k][1] = g1;
-                dot += g0 * pp.x + g1 * pp.y;
             }
         }
         dot = warp_sum(dot);
@@ -612,15 +630,15 @@ void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H,
 }
 
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
-                 int Lq, int Lk, DropCfg drop, cudaStream_t st) {
+                 int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens) {
     if (B <= 0) return;
     P5_CHECK(Lk <= 64 * SM_MAXP && (Lk % 2) == 0, "softmax_bwd: Lk must be even and <= 512");
     dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     const size_t sm = (size_t)(Lq + Lk) * sizeof(float);
     if (dtype == DT_F32)
-        softmax_bwd_kernel<float><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop);
+        softmax_bwd_kernel<float><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
     else
-        softmax_bwd_kernel<bf16><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop);
+        softmax_bwd_kernel<bf16><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
     LAUNCHED();
 }
 

@@ -104,6 +104,13 @@ int p5_forward(p5_handle h, const int32_t* input_ids, const int32_t* attention_m
                                   (size_t)B * Ld, cudaMemcpyDeviceToDevice, e->st));
     P5_API_END
 }
+int p5_set_enc_lengths(p5_handle h, const int32_t* lens_host, int B) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    e->pending_lens.clear();
+    if (lens_host && B > 0) e->pending_lens.assign(lens_host, lens_host + B);
+    P5_API_END
+}
 int p5_backward(p5_handle h, const float* dloss_tok) {
     P5_API_BEGIN
     Engine* e = E(h);

@@ -166,6 +166,10 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     bias_dec = dalloc_t<float>((int64_t)H * (2 * Ldb)); dbias_dec = dalloc_t<float>((int64_t)H * (2 * Ldb));
     lut_enc = dalloc_t<int>(2 * Lem); lut_dec = dalloc_t<int>(2 * Ldb);
     norm_partial = dalloc_t<float>(1024); norm_out = dalloc_t<float>(4);
+    lens_d = dalloc_t<int>(Bm + 1); offs_d = dalloc_t<int>(Bm + 1);
+    ids_p = dalloc_t<int>(Mem); ww_p = dalloc_t<int>(Mem);
+    qkv_pad = dalloc(Mem * 3 * A * e); ctx_pad = dalloc(Mem * A * e); dqkv_pad = dalloc(Mem * 3 * A * e);
+    if (!tc_attn) f_qkv_pad = dalloc_t<float>(Mem * 3 * A);
     P5_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -274,6 +278,22 @@ void Engine::set_geometry(int B_, int Le_user_, int Ld_) {
     P5_CHECK(Ld_ >= 1 && Ld_ <= Ldm, "decoder length exceeds max_dec_len");
     B = B_; Le_user = Le_user_; Le = (int)round_up(Le_user_, 8); Ld = Ld_;
     Me = (int64_t)B * Le; Md = (int64_t)B * Ld;
+    packed = false; Mt = Me;
+}
+
+void Engine::apply_lengths() {
+    if ((int)pending_lens.size() != B) { pending_lens.clear(); return; }   // none (or stale) -> padded layout
+    lens_h = pending_lens;
+    pending_lens.clear();
+    offs_h.assign(B + 1, 0);
+    for (int b = 0; b < B; ++b) {
+        P5_CHECK(lens_h[b] >= 1 && lens_h[b] <= Le_user, "encoder length out of range");
+        offs_h[b + 1] = offs_h[b] + lens_h[b];
+    }
+    Mt = offs_h[B];
+    packed = true;
+    P5_CUDA(cudaMemcpyAsync(lens_d, lens_h.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    P5_CUDA(cudaMemcpyAsync(offs_d, offs_h.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
 }
 
 void Engine::load_inputs(const int32_t* ids, const int32_t* mask, const int32_t* ww, const int32_t* lab) {
@@ -287,6 +307,10 @@ void Engine::load_inputs(const int32_t* ids, const int32_t* mask, const int32_t*
     P5_CUDA(cudaMemcpy2DAsync(mask_e, pitch, mask, wbytes, wbytes, B, cudaMemcpyDeviceToDevice, st));
     if (ww) P5_CUDA(cudaMemcpy2DAsync(ww_e, pitch, ww, wbytes, wbytes, B, cudaMemcpyDeviceToDevice, st));
     else P5_CUDA(cudaMemsetAsync(ww_e, 0xff, Me * 4, st));  // -1 = no whole-word embedding
+    if (packed) {
+        pack_ints(ids_e, ids_p, offs_d, lens_d, B, Le, st);
+        pack_ints(ww_e, ww_p, offs_d, lens_d, B, Le, st);
+    }
     if (lab) {
         P5_CUDA(cudaMemcpyAsync(labels, lab, Md * 4, cudaMemcpyDeviceToDevice, st));
         shift_right_kernel<<<(unsigned)cdiv(Md, 256), 256, 0, st>>>(labels, dec_ids, B, Ld);
@@ -366,55 +390,78 @@ void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void
 // ------------------------------------------------------------------------------------------------------------
 // encoder self-attention
 // ------------------------------------------------------------------------------------------------------------
+// The attention kernels that work on the padded [B, Le] geometry (batched GEMMs of the backward, the SIMT kernels of
+// the parity mode) see packed activations through padded scratch copies: unpack -> kernel -> pack.
 void Engine::enc_attention_fwd(int l) {
     const int64_t SS1 = (int64_t)Le * Le;
     static int fused = -1;
     if (fused < 0) { const char* e = getenv("P5_ATTN"); fused = (e && strcmp(e, "unfused") == 0) ? 0 : 1; }
-    if (dt == DT_BF16 && fused &&
-        fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, P_e[l], ctx_e[l], A, drop(S_ENC_P, l), st))
-        return;
+    const DropCfg dc = drop(S_ENC_P, l);
+    if (dt == DT_BF16 && (fused || packed)) {
+        const bool ok = fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, P_e[l], ctx_e[l], A, dc, st,
+                                  packed ? offs_d : nullptr, packed ? lens_d : nullptr, Mt);
+        P5_CHECK(ok || !packed, "packed encoder attention needs the fused kernel (Le <= 512)");
+        if (ok) return;
+    }
+    const void* qkv = qkv_e[l];
+    void* ctx = ctx_e[l];
+    if (packed) {
+        unpack_rows(qkv_e[l], qkv_pad, offs_d, lens_d, B, Le, (int64_t)3 * A * esz(), st);
+        qkv = qkv_pad; ctx = ctx_pad;
+    }
     if (dt == DT_BF16) {
         GemmProblem p;   // S = Q K^T   (unscaled, HF:modeling_t5.py:308)
         p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;
-        p.A.ptr = qkv_e[l]; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = 3 * A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * 3 * A;
-        p.B = p.A; p.B.ptr = poff(qkv_e[l], A, dt);
+        p.A.ptr = qkv; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = 3 * A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * 3 * A;
+        p.B = p.A; p.B.ptr = poff(qkv, A, dt);
         p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
         gemm(p);
-        const DropCfg dc = drop(S_ENC_P, l);
         softmax_fwd(S_scr, bias_enc, mask_e, P_e[l], Pd_scr, dt, B, H, Le, Le, 0, dc, st);
         GemmProblem q;   // ctx = Pd V
         q.M = Le; q.N = 64; q.K = Le; q.nb1 = H; q.nb2 = B;
         q.A.ptr = dc.thr ? Pd_scr : P_e[l]; q.A.dtype = dt; q.A.major = MAJOR_K; q.A.ld = Le; q.A.bs1 = SS1; q.A.bs2 = SS1 * H;
-        q.B.ptr = poff(qkv_e[l], 2 * A, dt); q.B.dtype = dt; q.B.major = MAJOR_MN; q.B.ld = 3 * A; q.B.bs1 = 64;
+        q.B.ptr = poff(qkv, 2 * A, dt); q.B.dtype = dt; q.B.major = MAJOR_MN; q.B.ld = 3 * A; q.B.bs1 = 64;
         q.B.bs2 = (int64_t)Le * 3 * A;
-        q.epi.C = ctx_e[l]; q.epi.c_dtype = dt; q.epi.ldc = A; q.epi.cs1 = 64; q.epi.cs2 = (int64_t)Le * A;
+        q.epi.C = ctx; q.epi.c_dtype = dt; q.epi.ldc = A; q.epi.cs1 = 64; q.epi.cs2 = (int64_t)Le * A;
         gemm(q);
     } else {
         AttnArgs a;
         a.B = B; a.H = H; a.Lq = Le; a.Lk = Le;
-        a.q = {qkv_e[l], dt, 3 * A, (int64_t)Le * 3 * A};
-        a.k = {poff(qkv_e[l], A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
-        a.v = {poff(qkv_e[l], 2 * A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.q = {qkv, dt, 3 * A, (int64_t)Le * 3 * A};
+        a.k = {poff(qkv, A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.v = {poff(qkv, 2 * A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
         a.bias_rel = bias_enc; a.bias_off = Le - 1; a.n_delta = 2 * Le - 1;
-        a.key_mask = mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = drop(S_ENC_P, l);
-        attn_simt_fwd(a, ctx_e[l], dt, A, (int64_t)Le * A, lse_e[l], st);
+        a.key_mask = mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
+        attn_simt_fwd(a, ctx, dt, A, (int64_t)Le * A, lse_e[l], st);
     }
+    if (packed) pack_rows(ctx_pad, ctx_e[l], offs_d, lens_d, B, Le, (int64_t)A * esz(), st);
 }
 
-void Engine::enc_attention_bwd(int l, const void* dctx, void* dqkv) {
+void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
     const int64_t SS1 = (int64_t)Le * Le;
     const DropCfg dc = drop(S_ENC_P, l);
+    const void* qkv = qkv_e[l];
+    const void* dctx = dctx_in;
+    void* dqkv = dqkv_out;
+    const void* ctx_fwd = ctx_e[l];
+    if (packed) {
+        unpack_rows(qkv_e[l], qkv_pad, offs_d, lens_d, B, Le, (int64_t)3 * A * esz(), st);
+        unpack_rows(dctx_in, ctx_pad, offs_d, lens_d, B, Le, (int64_t)A * esz(), st);
+        qkv = qkv_pad; dctx = ctx_pad;
+        dqkv = dt == DT_F32 ? (void*)f_qkv_pad : dqkv_pad;
+    }
     if (dt == DT_BF16) {
         GemmProblem p;   // dPd = dctx V^T
         p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;
         p.A.ptr = dctx; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * A;
-        p.B.ptr = poff(qkv_e[l], 2 * A, dt); p.B.dtype = dt; p.B.major = MAJOR_K; p.B.ld = 3 * A; p.B.bs1 = 64;
+        p.B.ptr = poff(qkv, 2 * A, dt); p.B.dtype = dt; p.B.major = MAJOR_K; p.B.ld = 3 * A; p.B.bs1 = 64;
         p.B.bs2 = (int64_t)Le * 3 * A;
         p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
         gemm(p);
-        softmax_bwd(S_scr, P_e[l], dS_scr, dc.thr ? Pd_scr : nullptr, dt, nullptr, B, H, Le, Le, dc, st);
+        const bool regen = dc.thr || packed;   // packed: P_save holds stale rows/columns outside the sequences
+        softmax_bwd(S_scr, P_e[l], dS_scr, regen ? Pd_scr : nullptr, dt, nullptr, B, H, Le, Le, dc, st, packed ? lens_d : nullptr);
         relbias_diag_sum(dS_scr, dt, dbias_enc, B, H, Le, Le, st);
-        const void* Pd = dc.thr ? Pd_scr : P_e[l];
+        const void* Pd = regen ? Pd_scr : P_e[l];
         GemmProblem v;   // dV[j,c] = sum_i Pd[i,j] dctx[i,c]
         v.M = Le; v.N = 64; v.K = Le; v.nb1 = H; v.nb2 = B;
         v.A.ptr = Pd; v.A.dtype = dt; v.A.major = MAJOR_MN; v.A.ld = Le; v.A.bs1 = SS1; v.A.bs2 = SS1 * H;
@@ -424,30 +471,35 @@ void Engine::enc_attention_bwd(int l, const void* dctx, void* dqkv) {
         GemmProblem q;   // dQ[i,c] = sum_j dS[i,j] K[j,c]
         q.M = Le; q.N = 64; q.K = Le; q.nb1 = H; q.nb2 = B;
         q.A.ptr = dS_scr; q.A.dtype = dt; q.A.major = MAJOR_K; q.A.ld = Le; q.A.bs1 = SS1; q.A.bs2 = SS1 * H;
-        q.B.ptr = poff(qkv_e[l], A, dt); q.B.dtype = dt; q.B.major = MAJOR_MN; q.B.ld = 3 * A; q.B.bs1 = 64;
+        q.B.ptr = poff(qkv, A, dt); q.B.dtype = dt; q.B.major = MAJOR_MN; q.B.ld = 3 * A; q.B.bs1 = 64;
         q.B.bs2 = (int64_t)Le * 3 * A;
         q.epi.C = dqkv; q.epi.c_dtype = dt; q.epi.ldc = 3 * A; q.epi.cs1 = 64; q.epi.cs2 = (int64_t)Le * 3 * A;
         gemm(q);
         GemmProblem k;   // dK[j,c] = sum_i dS[i,j] Q[i,c]
         k.M = Le; k.N = 64; k.K = Le; k.nb1 = H; k.nb2 = B;
         k.A.ptr = dS_scr; k.A.dtype = dt; k.A.major = MAJOR_MN; k.A.ld = Le; k.A.bs1 = SS1; k.A.bs2 = SS1 * H;
-        k.B.ptr = qkv_e[l]; k.B.dtype = dt; k.B.major = MAJOR_MN; k.B.ld = 3 * A; k.B.bs1 = 64; k.B.bs2 = (int64_t)Le * 3 * A;
+        k.B.ptr = qkv; k.B.dtype = dt; k.B.major = MAJOR_MN; k.B.ld = 3 * A; k.B.bs1 = 64; k.B.bs2 = (int64_t)Le * 3 * A;
         k.epi.C = poff(dqkv, A, dt); k.epi.c_dtype = dt; k.epi.ldc = 3 * A; k.epi.cs1 = 64; k.epi.cs2 = (int64_t)Le * 3 * A;
         gemm(k);
     } else {
-        // fp32 parity path: dqkv IS the fp32 scratch
+        // fp32 parity path: dqkv IS an fp32 buffer
+        if (packed) {   // the forward output in padded geometry (for delta = sum dO * O)
+            unpack_rows(ctx_e[l], dqkv_pad, offs_d, lens_d, B, Le, (int64_t)A * esz(), st);
+            ctx_fwd = dqkv_pad;
+        }
         if (attn_bwd_needs_zero(Le)) P5_CUDA(cudaMemsetAsync(dqkv, 0, Me * 3 * A * sizeof(float), st));
         AttnArgs a;
         a.B = B; a.H = H; a.Lq = Le; a.Lk = Le;
-        a.q = {qkv_e[l], dt, 3 * A, (int64_t)Le * 3 * A};
-        a.k = {poff(qkv_e[l], A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
-        a.v = {poff(qkv_e[l], 2 * A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.q = {qkv, dt, 3 * A, (int64_t)Le * 3 * A};
+        a.k = {poff(qkv, A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
+        a.v = {poff(qkv, 2 * A, dt), dt, 3 * A, (int64_t)Le * 3 * A};
         a.bias_rel = bias_enc; a.bias_off = Le - 1; a.n_delta = 2 * Le - 1;
         a.key_mask = mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
         float* f = (float*)dqkv;
-        attn_simt_bwd(a, ctx_e[l], dctx, dt, A, (int64_t)Le * A, lse_e[l], f, 3 * A, (int64_t)Le * 3 * A, f + A,
+        attn_simt_bwd(a, ctx_fwd, dctx, dt, A, (int64_t)Le * A, lse_e[l], f, 3 * A, (int64_t)Le * 3 * A, f + A,
                       f + 2 * A, 3 * A, (int64_t)Le * 3 * A, dbias_enc, st);
     }
+    if (packed) pack_rows(dqkv, dqkv_out, offs_d, lens_d, B, Le, (int64_t)3 * A * esz(), st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -455,20 +507,22 @@ void Engine::enc_attention_bwd(int l, const void* dctx, void* dqkv) {
 // ------------------------------------------------------------------------------------------------------------
 void Engine::encoder_forward() {
     build_bias(true, Le);
-    embed_fwd(P + off_shared, P + off_ww, ids_e, ww_e, xe[0], (int)Me, d, V, cfg.whole_word_rows, drop(S_EMB_E, 0), st);
+    const int* ids_in = packed ? ids_p : ids_e;
+    const int* ww_in = packed ? ww_p : ww_e;
+    embed_fwd(P + off_shared, P + off_ww, ids_in, ww_in, xe[0], (int)Mt, d, V, cfg.whole_word_rows, drop(S_EMB_E, 0), st);
     DropCfg none;
     for (int l = 0; l < NE; ++l) {
         const EncLayerOff& w = enc[l];
         float *x_in = xe[2 * l], *x_mid = xe[2 * l + 1], *x_out = xe[2 * l + 2];
-        rmsnorm_fwd(x_in, P + w.ln0, ne[2 * l], dt, rstd_e[2 * l], (int)Me, d, cfg.ln_eps, none, st);
-        linear_fwd(ne[2 * l], d, w.sa.q, 3 * A, d, (int)Me, qkv_e[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
+        rmsnorm_fwd(x_in, P + w.ln0, ne[2 * l], dt, rstd_e[2 * l], (int)Mt, d, cfg.ln_eps, none, st);
+        linear_fwd(ne[2 * l], d, w.sa.q, 3 * A, d, (int)Mt, qkv_e[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
         enc_attention_fwd(l);
-        linear_fwd(ctx_e[l], A, w.sa.o, d, A, (int)Me, x_mid, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, x_in,
+        linear_fwd(ctx_e[l], A, w.sa.o, d, A, (int)Mt, x_mid, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, x_in,
                    drop(S_ENC_O, l));
-        rmsnorm_fwd(x_mid, P + w.ln1, ne[2 * l + 1], dt, rstd_e[2 * l + 1], (int)Me, d, cfg.ln_eps, none, st);
-        ffn_fwd(ne[2 * l + 1], Me, w.ff, z_e[l], h_e[l], x_mid, x_out, S_ENC_ACT, S_ENC_WO, l);
+        rmsnorm_fwd(x_mid, P + w.ln1, ne[2 * l + 1], dt, rstd_e[2 * l + 1], (int)Mt, d, cfg.ln_eps, none, st);
+        ffn_fwd(ne[2 * l + 1], Mt, w.ff, z_e[l], h_e[l], x_mid, x_out, S_ENC_ACT, S_ENC_WO, l);
     }
-    rmsnorm_fwd(xe[2 * NE], P + off_enc_final, enc_out, dt, rstd_e[2 * NE], (int)Me, d, cfg.ln_eps, drop(S_ENC_FINAL, 0), st);
+    rmsnorm_fwd(xe[2 * NE], P + off_enc_final, enc_out, dt, rstd_e[2 * NE], (int)Mt, d, cfg.ln_eps, drop(S_ENC_FINAL, 0), st);
 }
 
 static AttnArgs dec_self_args(Engine& e, int l, DropCfg dc) {
@@ -491,6 +545,9 @@ static AttnArgs dec_cross_args(Engine& e, int l, DropCfg dc) {
     a.v = {poff(e.ckv[l], A, e.dt), e.dt, 2 * A, (int64_t)Le * 2 * A};
     a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0;   // cross-attention position bias is zero (HF:...:317-322)
     a.key_mask = e.mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
+    if (e.packed) {   // encoder rows are packed: per-user row offset + key count replace (batch stride, key mask)
+        a.key_mask = nullptr; a.kv_off = e.offs_d; a.kv_len = e.lens_d;
+    }
     return a;
 }
 
@@ -508,7 +565,7 @@ void Engine::decoder_forward() {
                    drop(S_DEC_SO, l));
         rmsnorm_fwd(y1, P + w.ln1, nd[3 * l + 1], dt, rstd_d[3 * l + 1], (int)Md, d, cfg.ln_eps, none, st);
         linear_fwd(nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, cq[l], dt, A, 0, 1.f, nullptr, nullptr, none);
-        linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Me, ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
+        linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Mt, ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
         attn_simt_fwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], dt, A, (int64_t)Ld * A, clse[l], st);
         linear_fwd(cctx[l], A, w.ca.o, d, A, (int)Md, y2, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, y1,
                    drop(S_DEC_CO, l));
@@ -529,6 +586,7 @@ void Engine::forward(const int32_t* ids, const int32_t* mask, const int32_t* ww,
                      int Ld_, bool train, uint64_t seed_) {
     P5_CUDA(cudaSetDevice(device));
     set_geometry(B_, Le_, Ld_);
+    apply_lengths();
     training = train; seed = seed_;
     if (shadow_stale) refresh_shadow();
     load_inputs(ids, mask, ww, lab);
@@ -558,7 +616,7 @@ void Engine::backward() {
     float* dy = dx_a;
     rmsnorm_bwd(g_d2, dt, yd[3 * ND], rstd_d[3 * ND], P + off_dec_final, nullptr, dy, G + off_dec_final, (int)Md, d,
                 drop(S_DEC_FINAL, 0), st, g_d, dt, drop(S_DEC_WO, ND - 1));
-    P5_CUDA(cudaMemsetAsync(d_encout, 0, Me * d * sizeof(float), st));
+    P5_CUDA(cudaMemsetAsync(d_encout, 0, Mt * d * sizeof(float), st));
     P5_CUDA(cudaMemsetAsync(dbias_dec, 0, (size_t)H * (2 * Ld) * sizeof(float), st));
     DropCfg none;
     // ---- decoder blocks
@@ -571,13 +629,13 @@ void Engine::backward() {
         // cross attention (g_d = dropout-cast(dy))
         linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Me * 2 * A * sizeof(float), st));
+        if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Mt * 2 * A * sizeof(float), st));
         attn_simt_bwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], g_ctx, dt, A, (int64_t)Ld * A, clse[l], f_qkv, A,
                       (int64_t)Ld * A, f_ckv, f_ckv + A, 2 * A, (int64_t)Le * 2 * A, nullptr, st);
         void* gq = as_T(f_qkv, g_qkv, Md * A);
-        void* gkv = as_T(f_ckv, g_ckv, Me * 2 * A);
-        linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Me, 1.f);
-        linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Me, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
+        void* gkv = as_T(f_ckv, g_ckv, Mt * 2 * A);
+        linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f);
+        linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Mt, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
         linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f);
         linear_dgrad(gq, A, w.ca.q, A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
         rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st, g_d, dt,
@@ -601,22 +659,22 @@ void Engine::backward() {
 
     // ---- encoder
     float* dx = dx_a;
-    rmsnorm_bwd(d_encout, DT_F32, xe[2 * NE], rstd_e[2 * NE], P + off_enc_final, nullptr, dx, G + off_enc_final, (int)Me, d,
+    rmsnorm_bwd(d_encout, DT_F32, xe[2 * NE], rstd_e[2 * NE], P + off_enc_final, nullptr, dx, G + off_enc_final, (int)Mt, d,
                 drop(S_ENC_FINAL, 0), st, g_d, dt, drop(S_ENC_WO, NE - 1));
     P5_CUDA(cudaMemsetAsync(dbias_enc, 0, (size_t)H * (2 * Le) * sizeof(float), st));
     for (int l = NE - 1; l >= 0; --l) {
         const EncLayerOff& w = enc[l];
         float *x_in = xe[2 * l], *x_mid = xe[2 * l + 1];
-        ffn_bwd(dx, Me, w.ff, ne[2 * l + 1], z_e[l], h_e[l], g_d2, S_ENC_ACT, S_ENC_WO, l);
-        rmsnorm_bwd(g_d2, dt, x_mid, rstd_e[2 * l + 1], P + w.ln1, dx, dx, G + w.ln1, (int)Me, d, none, st, g_d, dt,
+        ffn_bwd(dx, Mt, w.ff, ne[2 * l + 1], z_e[l], h_e[l], g_d2, S_ENC_ACT, S_ENC_WO, l);
+        rmsnorm_bwd(g_d2, dt, x_mid, rstd_e[2 * l + 1], P + w.ln1, dx, dx, G + w.ln1, (int)Mt, d, none, st, g_d, dt,
                     drop(S_ENC_O, l));
-        linear_wgrad(g_d, d, ctx_e[l], A, w.sa.o, d, A, (int)Me, 1.f);
-        linear_dgrad(g_d, d, w.sa.o, d, A, (int)Me, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        linear_wgrad(g_d, d, ctx_e[l], A, w.sa.o, d, A, (int)Mt, 1.f);
+        linear_dgrad(g_d, d, w.sa.o, d, A, (int)Mt, g_ctx, dt, A, 0, 1.f, nullptr, false);
         void* dqkv = dt == DT_F32 ? (void*)f_qkv : g_qkv;
         enc_attention_bwd(l, g_ctx, dqkv);
-        linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Me, 1.f);
-        linear_dgrad(dqkv, 3 * A, w.sa.q, 3 * A, d, (int)Me, g_d2, dt, d, 0, 1.f, nullptr, false);
-        rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Me, d, none, st, l > 0 ? g_d : nullptr, dt,
+        linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Mt, 1.f);
+        linear_dgrad(dqkv, 3 * A, w.sa.q, 3 * A, d, (int)Mt, g_d2, dt, d, 0, 1.f, nullptr, false);
+        rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Mt, d, none, st, l > 0 ? g_d : nullptr, dt,
                     drop(S_ENC_WO, l > 0 ? l - 1 : 0));
         // block l >= 1 is final (block 0 also holds the shared relative bias, reduced with the embeddings at the end)
         if (overlap_comm && l >= 1) {
@@ -624,7 +682,8 @@ void Engine::backward() {
             comm_allreduce_range(this, w.sa.q, hi - w.sa.q);
         }
     }
-    embed_bwd(dx, ids_e, ww_e, G + off_shared, G + off_ww, (int)Me, d, V, cfg.whole_word_rows, drop(S_EMB_E, 0), st);
+    embed_bwd(dx, packed ? ids_p : ids_e, packed ? ww_p : ww_e, G + off_shared, G + off_ww, (int)Mt, d, V, cfg.whole_word_rows,
+              drop(S_EMB_E, 0), st);
     relbias_scatter_grad(dbias_enc, lut_enc, G + off_enc_rel, H, 2 * Le - 1, st);
 }
 

@@ -61,6 +61,15 @@ struct Engine {
     int B = 0, Le = 0, Ld = 0;          // current step geometry (Le padded to a multiple of 8)
     int Le_user = 0;
     int64_t Me = 0, Md = 0;
+    // packed (padding-free) encoder token layout: active when the caller supplied the encoder lengths for this step
+    // (p5_set_enc_lengths).  All token-wise encoder work then runs on Mt = sum(lens) rows instead of B*Le.
+    bool packed = false;
+    int64_t Mt = 0;                      // encoder token rows actually processed (Me when not packed)
+    std::vector<int> lens_h, offs_h;     // host copies (offs has B+1 entries)
+    std::vector<int> pending_lens;       // set by p5_set_enc_lengths, consumed by the next forward
+    int *lens_d = nullptr, *offs_d = nullptr, *ids_p = nullptr, *ww_p = nullptr;
+    void *qkv_pad = nullptr, *ctx_pad = nullptr, *dqkv_pad = nullptr;   // padded scratch around the attention backward
+    float* f_qkv_pad = nullptr;
     bool training = false;
     uint64_t seed = 0;
     bool have_fwd = false;
@@ -116,6 +125,7 @@ struct Engine {
     void refresh_shadow();
     void set_geometry(int B, int Le_user, int Ld);
     void load_inputs(const int32_t* ids, const int32_t* mask, const int32_t* ww, const int32_t* labels);
+    void apply_lengths();   // consumes pending_lens -> packed / Mt / offs / lens
     void build_bias(bool encoder, int L);
 
     // GEMM helpers (C = A * B^T forms; see engine.cu)

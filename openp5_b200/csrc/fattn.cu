@@ -33,6 +33,8 @@ struct FaParams {
     bf16* ctx;               // [B*Lq, ld_ctx]
     int64_t ld_ctx;
     uint32_t sK, sV, sQ, sP, sBias, sMask, sStat, sBar;   // smem offsets from the 1024-aligned base
+    const int* offs;         // packed (padding-free) token layout: first row of batch b in qkv / ctx; null = padded [B, L]
+    const int* lens;         // packed: tokens of batch b (queries == keys); rows/keys >= len are skipped / masked
     DropCfg drop;
 };
 
@@ -95,17 +97,22 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             int qb = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int b = pair / P.H, h = pair % P.H;
+                // packed layout: the pair's rows start at offs[b] of a [Mtot, .] matrix (batch coordinate 0) and only
+                // ceil(len / 128) key blocks / query tiles exist
+                const int len = P.lens ? P.lens[b] : Lk;
+                const int row0 = P.offs ? P.offs[b] : 0, bc = P.offs ? 0 : b;
+                const int nkb = (len + KB - 1) / KB, nqt = (len + QT - 1) / QT;
                 mbar_wait(kv_empty, kv_ph ^ 1);
                 mbar_expect_tx(kv_full, (uint32_t)(2 * nkb * KB * 128));
                 for (int kb = 0; kb < nkb; ++kb) {
-                    tma_load_4d(sK + kb * (KB * 128), &tmK, kv_full, 0, kb * KB, h, b);
-                    tma_load_4d(sV + kb * (KB * 128), &tmV, kv_full, 0, kb * KB, h, b);
+                    tma_load_4d(sK + kb * (KB * 128), &tmK, kv_full, 0, row0 + kb * KB, h, bc);
+                    tma_load_4d(sV + kb * (KB * 128), &tmV, kv_full, 0, row0 + kb * KB, h, bc);
                 }
                 kv_ph ^= 1;
                 for (int qt = 0; qt < nqt; ++qt) {
                     mbar_wait(q_empty(qb), q_ph[qb] ^ 1);
                     mbar_expect_tx(q_full(qb), QT * 128);
-                    tma_load_4d(sQ + qb * (QT * 128), &tmQ, q_full(qb), 0, qt * QT, h, b);
+                    tma_load_4d(sQ + qb * (QT * 128), &tmQ, q_full(qb), 0, row0 + qt * QT, h, bc);
                     q_ph[qb] ^= 1;
                     qb = (qb + 1) % P.nq_buf;
                 }
@@ -133,6 +140,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 sb ^= 1;
             };
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const int len = P.lens ? P.lens[pair / P.H] : Lk;
+                const int nkb = (len + KB - 1) / KB, nqt = (len + QT - 1) / QT;
                 mbar_wait(kv_full, kv_ph);
                 kv_ph ^= 1;
                 for (int qt = 0; qt < nqt; ++qt) {
@@ -174,12 +183,14 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int n_delta = Lq + Lk - 1;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
+            const int len = P.lens ? P.lens[b] : Lk;
+            const int nkb = (len + KB - 1) / KB;
             mbar_wait(bm_empty, bm_ph ^ 1);
             // entries past n_delta are only touched for padded keys (masked with -inf): keep them finite
             for (int e = lane; e < Lq + nkb * KB; e += 32)
                 bias_s[e] = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] : 0.f;
             for (int j = lane; j < nkb * KB; j += 32)
-                mask_s[j] = (j < Lk && (!P.key_mask || P.key_mask[b * Lk + j] != 0)) ? 0.f : (j < Lk ? MASK_MIN : -INFINITY);
+                mask_s[j] = (j < len && (!P.key_mask || P.key_mask[b * Lk + j] != 0)) ? 0.f : (j < len ? MASK_MIN : -INFINITY);
             __syncwarp();
             if (lane == 0) mbar_arrive(bm_full);
             bm_ph ^= 1;
@@ -194,11 +205,14 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         int sb = 0, pb = 0;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
+            const int len = P.lens ? P.lens[b] : Lq;
+            const int nkb = (len + KB - 1) / KB, nqt = (len + QT - 1) / QT;
+            const int64_t ctx_row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * Lq;
             mbar_wait(bm_full, bm_ph);
             bm_ph ^= 1;
             for (int qt = 0; qt < nqt; ++qt) {
                 const int i = qt * QT + r;                // query position
-                const bool row_ok = i < Lq;
+                const bool row_ok = i < len;
                 const float* brow = bias_s + (row_ok ? (Lq - 1 - i) : 0);   // bias for key j is brow[j]
                 const int64_t grow = (((int64_t)b * P.H + h) * Lq + i) * Lk;
                 // ---------------- pass 1: m = max_j s_ij, l = sum_j exp(s_ij - m) over this warpgroup's columns
@@ -319,7 +333,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_empty);
                     if (row_ok) {
-                        bf16* dst = P.ctx + ((int64_t)b * Lq + i) * P.ld_ctx + h * 64 + wg * 32;
+                        bf16* dst = P.ctx + (ctx_row0 + i) * P.ld_ctx + h * 64 + wg * 32;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint4 w;
@@ -348,7 +362,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // qkv: [B*L, 3A] bf16 (q | k | v column blocks, heads 64 wide).  Returns false if the shape is not supported.
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
-               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st) {
+               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st, const int* offs, const int* lens,
+               int64_t packed_rows) {
     if (L > 512 || L % 8 != 0 || ld_qkv % 8 != 0) return false;
     static int num_sms = 0;
     if (!num_sms) {
@@ -368,7 +383,8 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.sBar = P.sStat + 2 * QT * 8;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
-    P.bias_rel = bias_rel; P.key_mask = key_mask; P.P_save = (bf16*)P_save; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
+    P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
+    P.offs = offs; P.lens = lens;
     P.drop = drop;
     static size_t max_set = 0;
     if (smem > max_set) {
@@ -376,8 +392,10 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
         max_set = smem;
     }
     // 4-D views (c, pos, h, b): row stride ld_qkv, head stride 64 elements, batch stride L*ld_qkv
-    const uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)ld_qkv * 2, 128, (uint64_t)L * ld_qkv * 2};
+    // padded: (c, pos, h, b) with batch stride L*ld.  packed: one [packed_rows, .] matrix, batch dim 1 (TMA zero-fills
+    // rows past packed_rows; rows of the NEXT sequence that fall into a box are masked by `lens`)
+    const uint64_t dims[4] = {64, (uint64_t)(offs ? packed_rows : L), (uint64_t)H, (uint64_t)(offs ? 1 : B)};
+    const uint64_t strides[3] = {(uint64_t)ld_qkv * 2, 128, (uint64_t)(offs ? packed_rows : L) * ld_qkv * 2};
     const uint32_t box[4] = {64, 128, 1, 1};
     const bf16* base = (const bf16*)qkv;
     CUtensorMap tmQ = tmap_bf16_4d(base, dims, strides, box);

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the T5 block: embedding gather, RMSNorm fwd/bwd, dropout-cast, gated-GELU, cross-entropy,
 // runner loss, relative-position-bias tables.  Coalesced / vectorised; statistics in fp32.
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace p5 {
 extern int g_launches;
@@ -406,6 +407,60 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict_
 void add_f32(float* dst, const float* src, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
     add_f32_kernel<<<ew_grid(n, 1), 256, 0, st>>>(dst, src, n);
+    LAUNCHED();
+}
+
+// =================================================================================================================
+// packed (variable-length) <-> padded row layouts.  offs[b] = first packed row of sequence b, lens[b] = valid tokens
+// =================================================================================================================
+// dst_packed[offs[b] + i, :] = src_padded[b*L + i, :]  (i < lens[b]); W elements per row, 16-byte chunks
+__global__ void pack_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ offs,
+                                 const int* __restrict__ lens, int L, int chunks) {
+    const int b = blockIdx.y;
+    const int len = lens[b];
+    const int64_t n = (int64_t)len * chunks;
+    const uint4* s = src + (int64_t)b * L * chunks;
+    uint4* d = dst + (int64_t)offs[b] * chunks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+// dst_padded[b*L + i, :] = i < lens[b] ? src_packed[offs[b] + i, :] : 0
+__global__ void unpack_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ offs,
+                                   const int* __restrict__ lens, int L, int chunks) {
+    const int b = blockIdx.y;
+    const int len = lens[b];
+    const int64_t n = (int64_t)L * chunks, nv = (int64_t)len * chunks;
+    const uint4* s = src + (int64_t)offs[b] * chunks;
+    uint4* d = dst + (int64_t)b * L * chunks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = i < nv ? s[i] : make_uint4(0, 0, 0, 0);
+}
+void pack_rows(const void* src_padded, void* dst_packed, const int* offs, const int* lens, int B, int L, int64_t row_bytes,
+               cudaStream_t st) {
+    if (B <= 0) return;
+    P5_CHECK(row_bytes % 16 == 0, "pack_rows: row size must be a multiple of 16 bytes");
+    const int chunks = (int)(row_bytes / 16);
+    dim3 grid((unsigned)std::min<int64_t>(64, cdiv((int64_t)L * chunks, 256)), (unsigned)B);
+    pack_rows_kernel<<<grid, 256, 0, st>>>((const uint4*)src_padded, (uint4*)dst_packed, offs, lens, L, chunks);
+    LAUNCHED();
+}
+void unpack_rows(const void* src_packed, void* dst_padded, const int* offs, const int* lens, int B, int L, int64_t row_bytes,
+                 cudaStream_t st) {
+    if (B <= 0) return;
+    P5_CHECK(row_bytes % 16 == 0, "unpack_rows: row size must be a multiple of 16 bytes");
+    const int chunks = (int)(row_bytes / 16);
+    dim3 grid((unsigned)std::min<int64_t>(64, cdiv((int64_t)L * chunks, 256)), (unsigned)B);
+    unpack_rows_kernel<<<grid, 256, 0, st>>>((const uint4*)src_packed, (uint4*)dst_padded, offs, lens, L, chunks);
+    LAUNCHED();
+}
+// packed int arrays from padded [B, L] (token ids / whole-word ids)
+__global__ void pack_ints_kernel(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ offs,
+                                 const int* __restrict__ lens, int L) {
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < lens[b]; i += blockDim.x) dst[offs[b] + i] = src[b * L + i];
+}
+void pack_ints(const int* src_padded, int* dst_packed, const int* offs, const int* lens, int B, int L, cudaStream_t st) {
+    if (B <= 0) return;
+    pack_ints_kernel<<<B, 256, 0, st>>>(src_padded, dst_packed, offs, lens, L);
     LAUNCHED();
 }
 

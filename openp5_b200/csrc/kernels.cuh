@@ -37,6 +37,13 @@ void cast_block_f32_to(const float* in, int64_t ld_in, void* out, int out_dtype,
                        cudaStream_t st);
 void add_f32(float* dst, const float* src, int64_t n, cudaStream_t st);
 
+// packed (variable-length, padding removed) <-> padded [B, L] row layouts; offs[b] = first packed row, lens[b] = tokens
+void pack_rows(const void* src_padded, void* dst_packed, const int* offs, const int* lens, int B, int L, int64_t row_bytes,
+               cudaStream_t st);
+void unpack_rows(const void* src_packed, void* dst_padded, const int* offs, const int* lens, int B, int L, int64_t row_bytes,
+                 cudaStream_t st);
+void pack_ints(const int* src_padded, int* dst_packed, const int* offs, const int* lens, int B, int L, cudaStream_t st);
+
 // gated-GELU (HF:modeling_t5.py:106-132): z = [z0 | z1] per row (ld = 2*ff); h = drop(gelu_new(z0) * z1)
 void gated_gelu_fwd(const void* z, void* h, int dtype, int M, int ff, DropCfg drop, cudaStream_t st);
 void gated_gelu_bwd(const void* z, const void* dh, void* dz, int dtype, int M, int ff, DropCfg drop, cudaStream_t st);
@@ -71,6 +78,8 @@ struct AttnArgs {
     int causal;              // 1: key j > query i is masked (decoder self-attention); q_pos_offset shifts i
     int q_pos_offset;        // position of query row 0 (decode step with KV cache)
     const int* row_map;      // optional [B] indirection for K/V/mask batch index (beam -> user), null = identity
+    const int* kv_off = nullptr;   // packed K/V: first row of batch kb (replaces kb * bs); null = padded layout
+    const int* kv_len = nullptr;   // packed K/V: number of keys of batch kb (replaces Lk and the key mask)
     DropCfg drop;
 };
 // fused SIMT attention (fp32 math): O[b, i, h*64 + c] (ld_o) and LSE[b, h, i]
@@ -89,13 +98,17 @@ void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype
 void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, void* P_save, void* Pd, int dtype, int B,
                  int H, int Lq, int Lk, int causal, DropCfg drop, cudaStream_t st);
 //   dP_in = gradient wrt Pd (fp32); dS = P * (mask(dP) - rowsum(mask(dP) * P)) -> dS (dtype);  Pd regenerated
+// lens (optional, packed training): rows / columns >= lens[b] hold no probabilities -> dS and Pd are written as zeros
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
-                 int Lq, int Lk, DropCfg drop, cudaStream_t st);
+                 int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens = nullptr);
 
 // fused tcgen05 encoder self-attention forward (fattn.cu): qkv [B*L, 3A] bf16 -> ctx [B*L, A] bf16 (+ P_save bf16
 // [B,H,L,L] normalised un-dropped probabilities for the backward).  Returns false when the shape is unsupported.
+// packed mode (offs/lens non-null): qkv / ctx are [packed_rows, .] with sequence b at rows offs[b] .. offs[b]+lens[b];
+// P_save keeps the padded [B,H,L,L] geometry (rows/cols < lens[b] written).
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
-               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st);
+               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st, const int* offs = nullptr,
+               const int* lens = nullptr, int64_t packed_rows = 0);
 
 // dbias_rel[h, j - i + Lq - 1] += sum_{b,i} dS[b,h,i,j]   (dS [B,H,Lq,Lk], register accumulation per diagonal)
 void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H, int Lq, int Lk, cudaStream_t st);

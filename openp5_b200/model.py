@@ -222,6 +222,20 @@ class P5B200:
         if cur.cuda_stream != self.stream.cuda_stream:
             raise _lib.P5LibraryError("P5B200 must be driven on the CUDA stream it was created on")
 
+    # ---------------------------------------------------------------- encoder lengths (padding removal)
+    def _set_enc_lengths(self, enc_lengths, attention_mask):
+        """Tell the engine how many (right-padded) tokens each encoder row holds, so that it processes sum(lens)
+        rows instead of B*Le.  Lengths come from the caller, or for free from a HOST attention mask (the collator's
+        tensors start on the CPU, ref Collator.py:8-34); a device-resident mask without lengths keeps the padded path."""
+        if enc_lengths is None and attention_mask is not None and not attention_mask.is_cuda:
+            enc_lengths = attention_mask.sum(dim=1)
+        if enc_lengths is None:
+            return
+        if torch.is_tensor(enc_lengths):
+            enc_lengths = enc_lengths.to("cpu", torch.int32).tolist()
+        arr = (C.c_int32 * len(enc_lengths))(*[int(x) for x in enc_lengths])
+        _lib.check(self.lib.p5_set_enc_lengths(self.handle, arr, len(enc_lengths)))
+
     # ---------------------------------------------------------------- forward / backward
     def _forward_raw(self, ids, mask, ww, labels, training, seed, want_logits):
         B, Le = ids.shape
@@ -239,10 +253,11 @@ class P5B200:
         _lib.check(self.lib.p5_backward(self.handle, dloss.data_ptr()))
 
     def __call__(self, input_ids=None, whole_word_ids=None, attention_mask=None, labels=None, return_dict=True,
-                 return_logits=True, **_unused):
+                 return_logits=True, enc_lengths=None, **_unused):
         """ref P5_T5.forward: returns {"loss": flat un-reduced per-token CE [B*Ld], "logits": [B, Ld, V]}"""
         self._on_stream()
         self._sync_params()
+        self._set_enc_lengths(enc_lengths, attention_mask)
         ids = _i32(input_ids, self.device)
         mask = _i32(attention_mask if attention_mask is not None else (input_ids != 0), self.device)
         ww = _i32(whole_word_ids, self.device) if whole_word_ids is not None else None
@@ -262,12 +277,13 @@ class P5B200:
     # ---------------------------------------------------------------- fused training step (fast path)
     def train_step(self, input_ids, whole_word_ids, attention_mask, labels, labels_attention, *, lr: float,
                    clip: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.01,
-                   seed: Optional[int] = None, step: Optional[int] = None) -> torch.Tensor:
+                   seed: Optional[int] = None, step: Optional[int] = None, enc_lengths=None) -> torch.Tensor:
         """One optimisation step = ref DistributedRunner.py:63-87 (forward, runner loss, backward, clip, AdamW,
         zero_grad) + the gradient all-reduce DDP was meant to do.  Returns the scalar loss as a device tensor
         (no host sync)."""
         self._on_stream()
         self._sync_params(fast_path=True)
+        self._set_enc_lengths(enc_lengths, attention_mask)
         ids = _i32(input_ids, self.device)
         mask = _i32(attention_mask, self.device)
         ww = _i32(whole_word_ids, self.device) if whole_word_ids is not None else None

@@ -12,7 +12,9 @@ sys.path.insert(0, ROOT)
 
 CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fused_fp32_tiny", "adamw_fp32_tiny",
          "gen_fp32_tiny", "gen_bf16_tiny", "fwd_fp32_small", "bwd_fp32_small", "bwd_bf16_small", "gated_fp32_tiny",
-         "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256", "bwd_bf16_small_le512", "bwd_fp32_small_le300"]
+         "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256", "bwd_bf16_small_le512", "bwd_fp32_small_le300",
+         "bwd_fp32_tiny_packed", "bwd_fp32_small_packed", "bwd_bf16_small_packed", "bwd_bf16_base_le256_packed",
+         "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed"]
 
 
 def setup(case):
@@ -83,7 +85,9 @@ def run_case(case):
                                               C.c_uint64(1)))
             loss = loss[0]
         else:
-            out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev))
+            lens = attn.sum(1) if "packed" in case else None
+            out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev),
+                    enc_lengths=lens)
             B, Ld = labels.shape
             lm = (oattn.to(dev) != 0).float()
             loss = ((out["loss"].view(B, Ld) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
@@ -118,7 +122,8 @@ def run_case(case):
             for k in wo:
                 po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, lr, eps=1e-6, weight_decay=0.01)
             m.training = False
-            loss = m.train_step(ids.to(dev), ww.to(dev), attn.to(dev), labels.to(dev), oattn.to(dev), lr=lr, clip=1.0, step=step)
+            loss = m.train_step(ids.to(dev), ww.to(dev), attn.to(dev), labels.to(dev), oattn.to(dev), lr=lr, clip=1.0, step=step,
+                                enc_lengths=attn.sum(1) if "packed" in case else None)
             losses.append((loss.item(), l_o.item()))
         worst = max(relerr(p.detach().cpu(), wo[k]) for k, p in m.named_parameters())
         res["losses"] = losses
