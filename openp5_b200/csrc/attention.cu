@@ -534,7 +534,9 @@ void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, voi
     LAUNCHED();
 }
 
-template <typename T>
+// NP = column pairs per lane (Lk <= 64 * NP); each warp works on TWO rows at a time so that twice as many
+// independent loads are in flight (the kernel is latency-, not bandwidth-limited at one row per warp)
+template <typename T, int NP>
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __restrict__ dS, T* __restrict__ Pd_out,
                    float* __restrict__ dbias_rel, int H, int Lq, int Lk, DropCfg drop, const int* __restrict__ lens) {
@@ -549,45 +551,55 @@ softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __
         for (int e = threadIdx.x; e < n_delta; e += blockDim.x) sdb[e] = 0.f;
         __syncthreads();
     }
-    for (int i = blockIdx.y * nw + warp; i < Lq; i += nw * gridDim.y) {
-        const int64_t row = ((int64_t)bh * Lq + i) * Lk;
-        float p[SM_MAXP][2], dp[SM_MAXP][2];
-        float dot = 0.f;
+    for (int i0 = 2 * (blockIdx.y * nw + warp); i0 < Lq; i0 += 2 * nw * gridDim.y) {
+        float p[2][NP][2], dp[2][NP][2];
+        float dot[2] = {0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < SM_MAXP; ++k) {
-            const int j = 2 * (lane + 32 * k);
-            p[k][0] = p[k][1] = dp[k][0] = dp[k][1] = 0.f;
-            if (j < Lk) {
-                if (i < len && j < len) {
-                    float2 pp = ld_pair<T>(P + row + j);
-                    if (j + 1 >= len) pp.y = 0.f;             // pair straddling the sequence end
-                    const float2 g = *reinterpret_cast<const float2*>(dPd + row + j);
-                    float g0 = g.x, g1 = g.y;
-                    if (drop.thr) {
-                        bool k0, k1;
-                        drop_pair(drop, (uint64_t)(row + j) >> 1, k0, k1);
-                        g0 = k0 ? g0 * drop.inv_keep : 0.f;
-                        g1 = k1 ? g1 * drop.inv_keep : 0.f;
-                        if (Pd_out) st_pair<T>(Pd_out + row + j, k0 ? pp.x * drop.inv_keep : 0.f, k1 ? pp.y * drop.inv_keep : 0.f);
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = i0 + rr;
+            const int64_t row = ((int64_t)bh * Lq + i) * Lk;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const int j = 2 * (lane + 32 * k);
+                p[rr][k][0] = p[rr][k][1] = dp[rr][k][0] = dp[rr][k][1] = 0.f;
+                if (i < Lq && j < Lk) {
+                    if (i < len && j < len) {
+                        float2 pp = ld_pair<T>(P + row + j);
+                        if (j + 1 >= len) pp.y = 0.f;             // pair straddling the sequence end
+                        const float2 g = *reinterpret_cast<const float2*>(dPd + row + j);
+                        float g0 = g.x, g1 = g.y;
+                        if (drop.thr) {
+                            bool k0, k1;
+                            drop_pair(drop, (uint64_t)(row + j) >> 1, k0, k1);
+                            g0 = k0 ? g0 * drop.inv_keep : 0.f;
+                            g1 = k1 ? g1 * drop.inv_keep : 0.f;
+                            if (Pd_out) st_pair<T>(Pd_out + row + j, k0 ? pp.x * drop.inv_keep : 0.f, k1 ? pp.y * drop.inv_keep : 0.f);
+                        } else if (Pd_out) {
+                            st_pair<T>(Pd_out + row + j, pp.x, pp.y);   // packed, no dropout: clean copy of P
+                        }
+                        if (pp.y == 0.f) g1 = 0.f;
+                        p[rr][k][0] = pp.x; p[rr][k][1] = pp.y; dp[rr][k][0] = g0; dp[rr][k][1] = g1;
+                        dot[rr] += g0 * pp.x + g1 * pp.y;
                     } else if (Pd_out) {
-                        st_pair<T>(Pd_out + row + j, pp.x, pp.y);   // packed, no dropout: clean copy of P
+                        st_pair<T>(Pd_out + row + j, 0.f, 0.f);   // outside the sequence: exact zeros
                     }
-                    if (pp.y == 0.f) g1 = 0.f;
-                    p[k][0] = pp.x; p[k][1] = pp.y; dp[k][0] = g0; dp[k][1] = g1;
-                    dot += g0 * pp.x + g1 * pp.y;
-                } else if (Pd_out) {
-                    st_pair<T>(Pd_out + row + j, 0.f, 0.f);   // outside the sequence: exact zeros
                 }
             }
         }
-        dot = warp_sum(dot);
+        dot[0] = warp_sum(dot[0]);
+        dot[1] = warp_sum(dot[1]);
 #pragma unroll
-        for (int k = 0; k < SM_MAXP; ++k) {
-            const int j = 2 * (lane + 32 * k);
-            if (j < Lk) {
-                const float d0 = p[k][0] * (dp[k][0] - dot), d1 = p[k][1] * (dp[k][1] - dot);
-                st_pair<T>(dS + row + j, d0, d1);
-                if (dbias_rel) { atomicAdd(&sdb[j - i + Lq - 1], d0); atomicAdd(&sdb[j + 1 - i + Lq - 1], d1); }
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = i0 + rr;
+            const int64_t row = ((int64_t)bh * Lq + i) * Lk;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const int j = 2 * (lane + 32 * k);
+                if (i < Lq && j < Lk) {
+                    const float d0 = p[rr][k][0] * (dp[rr][k][0] - dot[rr]), d1 = p[rr][k][1] * (dp[rr][k][1] - dot[rr]);
+                    st_pair<T>(dS + row + j, d0, d1);
+                    if (dbias_rel) { atomicAdd(&sdb[j - i + Lq - 1], d0); atomicAdd(&sdb[j + 1 - i + Lq - 1], d1); }
+                }
             }
         }
     }
@@ -635,10 +647,13 @@ void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dt
     P5_CHECK(Lk <= 64 * SM_MAXP && (Lk % 2) == 0, "softmax_bwd: Lk must be even and <= 512");
     dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     const size_t sm = (size_t)(Lq + Lk) * sizeof(float);
-    if (dtype == DT_F32)
-        softmax_bwd_kernel<float><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
-    else
-        softmax_bwd_kernel<bf16><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+    if (dtype == DT_F32) {
+        if (Lk <= 256) softmax_bwd_kernel<float, 4><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+        else softmax_bwd_kernel<float, 8><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+    } else {
+        if (Lk <= 256) softmax_bwd_kernel<bf16, 4><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+        else softmax_bwd_kernel<bf16, 8><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+    }
     LAUNCHED();
 }
 

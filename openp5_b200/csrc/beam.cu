@@ -532,6 +532,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
 
     // ---- encoder once per user (eval mode) + cross K/V once per user
     e->set_geometry(B, Le_user, 1);
+    e->pending_lens.clear();   // generate() always uses the padded encoder layout
     e->training = false; e->seed = 0;
     if (e->shadow_stale) e->refresh_shadow();
     e->load_inputs(ids, mask, ww, nullptr);

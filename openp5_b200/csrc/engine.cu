@@ -106,7 +106,8 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
 
     // ---- workspace
     Bm = c.max_batch; Lem = (int)round_up(c.max_enc_len, 8); Ldm = c.max_dec_len;
-    const int64_t Mem = (int64_t)Bm * Lem, Mdm = (int64_t)Bm * Ldm, Mx = Mem > Mdm ? Mem : Mdm;
+    // +512 rows: the packed layout rounds its row count up to a multiple of 512 with inert filler rows
+    const int64_t Mem = (int64_t)Bm * Lem + 512, Mdm = (int64_t)Bm * Ldm, Mx = Mem > Mdm ? Mem : Mdm;
     const size_t e = esz();
     ids_e = dalloc_t<int>(Mem); mask_e = dalloc_t<int>(Mem); ww_e = dalloc_t<int>(Mem);
     labels = dalloc_t<int>(Mdm); dec_ids = dalloc_t<int>(Mdm); lmask = dalloc_t<int>(Mdm);
@@ -278,7 +279,7 @@ void Engine::set_geometry(int B_, int Le_user_, int Ld_) {
     P5_CHECK(Ld_ >= 1 && Ld_ <= Ldm, "decoder length exceeds max_dec_len");
     B = B_; Le_user = Le_user_; Le = (int)round_up(Le_user_, 8); Ld = Ld_;
     Me = (int64_t)B * Le; Md = (int64_t)B * Ld;
-    packed = false; Mt = Me;
+    packed = false; Mt = Me; Mt_true = Me;
 }
 
 void Engine::apply_lengths() {
@@ -290,7 +291,10 @@ void Engine::apply_lengths() {
         P5_CHECK(lens_h[b] >= 1 && lens_h[b] <= Le_user, "encoder length out of range");
         offs_h[b + 1] = offs_h[b] + lens_h[b];
     }
-    Mt = offs_h[B];
+    // Round the packed row count up to a multiple of 512 with FILLER rows (pad token 0, attended by nobody, gradient
+    // exactly zero): token-dimension split-K of the weight-gradient GEMMs needs a row count with power-of-two divisors.
+    Mt_true = offs_h[B];
+    Mt = round_up(Mt_true, 512);
     packed = true;
     P5_CUDA(cudaMemcpyAsync(lens_d, lens_h.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
     P5_CUDA(cudaMemcpyAsync(offs_d, offs_h.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -308,6 +312,10 @@ void Engine::load_inputs(const int32_t* ids, const int32_t* mask, const int32_t*
     if (ww) P5_CUDA(cudaMemcpy2DAsync(ww_e, pitch, ww, wbytes, wbytes, B, cudaMemcpyDeviceToDevice, st));
     else P5_CUDA(cudaMemsetAsync(ww_e, 0xff, Me * 4, st));  // -1 = no whole-word embedding
     if (packed) {
+        if (Mt > Mt_true) {   // filler rows: pad token, no whole-word embedding
+            P5_CUDA(cudaMemsetAsync(ids_p + Mt_true, 0, (Mt - Mt_true) * sizeof(int), st));
+            P5_CUDA(cudaMemsetAsync(ww_p + Mt_true, 0xff, (Mt - Mt_true) * sizeof(int), st));
+        }
         pack_ints(ids_e, ids_p, offs_d, lens_d, B, Le, st);
         pack_ints(ww_e, ww_p, offs_d, lens_d, B, Le, st);
     }
@@ -459,8 +467,7 @@ void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
         p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
         gemm(p);
         const bool regen = dc.thr || packed;   // packed: P_save holds stale rows/columns outside the sequences
-        softmax_bwd(S_scr, P_e[l], dS_scr, regen ? Pd_scr : nullptr, dt, nullptr, B, H, Le, Le, dc, st, packed ? lens_d : nullptr);
-        relbias_diag_sum(dS_scr, dt, dbias_enc, B, H, Le, Le, st);
+        softmax_bwd(S_scr, P_e[l], dS_scr, regen ? Pd_scr : nullptr, dt, dbias_enc, B, H, Le, Le, dc, st, packed ? lens_d : nullptr);
         const void* Pd = regen ? Pd_scr : P_e[l];
         GemmProblem v;   // dV[j,c] = sum_i Pd[i,j] dctx[i,c]
         v.M = Le; v.N = 64; v.K = Le; v.nb1 = H; v.nb2 = B;
@@ -499,7 +506,11 @@ void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
         attn_simt_bwd(a, ctx_fwd, dctx, dt, A, (int64_t)Le * A, lse_e[l], f, 3 * A, (int64_t)Le * 3 * A, f + A,
                       f + 2 * A, 3 * A, (int64_t)Le * 3 * A, dbias_enc, st);
     }
-    if (packed) pack_rows(dqkv, dqkv_out, offs_d, lens_d, B, Le, (int64_t)3 * A * esz(), st);
+    if (packed) {
+        pack_rows(dqkv, dqkv_out, offs_d, lens_d, B, Le, (int64_t)3 * A * esz(), st);
+        if (Mt > Mt_true)   // filler rows carry zero gradient (pack_rows writes the real rows only)
+            P5_CUDA(cudaMemsetAsync((char*)dqkv_out + Mt_true * 3 * A * esz(), 0, (Mt - Mt_true) * 3 * A * esz(), st));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -632,6 +643,8 @@ void Engine::backward() {
         if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Mt * 2 * A * sizeof(float), st));
         attn_simt_bwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], g_ctx, dt, A, (int64_t)Ld * A, clse[l], f_qkv, A,
                       (int64_t)Ld * A, f_ckv, f_ckv + A, 2 * A, (int64_t)Le * 2 * A, nullptr, st);
+        if (packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
+            P5_CUDA(cudaMemsetAsync(f_ckv + Mt_true * 2 * A, 0, (Mt - Mt_true) * 2 * A * sizeof(float), st));
         void* gq = as_T(f_qkv, g_qkv, Md * A);
         void* gkv = as_T(f_ckv, g_ckv, Mt * 2 * A);
         linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f);

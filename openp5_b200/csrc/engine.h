@@ -65,6 +65,7 @@ struct Engine {
     // (p5_set_enc_lengths).  All token-wise encoder work then runs on Mt = sum(lens) rows instead of B*Le.
     bool packed = false;
     int64_t Mt = 0;                      // encoder token rows actually processed (Me when not packed)
+    int64_t Mt_true = 0;                 // packed: real tokens (Mt = Mt_true rounded up to 512 with inert filler rows)
     std::vector<int> lens_h, offs_h;     // host copies (offs has B+1 entries)
     std::vector<int> pending_lens;       // set by p5_set_enc_lengths, consumed by the next forward
     int *lens_d = nullptr, *offs_d = nullptr, *ids_p = nullptr, *ww_p = nullptr;

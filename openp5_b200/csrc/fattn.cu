@@ -8,7 +8,8 @@
 //   warp 1    : MMA issuer.  pass 1: S_blk = Q K_blk^T (128x128x64) per 128-key block -> TMEM (double buffered)
 //               pass 2: S_blk again, then O += P_blk V_blk (128x64x128) with P_blk read from smem
 //   warp 2    : TMEM allocator (2 x 128 columns S + 64 columns O)
-//   warps 4-11: softmax, two warpgroups.  thread = (query row, half of the 128 key columns of a block).
+//   warps 4-19: softmax, four warpgroups.  thread = (query row, 32 of the 128 key columns of a block); four warps per
+//               scheduler hide the ALU / MUFU / LDS latencies of the softmax arithmetic.
 //               pass 1: row max / sum (online over blocks; the two halves are combined through smem);
 //               pass 2: p = exp(s - m) / l -> P_save (bf16, for the backward), dropout -> bf16 -> swizzled smem A tile
 // Two passes over the key blocks (QK^T is recomputed: K = 64, cheap) make the written P exactly normalised and avoid
@@ -21,7 +22,8 @@ namespace p5 {
 extern int g_launches;
 #define MASK_MIN (-FLT_MAX)
 
-static constexpr int FA_THREADS = 384;   // 4 control warps + 2 softmax warpgroups (each owns half of the key columns)
+static constexpr int NWG = 4;              // softmax warpgroups: each owns 128 / NWG = 32 key columns of every block
+static constexpr int FA_THREADS = 128 + NWG * 128;   // 4 control warps + NWG softmax warpgroups
 static constexpr int QT = 128;      // query rows per tile
 static constexpr int KB = 128;      // keys per block
 
@@ -52,7 +54,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t sK = base + P.sK, sV = base + P.sV, sQ = base + P.sQ, sP = base + P.sP, bar = base + P.sBar;
     float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
     float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
-    float2* stat_s = reinterpret_cast<float2*>(gbase + P.sStat);   // [2][128] (m, l) per warpgroup and row
+    float2* stat_s = reinterpret_cast<float2*>(gbase + P.sStat);   // [NWG][128] (m, l) per warpgroup and row
     // barriers (8 bytes each)
     const uint32_t kv_full = bar, kv_empty = bar + 8;
     auto q_full = [&](int i) { return bar + 16 + 8 * i; };
@@ -74,11 +76,11 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1);
-            mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8);
-            mbar_init(p_full(i), 8); mbar_init(p_empty(i), 1);
+            mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4 * NWG);
+            mbar_init(p_full(i), 4 * NWG); mbar_init(p_empty(i), 1);
         }
-        mbar_init(o_full, 1); mbar_init(o_empty, 8);
-        mbar_init(bm_full, 1); mbar_init(bm_empty, 8);
+        mbar_init(o_full, 1); mbar_init(o_empty, 4 * NWG);
+        mbar_init(bm_full, 1); mbar_init(bm_empty, 4 * NWG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -197,7 +199,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ========================= softmax warps =========================
-        const int wg = (warp - 4) >> 2;                   // warpgroup: key columns [wg*64, wg*64+64) of every block
+        const int wg = (warp - 4) >> 2;                   // warpgroup: key columns [wg*32, wg*32+32) of every block
         const int sw = warp & 3;
         const int r = sw * 32 + lane;                     // row of the query tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
@@ -221,24 +223,23 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     mbar_wait(s_full(sb), sf_ph[sb]);
                     sf_ph[sb] ^= 1;
                     tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    {
                         uint32_t v[32];
-                        tmem_ld32(tS[sb] + lane_off + wg * 64 + c * 32, v);
+                        tmem_ld32(tS[sb] + lane_off + wg * 32, v);
                         tmem_ld_wait();
-                        const int j0 = kb * KB + wg * 64 + c * 32;
+                        const int j0 = kb * KB + wg * 32;
                         float cm = -INFINITY;
-                        float s[32];
 #pragma unroll
                         for (int t = 0; t < 32; ++t) {
-                            s[t] = __uint_as_float(v[t]) + brow[j0 + t] + mask_s[j0 + t];
-                            cm = fmaxf(cm, s[t]);
+                            const float sv = __uint_as_float(v[t]) + brow[j0 + t] + mask_s[j0 + t];
+                            v[t] = __float_as_uint(sv);
+                            cm = fmaxf(cm, sv);
                         }
                         const float mn = fmaxf(m, cm);
                         if (mn > -INFINITY) {
                             float acc = 0.f;
 #pragma unroll
-                            for (int t = 0; t < 32; ++t) acc += __expf(s[t] - mn);
+                            for (int t = 0; t < 32; ++t) acc += __expf(__uint_as_float(v[t]) - mn);
                             l = l * __expf(m - mn) + acc;
                             m = mn;
                         }
@@ -248,15 +249,19 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     if (lane == 0) mbar_arrive(s_empty(sb));
                     sb ^= 1;
                 }
-                // combine the two column halves of the row
+                // combine the column slices of the row
                 stat_s[wg * QT + r] = make_float2(m, l);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
                 {
-                    const float2 o = stat_s[(wg ^ 1) * QT + r];
-                    const float mm = fmaxf(m, o.x);
+                    float mm = m;
+#pragma unroll
+                    for (int g2 = 0; g2 < NWG; ++g2) mm = fmaxf(mm, stat_s[g2 * QT + r].x);
                     float ll = 0.f;
-                    if (m > -INFINITY) ll += l * __expf(m - mm);
-                    if (o.x > -INFINITY) ll += o.y * __expf(o.x - mm);
+#pragma unroll
+                    for (int g2 = 0; g2 < NWG; ++g2) {
+                        const float2 o = stat_s[g2 * QT + r];
+                        if (o.x > -INFINITY) ll += o.y * __expf(o.x - mm);
+                    }
                     m = mm; l = ll;
                 }
                 const float inv_l = 1.f / l;
@@ -267,13 +272,13 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     tc_fence_after();
                     mbar_wait(p_empty(pb), pe_ph[pb] ^ 1);   // the MMA that read this P buffer has retired
                     pe_ph[pb] ^= 1;
-                    const uint32_t p_chunk = sP + pb * (QT * KB * 2) + wg * (QT * 128) + r * 128;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    // this warpgroup's 32 keys live in 64-key chunk (wg >> 1), 16-byte units (wg & 1) * 4 .. + 3
+                    const uint32_t p_chunk = sP + pb * (QT * KB * 2) + (wg >> 1) * (QT * 128) + r * 128;
+                    {
                         uint32_t v[32];
-                        tmem_ld32(tS[sb] + lane_off + wg * 64 + c * 32, v);
+                        tmem_ld32(tS[sb] + lane_off + wg * 32, v);
                         tmem_ld_wait();
-                        const int j0 = kb * KB + wg * 64 + c * 32;
+                        const int j0 = kb * KB + wg * 32;
                         uint32_t pk[16], pd[16];
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
@@ -304,11 +309,10 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                 }
                             }
                         }
-                        // smem A tile, K-major SWIZZLE_128B: this warpgroup's 64-key chunk = [128 rows][128 B],
-                        // 16-byte units XOR (row & 7)
+                        // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const uint32_t addr = p_chunk + (uint32_t)(((c * 4 + q) ^ (r & 7)) << 4);
+                            const uint32_t addr = p_chunk + (uint32_t)((((wg & 1) * 4 + q) ^ (r & 7)) << 4);
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[4 * q]), "r"(pd[4 * q + 1]),
                                          "r"(pd[4 * q + 2]), "r"(pd[4 * q + 3]) : "memory");
                         }
@@ -321,21 +325,21 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     sb ^= 1;
                     pb ^= 1;
                 }
-                // ---------------- O -> ctx (this warpgroup writes 32 of the 64 head columns)
+                // ---------------- O -> ctx (this warpgroup writes 16 of the 64 head columns)
                 mbar_wait(o_full, of_ph);
                 of_ph ^= 1;
                 tc_fence_after();
                 {
-                    uint32_t o[32];
-                    tmem_ld32(tO + lane_off + wg * 32, o);
+                    uint32_t o[16];
+                    tmem_ld16(tO + lane_off + wg * 16, o);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_empty);
                     if (row_ok) {
-                        bf16* dst = P.ctx + (ctx_row0 + i) * P.ld_ctx + h * 64 + wg * 32;
+                        bf16* dst = P.ctx + (ctx_row0 + i) * P.ld_ctx + h * 64 + wg * 16;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int q = 0; q < 2; ++q) {
                             uint4 w;
                             w.x = pack_bf16x2(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1]));
                             w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3]));
@@ -380,7 +384,7 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.sBias = P.sP + 2 * QT * KB * 2;
     P.sMask = P.sBias + (uint32_t)round_up((L + P.nkb * KB) * 4, 16);
     P.sStat = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
-    P.sBar = P.sStat + 2 * QT * 8;
+    P.sBar = P.sStat + NWG * QT * 8;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
     P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;

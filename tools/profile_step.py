@@ -15,12 +15,14 @@ m = P5B200("t5-base", vocab_size=32100, precision="bf16", dropout=0.1, max_batch
 random_init_(m, seed=2023)
 items = synth_items(3416, seed=2023)
 if mode == "train":
-    b = [t.cuda() for t in synth_batch(B, Le, Ld, 32100, items, seed=1)]
+    hb = synth_batch(B, Le, Ld, 32100, items, seed=1)
+    lens = hb[1].sum(1).tolist() if os.environ.get("P5_PADDED") != "1" else None   # packed (padding-free) by default
+    b = [t.cuda() for t in hb]
     for s in range(3):
-        m.train_step(b[0], b[2], b[1], b[3], b[4], lr=1e-3, clip=1.0)
+        m.train_step(b[0], b[2], b[1], b[3], b[4], lr=1e-3, clip=1.0, enc_lengths=lens)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    m.train_step(b[0], b[2], b[1], b[3], b[4], lr=1e-3, clip=1.0)
+    m.train_step(b[0], b[2], b[1], b[3], b[4], lr=1e-3, clip=1.0, enc_lengths=lens)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 else:
