@@ -138,6 +138,7 @@ struct GenWs {
     void *n = nullptr, *qkv = nullptr, *ctx = nullptr, *cq = nullptr, *h = nullptr, *z = nullptr;
     std::vector<void*> Kc, Vc;
     float *logits = nullptr, *rowmax = nullptr, *logsum = nullptr;
+    float* xS = nullptr; void* xP = nullptr; int xLe = 0;   // cross-attention scores / probabilities [B, H, K, Le]
     int* seq[2] = {nullptr, nullptr};      // running sequences [R, T]
     int* fin_seq[2] = {nullptr, nullptr};  // finished sequences [R, T]
     int* src[2] = {nullptr, nullptr};      // KV-cache row indirection [R, T]
@@ -155,9 +156,9 @@ void free_gen_ws(GenWs* g) {
     for (void* p : g->allocs) cudaFree(p);
     delete g;
 }
-static GenWs* get_gen_ws(Engine* e, int R, int T, int K, int B, int cand_cap) {
+static GenWs* get_gen_ws(Engine* e, int R, int T, int K, int B, int cand_cap, int Le) {
     GenWs* g = e->gen;
-    if (g && g->Rm >= R && g->Tm >= T && g->Km >= K && g->Bm >= B && g->scr_cap >= cand_cap) return g;
+    if (g && g->Rm >= R && g->Tm >= T && g->Km >= K && g->Bm >= B && g->scr_cap >= cand_cap && g->xLe >= Le) return g;
     if (g) { P5_CUDA(cudaStreamSynchronize(e->st)); free_gen_ws(g); e->gen = nullptr; }
     g = new GenWs();
     auto al = [&](size_t bytes) { void* p = nullptr; P5_CUDA(cudaMalloc(&p, bytes ? bytes : 256)); g->allocs.push_back(p); return p; };
@@ -171,6 +172,9 @@ static GenWs* get_gen_ws(Engine* e, int R, int T, int K, int B, int cand_cap) {
     g->Kc.resize(e->ND); g->Vc.resize(e->ND);
     for (int l = 0; l < e->ND; ++l) { g->Kc[l] = al((size_t)R * T * A * es); g->Vc[l] = al((size_t)R * T * A * es); }
     g->logits = (float*)al((size_t)R * e->Vpad * 4);
+    g->xLe = Le;
+    g->xS = (float*)al((size_t)R * e->H * Le * 4);
+    g->xP = al((size_t)R * e->H * Le * es);
     g->rowmax = (float*)al((size_t)R * 4); g->logsum = (float*)al((size_t)R * 4);
     for (int i = 0; i < 2; ++i) {
         g->seq[i] = (int*)al((size_t)R * T * 4); g->fin_seq[i] = (int*)al((size_t)R * T * 4);
@@ -528,7 +532,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         if (trie->h_tok[k] == 0) root_child = trie->h_node[k];
     P5_CHECK(root_child >= 0, "trie paths must start with the decoder start token 0");
     const int cand_cap = K * (trie->max_fanout > 0 ? trie->max_fanout : 1);
-    GenWs* g = get_gen_ws(e, R, T, K, B, cand_cap);
+    GenWs* g = get_gen_ws(e, R, T, K, B, cand_cap, (int)round_up(Le_user, 8));
 
     // ---- encoder once per user (eval mode) + cross K/V once per user
     e->set_geometry(B, Le_user, 1);
@@ -591,6 +595,25 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
             resid_gemm(g->ctx, A, w.sa.o, d, A);
             rmsnorm_fwd(g->y, e->P + w.ln1, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
             e->linear_fwd(g->n, d, w.ca.q, A, d, R, g->cq, dt, A, 0, 1.f, nullptr, nullptr, none);
+            if (dt == DT_BF16) {
+                // cross-attention on the tensor cores: the K beams of a user are the M rows of one batched GEMM per
+                // (user, head) against that user's cross K/V (stored once per user): S = Q K^T -> softmax -> P V
+                const int64_t KL = (int64_t)K * Le;
+                GemmProblem sp;
+                sp.M = K; sp.N = Le; sp.K = 64; sp.nb1 = H; sp.nb2 = B;
+                sp.A.ptr = g->cq; sp.A.dtype = dt; sp.A.major = MAJOR_K; sp.A.ld = A; sp.A.bs1 = 64; sp.A.bs2 = (int64_t)K * A;
+                sp.B.ptr = e->ckv[l]; sp.B.dtype = dt; sp.B.major = MAJOR_K; sp.B.ld = 2 * A; sp.B.bs1 = 64; sp.B.bs2 = (int64_t)Le * 2 * A;
+                sp.epi.C = g->xS; sp.epi.c_dtype = DT_F32; sp.epi.ldc = Le; sp.epi.cs1 = KL; sp.epi.cs2 = KL * H;
+                e->gemm(sp);
+                softmax_fwd(g->xS, nullptr, e->mask_e, g->xP, nullptr, dt, B, H, K, Le, 0, none, st);
+                GemmProblem pv;
+                pv.M = K; pv.N = 64; pv.K = Le; pv.nb1 = H; pv.nb2 = B;
+                pv.A.ptr = g->xP; pv.A.dtype = dt; pv.A.major = MAJOR_K; pv.A.ld = Le; pv.A.bs1 = KL; pv.A.bs2 = KL * H;
+                pv.B.ptr = (const char*)e->ckv[l] + (size_t)A * e->esz(); pv.B.dtype = dt; pv.B.major = MAJOR_MN; pv.B.ld = 2 * A;
+                pv.B.bs1 = 64; pv.B.bs2 = (int64_t)Le * 2 * A;
+                pv.epi.C = g->ctx; pv.epi.c_dtype = dt; pv.epi.ldc = A; pv.epi.cs1 = 64; pv.epi.cs2 = (int64_t)K * A;
+                e->gemm(pv);
+            } else {
             AttnArgs a;   // the K beams of a user are the query rows against that user's cross K/V
             a.B = B; a.H = H; a.Lq = K; a.Lk = Le;
             a.q = {g->cq, dt, A, (int64_t)K * A};
@@ -599,6 +622,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
             a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0; a.key_mask = e->mask_e; a.causal = 0; a.q_pos_offset = 0;
             a.row_map = nullptr;
             attn_simt_fwd(a, g->ctx, dt, A, (int64_t)K * A, nullptr, st);
+            }
             resid_gemm(g->ctx, A, w.ca.o, d, A);
             rmsnorm_fwd(g->y, e->P + w.ln2, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
             if (!e->gated) {
