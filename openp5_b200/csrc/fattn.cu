@@ -7,7 +7,7 @@
 //   warp 0    : TMA producer (K, V per pair; Q per tile)
 //   warp 1    : MMA issuer.  pass 1: S_blk = Q K_blk^T (128x128x64) per 128-key block -> TMEM (double buffered)
 //               pass 2: S_blk again, then O += P_blk V_blk (128x64x128) with P_blk read from smem
-//   warp 2    : TMEM allocator (2 x 128 columns S + 64 columns O)
+//   warp 2    : TMEM allocator (3 x 128 columns S + 64 columns O)
 //   warps 4-19: softmax, four warpgroups.  thread = (query row, 32 of the 128 key columns of a block); four warps per
 //               scheduler hide the ALU / MUFU / LDS latencies of the softmax arithmetic.
 //               pass 1: row max / sum (online over blocks; the two halves are combined through smem);
@@ -26,6 +26,7 @@ static constexpr int NWG = 4;              // softmax warpgroups: each owns 128 
 static constexpr int FA_THREADS = 128 + NWG * 128;   // 4 control warps + NWG softmax warpgroups
 static constexpr int QT = 128;      // query rows per tile
 static constexpr int KB = 128;      // keys per block
+static constexpr int NSB = 3;       // S = Q K^T buffers in TMEM (3 x 128 columns + 64 columns of O <= 512)
 
 struct FaParams {
     int B, H, Lq, Lk, nkb, nqt, nq_buf;
@@ -59,13 +60,13 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t kv_full = bar, kv_empty = bar + 8;
     auto q_full = [&](int i) { return bar + 16 + 8 * i; };
     auto q_empty = [&](int i) { return bar + 32 + 8 * i; };
-    auto s_full = [&](int i) { return bar + 48 + 8 * i; };
-    auto s_empty = [&](int i) { return bar + 64 + 8 * i; };
-    auto p_full = [&](int i) { return bar + 80 + 8 * i; };
-    auto p_empty = [&](int i) { return bar + 96 + 8 * i; };
-    const uint32_t o_full = bar + 112, o_empty = bar + 120, bm_full = bar + 128, bm_empty = bar + 136;
-    const uint32_t tmem_holder = bar + 144;
-    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 144);
+    auto s_full = [&](int i) { return bar + 48 + 8 * i; };     // NSB score buffers in TMEM (deeper MMA prefetch)
+    auto s_empty = [&](int i) { return bar + 72 + 8 * i; };
+    auto p_full = [&](int i) { return bar + 96 + 8 * i; };
+    auto p_empty = [&](int i) { return bar + 112 + 8 * i; };
+    const uint32_t o_full = bar + 128, o_empty = bar + 136, bm_full = bar + 144, bm_empty = bar + 152;
+    const uint32_t tmem_holder = bar + 160;
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 160);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pairs = P.B * P.H;
@@ -76,9 +77,9 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1);
-            mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4 * NWG);
             mbar_init(p_full(i), 4 * NWG); mbar_init(p_empty(i), 1);
         }
+        for (int i = 0; i < NSB; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4 * NWG); }
         mbar_init(o_full, 1); mbar_init(o_empty, 4 * NWG);
         mbar_init(bm_full, 1); mbar_init(bm_empty, 4 * NWG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -89,8 +90,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder_ptr;
-    const uint32_t tS[2] = {tmem, tmem + 128};
-    const uint32_t tO = tmem + 256;
+    const uint32_t tS[NSB] = {tmem, tmem + 128, tmem + 256};
+    const uint32_t tO = tmem + 384;
 
     if (warp == 0) {
         // ========================= TMA producer =========================
@@ -128,7 +129,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                                      ((uint32_t)(128 >> 4) << 24);
-            uint32_t kv_ph = 0, q_ph[2] = {0, 0}, se_ph[2] = {0, 0}, pf_ph[2] = {0, 0}, oe_ph = 0;
+            uint32_t kv_ph = 0, q_ph[2] = {0, 0}, se_ph[NSB] = {0, 0, 0}, pf_ph[2] = {0, 0}, oe_ph = 0;
             int qb = 0, sb = 0, pb = 0;
             auto issue_s = [&](int kb, uint32_t q_addr) {
                 mbar_wait(s_empty(sb), se_ph[sb] ^ 1);
@@ -139,7 +140,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     umma_bf16(tS[sb], make_smem_desc(q_addr + k * 32, 16, 1024),
                               make_smem_desc(sK + kb * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
                 umma_commit(s_full(sb));
-                sb ^= 1;
+                sb = (sb + 1) % NSB;
             };
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int len = P.lens ? P.lens[pair / P.H] : Lk;
@@ -203,7 +204,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int sw = warp & 3;
         const int r = sw * 32 + lane;                     // row of the query tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
-        uint32_t sf_ph[2] = {0, 0}, pe_ph[2] = {0, 0}, of_ph = 0, bm_ph = 0;
+        uint32_t sf_ph[NSB] = {0, 0, 0}, pe_ph[2] = {0, 0}, of_ph = 0, bm_ph = 0;
         int sb = 0, pb = 0;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
@@ -247,7 +248,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s_empty(sb));
-                    sb ^= 1;
+                    sb = (sb + 1) % NSB;
                 }
                 // combine the column slices of the row
                 stat_s[wg * QT + r] = make_float2(m, l);
@@ -322,7 +323,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(s_empty(sb)); mbar_arrive(p_full(pb)); }
-                    sb ^= 1;
+                    sb = (sb + 1) % NSB;
                     pb ^= 1;
                 }
                 // ---------------- O -> ctx (this warpgroup writes 16 of the 64 head columns)
