@@ -612,6 +612,140 @@ softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __
     }
 }
 
+// raw register form of a loaded probability pair: bf16 pairs stay packed (one register) until they are used
+template <typename T> struct PairRaw;
+template <> struct PairRaw<float> {
+    float2 v;
+    __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float2*>(p); }
+    __device__ __forceinline__ void keep(bool c0, bool c1) { v.x = c0 ? v.x : 0.f; v.y = c1 ? v.y : 0.f; }
+    __device__ __forceinline__ float2 get() const { return v; }
+};
+template <> struct PairRaw<bf16> {
+    uint32_t v;
+    __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint32_t*>(p); }
+    __device__ __forceinline__ void keep(bool c0, bool c1) { v &= (c0 ? 0x0000ffffu : 0u) | (c1 ? 0xffff0000u : 0u); }
+    __device__ __forceinline__ float2 get() const { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
+};
+
+// Square (Lq == Lk == 64 * NP) fast path of softmax_bwd for the encoder self-attention.  Two things made the generic
+// kernel slow (ncu: 0.33 IPC, 78 regs, 16 ATOMS.CAST.SPIN loops per lane per row pair): nested bounds branches kept
+// the loads from being batched, and the relative-bias gradient went through shared-memory float atomics.  Here
+//  * every load of a row pair is issued up front, validity is applied with selects (no branches in the row loop);
+//  * lane slots are SKEWED by the row: slot q of row pair m covers column pair (q + m) mod L/2, so j - i of a slot
+//    is constant (2q-1, 2q, 2q+1) while the warp walks down the rows and the diagonal sums stay in registers; they
+//    are flushed to shared memory only when a slot wraps around (once per slot) and at the end.
+template <typename T, int NP>
+__global__ void __launch_bounds__(256, (NP <= 4 ? 3 : 2))
+softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __restrict__ dS, T* __restrict__ Pd_out,
+                      float* __restrict__ dbias_rel, int H, int L, DropCfg drop, const int* __restrict__ lens) {
+    extern __shared__ float sdb[];  // [2L - 1]
+    const int bh = blockIdx.x, h = bh % H;
+    const int len = lens ? lens[bh / H] : L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int HALF = 32 * NP;   // column pairs per row
+    const int n_delta = 2 * L - 1;
+    if (dbias_rel) {
+        for (int e = threadIdx.x; e < n_delta; e += blockDim.x) sdb[e] = 0.f;
+        __syncthreads();
+    }
+    float acc[NP][3];
+    bool wprev[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = 0.f; wprev[k] = false; }
+    auto flush = [&](int k) {
+        const int base = 2 * (lane + 32 * k) - 1 - (wprev[k] ? L : 0) + L - 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = acc[k][c];
+            const int dl = base + c;
+            if (v != 0.f && dl >= 0 && dl < n_delta) atomicAdd(&sdb[dl], v);
+            acc[k][c] = 0.f;
+        }
+    };
+    for (int m = blockIdx.y * nw + warp; m < HALF; m += nw * gridDim.y) {
+        const int i0 = 2 * m;
+        const int64_t row0 = ((int64_t)bh * L + i0) * L;
+        if (i0 >= len) {   // warp-uniform: both rows lie outside the sequence -> exact zeros
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const int64_t off = row0 + (int64_t)rr * L + 2 * (lane + 32 * k);
+                    st_pair<T>(dS + off, 0.f, 0.f);
+                    if (Pd_out) st_pair<T>(Pd_out + off, 0.f, 0.f);
+                }
+            continue;
+        }
+        const T* __restrict__ Pr = P + row0;
+        const float* __restrict__ Gr = dPd + row0;
+        T* __restrict__ dSr = dS + row0;
+        T* __restrict__ Pdr = Pd_out ? Pd_out + row0 : nullptr;
+        const uint32_t pair0 = (uint32_t)((uint64_t)row0 >> 1);   // pair index of the row start (B*H*L*L/2 < 2^32)
+        PairRaw<T> pp[2][NP];
+        float2 g[2][NP];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const int o = rr * L + 2 * ((lane + 32 * k + m) & (HALF - 1));
+                pp[rr][k].load(Pr + o);
+                g[rr][k] = *reinterpret_cast<const float2*>(Gr + o);
+            }
+        float dot[2] = {0.f, 0.f};
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const bool rv = i0 + rr < len;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const int j = 2 * ((lane + 32 * k + m) & (HALF - 1));
+                const int o = rr * L + j;
+                const bool c0 = rv && j < len, c1 = rv && j + 1 < len;
+                pp[rr][k].keep(c0, c1);
+                const float2 pv = pp[rr][k].get();
+                const float p0 = pv.x, p1 = pv.y;
+                float g0 = c0 ? g[rr][k].x : 0.f, g1 = c1 ? g[rr][k].y : 0.f;
+                if (drop.thr) {
+                    bool k0, k1;
+                    drop_pair(drop, (uint64_t)(pair0 + (uint32_t)(o >> 1)), k0, k1);
+                    g0 = k0 ? g0 * drop.inv_keep : 0.f;
+                    g1 = k1 ? g1 * drop.inv_keep : 0.f;
+                    if (Pdr) st_pair<T>(Pdr + o, k0 ? p0 * drop.inv_keep : 0.f, k1 ? p1 * drop.inv_keep : 0.f);
+                } else if (Pdr) {
+                    st_pair<T>(Pdr + o, p0, p1);
+                }
+                g[rr][k] = make_float2(g0, g1);
+                dot[rr] += g0 * p0 + g1 * p1;
+            }
+        }
+        dot[0] = warp_sum(dot[0]);
+        dot[1] = warp_sum(dot[1]);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const int qm = lane + 32 * k + m;
+            const int j = 2 * (qm & (HALF - 1));
+            const bool w = qm >= HALF;
+            if (dbias_rel && w != wprev[k]) { flush(k); wprev[k] = w; }
+            const float2 pe = pp[0][k].get(), po = pp[1][k].get();
+            const float e0 = pe.x * (g[0][k].x - dot[0]), e1 = pe.y * (g[0][k].y - dot[0]);   // row 2m
+            const float o0 = po.x * (g[1][k].x - dot[1]), o1 = po.y * (g[1][k].y - dot[1]);   // row 2m+1
+            st_pair<T>(dSr + j, e0, e1);
+            st_pair<T>(dSr + L + j, o0, o1);
+            acc[k][0] += o0;          // j - i = 2q - 1
+            acc[k][1] += e0 + o1;     //         2q
+            acc[k][2] += e1;          //         2q + 1
+        }
+    }
+    if (dbias_rel) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) flush(k);
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_delta; e += blockDim.x) {
+            const float v = sdb[e];
+            if (v != 0.f) atomicAdd(dbias_rel + h * n_delta + e, v);
+        }
+    }
+}
+
 // d(bias_rel)[h, j - i + Lq - 1] += sum_{b, i} dS[b, h, i, j]: thread = diagonal, rows streamed with coalesced loads,
 // register accumulation, one global atomic per (CTA, diagonal).  (Doing this with shared-memory atomics inside
 // softmax_bwd cost more than the softmax itself: 8 ATOMS per lane per row.)
@@ -645,8 +779,21 @@ void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dt
                  int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens) {
     if (B <= 0) return;
     P5_CHECK(Lk <= 64 * SM_MAXP && (Lk % 2) == 0, "softmax_bwd: Lk must be even and <= 512");
-    dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     const size_t sm = (size_t)(Lq + Lk) * sizeof(float);
+    static const bool generic_only = getenv("P5_SMBWD_GENERIC") != nullptr;
+    if (Lq == Lk && (Lk == 64 || Lk == 128 || Lk == 256 || Lk == 512) && !generic_only) {
+        dim3 g2((unsigned)(B * H), (unsigned)(Lk >= 256 ? 4 : (Lk >= 128 ? 2 : 1)));
+#define P5_SMBWD_SQ(TT, NPV) softmax_bwd_sq_kernel<TT, NPV><<<g2, 256, sm, st>>>(dPd, (const TT*)P, (TT*)dS, (TT*)Pd_out, dbias_rel, H, Lk, drop, lens)
+        if (dtype == DT_F32) {
+            if (Lk == 64) P5_SMBWD_SQ(float, 1); else if (Lk == 128) P5_SMBWD_SQ(float, 2); else if (Lk == 256) P5_SMBWD_SQ(float, 4); else P5_SMBWD_SQ(float, 8);
+        } else {
+            if (Lk == 64) P5_SMBWD_SQ(bf16, 1); else if (Lk == 128) P5_SMBWD_SQ(bf16, 2); else if (Lk == 256) P5_SMBWD_SQ(bf16, 4); else P5_SMBWD_SQ(bf16, 8);
+        }
+#undef P5_SMBWD_SQ
+        LAUNCHED();
+        return;
+    }
+    dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     if (dtype == DT_F32) {
         if (Lk <= 256) softmax_bwd_kernel<float, 4><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
         else softmax_bwd_kernel<float, 8><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
