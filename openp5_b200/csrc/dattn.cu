@@ -1,0 +1,535 @@
+// Decoder attention of the TRAIN step in bf16 mode (HF:models/t5/modeling_t5.py:253-344, T5Attention called from the
+// decoder T5LayerSelfAttention / T5LayerCrossAttention): Lq = Ld <= 16 query rows per sequence, Lk <= 512 keys.
+//
+// Why its own kernel: with 8 target tokens per user a (b, h) pair has 8 x Lk scores.  A tcgen05 tile needs 128 query
+// rows (16x padding, three launches with S round-tripped through HBM), and the fp32 SIMT kernel spent 53 us forward /
+// 110 us backward per layer on the cross-attention issuing scalar FMAs.  Here one CTA owns a (b, h) pair and runs the
+// four contractions on m16n8k16 mma.sync tiles (the query block is exactly one M=16 tile), everything else in
+// registers:
+//   * Q / K / dO / V fragments are loaded straight from global memory with 2 x 16-byte loads per row.  The d_kv = 64
+//     contraction index is PERMUTED (thread t of a quad owns d in [16t, 16t+16)), which is legal because A and B use
+//     the same permutation and a dot product does not care about the order of its terms;
+//   * each warp owns a contiguous key range; softmax statistics are combined across warps through shared memory;
+//   * P (forward) and dS (backward) go from the accumulator layout directly into the A operand of P.V / dS.K;
+//   * V (forward) / K (backward) are staged once in shared memory with cp.async (128-byte rows, 16-byte chunks XOR-
+//     swizzled by row) and read with ldmatrix.trans as B operands; dV = Pd^T dO and dK = dS^T Q read Pd / dS back from
+//     a per-warp shared tile with ldmatrix.trans (transposed A operand);
+//   * dropout uses the same counter hash and element index as attn_simt_* so forward and backward agree by
+//     construction; gradients are written as bf16 in place (no fp32 staging buffer, no cast, no memset).
+#include "kernels.cuh"
+#include <float.h>
+
+namespace p5 {
+extern int g_launches;
+#define LAUNCHED() do { P5_CUDA(cudaGetLastError()); ++g_launches; } while (0)
+
+namespace {
+
+struct DAttnDev {
+    int B, H, Lq, Lk;
+    const bf16 *q, *k, *v;
+    int64_t q_ld, q_bs, k_ld, k_bs, v_ld, v_bs;
+    const float* bias_rel; int bias_off, n_delta;
+    const int* key_mask;
+    int causal;
+    const int* kv_off; const int* kv_len;
+    DropCfg drop;
+};
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(saddr), "l"(g));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 16 consecutive bf16 (32 bytes) of one row as 8 packed pairs; zeros when !ok
+__device__ __forceinline__ void ld_row16(uint32_t (&r)[8], const bf16* p, bool ok) {
+    uint4 x = make_uint4(0, 0, 0, 0), y = make_uint4(0, 0, 0, 0);
+    if (ok) {
+        x = *reinterpret_cast<const uint4*>(p);
+        y = *reinterpret_cast<const uint4*>(p + 8);
+    }
+    r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w; r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
+}
+
+// swizzled [rows][64] bf16 tile: byte offset of 16-byte chunk c of row r
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// stage rows [key0, key0 + nrows) of a [*, 64]-column slice into a swizzled tile at local rows [lrow0, ...); rows >= Lk are zero
+__device__ __forceinline__ void stage_rows(uint8_t* tile, int lrow0, const bf16* src, int64_t ld, int key0, int nrows, int Lk,
+                                           int lane) {
+    for (int e = lane; e < nrows * 8; e += 32) {
+        const int r = e >> 3, c = e & 7;
+        uint8_t* dst = tile + swz(lrow0 + r, c);
+        if (key0 + r < Lk) cp_async16(smem_u32(dst), src + (int64_t)(key0 + r) * ld + c * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+struct ScoreCtx {
+    int Lq, Lk, LkMask, causal, bias_off, n_delta;
+    const float* bias;      // bias_rel + h * n_delta or null
+    const int* mask;        // key_mask + b * a.Lk or null
+};
+__device__ __forceinline__ bool score_valid(const ScoreCtx& c, int r, int j) {
+    return r < c.Lq && j < c.Lk && (!c.causal || j <= r) && (!c.mask || c.mask[j] != 0);
+}
+__device__ __forceinline__ int bias_index(const ScoreCtx& c, int r, int j) {
+    int di = j - r + c.bias_off;
+    return di < 0 ? 0 : (di >= c.n_delta ? c.n_delta - 1 : di);
+}
+
+// S (or dPd) tiles of this warp: acc[nt] += A(rows of the query block, fragments lo/hi) . B(rows key0 + 8 nt + g)^T
+template <int NT, bool LQ16>
+__device__ __forceinline__ void qk_tiles(float (&acc)[NT][4], const uint32_t (&alo)[8], const uint32_t (&ahi)[8], const bf16* kbase,
+                                         int64_t ld, int key0, int ntw, int Lk, int g, int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        if (nt < ntw) {
+            const int j = key0 + 8 * nt + g;
+            uint32_t kr[8];
+            ld_row16(kr, kbase + (int64_t)j * ld + 16 * t, j < Lk);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                mma16816(acc[nt], alo[2 * s], LQ16 ? ahi[2 * s] : 0u, alo[2 * s + 1], LQ16 ? ahi[2 * s + 1] : 0u, kr[2 * s],
+                         kr[2 * s + 1]);
+        }
+    }
+}
+
+// acc[8 d-tiles] += A(P or dS in accumulator layout, this warp's keys) . B(tile rows = keys, via ldmatrix.trans)
+template <int NT>
+__device__ __forceinline__ void pv_tiles(float (&o)[8][4], const float (&p)[NT][4], const uint8_t* tile, int lrow0, int ntw, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+        if (2 * kk < ntw) {
+            const uint32_t a0 = pack_bf16(p[2 * kk][0], p[2 * kk][1]), a1 = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+            const uint32_t a2 = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]), a3 = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+            const int row = lrow0 + 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(b0, b1, b2, b3, smem_u32(tile + swz(row, 2 * c2 + (lane >> 4))));
+                mma16816(o[2 * c2], a0, a1, a2, a3, b0, b1);
+                mma16816(o[2 * c2 + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+    }
+}
+
+template <int NT, int NW> struct DCfg {
+    static constexpr int KW = NT * 8;                          // max keys per warp
+    static constexpr int TILE = NW * KW * 128;                 // staged K or V rows (bytes)
+    static constexpr int ORED = NW * 16 * 64 * 4;              // cross-warp partial outputs (fp32)
+    static constexpr int PSTRIDE = (KW + 8) * 2;               // bytes per query row of the per-warp Pd / dS tiles
+    static constexpr int FWD_SMEM = (TILE > ORED ? TILE : ORED) + NW * 16 * 2 * 4;
+    static constexpr int BWD_SMEM = TILE + ORED + 2 * 16 * 128 + NW * 2 * 16 * PSTRIDE + NW * 16 * 4;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// forward: O[b, i, h*64 + c] (bf16) and LSE[b, h, i]
+// ------------------------------------------------------------------------------------------------------------
+template <int NT, int NW, bool LQ16>
+__global__ void __launch_bounds__(NW * 32)
+dattn_fwd_kernel(DAttnDev a, bf16* __restrict__ O, int64_t ld_o, int64_t bs_o, float* __restrict__ lse) {
+    using C = DCfg<NT, NW>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* Vs = smem;                                              // later aliased by the fp32 partial outputs
+    float* red = reinterpret_cast<float*>(smem + (C::TILE > C::ORED ? C::TILE : C::ORED));   // [2][NW][16]
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int Lk = a.kv_len ? a.kv_len[b] : a.Lk;
+    const int64_t k_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.k_ld : (int64_t)b * a.k_bs;
+    const int64_t v_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.v_ld : (int64_t)b * a.v_bs;
+    const int kpw = min(C::KW, (((Lk + NW - 1) / NW) + 15) & ~15);   // keys per warp (multiple of 16)
+    const int key0 = warp * kpw, ntw = kpw >> 3;
+    const bf16* kb = a.k + k_boff + h * 64;
+    const bf16* vb = a.v + v_boff + h * 64;
+
+    stage_rows(Vs, warp * C::KW, vb, a.v_ld, key0, kpw, Lk, lane);     // V rows of this warp -> smem (async)
+
+    uint32_t qlo[8], qhi[8];
+    const bf16* qb = a.q + (int64_t)b * a.q_bs + h * 64 + 16 * t;
+    ld_row16(qlo, qb + (int64_t)g * a.q_ld, g < a.Lq);
+    if (LQ16) ld_row16(qhi, qb + (int64_t)(g + 8) * a.q_ld, g + 8 < a.Lq);
+
+    float s[NT][4];
+    qk_tiles<NT, LQ16>(s, qlo, qhi, kb, a.k_ld, key0, ntw, Lk, g, t);
+
+    ScoreCtx sc{a.Lq, Lk, a.Lk, a.causal, a.bias_off, a.n_delta, a.bias_rel ? a.bias_rel + h * a.n_delta : nullptr,
+                a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr};
+    float mx[2] = {-FLT_MAX, -FLT_MAX};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = g + 8 * (e >> 1), j = key0 + 8 * nt + 2 * t + (e & 1);
+            float v = -FLT_MAX;
+            if (nt < ntw && (LQ16 || e < 2) && score_valid(sc, r, j)) v = s[nt][e] + (sc.bias ? sc.bias[bias_index(sc, r, j)] : 0.f);
+            s[nt][e] = v;
+            mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 1));
+        mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 2));
+    }
+    if (NW > 1) {
+        if (t == 0) { red[warp * 16 + g] = mx[0]; red[warp * 16 + g + 8] = mx[1]; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { mx[0] = fmaxf(mx[0], red[w * 16 + g]); mx[1] = fmaxf(mx[1], red[w * 16 + g + 8]); }
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = (s[nt][e] == -FLT_MAX) ? 0.f : __expf(s[nt][e] - mx[e >> 1]);
+            s[nt][e] = p;
+            sum[e >> 1] += p;
+        }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], 1);
+        sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], 2);
+    }
+    if (NW > 1) {
+        float* red2 = red + NW * 16;
+        if (t == 0) { red2[warp * 16 + g] = sum[0]; red2[warp * 16 + g + 8] = sum[1]; }
+        __syncthreads();
+        sum[0] = sum[1] = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { sum[0] += red2[w * 16 + g]; sum[1] += red2[w * 16 + g + 8]; }
+    }
+    if (warp == 0 && t == 0 && lse) {
+        if (g < a.Lq) lse[((int64_t)b * a.H + h) * a.Lq + g] = mx[0] + logf(sum[0]);
+        if (LQ16 && g + 8 < a.Lq) lse[((int64_t)b * a.H + h) * a.Lq + g + 8] = mx[1] + logf(sum[1]);
+    }
+    const float inv[2] = {sum[0] > 0.f ? 1.f / sum[0] : 0.f, sum[1] > 0.f ? 1.f / sum[1] : 0.f};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = g + 8 * (e >> 1), j = key0 + 8 * nt + 2 * t + (e & 1);
+            float p = s[nt][e] * inv[e >> 1];
+            if (a.drop.thr && p != 0.f) {
+                const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + r) * (uint64_t)Lk + j;
+                p = drop_keep(a.drop.seed, a.drop.site, idx, a.drop.thr) ? p * a.drop.inv_keep : 0.f;
+            }
+            s[nt][e] = p;
+        }
+    // ---- O = P V
+    float o[8][4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c][0] = o[c][1] = o[c][2] = o[c][3] = 0.f;
+    cp_async_wait_all();
+    __syncwarp();
+    pv_tiles<NT>(o, s, Vs, warp * C::KW, ntw, lane);
+    if (NW > 1) {
+        __syncthreads();                       // every warp is done with its V rows: reuse the tile for the partial sums
+        float* part = reinterpret_cast<float*>(smem);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<float2*>(part + (warp * 16 + g) * 64 + 8 * c + 2 * t) = make_float2(o[c][0], o[c][1]);
+            *reinterpret_cast<float2*>(part + (warp * 16 + g + 8) * 64 + 8 * c + 2 * t) = make_float2(o[c][2], o[c][3]);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 16 * 8; e += NW * 32) {      // (row, 8-column chunk)
+            const int r = e >> 3, c8 = (e & 7) * 8;
+            if (r >= a.Lq) continue;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] += part[(w * 16 + r) * 64 + c8 + q];
+            uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(O + (int64_t)b * bs_o + (int64_t)r * ld_o + h * 64 + c8) = pk;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            bf16* op = O + (int64_t)b * bs_o + h * 64 + 8 * c + 2 * t;
+            if (g < a.Lq) *reinterpret_cast<uint32_t*>(op + (int64_t)g * ld_o) = pack_bf16(o[c][0], o[c][1]);
+            if (LQ16 && g + 8 < a.Lq) *reinterpret_cast<uint32_t*>(op + (int64_t)(g + 8) * ld_o) = pack_bf16(o[c][2], o[c][3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward: P recomputed from LSE; dQ, dK, dV written as bf16; d(bias_rel) accumulated atomically (self-attention)
+// ------------------------------------------------------------------------------------------------------------
+template <int NT, int NW, bool LQ16>
+__global__ void __launch_bounds__(NW * 32)
+dattn_bwd_kernel(DAttnDev a, const bf16* __restrict__ dO, int64_t ld_do, int64_t bs_do, const float* __restrict__ lse,
+                 bf16* __restrict__ dQ, int64_t ld_dq, int64_t bs_dq, bf16* __restrict__ dK, bf16* __restrict__ dV, int64_t ld_dkv,
+                 int64_t bs_dkv, float* __restrict__ dbias_rel) {
+    using C = DCfg<NT, NW>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* Ks = smem;                                               // [NW*KW][64] swizzled
+    float* part = reinterpret_cast<float*>(smem + C::TILE);           // [NW][16][64] dQ partials
+    uint8_t* Qs = smem + C::TILE + C::ORED;                           // [16][64] swizzled
+    uint8_t* dOs = Qs + 16 * 128;                                     // [16][64] swizzled
+    uint8_t* PdS = dOs + 16 * 128;                                    // per warp: Pd [16][KW+8], dS [16][KW+8] (bf16)
+    float* red = reinterpret_cast<float*>(PdS + NW * 2 * 16 * C::PSTRIDE);   // [NW][16]
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int Lk = a.kv_len ? a.kv_len[b] : a.Lk;
+    const int64_t k_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.k_ld : (int64_t)b * a.k_bs;
+    const int64_t v_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.v_ld : (int64_t)b * a.v_bs;
+    const int64_t dkv_boff = a.kv_off ? (int64_t)a.kv_off[b] * ld_dkv : (int64_t)b * bs_dkv;
+    const int kpw = min(C::KW, (((Lk + NW - 1) / NW) + 15) & ~15);
+    const int key0 = warp * kpw, ntw = kpw >> 3;
+    const bf16* kb = a.k + k_boff + h * 64;
+    const bf16* vb = a.v + v_boff + h * 64;
+    const bf16* qb = a.q + (int64_t)b * a.q_bs + h * 64;
+    const bf16* gb = dO + (int64_t)b * bs_do + h * 64;
+
+    stage_rows(Ks, warp * C::KW, kb, a.k_ld, key0, kpw, Lk, lane);      // K rows of this warp (B operand of dQ = dS K)
+    for (int e = threadIdx.x; e < 2 * 16 * 8; e += NW * 32) {             // Q and dO tiles (B operands of dK, dV)
+        const int which = e >> 7, r = (e >> 3) & 15, c = e & 7;
+        uint8_t* dst = (which ? dOs : Qs) + swz(r, c);
+        const bf16* src = which ? gb + (int64_t)r * ld_do : qb + (int64_t)r * a.q_ld;
+        if (r < a.Lq) cp_async16(smem_u32(dst), src + c * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+
+    uint32_t alo[8], ahi[8];
+    float s[NT][4], dp[NT][4];
+    ld_row16(alo, qb + (int64_t)g * a.q_ld + 16 * t, g < a.Lq);
+    if (LQ16) ld_row16(ahi, qb + (int64_t)(g + 8) * a.q_ld + 16 * t, g + 8 < a.Lq);
+    qk_tiles<NT, LQ16>(s, alo, ahi, kb, a.k_ld, key0, ntw, Lk, g, t);               // S = Q K^T
+    ld_row16(alo, gb + (int64_t)g * ld_do + 16 * t, g < a.Lq);
+    if (LQ16) ld_row16(ahi, gb + (int64_t)(g + 8) * ld_do + 16 * t, g + 8 < a.Lq);
+    qk_tiles<NT, LQ16>(dp, alo, ahi, vb, a.v_ld, key0, ntw, Lk, g, t);              // dPd = dO V^T
+
+    ScoreCtx sc{a.Lq, Lk, a.Lk, a.causal, a.bias_off, a.n_delta, a.bias_rel ? a.bias_rel + h * a.n_delta : nullptr,
+                a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr};
+    float l[2] = {0.f, 0.f};
+    if (g < a.Lq) l[0] = lse[((int64_t)b * a.H + h) * a.Lq + g];
+    if (LQ16 && g + 8 < a.Lq) l[1] = lse[((int64_t)b * a.H + h) * a.Lq + g + 8];
+    // p, pd (-> dp slot keeps dP), delta
+    float dlt[2] = {0.f, 0.f};
+    uint8_t* Pd_w = PdS + warp * 2 * 16 * C::PSTRIDE;
+    uint8_t* dS_w = Pd_w + 16 * C::PSTRIDE;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        float pd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = g + 8 * (e >> 1), j = key0 + 8 * nt + 2 * t + (e & 1);
+            float p = 0.f, gdp = 0.f;
+            pd[e] = 0.f;
+            if (nt < ntw && (LQ16 || e < 2) && score_valid(sc, r, j)) {
+                p = __expf(s[nt][e] + (sc.bias ? sc.bias[bias_index(sc, r, j)] : 0.f) - l[e >> 1]);
+                gdp = dp[nt][e];
+                pd[e] = p;
+                if (a.drop.thr) {
+                    const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + r) * (uint64_t)Lk + j;
+                    const bool keep = drop_keep(a.drop.seed, a.drop.site, idx, a.drop.thr);
+                    pd[e] = keep ? p * a.drop.inv_keep : 0.f;
+                    gdp = keep ? gdp * a.drop.inv_keep : 0.f;
+                }
+            }
+            s[nt][e] = p;
+            dp[nt][e] = gdp;
+            dlt[e >> 1] += p * gdp;
+        }
+        if (nt < ntw) {     // dropped probabilities -> per-warp tile (A operand of dV = Pd^T dO)
+            *reinterpret_cast<uint32_t*>(Pd_w + g * C::PSTRIDE + (8 * nt + 2 * t) * 2) = pack_bf16(pd[0], pd[1]);
+            *reinterpret_cast<uint32_t*>(Pd_w + (g + 8) * C::PSTRIDE + (8 * nt + 2 * t) * 2) = pack_bf16(pd[2], pd[3]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        dlt[q] += __shfl_xor_sync(0xffffffffu, dlt[q], 1);
+        dlt[q] += __shfl_xor_sync(0xffffffffu, dlt[q], 2);
+    }
+    if (NW > 1) {
+        if (t == 0) { red[warp * 16 + g] = dlt[0]; red[warp * 16 + g + 8] = dlt[1]; }
+        cp_async_wait_all();
+        __syncthreads();               // also publishes the Q / dO tiles
+        dlt[0] = dlt[1] = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { dlt[0] += red[w * 16 + g]; dlt[1] += red[w * 16 + g + 8]; }
+    } else {
+        cp_async_wait_all();
+        __syncwarp();
+    }
+    // dS = P o (dP - delta)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float ds = s[nt][e] * (dp[nt][e] - dlt[e >> 1]);
+            s[nt][e] = ds;
+            if (dbias_rel && ds != 0.f) {
+                const int r = g + 8 * (e >> 1), j = key0 + 8 * nt + 2 * t + (e & 1);
+                atomicAdd(dbias_rel + h * a.n_delta + bias_index(sc, r, j), ds);
+            }
+        }
+        if (nt < ntw) {
+            *reinterpret_cast<uint32_t*>(dS_w + g * C::PSTRIDE + (8 * nt + 2 * t) * 2) = pack_bf16(s[nt][0], s[nt][1]);
+            *reinterpret_cast<uint32_t*>(dS_w + (g + 8) * C::PSTRIDE + (8 * nt + 2 * t) * 2) = pack_bf16(s[nt][2], s[nt][3]);
+        }
+    }
+    __syncwarp();
+    // ---- dQ partial = dS K (this warp's keys)
+    {
+        float o[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c][0] = o[c][1] = o[c][2] = o[c][3] = 0.f;
+        pv_tiles<NT>(o, s, Ks, warp * C::KW, ntw, lane);
+        if (NW > 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                *reinterpret_cast<float2*>(part + (warp * 16 + g) * 64 + 8 * c + 2 * t) = make_float2(o[c][0], o[c][1]);
+                *reinterpret_cast<float2*>(part + (warp * 16 + g + 8) * 64 + 8 * c + 2 * t) = make_float2(o[c][2], o[c][3]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                bf16* op = dQ + (int64_t)b * bs_dq + h * 64 + 8 * c + 2 * t;
+                if (g < a.Lq) *reinterpret_cast<uint32_t*>(op + (int64_t)g * ld_dq) = pack_bf16(o[c][0], o[c][1]);
+                if (LQ16 && g + 8 < a.Lq) *reinterpret_cast<uint32_t*>(op + (int64_t)(g + 8) * ld_dq) = pack_bf16(o[c][2], o[c][3]);
+            }
+        }
+    }
+    // ---- dV = Pd^T dO, dK = dS^T Q for this warp's keys: M = keys (16 per tile), K = 16 query rows, N = 64
+    {
+        uint32_t bq[8][2], bg[8][2];      // B fragments of Q and dO for the 8 d-tiles (k = query row)
+        const int qrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) {
+            ldsm_x4_t(bq[2 * c2][0], bq[2 * c2][1], bq[2 * c2 + 1][0], bq[2 * c2 + 1][1], smem_u32(Qs + swz(qrow, 2 * c2 + (lane >> 4))));
+            ldsm_x4_t(bg[2 * c2][0], bg[2 * c2][1], bg[2 * c2 + 1][0], bg[2 * c2 + 1][1], smem_u32(dOs + swz(qrow, 2 * c2 + (lane >> 4))));
+        }
+        const int arow = (lane & 7) + ((lane >> 4) & 1) * 8;         // query row of the transposed A tiles
+        const int acol = ((lane >> 3) & 1) * 8;                      // key offset inside the 16-key tile
+#pragma unroll
+        for (int mt = 0; mt < NT / 2; ++mt) {
+            if (2 * mt >= ntw) continue;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {               // 0: dV from Pd / dO, 1: dK from dS / Q
+                const uint8_t* At = which ? dS_w : Pd_w;
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4_t(a0, a1, a2, a3, smem_u32(At + arow * C::PSTRIDE + (16 * mt + acol) * 2));
+                float o[8][4];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    o[c][0] = o[c][1] = o[c][2] = o[c][3] = 0.f;
+                    if (which) mma16816(o[c], a0, a1, a2, a3, bq[c][0], bq[c][1]);
+                    else mma16816(o[c], a0, a1, a2, a3, bg[c][0], bg[c][1]);
+                }
+                bf16* out = (which ? dK : dV) + dkv_boff + h * 64;
+                const int j0 = key0 + 16 * mt + g;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (j0 < Lk) *reinterpret_cast<uint32_t*>(out + (int64_t)j0 * ld_dkv + 8 * c + 2 * t) = pack_bf16(o[c][0], o[c][1]);
+                    if (j0 + 8 < Lk) *reinterpret_cast<uint32_t*>(out + (int64_t)(j0 + 8) * ld_dkv + 8 * c + 2 * t) = pack_bf16(o[c][2], o[c][3]);
+                }
+            }
+        }
+    }
+    if (NW > 1) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 16 * 8; e += NW * 32) {
+            const int r = e >> 3, c8 = (e & 7) * 8;
+            if (r >= a.Lq) continue;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] += part[(w * 16 + r) * 64 + c8 + q];
+            uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(dQ + (int64_t)b * bs_dq + (int64_t)r * ld_dq + h * 64 + c8) = pk;
+        }
+    }
+}
+
+DAttnDev to_dev(const AttnArgs& a) {
+    DAttnDev d;
+    d.B = a.B; d.H = a.H; d.Lq = a.Lq; d.Lk = a.Lk;
+    d.q = (const bf16*)a.q.ptr; d.k = (const bf16*)a.k.ptr; d.v = (const bf16*)a.v.ptr;
+    d.q_ld = a.q.ld; d.q_bs = a.q.bs; d.k_ld = a.k.ld; d.k_bs = a.k.bs; d.v_ld = a.v.ld; d.v_bs = a.v.bs;
+    d.bias_rel = a.bias_rel; d.bias_off = a.bias_off; d.n_delta = a.n_delta;
+    d.key_mask = a.key_mask; d.causal = a.causal; d.kv_off = a.kv_off; d.kv_len = a.kv_len; d.drop = a.drop;
+    return d;
+}
+
+template <int NT, int NW, bool LQ16>
+void launch_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
+    constexpr int sm = DCfg<NT, NW>::FWD_SMEM;
+    static bool set = false;
+    if (!set) { P5_CUDA(cudaFuncSetAttribute(dattn_fwd_kernel<NT, NW, LQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); set = true; }
+    dattn_fwd_kernel<NT, NW, LQ16><<<(unsigned)(a.B * a.H), NW * 32, sm, st>>>(to_dev(a), (bf16*)O, ld_o, bs_o, lse);
+    LAUNCHED();
+}
+template <int NT, int NW, bool LQ16>
+void launch_bwd(const AttnArgs& a, const void* dO, int64_t ld_do, int64_t bs_do, const float* lse, void* dQ, int64_t ld_dq,
+                int64_t bs_dq, void* dK, void* dV, int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, cudaStream_t st) {
+    constexpr int sm = DCfg<NT, NW>::BWD_SMEM;
+    static bool set = false;
+    if (!set) { P5_CUDA(cudaFuncSetAttribute(dattn_bwd_kernel<NT, NW, LQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); set = true; }
+    dattn_bwd_kernel<NT, NW, LQ16><<<(unsigned)(a.B * a.H), NW * 32, sm, st>>>(to_dev(a), (const bf16*)dO, ld_do, bs_do, lse, (bf16*)dQ,
+                                                                              ld_dq, bs_dq, (bf16*)dK, (bf16*)dV, ld_dkv, bs_dkv, dbias_rel);
+    LAUNCHED();
+}
+
+}  // namespace
+
+bool dattn_supported(const AttnArgs& a) {
+    static const bool off = getenv("P5_NO_DATTN") != nullptr;
+    if (off) return false;
+    auto al = [](const AttnView& v) { return v.dtype == DT_BF16 && (v.ld % 8) == 0 && (v.bs % 8) == 0 && ((uintptr_t)v.ptr % 16) == 0; };
+    return a.Lq >= 1 && a.Lq <= 16 && a.Lk >= 1 && a.Lk <= 512 && al(a.q) && al(a.k) && al(a.v) && a.row_map == nullptr &&
+           a.q_pos_offset == 0;
+}
+
+#define P5_DATTN_DISPATCH(FN, ...)                                                              \
+    do {                                                                                        \
+        const bool hi = a.Lq > 8;                                                               \
+        if (a.Lk <= 16) { if (hi) FN<2, 1, true>(__VA_ARGS__); else FN<2, 1, false>(__VA_ARGS__); }          \
+        else if (a.Lk <= 64) { if (hi) FN<2, 4, true>(__VA_ARGS__); else FN<2, 4, false>(__VA_ARGS__); }     \
+        else if (a.Lk <= 256) { if (hi) FN<8, 4, true>(__VA_ARGS__); else FN<8, 4, false>(__VA_ARGS__); }    \
+        else { if (hi) FN<8, 8, true>(__VA_ARGS__); else FN<8, 8, false>(__VA_ARGS__); }                     \
+    } while (0)
+
+void dattn_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
+    if (a.B <= 0) return;
+    P5_CHECK(dattn_supported(a), "dattn_fwd: unsupported geometry");
+    P5_CHECK((ld_o % 8) == 0 && (bs_o % 8) == 0, "dattn_fwd: output rows must be 16-byte aligned");
+    P5_DATTN_DISPATCH(launch_fwd, a, O, ld_o, bs_o, lse, st);
+}
+
+void dattn_bwd(const AttnArgs& a, const void* dO, int64_t ld_do, int64_t bs_do, const float* lse, void* dQ, int64_t ld_dq,
+               int64_t bs_dq, void* dK, void* dV, int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, cudaStream_t st) {
+    if (a.B <= 0) return;
+    P5_CHECK(dattn_supported(a), "dattn_bwd: unsupported geometry");
+    P5_CHECK((ld_do % 8) == 0 && (bs_do % 8) == 0 && (ld_dq % 8) == 0 && (bs_dq % 8) == 0 && (ld_dkv % 8) == 0 && (bs_dkv % 8) == 0,
+             "dattn_bwd: rows must be 16-byte aligned");
+    P5_DATTN_DISPATCH(launch_bwd, a, dO, ld_do, bs_do, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv, bs_dkv, dbias_rel, st);
+}
+
+}  // namespace p5

@@ -571,13 +571,21 @@ void Engine::decoder_forward() {
         float *y0 = yd[3 * l], *y1 = yd[3 * l + 1], *y2 = yd[3 * l + 2], *y3 = yd[3 * l + 3];
         rmsnorm_fwd(y0, P + w.ln0, nd[3 * l], dt, rstd_d[3 * l], (int)Md, d, cfg.ln_eps, none, st);
         linear_fwd(nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, sqkv[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
-        attn_simt_fwd(dec_self_args(*this, l, drop(S_DEC_SP, l)), sctx[l], dt, A, (int64_t)Ld * A, slse[l], st);
+        {
+            const AttnArgs sa = dec_self_args(*this, l, drop(S_DEC_SP, l));
+            if (dattn_supported(sa)) dattn_fwd(sa, sctx[l], A, (int64_t)Ld * A, slse[l], st);
+            else attn_simt_fwd(sa, sctx[l], dt, A, (int64_t)Ld * A, slse[l], st);
+        }
         linear_fwd(sctx[l], A, w.sa.o, d, A, (int)Md, y1, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, y0,
                    drop(S_DEC_SO, l));
         rmsnorm_fwd(y1, P + w.ln1, nd[3 * l + 1], dt, rstd_d[3 * l + 1], (int)Md, d, cfg.ln_eps, none, st);
         linear_fwd(nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, cq[l], dt, A, 0, 1.f, nullptr, nullptr, none);
         linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Mt, ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
-        attn_simt_fwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], dt, A, (int64_t)Ld * A, clse[l], st);
+        {
+            const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
+            if (dattn_supported(ca)) dattn_fwd(ca, cctx[l], A, (int64_t)Ld * A, clse[l], st);
+            else attn_simt_fwd(ca, cctx[l], dt, A, (int64_t)Ld * A, clse[l], st);
+        }
         linear_fwd(cctx[l], A, w.ca.o, d, A, (int)Md, y2, DT_F32, d, EPI_ADD_RESID | EPI_DROPOUT, 1.f, nullptr, y1,
                    drop(S_DEC_CO, l));
         rmsnorm_fwd(y2, P + w.ln2, nd[3 * l + 2], dt, rstd_d[3 * l + 2], (int)Md, d, cfg.ln_eps, none, st);
@@ -640,13 +648,24 @@ void Engine::backward() {
         // cross attention (g_d = dropout-cast(dy))
         linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Mt * 2 * A * sizeof(float), st));
-        attn_simt_bwd(dec_cross_args(*this, l, drop(S_DEC_CP, l)), cctx[l], g_ctx, dt, A, (int64_t)Ld * A, clse[l], f_qkv, A,
-                      (int64_t)Ld * A, f_ckv, f_ckv + A, 2 * A, (int64_t)Le * 2 * A, nullptr, st);
-        if (packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
-            P5_CUDA(cudaMemsetAsync(f_ckv + Mt_true * 2 * A, 0, (Mt - Mt_true) * 2 * A * sizeof(float), st));
-        void* gq = as_T(f_qkv, g_qkv, Md * A);
-        void* gkv = as_T(f_ckv, g_ckv, Mt * 2 * A);
+        void *gq, *gkv;
+        const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
+        if (dattn_supported(ca)) {   // bf16: tensor-core kernel writes dQ and dK|dV as bf16 in place
+            dattn_bwd(ca, g_ctx, A, (int64_t)Ld * A, clse[l], g_qkv, A, (int64_t)Ld * A, g_ckv, poff(g_ckv, A, dt), 2 * A,
+                      (int64_t)Le * 2 * A, nullptr, st);
+            if (packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
+                P5_CUDA(cudaMemsetAsync(poff(g_ckv, Mt_true * 2 * A, dt), 0, (Mt - Mt_true) * 2 * A * dtype_size(dt), st));
+            gq = g_qkv;
+            gkv = g_ckv;
+        } else {
+            if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Mt * 2 * A * sizeof(float), st));
+            attn_simt_bwd(ca, cctx[l], g_ctx, dt, A, (int64_t)Ld * A, clse[l], f_qkv, A, (int64_t)Ld * A, f_ckv, f_ckv + A, 2 * A,
+                          (int64_t)Le * 2 * A, nullptr, st);
+            if (packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
+                P5_CUDA(cudaMemsetAsync(f_ckv + Mt_true * 2 * A, 0, (Mt - Mt_true) * 2 * A * sizeof(float), st));
+            gq = as_T(f_qkv, g_qkv, Md * A);
+            gkv = as_T(f_ckv, g_ckv, Mt * 2 * A);
+        }
         linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f);
         linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Mt, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
         linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f);
@@ -656,10 +675,18 @@ void Engine::backward() {
         // self attention (g_d = dropout-cast(dy))
         linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
-        attn_simt_bwd(dec_self_args(*this, l, drop(S_DEC_SP, l)), sctx[l], g_ctx, dt, A, (int64_t)Ld * A, slse[l], f_qkv,
-                      3 * A, (int64_t)Ld * 3 * A, f_qkv + A, f_qkv + 2 * A, 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
-        void* gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
+        void* gqkv;
+        const AttnArgs sa = dec_self_args(*this, l, drop(S_DEC_SP, l));
+        if (dattn_supported(sa)) {
+            dattn_bwd(sa, g_ctx, A, (int64_t)Ld * A, slse[l], g_qkv, 3 * A, (int64_t)Ld * 3 * A, poff(g_qkv, A, dt),
+                      poff(g_qkv, 2 * A, dt), 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
+            gqkv = g_qkv;
+        } else {
+            if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
+            attn_simt_bwd(sa, sctx[l], g_ctx, dt, A, (int64_t)Ld * A, slse[l], f_qkv, 3 * A, (int64_t)Ld * 3 * A, f_qkv + A,
+                          f_qkv + 2 * A, 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
+            gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
+        }
         linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f);
         linear_dgrad(gqkv, 3 * A, w.sa.q, 3 * A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
         rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st, l > 0 ? g_d : nullptr, dt,

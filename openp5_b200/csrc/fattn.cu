@@ -20,7 +20,12 @@
 
 namespace p5 {
 extern int g_launches;
-#define MASK_MIN (-FLT_MAX)
+#define LOG2E 1.4426950408889634f
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 static constexpr int NWG = 4;              // softmax warpgroups: each owns 128 / NWG = 32 key columns of every block
 static constexpr int FA_THREADS = 128 + NWG * 128;   // 4 control warps + NWG softmax warpgroups
@@ -32,7 +37,9 @@ struct FaParams {
     int B, H, Lq, Lk, nkb, nqt, nq_buf;
     const float* bias_rel;   // [H, Lq + Lk - 1]
     const int* key_mask;     // [B, Lk]
-    bf16* P_save;            // [B, H, Lq, Lk] normalised probabilities (un-dropped)
+    bf16* P_save;            // [B, H, Lq, Lk] UN-normalised probabilities 2^(s2 - m2) (un-dropped)
+    float* row_scale;        // [B, H, Lq] 1 / row sum: P = P_save * row_scale
+    uint32_t bias_cs;        // stride (floats) between the four shifted copies of the bias row
     bf16* ctx;               // [B*Lq, ld_ctx]
     int64_t ld_ctx;
     uint32_t sK, sV, sQ, sP, sBias, sMask, sStat, sBar;   // smem offsets from the 1024-aligned base
@@ -55,7 +62,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t sK = base + P.sK, sV = base + P.sV, sQ = base + P.sQ, sP = base + P.sP, bar = base + P.sBar;
     float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
     float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
-    float2* stat_s = reinterpret_cast<float2*>(gbase + P.sStat);   // [NWG][128] (m, l) per warpgroup and row
+    float* statm_s = reinterpret_cast<float*>(gbase + P.sStat);    // [NWG][128] row max per warpgroup (log2 domain)
+    float* statl_s = statm_s + NWG * QT;                           // [NWG][128] row sum per warpgroup
     // barriers (8 bytes each)
     const uint32_t kv_full = bar, kv_empty = bar + 8;
     auto q_full = [&](int i) { return bar + 16 + 8 * i; };
@@ -182,18 +190,26 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
     } else if (warp == 3) {
         // ========================= bias / mask tables per (batch, head) =========================
+        // Everything is kept in the log2 domain (bias * log2(e)) so that a probability is one FFMA + one EX2.
+        // bias4_s holds FOUR copies of the bias row, copy c shifted by c entries: a thread whose first entry is
+        // o = (Lq-1-i) + j0 reads copy (o & 3) at the 16-byte aligned index o - (o & 3) with LDS.128.
         uint32_t bm_ph = 0;
         const int n_delta = Lq + Lk - 1;
+        const int cs = (int)P.bias_cs;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
             const int len = P.lens ? P.lens[b] : Lk;
             const int nkb = (len + KB - 1) / KB;
             mbar_wait(bm_empty, bm_ph ^ 1);
             // entries past n_delta are only touched for padded keys (masked with -inf): keep them finite
-            for (int e = lane; e < Lq + nkb * KB; e += 32)
-                bias_s[e] = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] : 0.f;
+            for (int e = lane; e < Lq + nkb * KB + 4; e += 32) {
+                const float v = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] * LOG2E : 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (e >= c) bias_s[c * cs + e - c] = v;
+            }
             for (int j = lane; j < nkb * KB; j += 32)
-                mask_s[j] = (j < len && (!P.key_mask || P.key_mask[b * Lk + j] != 0)) ? 0.f : (j < len ? MASK_MIN : -INFINITY);
+                mask_s[j] = (j < len && (!P.key_mask || P.key_mask[b * Lk + j] != 0)) ? 0.f : -INFINITY;
             __syncwarp();
             if (lane == 0) mbar_arrive(bm_full);
             bm_ph ^= 1;
@@ -206,6 +222,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
         uint32_t sf_ph[NSB] = {0, 0, 0}, pe_ph[2] = {0, 0}, of_ph = 0, bm_ph = 0;
         int sb = 0, pb = 0;
+        const uint32_t t16 = P.drop.thr >> 16;
+        const int cs = (int)P.bias_cs;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
             const int len = P.lens ? P.lens[b] : Lq;
@@ -216,10 +234,10 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int qt = 0; qt < nqt; ++qt) {
                 const int i = qt * QT + r;                // query position
                 const bool row_ok = i < len;
-                const float* brow = bias_s + (row_ok ? (Lq - 1 - i) : 0);   // bias for key j is brow[j]
+                const int o_row = row_ok ? (Lq - 1 - i) : 0;     // bias entry of key j is o_row + j
                 const int64_t grow = (((int64_t)b * P.H + h) * Lq + i) * Lk;
-                // ---------------- pass 1: m = max_j s_ij, l = sum_j exp(s_ij - m) over this warpgroup's columns
-                float m = -INFINITY, l = 0.f;
+                // ---------------- pass 1: m2 = max_j (s_ij + bias) * log2(e) over this warpgroup's columns
+                float m2 = -INFINITY;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(s_full(sb), sf_ph[sb]);
                     sf_ph[sb] ^= 1;
@@ -227,23 +245,33 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     {
                         uint32_t v[32];
                         tmem_ld32(tS[sb] + lane_off + wg * 32, v);
-                        tmem_ld_wait();
                         const int j0 = kb * KB + wg * 32;
+                        const int o = o_row + j0;
+                        const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
+                        const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
+                        tmem_ld_wait();
                         float cm = -INFINITY;
+                        if (full) {
 #pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const float sv = __uint_as_float(v[t]) + brow[j0 + t] + mask_s[j0 + t];
-                            v[t] = __float_as_uint(sv);
-                            cm = fmaxf(cm, sv);
-                        }
-                        const float mn = fmaxf(m, cm);
-                        if (mn > -INFINITY) {
-                            float acc = 0.f;
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 bb = b4[q];
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x));
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y));
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z));
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w));
+                            }
+                        } else {
+                            const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
 #pragma unroll
-                            for (int t = 0; t < 32; ++t) acc += __expf(__uint_as_float(v[t]) - mn);
-                            l = l * __expf(m - mn) + acc;
-                            m = mn;
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 bb = b4[q], mm = m4[q];
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x) + mm.x);
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y) + mm.y);
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z) + mm.z);
+                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w) + mm.w);
+                            }
                         }
+                        m2 = fmaxf(m2, cm);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -251,71 +279,77 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     sb = (sb + 1) % NSB;
                 }
                 // combine the column slices of the row
-                stat_s[wg * QT + r] = make_float2(m, l);
+                statm_s[wg * QT + r] = m2;
                 asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
-                {
-                    float mm = m;
 #pragma unroll
-                    for (int g2 = 0; g2 < NWG; ++g2) mm = fmaxf(mm, stat_s[g2 * QT + r].x);
-                    float ll = 0.f;
-#pragma unroll
-                    for (int g2 = 0; g2 < NWG; ++g2) {
-                        const float2 o = stat_s[g2 * QT + r];
-                        if (o.x > -INFINITY) ll += o.y * __expf(o.x - mm);
-                    }
-                    m = mm; l = ll;
-                }
-                const float inv_l = 1.f / l;
-                // ---------------- pass 2: P, dropout, smem A tile
+                for (int g2 = 0; g2 < NWG; ++g2) m2 = fmaxf(m2, statm_s[g2 * QT + r]);
+                if (!(m2 > -INFINITY)) m2 = 0.f;            // rows past the sequence end (never stored)
+                // ---------------- pass 2: p~ = 2^(s2 - m2) (UN-normalised), dropout, smem A tile; l = sum p~
+                float l = 0.f;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(s_full(sb), sf_ph[sb]);
                     sf_ph[sb] ^= 1;
                     tc_fence_after();
-                    mbar_wait(p_empty(pb), pe_ph[pb] ^ 1);   // the MMA that read this P buffer has retired
-                    pe_ph[pb] ^= 1;
                     // this warpgroup's 32 keys live in 64-key chunk (wg >> 1), 16-byte units (wg & 1) * 4 .. + 3
                     const uint32_t p_chunk = sP + pb * (QT * KB * 2) + (wg >> 1) * (QT * 128) + r * 128;
                     {
                         uint32_t v[32];
                         tmem_ld32(tS[sb] + lane_off + wg * 32, v);
-                        tmem_ld_wait();
                         const int j0 = kb * KB + wg * 32;
-                        uint32_t pk[16], pd[16];
+                        const int o = o_row + j0;
+                        const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
+                        const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
+                        const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
+                        const uint32_t pair0 = (uint32_t)((uint64_t)(grow + j0) >> 1);
+                        tmem_ld_wait();
+                        mbar_wait(p_empty(pb), pe_ph[pb] ^ 1);   // the MMA that read this P buffer has retired
+                        pe_ph[pb] ^= 1;
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const int j = j0 + 2 * t;
-                            const float s0 = __uint_as_float(v[2 * t]) + brow[j] + mask_s[j];
-                            const float s1 = __uint_as_float(v[2 * t + 1]) + brow[j + 1] + mask_s[j + 1];
-                            const float p0 = __expf(s0 - m) * inv_l, p1 = __expf(s1 - m) * inv_l;
-                            pk[t] = pack_bf16x2(p0, p1);
-                            if (P.drop.thr) {
-                                const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(grow + j) >> 1);
-                                const uint32_t t16 = P.drop.thr >> 16;
-                                pd[t] = pack_bf16x2((hsh & 0xffffu) >= t16 ? p0 * P.drop.inv_keep : 0.f,
-                                                    (hsh >> 16) >= t16 ? p1 * P.drop.inv_keep : 0.f);
-                            } else {
-                                pd[t] = pk[t];
+                        for (int q = 0; q < 4; ++q) {            // 8 keys per step: one 16-byte store each way
+                            float pr[8];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const float4 bb = b4[2 * q + u];
+                                float x0 = fmaf(__uint_as_float(v[8 * q + 4 * u]), LOG2E, bb.x);
+                                float x1 = fmaf(__uint_as_float(v[8 * q + 4 * u + 1]), LOG2E, bb.y);
+                                float x2 = fmaf(__uint_as_float(v[8 * q + 4 * u + 2]), LOG2E, bb.z);
+                                float x3 = fmaf(__uint_as_float(v[8 * q + 4 * u + 3]), LOG2E, bb.w);
+                                if (!full) {
+                                    const float4 mm = m4[2 * q + u];
+                                    x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                }
+                                pr[4 * u] = ex2_approx(x0 - m2); pr[4 * u + 1] = ex2_approx(x1 - m2);
+                                pr[4 * u + 2] = ex2_approx(x2 - m2); pr[4 * u + 3] = ex2_approx(x3 - m2);
                             }
-                        }
-                        // global P_save (normalised, un-dropped): 64 contiguous bytes of this row
-                        if (row_ok && P.P_save) {
+                            l += ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+                            uint32_t pk[4], pd[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
+                            for (int u = 0; u < 4; ++u) pk[u] = pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
+                            if (P.drop.thr) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + u));
+                                    pd[u] = pack_bf16x2((hsh & 0xffffu) >= t16 ? pr[2 * u] * P.drop.inv_keep : 0.f,
+                                                        (hsh >> 16) >= t16 ? pr[2 * u + 1] * P.drop.inv_keep : 0.f);
+                                }
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) pd[u] = pk[u];
+                            }
+                            // global P_save (un-normalised, un-dropped; the backward multiplies by row_scale)
+                            if (row_ok && P.P_save) {
                                 const int j = j0 + 8 * q;
                                 if (j + 8 <= Lk) {
-                                    *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                    *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                                 } else {
                                     for (int t = 0; t < 4; ++t)
-                                        if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[4 * q + t];
+                                        if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[t];
                                 }
                             }
-                        }
-                        // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                            // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
                             const uint32_t addr = p_chunk + (uint32_t)((((wg & 1) * 4 + q) ^ (r & 7)) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[4 * q]), "r"(pd[4 * q + 1]),
-                                         "r"(pd[4 * q + 2]), "r"(pd[4 * q + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[0]), "r"(pd[1]), "r"(pd[2]),
+                                         "r"(pd[3]) : "memory");
                         }
                     }
                     // S buffer free; P tile complete: make the generic-proxy smem writes visible to the tensor core
@@ -326,6 +360,14 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     sb = (sb + 1) % NSB;
                     pb ^= 1;
                 }
+                // row sum over the four column slices -> 1 / l normalises O here and P_save in the backward
+                statl_s[wg * QT + r] = l;
+                asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+                l = 0.f;
+#pragma unroll
+                for (int g2 = 0; g2 < NWG; ++g2) l += statl_s[g2 * QT + r];
+                const float inv_l = l > 0.f ? 1.f / l : 0.f;
+                if (wg == 0 && row_ok && P.row_scale) P.row_scale[((int64_t)b * P.H + h) * Lq + i] = inv_l;
                 // ---------------- O -> ctx (this warpgroup writes 16 of the 64 head columns)
                 mbar_wait(o_full, of_ph);
                 of_ph ^= 1;
@@ -342,10 +384,10 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             uint4 w;
-                            w.x = pack_bf16x2(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1]));
-                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3]));
-                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5]));
-                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7]));
+                            w.x = pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l);
+                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
+                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
+                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
                             *reinterpret_cast<uint4*>(dst + 8 * q) = w;
                         }
                     }
@@ -367,8 +409,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // qkv: [B*L, 3A] bf16 (q | k | v column blocks, heads 64 wide).  Returns false if the shape is not supported.
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
-               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st, const int* offs, const int* lens,
-               int64_t packed_rows) {
+               void* P_save, float* row_scale, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st, const int* offs,
+               const int* lens, int64_t packed_rows) {
     if (L > 512 || L % 8 != 0 || ld_qkv % 8 != 0) return false;
     static int num_sms = 0;
     if (!num_sms) {
@@ -383,12 +425,13 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.nq_buf = (kv_bytes <= 48 * 1024) ? 2 : 1;
     P.sK = 0; P.sV = kv_bytes; P.sQ = 2 * kv_bytes; P.sP = P.sQ + P.nq_buf * QT * 128;
     P.sBias = P.sP + 2 * QT * KB * 2;
-    P.sMask = P.sBias + (uint32_t)round_up((L + P.nkb * KB) * 4, 16);
+    P.bias_cs = (uint32_t)(((L + P.nkb * KB + 4 + 31) & ~31) + 8);   // copies land in different bank groups
+    P.sMask = P.sBias + (uint32_t)round_up(4 * P.bias_cs * 4, 16);
     P.sStat = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
     P.sBar = P.sStat + NWG * QT * 8;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
-    P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
+    P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.row_scale = row_scale; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
     P.offs = offs; P.lens = lens;
     P.drop = drop;
     static size_t max_set = 0;

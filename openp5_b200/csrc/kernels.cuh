@@ -92,6 +92,14 @@ void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype
                    const float* lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV, int64_t ld_dkv,
                    int64_t bs_dkv, float* dbias_rel, cudaStream_t st);
 
+// decoder attention of the bf16 train step on mma.sync tiles (dattn.cu): Lq <= 16, Lk <= 512, all views bf16 with
+// 16-byte aligned rows.  Same semantics / dropout stream as attn_simt_*; gradients are written as bf16 in place
+// (every (key row, head) slice is owned by exactly one CTA: no zero-fill, no fp32 staging).
+bool dattn_supported(const AttnArgs& a);
+void dattn_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st);
+void dattn_bwd(const AttnArgs& a, const void* dO, int64_t ld_do, int64_t bs_do, const float* lse, void* dQ, int64_t ld_dq,
+               int64_t bs_dq, void* dK, void* dV, int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, cudaStream_t st);
+
 // materialised softmax for the tensor-core attention path: S fp32 [B,H,Lq,Lk]
 //   P  = softmax(S + bias + mask)             -> P_save (dtype)           (needed by backward)
 //   Pd = drop(P)                              -> Pd (dtype, may alias P_save when dropout is off)

@@ -14,7 +14,8 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "gen_fp32_tiny", "gen_bf16_tiny", "fwd_fp32_small", "bwd_fp32_small", "bwd_bf16_small", "gated_fp32_tiny",
          "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256", "bwd_bf16_small_le512", "bwd_fp32_small_le300",
          "bwd_fp32_tiny_packed", "bwd_fp32_small_packed", "bwd_bf16_small_packed", "bwd_bf16_base_le256_packed",
-         "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed"]
+         "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed", "bwd_bf16_small_ld12", "bwd_fp32_small_ld12",
+         "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed"]
 
 
 def setup(case):
@@ -32,6 +33,8 @@ def setup(case):
     else:
         cfg = po.t5_cfg("t5-tiny", vocab_size=1200)
         B, Le, Ld, n_items = 3, 21, 8, 60
+    if "ld12" in case:
+        Ld = 12          # second half of the 16-row query tile of the decoder attention kernels
     if "gated" in case:
         cfg.ffn_gated_gelu = True
     w = po.init_weights(cfg, seed=1)
@@ -56,7 +59,7 @@ def relerr(a, b):
 def run_case(case):
     import torch
     po, cfg, w, items, (ids, attn, ww, labels, oattn) = setup(case)
-    prec = "bf16" if "bf16" in case else "fp32"
+    prec = "bf16" if ("bf16" in case or case.startswith("xcheck")) else "fp32"
     tol = 6e-2 if prec == "bf16" else 2e-4
     dev = "cuda"
     res = dict(name=case)
@@ -153,6 +156,41 @@ def run_case(case):
             res["ok"] = same and res["score_err"] < 1e-4 and res["trie_get_ok"]
         else:
             res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
+    elif case.startswith("xcheck"):
+        # decoder attention: mma.sync kernels (dattn.cu) vs the fp32-math SIMT kernels at the SAME dropout seed.
+        # Both regenerate the mask from the same counter hash, so gradients must agree to bf16 rounding.
+        dump = os.environ.get("P5_XCHECK_DUMP")
+        if dump:
+            m = make_model(cfg, w, prec, dropout=0.1).train()
+            m._step_seed = 1234
+            a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+            m.zero_grad()
+            lens = attn.sum(1) if "packed" in case else None
+            out = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3], enc_lengths=lens)
+            out["loss"].mean().backward()
+            torch.save({"loss": out["loss"].detach().cpu(), **{k: p.grad.detach().cpu() for k, p in m.named_parameters()}}, dump)
+            res["ok"] = True
+            return res
+        outs = []
+        for tag, extra in (("dattn", {}), ("simt", {"P5_NO_DATTN": "1"})):
+            path = "/tmp/p5_xcheck_%s_%s.pt" % (case, tag)
+            env = dict(os.environ, P5_XCHECK_DUMP=path, **extra)
+            p = subprocess.run([sys.executable, __file__, "--case", case], capture_output=True, text=True, timeout=280, env=env)
+            if not os.path.exists(path):
+                res["ok"] = False
+                res["error"] = (p.stdout[-400:] + p.stderr[-600:])
+                return res
+            outs.append(torch.load(path))
+            os.remove(path)
+        worst, worst_name = 0.0, ""
+        for k in outs[0]:
+            e = relerr(outs[0][k].float(), outs[1][k].float())
+            if e > worst:
+                worst, worst_name = e, k
+        res["worst_rel"] = worst
+        res["worst_name"] = worst_name
+        res["loss_rel"] = relerr(outs[0]["loss"], outs[1]["loss"])
+        res["ok"] = worst < 0.08 and res["loss_rel"] < 0.02
     elif case.startswith("dropout"):
         m = make_model(cfg, w, prec, dropout=0.1).train()
         a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
