@@ -95,6 +95,8 @@ __device__ __forceinline__ void load_kv_tile(float (*dst)[KS], const void* base,
 template <int RPW>
 __global__ void __launch_bounds__(256)
 attn_simt_fwd_kernel(AttnDev a, void* O, int o_dt, int64_t ld_o, int64_t bs_o, float* lse) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     constexpr int QB = 8 * RPW;
     extern __shared__ __align__(16) float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);                       // [QB][64]
@@ -224,7 +226,7 @@ static void launch_attn_fwd(const AttnArgs& a, void* O, int o_dtype, int64_t ld_
     }
     AttnDev d = to_dev(a);
     dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
-    attn_simt_fwd_kernel<RPW><<<grid, 256, sm, st>>>(d, O, o_dtype, ld_o, bs_o, lse);
+    launch_k(attn_simt_fwd_kernel<RPW>, grid, 256, sm, st, d, O, o_dtype, ld_o, bs_o, lse);
     LAUNCHED();
 }
 
@@ -246,6 +248,8 @@ __global__ void __launch_bounds__(256)
 attn_simt_bwd_kernel(AttnDev a, const void* O, const void* dO, int o_dt, int64_t ld_o, int64_t bs_o,
                      const float* __restrict__ lse, float* dQ, int64_t ld_dq, int64_t bs_dq, float* dK, float* dV,
                      int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, int atomic_kv) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     constexpr int QB = 8 * RPW;
     extern __shared__ __align__(16) float smem[];
     float (*Qs)[DK] = reinterpret_cast<float (*)[DK]>(smem);
@@ -427,7 +431,7 @@ static void launch_attn_bwd(const AttnArgs& a, const void* O, const void* dO, in
     AttnDev d = to_dev(a);
     dim3 grid((unsigned)cdiv(a.Lq, QB), (unsigned)a.H, (unsigned)a.B);
     // with a single q-block per (b, h) every dK/dV element has exactly one producer: plain stores, no memset needed
-    attn_simt_bwd_kernel<RPW><<<grid, 256, sm, st>>>(d, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv,
+    launch_k(attn_simt_bwd_kernel<RPW>, grid, 256, sm, st, d, O, dO, o_dtype, ld_o, bs_o, lse, dQ, ld_dq, bs_dq, dK, dV, ld_dkv,
                                                      bs_dkv, dbias_rel, grid.x > 1 ? 1 : 0);
     LAUNCHED();
 }
@@ -469,6 +473,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ bias_rel, const int* __restrict__ key_mask,
                    T* __restrict__ P_save, T* __restrict__ Pd, int H, int Lq, int Lk, int causal, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     extern __shared__ float sh_mask[];   // [Lk] additive key mask of this batch row (0 or finfo.min)
     const int bh = blockIdx.x, b = bh / H, h = bh % H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -528,9 +534,9 @@ void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, voi
     dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     const size_t sm = (size_t)Lk * sizeof(float);
     if (dtype == DT_F32)
-        softmax_fwd_kernel<float><<<grid, 256, sm, st>>>(S, bias_rel, key_mask, (float*)P_save, (float*)Pd, H, Lq, Lk, causal, drop);
+        launch_k(softmax_fwd_kernel<float>, grid, 256, sm, st, S, bias_rel, key_mask, (float*)P_save, (float*)Pd, H, Lq, Lk, causal, drop);
     else
-        softmax_fwd_kernel<bf16><<<grid, 256, sm, st>>>(S, bias_rel, key_mask, (bf16*)P_save, (bf16*)Pd, H, Lq, Lk, causal, drop);
+        launch_k(softmax_fwd_kernel<bf16>, grid, 256, sm, st, S, bias_rel, key_mask, (bf16*)P_save, (bf16*)Pd, H, Lq, Lk, causal, drop);
     LAUNCHED();
 }
 
@@ -539,7 +545,10 @@ void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, voi
 template <typename T, int NP>
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __restrict__ dS, T* __restrict__ Pd_out,
-                   float* __restrict__ dbias_rel, int H, int Lq, int Lk, DropCfg drop, const int* __restrict__ lens) {
+                   float* __restrict__ dbias_rel, int H, int Lq, int Lk, DropCfg drop, const int* __restrict__ lens,
+                   const float* __restrict__ row_scale) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     extern __shared__ float sdb[];  // [n_delta]
     const int bh = blockIdx.x, h = bh % H;
     // packed training: only the first len rows / columns of this (b, h) hold probabilities; everything else is
@@ -565,6 +574,7 @@ softmax_bwd_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __
                 if (i < Lq && j < Lk) {
                     if (i < len && j < len) {
                         float2 pp = ld_pair<T>(P + row + j);
+                        if (row_scale) { const float rs = row_scale[(int64_t)bh * Lq + i]; pp.x *= rs; pp.y *= rs; }
                         if (j + 1 >= len) pp.y = 0.f;             // pair straddling the sequence end
                         const float2 g = *reinterpret_cast<const float2*>(dPd + row + j);
                         float g0 = g.x, g1 = g.y;
@@ -637,7 +647,10 @@ template <> struct PairRaw<bf16> {
 template <typename T, int NP>
 __global__ void __launch_bounds__(256, (NP <= 4 ? 3 : 2))
 softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T* __restrict__ dS, T* __restrict__ Pd_out,
-                      float* __restrict__ dbias_rel, int H, int L, DropCfg drop, const int* __restrict__ lens) {
+                      float* __restrict__ dbias_rel, int H, int L, DropCfg drop, const int* __restrict__ lens,
+                      const float* __restrict__ row_scale) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     extern __shared__ float sdb[];  // [2L - 1]
     const int bh = blockIdx.x, h = bh % H;
     const int len = lens ? lens[bh / H] : L;
@@ -683,6 +696,11 @@ softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T*
         const uint32_t pair0 = (uint32_t)((uint64_t)row0 >> 1);   // pair index of the row start (B*H*L*L/2 < 2^32)
         PairRaw<T> pp[2][NP];
         float2 g[2][NP];
+        float rs[2] = {1.f, 1.f};      // P = P_raw * row_scale (un-normalised probabilities saved by fattn_fwd)
+        if (row_scale) {
+            rs[0] = row_scale[(int64_t)bh * L + i0];
+            rs[1] = i0 + 1 < len ? row_scale[(int64_t)bh * L + i0 + 1] : 0.f;
+        }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -702,7 +720,7 @@ softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T*
                 const bool c0 = rv && j < len, c1 = rv && j + 1 < len;
                 pp[rr][k].keep(c0, c1);
                 const float2 pv = pp[rr][k].get();
-                const float p0 = pv.x, p1 = pv.y;
+                const float p0 = pv.x * rs[rr], p1 = pv.y * rs[rr];
                 float g0 = c0 ? g[rr][k].x : 0.f, g1 = c1 ? g[rr][k].y : 0.f;
                 if (drop.thr) {
                     bool k0, k1;
@@ -726,8 +744,8 @@ softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T*
             const bool w = qm >= HALF;
             if (dbias_rel && w != wprev[k]) { flush(k); wprev[k] = w; }
             const float2 pe = pp[0][k].get(), po = pp[1][k].get();
-            const float e0 = pe.x * (g[0][k].x - dot[0]), e1 = pe.y * (g[0][k].y - dot[0]);   // row 2m
-            const float o0 = po.x * (g[1][k].x - dot[1]), o1 = po.y * (g[1][k].y - dot[1]);   // row 2m+1
+            const float e0 = pe.x * rs[0] * (g[0][k].x - dot[0]), e1 = pe.y * rs[0] * (g[0][k].y - dot[0]);   // row 2m
+            const float o0 = po.x * rs[1] * (g[1][k].x - dot[1]), o1 = po.y * rs[1] * (g[1][k].y - dot[1]);   // row 2m+1
             st_pair<T>(dSr + j, e0, e1);
             st_pair<T>(dSr + L + j, o0, o1);
             acc[k][0] += o0;          // j - i = 2q - 1
@@ -752,6 +770,8 @@ softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T*
 template <typename T>
 __global__ void __launch_bounds__(512)
 relbias_diag_sum_kernel(const T* __restrict__ dS, float* __restrict__ dbias_rel, int B, int H, int Lq, int Lk, int b_per_cta) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int h = blockIdx.x, b0 = blockIdx.y * b_per_cta;
     const int n_delta = Lq + Lk - 1;
     for (int dl = threadIdx.x; dl < n_delta; dl += blockDim.x) {
@@ -770,20 +790,20 @@ void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H,
     if (B <= 0) return;
     const int b_per_cta = 1;
     dim3 grid((unsigned)H, (unsigned)cdiv(B, b_per_cta));
-    if (dtype == DT_F32) relbias_diag_sum_kernel<float><<<grid, 512, 0, st>>>((const float*)dS, dbias_rel, B, H, Lq, Lk, b_per_cta);
-    else relbias_diag_sum_kernel<bf16><<<grid, 512, 0, st>>>((const bf16*)dS, dbias_rel, B, H, Lq, Lk, b_per_cta);
+    if (dtype == DT_F32) launch_k(relbias_diag_sum_kernel<float>, grid, 512, 0, st, (const float*)dS, dbias_rel, B, H, Lq, Lk, b_per_cta);
+    else launch_k(relbias_diag_sum_kernel<bf16>, grid, 512, 0, st, (const bf16*)dS, dbias_rel, B, H, Lq, Lk, b_per_cta);
     LAUNCHED();
 }
 
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
-                 int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens) {
+                 int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens, const float* row_scale) {
     if (B <= 0) return;
     P5_CHECK(Lk <= 64 * SM_MAXP && (Lk % 2) == 0, "softmax_bwd: Lk must be even and <= 512");
     const size_t sm = (size_t)(Lq + Lk) * sizeof(float);
     static const bool generic_only = getenv("P5_SMBWD_GENERIC") != nullptr;
     if (Lq == Lk && (Lk == 64 || Lk == 128 || Lk == 256 || Lk == 512) && !generic_only) {
         dim3 g2((unsigned)(B * H), (unsigned)(Lk >= 256 ? 4 : (Lk >= 128 ? 2 : 1)));
-#define P5_SMBWD_SQ(TT, NPV) softmax_bwd_sq_kernel<TT, NPV><<<g2, 256, sm, st>>>(dPd, (const TT*)P, (TT*)dS, (TT*)Pd_out, dbias_rel, H, Lk, drop, lens)
+#define P5_SMBWD_SQ(TT, NPV) launch_k(softmax_bwd_sq_kernel<TT, NPV>, g2, 256, sm, st, dPd, (const TT*)P, (TT*)dS, (TT*)Pd_out, dbias_rel, H, Lk, drop, lens, row_scale)
         if (dtype == DT_F32) {
             if (Lk == 64) P5_SMBWD_SQ(float, 1); else if (Lk == 128) P5_SMBWD_SQ(float, 2); else if (Lk == 256) P5_SMBWD_SQ(float, 4); else P5_SMBWD_SQ(float, 8);
         } else {
@@ -795,11 +815,11 @@ void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dt
     }
     dim3 grid((unsigned)(B * H), (unsigned)(Lq >= 128 ? 2 : 1));
     if (dtype == DT_F32) {
-        if (Lk <= 256) softmax_bwd_kernel<float, 4><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
-        else softmax_bwd_kernel<float, 8><<<grid, 256, sm, st>>>(dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+        if (Lk <= 256) launch_k(softmax_bwd_kernel<float, 4>, grid, 256, sm, st, dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens, row_scale);
+        else launch_k(softmax_bwd_kernel<float, 8>, grid, 256, sm, st, dPd, (const float*)P, (float*)dS, (float*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens, row_scale);
     } else {
-        if (Lk <= 256) softmax_bwd_kernel<bf16, 4><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
-        else softmax_bwd_kernel<bf16, 8><<<grid, 256, sm, st>>>(dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens);
+        if (Lk <= 256) launch_k(softmax_bwd_kernel<bf16, 4>, grid, 256, sm, st, dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens, row_scale);
+        else launch_k(softmax_bwd_kernel<bf16, 8>, grid, 256, sm, st, dPd, (const bf16*)P, (bf16*)dS, (bf16*)Pd_out, dbias_rel, H, Lq, Lk, drop, lens, row_scale);
     }
     LAUNCHED();
 }

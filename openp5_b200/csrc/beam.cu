@@ -106,6 +106,8 @@ __device__ __forceinline__ int trie_child(const int* off, const int* tok, const 
 // walks `prefix` from the root on the DEVICE copy and lists the children (Trie.get of the reference)
 __global__ void trie_get_kernel(const int* off, const int* tok, const int* node, const int* prefix, int n, int* out,
                                 int cap, int* n_out) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     int cur = 0;
     for (int i = 0; i < n && cur >= 0; ++i) cur = trie_child(off, tok, node, cur, prefix[i]);
     int cnt = 0;
@@ -120,7 +122,7 @@ int trie_get(Trie* t, const int32_t* prefix, int prefix_len, int32_t* out, int c
     P5_CUDA(cudaMalloc(&d_out, (cap + 1) * sizeof(int)));
     P5_CUDA(cudaMalloc(&d_n, sizeof(int)));
     if (prefix_len) P5_CUDA(cudaMemcpy(d_pre, prefix, prefix_len * sizeof(int), cudaMemcpyHostToDevice));
-    trie_get_kernel<<<1, 1>>>(t->d_off, t->d_tok, t->d_node, d_pre, prefix_len, d_out, cap, d_n);
+    launch_k(trie_get_kernel, 1, 1, 0, nullptr, t->d_off, t->d_tok, t->d_node, d_pre, prefix_len, d_out, cap, d_n);
     P5_CUDA(cudaGetLastError());
     int n = 0;
     P5_CUDA(cudaMemcpy(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost));
@@ -195,6 +197,8 @@ static GenWs* get_gen_ws(Engine* e, int R, int T, int K, int B, int cand_cap, in
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gen_init_kernel(int* seq, int* fin_seq, int* src, int* node, float* run_score, float* fin_score,
                                 int* is_fin, int* gen_len, int* cur_tok, int* unsat, int B, int K, int T, int root_child) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B * K) return;
     for (int t = 0; t < T; ++t) { seq[r * T + t] = 0; fin_seq[r * T + t] = 0; src[r * T + t] = r; }
@@ -212,6 +216,8 @@ __global__ void __launch_bounds__(64)
 decode_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ Kc, T* __restrict__ Vc, const int* __restrict__ src,
                         const float* __restrict__ bias_rel, int n_delta, int bias_off, T* __restrict__ ctx, int A, int Tm,
                         int pos) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     extern __shared__ float sm[];
     float* q = sm;            // [64]
     float* p = sm + 64;       // [pos+1]
@@ -250,6 +256,8 @@ decode_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ Kc, T* __rest
 __global__ void __launch_bounds__(512)
 rows_logsumexp_kernel(const float* __restrict__ logits, int64_t ld, int V, float* __restrict__ rowmax,
                       float* __restrict__ logsum) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ float sh[32];
     const int r = blockIdx.x;
     const float* l = logits + (int64_t)r * ld;
@@ -281,6 +289,8 @@ topk_candidates_kernel(const float* __restrict__ logits, int64_t ld, int V, cons
                        const int* __restrict__ node, const int* __restrict__ t_off, const int* __restrict__ t_tok,
                        int K, float* __restrict__ scr_score, int* __restrict__ scr_flat, int scr_cap,
                        float* __restrict__ cand_lp, int* __restrict__ cand_beam, int* __restrict__ cand_tok) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ int s_count;
     __shared__ float s_best[8];
     __shared__ int s_besti[8], s_bestf[8];
@@ -355,6 +365,8 @@ beam_update_kernel(const float* __restrict__ cand_lp, const int* __restrict__ ca
                    int* __restrict__ cur_tok, int* __restrict__ unsat, const int* __restrict__ t_off,
                    const int* __restrict__ t_tok, const int* __restrict__ t_node, int K, int T, int cur_len, int max_len,
                    int eos, float denom_fin, float denom_next) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     extern __shared__ int smi[];
     int* run_sel = smi;              // [K]   candidate index chosen for running slot k
     int* fin_sel = smi + K;          // [K]   merged index chosen for finished slot k
@@ -499,6 +511,8 @@ __global__ void gen_finalize_kernel(const int* __restrict__ fin_seq, const float
                                     const int* __restrict__ is_fin, const int* __restrict__ gen_len, int B, int K, int R,
                                     int T, int max_len, int32_t* __restrict__ seqs, float* __restrict__ scores,
                                     int* __restrict__ out_len) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ int s_max;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
@@ -549,7 +563,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
     e->build_bias(false, T);   // decoder relative bias for positions 0..T-1: [H, 2T-1], offset T-1
     const int n_delta = 2 * T - 1, bias_off = T - 1;
 
-    gen_init_kernel<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(g->seq[0], g->fin_seq[0], g->src[0], g->node[0], g->run_score[0],
+    launch_k(gen_init_kernel, (unsigned)cdiv(R, 128), 128, 0, st, g->seq[0], g->fin_seq[0], g->src[0], g->node[0], g->run_score[0],
                                                            g->fin_score[0], g->is_fin[0], g->gen_len[0], g->cur_tok, g->unsat,
                                                            B, K, T, root_child);
     LAUNCHED();
@@ -584,11 +598,11 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
             e->linear_fwd(g->n, d, w.sa.q, 3 * A, d, R, g->qkv, dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
             const size_t sm = (64 + pos + 1) * sizeof(float);
             if (dt == DT_F32)
-                decode_self_attn_kernel<float><<<dim3(H, R), 64, sm, st>>>((const float*)g->qkv, (float*)g->Kc[l], (float*)g->Vc[l],
+                launch_k(decode_self_attn_kernel<float>, dim3(H, R), 64, sm, st, (const float*)g->qkv, (float*)g->Kc[l], (float*)g->Vc[l],
                                                                          g->src[cur], e->bias_dec, n_delta, bias_off,
                                                                          (float*)g->ctx, A, T, pos);
             else
-                decode_self_attn_kernel<bf16><<<dim3(H, R), 64, sm, st>>>((const bf16*)g->qkv, (bf16*)g->Kc[l], (bf16*)g->Vc[l],
+                launch_k(decode_self_attn_kernel<bf16>, dim3(H, R), 64, sm, st, (const bf16*)g->qkv, (bf16*)g->Kc[l], (bf16*)g->Vc[l],
                                                                         g->src[cur], e->bias_dec, n_delta, bias_off,
                                                                         (bf16*)g->ctx, A, T, pos);
             LAUNCHED();
@@ -636,24 +650,23 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         rmsnorm_fwd(g->y, e->P + e->off_dec_final, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
         e->linear_fwd(g->n, d, e->off_shared, V, d, R, g->logits, DT_F32, Vpad, 0, hs, nullptr, nullptr, none);
         // ---- log-softmax normaliser, constrained top-2K, beam bookkeeping
-        rows_logsumexp_kernel<<<R, 512, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum);
+        launch_k(rows_logsumexp_kernel, R, 512, 0, st, g->logits, Vpad, V, g->rowmax, g->logsum);
         LAUNCHED();
-        topk_candidates_kernel<<<B, 256, 0, st>>>(g->logits, Vpad, V, g->rowmax, g->logsum, g->run_score[cur], g->node[cur],
+        launch_k(topk_candidates_kernel, B, 256, 0, st, g->logits, Vpad, V, g->rowmax, g->logsum, g->run_score[cur], g->node[cur],
                                                  trie->d_off, trie->d_tok, K, g->scr_score, g->scr_flat, g->scr_cap,
                                                  g->cand_lp, g->cand_beam, g->cand_tok);
         LAUNCHED();
         const int nxt = cur ^ 1;
         const float denom_fin = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
         const float denom_next = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
-        beam_update_kernel<<<B, 128, 8 * K * sizeof(int), st>>>(
-            g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
+        launch_k(beam_update_kernel, B, 128, 8 * K * sizeof(int), st, g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
             g->src[nxt], g->node[cur], g->node[nxt], g->run_score[nxt], g->fin_score[cur], g->fin_score[nxt], g->is_fin[cur],
             g->is_fin[nxt], g->gen_len[cur], g->gen_len[nxt], g->cur_tok, g->unsat, trie->d_off, trie->d_tok, trie->d_node, K,
             T, cur_len, max_len, 1 /*eos*/, denom_fin, denom_next);
         LAUNCHED();
         cur = nxt;
     }
-    gen_finalize_kernel<<<1, 256, 0, st>>>(g->fin_seq[cur], g->fin_score[cur], g->is_fin[cur], g->gen_len[cur], B, K, Rret, T,
+    launch_k(gen_finalize_kernel, 1, 256, 0, st, g->fin_seq[cur], g->fin_score[cur], g->is_fin[cur], g->gen_len[cur], B, K, Rret, T,
                                           max_len, seqs, scores, g->out_len);
     LAUNCHED();
     if (out_len_host) {

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <utility>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -78,12 +80,16 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
+// The (seed, site) pair is folded into a 64-bit key (k0, k1) by two full mixing rounds; the key depends only on
+// kernel-uniform values, so the compiler hoists it out of every element loop.  Per pair of elements the cost is one
+// mixing round: h = mix32(pair ^ k0) + k1.  (mix32 is a bijection with full avalanche, so for a fixed key the
+// counter stream is equidistributed; the additive k1 decorrelates the 16-bit halves between sites.  The pair
+// counter is truncated to 32 bits: masks repeat after 2^33 elements, far beyond any tensor of this engine.)
 __host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint32_t site, uint64_t idx) {
-    uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
-    uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
-    uint32_t h = mix32(lo ^ s0);
-    h = mix32(h + 0x9e3779b9U * (site + 1u) + hi * 0x85ebca6bU + s1);
-    return h;
+    const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+    const uint32_t k0 = mix32(mix32(s0 ^ 0x9e3779b9U) + 0x9e3779b9U * (site + 1u) + s1);
+    const uint32_t k1 = mix32(k0 ^ 0x85ebca6bU);
+    return mix32((uint32_t)idx ^ k0) + k1;
 }
 // One 32-bit hash serves an aligned PAIR of elements (2k, 2k+1): the low 16 bits decide the even element, the high
 // 16 bits the odd one (keep iff bits >= thr16, thr16 = round(p * 2^16)).  Kernels that own both elements of a pair
@@ -103,6 +109,35 @@ static inline uint32_t drop_threshold(float p) {
     if (t <= 0) return 0u;
     if (t >= 4294967295.0) return 4294967295u;
     return (uint32_t)t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A train step is ~700 short kernels on one stream and a decode position ~170;
+// with plain stream order every boundary costs grid drain + launch latency + the next kernel's prologue.  Every kernel
+// of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// griddepcontrol.wait (blocks until the previous grid has COMPLETED and flushed its memory) followed by
+// griddepcontrol.launch_dependents (lets the next grid's CTAs be scheduled as soon as every CTA of this grid has
+// started, i.e. into SM slots as they drain).  Data hazards are impossible by construction: no kernel touches global
+// memory before its wait, and since every kernel waits, completion order along the stream is transitive.  What
+// overlaps is CTA scheduling, barrier/TMEM/tensor-map set-up (placed before the wait in the tcgen05 kernels) and the
+// launch latency itself.  P5_NO_PDL=1 restores plain stream serialisation (the device instructions become no-ops).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = getenv("P5_NO_PDL") == nullptr;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -149,6 +149,8 @@ template <int NT, int NW> struct DCfg {
 template <int NT, int NW, bool LQ16>
 __global__ void __launch_bounds__(NW * 32)
 dattn_fwd_kernel(DAttnDev a, bf16* __restrict__ O, int64_t ld_o, int64_t bs_o, float* __restrict__ lse) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     using C = DCfg<NT, NW>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* Vs = smem;                                              // later aliased by the fp32 partial outputs
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(NW * 32)
 dattn_bwd_kernel(DAttnDev a, const bf16* __restrict__ dO, int64_t ld_do, int64_t bs_do, const float* __restrict__ lse,
                  bf16* __restrict__ dQ, int64_t ld_dq, int64_t bs_dq, bf16* __restrict__ dK, bf16* __restrict__ dV, int64_t ld_dkv,
                  int64_t bs_dkv, float* __restrict__ dbias_rel) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     using C = DCfg<NT, NW>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* Ks = smem;                                               // [NW*KW][64] swizzled
@@ -483,7 +487,7 @@ void launch_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* l
     constexpr int sm = DCfg<NT, NW>::FWD_SMEM;
     static bool set = false;
     if (!set) { P5_CUDA(cudaFuncSetAttribute(dattn_fwd_kernel<NT, NW, LQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); set = true; }
-    dattn_fwd_kernel<NT, NW, LQ16><<<(unsigned)(a.B * a.H), NW * 32, sm, st>>>(to_dev(a), (bf16*)O, ld_o, bs_o, lse);
+    launch_k(dattn_fwd_kernel<NT, NW, LQ16>, (unsigned)(a.B * a.H), NW * 32, sm, st, to_dev(a), (bf16*)O, ld_o, bs_o, lse);
     LAUNCHED();
 }
 template <int NT, int NW, bool LQ16>
@@ -492,7 +496,7 @@ void launch_bwd(const AttnArgs& a, const void* dO, int64_t ld_do, int64_t bs_do,
     constexpr int sm = DCfg<NT, NW>::BWD_SMEM;
     static bool set = false;
     if (!set) { P5_CUDA(cudaFuncSetAttribute(dattn_bwd_kernel<NT, NW, LQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); set = true; }
-    dattn_bwd_kernel<NT, NW, LQ16><<<(unsigned)(a.B * a.H), NW * 32, sm, st>>>(to_dev(a), (const bf16*)dO, ld_do, bs_do, lse, (bf16*)dQ,
+    launch_k(dattn_bwd_kernel<NT, NW, LQ16>, (unsigned)(a.B * a.H), NW * 32, sm, st, to_dev(a), (const bf16*)dO, ld_do, bs_do, lse, (bf16*)dQ,
                                                                               ld_dq, bs_dq, (bf16*)dK, (bf16*)dV, ld_dkv, bs_dkv, dbias_rel);
     LAUNCHED();
 }

@@ -118,7 +118,7 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     for (auto& p : ne) p = dalloc(Mem * d * e);
     enc_out = dalloc(Mem * d * e);
     qkv_e.resize(NE); ctx_e.resize(NE); h_e.resize(NE); z_e.assign(NE, nullptr); P_e.assign(NE, nullptr);
-    lse_e.assign(NE, nullptr);
+    lse_e.assign(NE, nullptr); p_unnorm.assign(NE, false);
     const int64_t SS = (int64_t)Bm * H * Lem * Lem;
     for (int i = 0; i < NE; ++i) {
         qkv_e[i] = dalloc(Mem * 3 * A * e);
@@ -126,7 +126,7 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
         h_e[i] = dalloc(Mem * ff * e);
         if (gated) z_e[i] = dalloc(Mem * 2 * ff * e);
         if (tc_attn) P_e[i] = dalloc(SS * e);
-        else lse_e[i] = dalloc_t<float>((int64_t)Bm * H * Lem);
+        lse_e[i] = dalloc_t<float>((int64_t)Bm * H * Lem);   // fp32 mode: LSE; bf16 mode: 1 / row sum of the fused kernel
     }
     if (tc_attn) {
         S_scr = dalloc_t<float>(SS);
@@ -265,6 +265,8 @@ void Engine::linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t l
 // inputs
 // ------------------------------------------------------------------------------------------------------------
 __global__ void shift_right_kernel(const int* __restrict__ labels, int* __restrict__ dec_ids, int B, int Ld) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Ld) return;
     const int t = i % Ld;
@@ -321,7 +323,7 @@ void Engine::load_inputs(const int32_t* ids, const int32_t* mask, const int32_t*
     }
     if (lab) {
         P5_CUDA(cudaMemcpyAsync(labels, lab, Md * 4, cudaMemcpyDeviceToDevice, st));
-        shift_right_kernel<<<(unsigned)cdiv(Md, 256), 256, 0, st>>>(labels, dec_ids, B, Ld);
+        launch_k(shift_right_kernel, (unsigned)cdiv(Md, 256), 256, 0, st, labels, dec_ids, B, Ld);
         P5_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -406,9 +408,10 @@ void Engine::enc_attention_fwd(int l) {
     if (fused < 0) { const char* e = getenv("P5_ATTN"); fused = (e && strcmp(e, "unfused") == 0) ? 0 : 1; }
     const DropCfg dc = drop(S_ENC_P, l);
     if (dt == DT_BF16 && (fused || packed)) {
-        const bool ok = fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, P_e[l], ctx_e[l], A, dc, st,
+        const bool ok = fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, P_e[l], lse_e[l], ctx_e[l], A, dc, st,
                                   packed ? offs_d : nullptr, packed ? lens_d : nullptr, Mt);
         P5_CHECK(ok || !packed, "packed encoder attention needs the fused kernel (Le <= 512)");
+        p_unnorm[l] = ok;     // P_e[l] holds un-normalised probabilities, lse_e[l] the 1 / row-sum factors
         if (ok) return;
     }
     const void* qkv = qkv_e[l];
@@ -466,8 +469,11 @@ void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
         p.B.bs2 = (int64_t)Le * 3 * A;
         p.epi.C = S_scr; p.epi.c_dtype = DT_F32; p.epi.ldc = Le; p.epi.cs1 = SS1; p.epi.cs2 = SS1 * H;
         gemm(p);
-        const bool regen = dc.thr || packed;   // packed: P_save holds stale rows/columns outside the sequences
-        softmax_bwd(S_scr, P_e[l], dS_scr, regen ? Pd_scr : nullptr, dt, dbias_enc, B, H, Le, Le, dc, st, packed ? lens_d : nullptr);
+        // regenerate Pd when dropout is on, when packed (P_save holds stale rows/columns outside the sequences) or when
+        // the fused forward saved un-normalised probabilities
+        const bool regen = dc.thr || packed || p_unnorm[l];
+        softmax_bwd(S_scr, P_e[l], dS_scr, regen ? Pd_scr : nullptr, dt, dbias_enc, B, H, Le, Le, dc, st, packed ? lens_d : nullptr,
+                    p_unnorm[l] ? lse_e[l] : nullptr);
         const void* Pd = regen ? Pd_scr : P_e[l];
         GemmProblem v;   // dV[j,c] = sum_i Pd[i,j] dctx[i,c]
         v.M = Le; v.N = 64; v.K = Le; v.nb1 = H; v.nb2 = B;

@@ -34,7 +34,7 @@ static constexpr int KB = 128;      // keys per block
 static constexpr int NSB = 3;       // S = Q K^T buffers in TMEM (3 x 128 columns + 64 columns of O <= 512)
 
 struct FaParams {
-    int B, H, Lq, Lk, nkb, nqt, nq_buf;
+    int B, H, Lq, Lk, nkb, nqt, nq_buf, np_buf;   // nq_buf / np_buf: Q-tile and P-tile buffers that fit next to K and V
     const float* bias_rel;   // [H, Lq + Lk - 1]
     const int* key_mask;     // [B, Lk]
     bf16* P_save;            // [B, H, Lq, Lk] UN-normalised probabilities 2^(s2 - m2) (un-dropped)
@@ -98,13 +98,15 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder_ptr;
-    const uint32_t tS[NSB] = {tmem, tmem + 128, tmem + 256};
+    pdl_wait();               // PDL: the set-up above overlaps the previous kernel's tail (see common.cuh)
+    pdl_launch_dependents();
+    auto tS = [&](int i) { return tmem + (uint32_t)i * 128u; };
     const uint32_t tO = tmem + 384;
 
     if (warp == 0) {
         // ========================= TMA producer =========================
         if (lane == 0) {
-            uint32_t kv_ph = 0, q_ph[2] = {0, 0};
+            uint32_t kv_ph = 0, q_ph = 0;   // phase bits, one per buffer (register-resident: no dynamically indexed arrays)
             int qb = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int b = pair / P.H, h = pair % P.H;
@@ -121,10 +123,10 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 }
                 kv_ph ^= 1;
                 for (int qt = 0; qt < nqt; ++qt) {
-                    mbar_wait(q_empty(qb), q_ph[qb] ^ 1);
+                    mbar_wait(q_empty(qb), ((q_ph >> qb) & 1u) ^ 1u);
                     mbar_expect_tx(q_full(qb), QT * 128);
                     tma_load_4d(sQ + qb * (QT * 128), &tmQ, q_full(qb), 0, row0 + qt * QT, h, bc);
-                    q_ph[qb] ^= 1;
+                    q_ph ^= 1u << qb;
                     qb = (qb + 1) % P.nq_buf;
                 }
             }
@@ -137,15 +139,15 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                                      ((uint32_t)(128 >> 4) << 24);
-            uint32_t kv_ph = 0, q_ph[2] = {0, 0}, se_ph[NSB] = {0, 0, 0}, pf_ph[2] = {0, 0}, oe_ph = 0;
+            uint32_t kv_ph = 0, q_ph = 0, se_ph = 0, pf_ph = 0, oe_ph = 0;   // phase bits per buffer
             int qb = 0, sb = 0, pb = 0;
             auto issue_s = [&](int kb, uint32_t q_addr) {
-                mbar_wait(s_empty(sb), se_ph[sb] ^ 1);
-                se_ph[sb] ^= 1;
+                mbar_wait(s_empty(sb), ((se_ph >> sb) & 1u) ^ 1u);
+                se_ph ^= 1u << sb;
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_bf16(tS[sb], make_smem_desc(q_addr + k * 32, 16, 1024),
+                    umma_bf16(tS(sb), make_smem_desc(q_addr + k * 32, 16, 1024),
                               make_smem_desc(sK + kb * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
                 umma_commit(s_full(sb));
                 sb = (sb + 1) % NSB;
@@ -156,8 +158,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 mbar_wait(kv_full, kv_ph);
                 kv_ph ^= 1;
                 for (int qt = 0; qt < nqt; ++qt) {
-                    mbar_wait(q_full(qb), q_ph[qb]);
-                    q_ph[qb] ^= 1;
+                    mbar_wait(q_full(qb), (q_ph >> qb) & 1u);
+                    q_ph ^= 1u << qb;
                     tc_fence_after();
                     const uint32_t q_addr = sQ + qb * (QT * 128);
                     // pass 1: statistics
@@ -169,8 +171,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     for (int kb = 0; kb < nkb; ++kb) {
                         if (kb + 1 < nkb) issue_s(kb + 1, q_addr);
                         else umma_commit(q_empty(qb));   // all QK^T of this tile issued: Q slot may be refilled once they retire
-                        mbar_wait(p_full(pb), pf_ph[pb]);
-                        pf_ph[pb] ^= 1;
+                        mbar_wait(p_full(pb), (pf_ph >> pb) & 1u);
+                        pf_ph ^= 1u << pb;
                         tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k) {
@@ -179,7 +181,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             umma_bf16(tO, da, db, idesc_o, (kb | k) != 0);
                         }
                         umma_commit(p_empty(pb));
-                        pb ^= 1;
+                        pb = (pb + 1 == P.np_buf) ? 0 : pb + 1;
                     }
                     umma_commit(o_full);
                     qb = (qb + 1) % P.nq_buf;
@@ -220,7 +222,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int sw = warp & 3;
         const int r = sw * 32 + lane;                     // row of the query tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
-        uint32_t sf_ph[NSB] = {0, 0, 0}, pe_ph[2] = {0, 0}, of_ph = 0, bm_ph = 0;
+        uint32_t sf_ph = 0, pe_ph = 0, of_ph = 0, bm_ph = 0;   // phase bits per buffer
         int sb = 0, pb = 0;
         const uint32_t t16 = P.drop.thr >> 16;
         const int cs = (int)P.bias_cs;
@@ -239,36 +241,31 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 // ---------------- pass 1: m2 = max_j (s_ij + bias) * log2(e) over this warpgroup's columns
                 float m2 = -INFINITY;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(s_full(sb), sf_ph[sb]);
-                    sf_ph[sb] ^= 1;
+                    mbar_wait(s_full(sb), (sf_ph >> sb) & 1u);
+                    sf_ph ^= 1u << sb;
                     tc_fence_after();
                     {
-                        uint32_t v[32];
-                        tmem_ld32(tS[sb] + lane_off + wg * 32, v);
                         const int j0 = kb * KB + wg * 32;
                         const int o = o_row + j0;
                         const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
+                        const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
                         const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
-                        tmem_ld_wait();
                         float cm = -INFINITY;
-                        if (full) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 bb = b4[q];
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x));
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y));
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z));
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w));
-                            }
-                        } else {
-                            const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
+                        for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time keeps the register count down
+                            uint32_t v[16];
+                            tmem_ld16(tS(sb) + lane_off + wg * 32 + hf * 16, v);
+                            tmem_ld_wait();
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 bb = b4[q], mm = m4[q];
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x) + mm.x);
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y) + mm.y);
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z) + mm.z);
-                                cm = fmaxf(cm, fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w) + mm.w);
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 bb = b4[4 * hf + q];
+                                float x0 = fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x), x1 = fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y);
+                                float x2 = fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z), x3 = fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w);
+                                if (!full) {
+                                    const float4 mm = m4[4 * hf + q];
+                                    x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                }
+                                cm = fmaxf(cm, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
                             }
                         }
                         m2 = fmaxf(m2, cm);
@@ -287,69 +284,74 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 // ---------------- pass 2: p~ = 2^(s2 - m2) (UN-normalised), dropout, smem A tile; l = sum p~
                 float l = 0.f;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(s_full(sb), sf_ph[sb]);
-                    sf_ph[sb] ^= 1;
+                    mbar_wait(s_full(sb), (sf_ph >> sb) & 1u);
+                    sf_ph ^= 1u << sb;
                     tc_fence_after();
                     // this warpgroup's 32 keys live in 64-key chunk (wg >> 1), 16-byte units (wg & 1) * 4 .. + 3
                     const uint32_t p_chunk = sP + pb * (QT * KB * 2) + (wg >> 1) * (QT * 128) + r * 128;
                     {
-                        uint32_t v[32];
-                        tmem_ld32(tS[sb] + lane_off + wg * 32, v);
                         const int j0 = kb * KB + wg * 32;
                         const int o = o_row + j0;
                         const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
                         const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
                         const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
                         const uint32_t pair0 = (uint32_t)((uint64_t)(grow + j0) >> 1);
-                        tmem_ld_wait();
-                        mbar_wait(p_empty(pb), pe_ph[pb] ^ 1);   // the MMA that read this P buffer has retired
-                        pe_ph[pb] ^= 1;
+                        mbar_wait(p_empty(pb), ((pe_ph >> pb) & 1u) ^ 1u);   // the MMA that read this P buffer has retired
+                        pe_ph ^= 1u << pb;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {            // 8 keys per step: one 16-byte store each way
-                            float pr[8];
+                        for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time keeps the register count down
+                            uint32_t v[16];
+                            tmem_ld16(tS(sb) + lane_off + wg * 32 + hf * 16, v);
+                            tmem_ld_wait();
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const float4 bb = b4[2 * q + u];
-                                float x0 = fmaf(__uint_as_float(v[8 * q + 4 * u]), LOG2E, bb.x);
-                                float x1 = fmaf(__uint_as_float(v[8 * q + 4 * u + 1]), LOG2E, bb.y);
-                                float x2 = fmaf(__uint_as_float(v[8 * q + 4 * u + 2]), LOG2E, bb.z);
-                                float x3 = fmaf(__uint_as_float(v[8 * q + 4 * u + 3]), LOG2E, bb.w);
-                                if (!full) {
-                                    const float4 mm = m4[2 * q + u];
-                                    x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                            for (int q2 = 0; q2 < 2; ++q2) {     // 8 keys per step: one 16-byte store each way
+                                const int q = 2 * hf + q2;
+                                float pr[8];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const float4 bb = b4[2 * q + u];
+                                    float x0 = fmaf(__uint_as_float(v[8 * q2 + 4 * u]), LOG2E, bb.x);
+                                    float x1 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 1]), LOG2E, bb.y);
+                                    float x2 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 2]), LOG2E, bb.z);
+                                    float x3 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 3]), LOG2E, bb.w);
+                                    if (!full) {
+                                        const float4 mm = m4[2 * q + u];
+                                        x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                    }
+                                    pr[4 * u] = ex2_approx(x0 - m2); pr[4 * u + 1] = ex2_approx(x1 - m2);
+                                    pr[4 * u + 2] = ex2_approx(x2 - m2); pr[4 * u + 3] = ex2_approx(x3 - m2);
                                 }
-                                pr[4 * u] = ex2_approx(x0 - m2); pr[4 * u + 1] = ex2_approx(x1 - m2);
-                                pr[4 * u + 2] = ex2_approx(x2 - m2); pr[4 * u + 3] = ex2_approx(x3 - m2);
-                            }
-                            l += ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
-                            uint32_t pk[4], pd[4];
+                                l += ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+                                uint32_t pk[4], pd[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) pk[u] = pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
-                            if (P.drop.thr) {
+                                for (int u = 0; u < 4; ++u) pk[u] = pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
+                                if (P.drop.thr) {
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + u));
-                                    pd[u] = pack_bf16x2((hsh & 0xffffu) >= t16 ? pr[2 * u] * P.drop.inv_keep : 0.f,
-                                                        (hsh >> 16) >= t16 ? pr[2 * u + 1] * P.drop.inv_keep : 0.f);
-                                }
-                            } else {
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) pd[u] = pk[u];
-                            }
-                            // global P_save (un-normalised, un-dropped; the backward multiplies by row_scale)
-                            if (row_ok && P.P_save) {
-                                const int j = j0 + 8 * q;
-                                if (j + 8 <= Lk) {
-                                    *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                    for (int u = 0; u < 4; ++u) {
+                                        const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + u));
+                                        pd[u] = pack_bf16x2((hsh & 0xffffu) >= t16 ? pr[2 * u] * P.drop.inv_keep : 0.f,
+                                                            (hsh >> 16) >= t16 ? pr[2 * u + 1] * P.drop.inv_keep : 0.f);
+                                    }
                                 } else {
-                                    for (int t = 0; t < 4; ++t)
-                                        if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[t];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) pd[u] = pk[u];
                                 }
+                                // global P_save (un-normalised, un-dropped; the backward multiplies by row_scale)
+                                if (row_ok && P.P_save) {
+                                    const int j = j0 + 8 * q;
+                                    if (j + 8 <= Lk) {
+                                        *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                    } else {
+#pragma unroll
+                                        for (int t = 0; t < 4; ++t)
+                                            if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[t];
+                                    }
+                                }
+                                // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
+                                const uint32_t addr = p_chunk + (uint32_t)((((wg & 1) * 4 + q) ^ (r & 7)) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[0]), "r"(pd[1]), "r"(pd[2]),
+                                             "r"(pd[3]) : "memory");
                             }
-                            // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
-                            const uint32_t addr = p_chunk + (uint32_t)((((wg & 1) * 4 + q) ^ (r & 7)) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[0]), "r"(pd[1]), "r"(pd[2]),
-                                         "r"(pd[3]) : "memory");
                         }
                     }
                     // S buffer free; P tile complete: make the generic-proxy smem writes visible to the tensor core
@@ -358,7 +360,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(s_empty(sb)); mbar_arrive(p_full(pb)); }
                     sb = (sb + 1) % NSB;
-                    pb ^= 1;
+                    pb = (pb + 1 == P.np_buf) ? 0 : pb + 1;
                 }
                 // row sum over the four column slices -> 1 / l normalises O here and P_save in the backward
                 statl_s[wg * QT + r] = l;
@@ -424,7 +426,8 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     const uint32_t kv_bytes = (uint32_t)P.nkb * KB * 128;
     P.nq_buf = (kv_bytes <= 48 * 1024) ? 2 : 1;
     P.sK = 0; P.sV = kv_bytes; P.sQ = 2 * kv_bytes; P.sP = P.sQ + P.nq_buf * QT * 128;
-    P.sBias = P.sP + 2 * QT * KB * 2;
+    P.np_buf = (kv_bytes <= 96 * 1024) ? 2 : 1;       // L = 512: K + V take 128 KB, one P tile is all that fits
+    P.sBias = P.sP + P.np_buf * QT * KB * 2;
     P.bias_cs = (uint32_t)(((L + P.nkb * KB + 4 + 31) & ~31) + 8);   // copies land in different bank groups
     P.sMask = P.sBias + (uint32_t)round_up(4 * P.bias_cs * 4, 16);
     P.sStat = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
@@ -451,7 +454,7 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     CUtensorMap tmV = tmap_bf16_4d(base + 2 * A, dims, strides, box);
     const int n_pairs = B * H;
     const int grid = n_pairs < num_sms ? n_pairs : num_sms;
-    fattn_fwd_kernel<<<grid, FA_THREADS, smem, st>>>(tmQ, tmK, tmV, P);
+    launch_k(fattn_fwd_kernel, grid, FA_THREADS, smem, st, tmQ, tmK, tmV, P);
     P5_CUDA(cudaGetLastError());
     ++g_launches;
     return true;

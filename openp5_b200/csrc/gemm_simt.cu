@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int M, int N, int K, int nb1, const TA* __restrict__ A, int64_t a_rs, int64_t a_ks, int64_t a_bs1,
                  int64_t a_bs2, const TB* __restrict__ B, int64_t b_rs, int64_t b_ks, int64_t b_bs1, int64_t b_bs2,
                  GemmEpilogue epi) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ float sA[SK][ST + 1];
     __shared__ float sB[SK][ST + 1];
     const int b = blockIdx.z;
@@ -79,7 +81,7 @@ static void launch_simt(const GemmProblem& p, cudaStream_t stream) {
     dim3 grid((unsigned)cdiv(p.N, ST), (unsigned)cdiv(p.M, ST), (unsigned)(p.nb1 * p.nb2));
     int64_t a_rs = p.A.major == MAJOR_K ? p.A.ld : 1, a_ks = p.A.major == MAJOR_K ? 1 : p.A.ld;
     int64_t b_rs = p.B.major == MAJOR_K ? p.B.ld : 1, b_ks = p.B.major == MAJOR_K ? 1 : p.B.ld;
-    gemm_simt_kernel<TA, TB><<<grid, 256, 0, stream>>>(p.M, p.N, p.K, p.nb1, (const TA*)p.A.ptr, a_rs, a_ks, p.A.bs1,
+    launch_k(gemm_simt_kernel<TA, TB>, grid, 256, 0, stream, p.M, p.N, p.K, p.nb1, (const TA*)p.A.ptr, a_rs, a_ks, p.A.bs1,
                                                         p.A.bs2, (const TB*)p.B.ptr, b_rs, b_ks, p.B.bs1, p.B.bs2,
                                                         p.epi);
     P5_CUDA(cudaGetLastError());

@@ -228,6 +228,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder_ptr;
+    // PDL: barrier init, TMEM allocation and tensor-map prefetch above overlap the tail of the previous kernel; nothing
+    // below touches global memory before the previous grid has completed
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -656,7 +660,7 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
         rec.flops = 2.0 * p.M * p.N * (double)p.K * p.nb1 * p.nb2; rec.bn = BN;
         cudaEventRecord(rec.e0, stream);
     }
-    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, P);
+    launch_k(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, P);
     P5_CUDA(cudaGetLastError());
     if (g_prof_on) { cudaEventRecord(rec.e1, stream); g_prof.push_back(rec); }
     ++g_tc_launches;

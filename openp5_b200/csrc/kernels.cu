@@ -41,6 +41,8 @@ template <int VEC>
 __global__ void embed_fwd_kernel(const float* __restrict__ E, const float* __restrict__ W, const int* __restrict__ ids,
                                  const int* __restrict__ ww, float* __restrict__ x, int M, int d, int vocab,
                                  int ww_rows, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -73,15 +75,17 @@ void embed_fwd(const float* E, const float* Wword, const int* ids, const int* ww
     const int rows_per_block = 8;
     dim3 grid((unsigned)cdiv(M, rows_per_block));
     if (d % 128 == 0)
-        embed_fwd_kernel<4><<<grid, rows_per_block * 32, 0, st>>>(E, Wword, ids, ww, x, M, d, vocab, ww_rows, drop);
+        launch_k(embed_fwd_kernel<4>, grid, rows_per_block * 32, 0, st, E, Wword, ids, ww, x, M, d, vocab, ww_rows, drop);
     else
-        embed_fwd_kernel<1><<<grid, rows_per_block * 32, 0, st>>>(E, Wword, ids, ww, x, M, d, vocab, ww_rows, drop);
+        launch_k(embed_fwd_kernel<1>, grid, rows_per_block * 32, 0, st, E, Wword, ids, ww, x, M, d, vocab, ww_rows, drop);
     LAUNCHED();
 }
 
 __global__ void embed_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ ids, const int* __restrict__ ww,
                                  float* __restrict__ dE, float* __restrict__ dW, int M, int d, int vocab, int ww_rows,
                                  DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -102,7 +106,7 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, const int* __rest
 void embed_bwd(const float* dx, const int* ids, const int* ww, float* dE, float* dWword, int M, int d, int vocab,
                int ww_rows, DropCfg drop, cudaStream_t st) {
     if (M <= 0) return;
-    embed_bwd_kernel<<<(unsigned)cdiv(M, 8), 256, 0, st>>>(dx, ids, ww, dE, dWword, M, d, vocab, ww_rows, drop);
+    launch_k(embed_bwd_kernel, (unsigned)cdiv(M, 8), 256, 0, st, dx, ids, ww, dE, dWword, M, d, vocab, ww_rows, drop);
     LAUNCHED();
 }
 
@@ -112,6 +116,8 @@ void embed_bwd(const float* dx, const int* ids, const int* ww, float* dE, float*
 template <typename T, int VEC>
 __global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ n,
                                    float* __restrict__ rstd, int M, int d, float eps, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -146,11 +152,11 @@ void rmsnorm_fwd(const float* x, const float* w, void* n, int n_dtype, float* rs
     dim3 grid((unsigned)cdiv(M, 8));
     const bool v4 = d % 128 == 0;
     if (n_dtype == DT_F32) {
-        if (v4) rmsnorm_fwd_kernel<float, 4><<<grid, 256, 0, st>>>(x, w, (float*)n, rstd, M, d, eps, drop);
-        else rmsnorm_fwd_kernel<float, 1><<<grid, 256, 0, st>>>(x, w, (float*)n, rstd, M, d, eps, drop);
+        if (v4) launch_k(rmsnorm_fwd_kernel<float, 4>, grid, 256, 0, st, x, w, (float*)n, rstd, M, d, eps, drop);
+        else launch_k(rmsnorm_fwd_kernel<float, 1>, grid, 256, 0, st, x, w, (float*)n, rstd, M, d, eps, drop);
     } else {
-        if (v4) rmsnorm_fwd_kernel<bf16, 4><<<grid, 256, 0, st>>>(x, w, (bf16*)n, rstd, M, d, eps, drop);
-        else rmsnorm_fwd_kernel<bf16, 1><<<grid, 256, 0, st>>>(x, w, (bf16*)n, rstd, M, d, eps, drop);
+        if (v4) launch_k(rmsnorm_fwd_kernel<bf16, 4>, grid, 256, 0, st, x, w, (bf16*)n, rstd, M, d, eps, drop);
+        else launch_k(rmsnorm_fwd_kernel<bf16, 1>, grid, 256, 0, st, x, w, (bf16*)n, rstd, M, d, eps, drop);
     }
     LAUNCHED();
 }
@@ -163,6 +169,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const T* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ rstd,
                    const float* __restrict__ w, const float* dres, float* dx,   // dres may alias dx (in-place)
                    float* __restrict__ dw, int M, int d, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     extern __shared__ float sdw[];  // [d]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < d; c += blockDim.x) sdw[c] = 0.f;
@@ -218,6 +226,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ rstd,
                        const float* __restrict__ w, const float* dres, float* dx, float* __restrict__ dw, int M,
                        DropCfg drop, bf16* __restrict__ dx_cast, DropCfg cast_drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     constexpr int d = NV * 128;
     __shared__ float sdw[d];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,9 +308,9 @@ static bool launch_rms_bwd_vec(const void* dn, const float* x, const float* rstd
                                cudaStream_t st) {
     dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
     switch (d) {
-        case 512: rmsnorm_bwd_vec_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
-        case 768: rmsnorm_bwd_vec_kernel<T, 6><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
-        case 1024: rmsnorm_bwd_vec_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
+        case 512: launch_k(rmsnorm_bwd_vec_kernel<T, 4>, grid, 256, 0, st, (const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
+        case 768: launch_k(rmsnorm_bwd_vec_kernel<T, 6>, grid, 256, 0, st, (const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
+        case 1024: launch_k(rmsnorm_bwd_vec_kernel<T, 8>, grid, 256, 0, st, (const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
         default: return false;
     }
 }
@@ -319,9 +329,9 @@ void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd
     dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
     const size_t sm = (size_t)d * sizeof(float);
     if (dn_dtype == DT_F32)
-        rmsnorm_bwd_kernel<float><<<grid, 256, sm, st>>>((const float*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
+        launch_k(rmsnorm_bwd_kernel<float>, grid, 256, sm, st, (const float*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
     else
-        rmsnorm_bwd_kernel<bf16><<<grid, 256, sm, st>>>((const bf16*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
+        launch_k(rmsnorm_bwd_kernel<bf16>, grid, 256, sm, st, (const bf16*)dn, x, rstd, w, dres, dx, dw, M, d, drop);
     LAUNCHED();
     if (dx_cast) drop_cast(dx, dx_cast, cast_dtype, (int64_t)M * d, cast_drop, st);
 }
@@ -331,6 +341,8 @@ void rmsnorm_bwd(const void* dn, int dn_dtype, const float* x, const float* rstd
 // =================================================================================================================
 template <typename T>
 __global__ void drop_cast_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t n, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 4 <= n) {
@@ -361,8 +373,8 @@ static inline unsigned ew_grid(int64_t n, int per_thread) {
 }
 void drop_cast(const float* in, void* out, int out_dtype, int64_t n, DropCfg drop, cudaStream_t st) {
     if (n <= 0) return;
-    if (out_dtype == DT_F32) drop_cast_kernel<float><<<ew_grid(n, 4), 256, 0, st>>>(in, (float*)out, n, drop);
-    else drop_cast_kernel<bf16><<<ew_grid(n, 4), 256, 0, st>>>(in, (bf16*)out, n, drop);
+    if (out_dtype == DT_F32) launch_k(drop_cast_kernel<float>, ew_grid(n, 4), 256, 0, st, in, (float*)out, n, drop);
+    else launch_k(drop_cast_kernel<bf16>, ew_grid(n, 4), 256, 0, st, in, (bf16*)out, n, drop);
     LAUNCHED();
 }
 void cast_f32_to(const float* in, void* out, int out_dtype, int64_t n, cudaStream_t st) {
@@ -370,6 +382,8 @@ void cast_f32_to(const float* in, void* out, int out_dtype, int64_t n, cudaStrea
     drop_cast(in, out, out_dtype, n, none, st);
 }
 __global__ void cast_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(in[i]);
 }
@@ -379,12 +393,14 @@ void cast_to_f32(const void* in, int in_dtype, float* out, int64_t n, cudaStream
         P5_CUDA(cudaMemcpyAsync(out, in, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
         return;
     }
-    cast_to_f32_kernel<<<ew_grid(n, 1), 256, 0, st>>>((const bf16*)in, out, n);
+    launch_k(cast_to_f32_kernel, ew_grid(n, 1), 256, 0, st, (const bf16*)in, out, n);
     LAUNCHED();
 }
 template <typename T>
 __global__ void cast_block_kernel(const float* __restrict__ in, int64_t ld_in, T* __restrict__ out, int64_t ld_out,
                                   int rows, int cols) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t n = (int64_t)rows * cols;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -396,17 +412,19 @@ void cast_block_f32_to(const float* in, int64_t ld_in, void* out, int out_dtype,
                        cudaStream_t st) {
     const int64_t n = (int64_t)rows * cols;
     if (n <= 0) return;
-    if (out_dtype == DT_F32) cast_block_kernel<float><<<ew_grid(n, 1), 256, 0, st>>>(in, ld_in, (float*)out, ld_out, rows, cols);
-    else cast_block_kernel<bf16><<<ew_grid(n, 1), 256, 0, st>>>(in, ld_in, (bf16*)out, ld_out, rows, cols);
+    if (out_dtype == DT_F32) launch_k(cast_block_kernel<float>, ew_grid(n, 1), 256, 0, st, in, ld_in, (float*)out, ld_out, rows, cols);
+    else launch_k(cast_block_kernel<bf16>, ew_grid(n, 1), 256, 0, st, in, ld_in, (bf16*)out, ld_out, rows, cols);
     LAUNCHED();
 }
 __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
 }
 void add_f32(float* dst, const float* src, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
-    add_f32_kernel<<<ew_grid(n, 1), 256, 0, st>>>(dst, src, n);
+    launch_k(add_f32_kernel, ew_grid(n, 1), 256, 0, st, dst, src, n);
     LAUNCHED();
 }
 
@@ -416,6 +434,8 @@ void add_f32(float* dst, const float* src, int64_t n, cudaStream_t st) {
 // dst_packed[offs[b] + i, :] = src_padded[b*L + i, :]  (i < lens[b]); W elements per row, 16-byte chunks
 __global__ void pack_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ offs,
                                  const int* __restrict__ lens, int L, int chunks) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int len = lens[b];
     const int64_t n = (int64_t)len * chunks;
@@ -426,6 +446,8 @@ __global__ void pack_rows_kernel(const uint4* __restrict__ src, uint4* __restric
 // dst_padded[b*L + i, :] = i < lens[b] ? src_packed[offs[b] + i, :] : 0
 __global__ void unpack_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ offs,
                                    const int* __restrict__ lens, int L, int chunks) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int len = lens[b];
     const int64_t n = (int64_t)L * chunks, nv = (int64_t)len * chunks;
@@ -440,7 +462,7 @@ void pack_rows(const void* src_padded, void* dst_packed, const int* offs, const 
     P5_CHECK(row_bytes % 16 == 0, "pack_rows: row size must be a multiple of 16 bytes");
     const int chunks = (int)(row_bytes / 16);
     dim3 grid((unsigned)std::min<int64_t>(64, cdiv((int64_t)L * chunks, 256)), (unsigned)B);
-    pack_rows_kernel<<<grid, 256, 0, st>>>((const uint4*)src_padded, (uint4*)dst_packed, offs, lens, L, chunks);
+    launch_k(pack_rows_kernel, grid, 256, 0, st, (const uint4*)src_padded, (uint4*)dst_packed, offs, lens, L, chunks);
     LAUNCHED();
 }
 void unpack_rows(const void* src_packed, void* dst_padded, const int* offs, const int* lens, int B, int L, int64_t row_bytes,
@@ -449,18 +471,20 @@ void unpack_rows(const void* src_packed, void* dst_padded, const int* offs, cons
     P5_CHECK(row_bytes % 16 == 0, "unpack_rows: row size must be a multiple of 16 bytes");
     const int chunks = (int)(row_bytes / 16);
     dim3 grid((unsigned)std::min<int64_t>(64, cdiv((int64_t)L * chunks, 256)), (unsigned)B);
-    unpack_rows_kernel<<<grid, 256, 0, st>>>((const uint4*)src_packed, (uint4*)dst_padded, offs, lens, L, chunks);
+    launch_k(unpack_rows_kernel, grid, 256, 0, st, (const uint4*)src_packed, (uint4*)dst_padded, offs, lens, L, chunks);
     LAUNCHED();
 }
 // packed int arrays from padded [B, L] (token ids / whole-word ids)
 __global__ void pack_ints_kernel(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ offs,
                                  const int* __restrict__ lens, int L) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < lens[b]; i += blockDim.x) dst[offs[b] + i] = src[b * L + i];
 }
 void pack_ints(const int* src_padded, int* dst_packed, const int* offs, const int* lens, int B, int L, cudaStream_t st) {
     if (B <= 0) return;
-    pack_ints_kernel<<<B, 256, 0, st>>>(src_padded, dst_packed, offs, lens, L);
+    launch_k(pack_ints_kernel, B, 256, 0, st, src_padded, dst_packed, offs, lens, L);
     LAUNCHED();
 }
 
@@ -479,6 +503,8 @@ __device__ __forceinline__ float gelu_new_grad(float x) {
 }
 template <typename T>
 __global__ void gated_gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ h, int M, int ff, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t n = (int64_t)M * ff;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -491,6 +517,8 @@ __global__ void gated_gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ h
 template <typename T>
 __global__ void gated_gelu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, T* __restrict__ dz, int M,
                                       int ff, DropCfg drop) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t n = (int64_t)M * ff;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -505,17 +533,17 @@ __global__ void gated_gelu_bwd_kernel(const T* __restrict__ z, const T* __restri
 void gated_gelu_fwd(const void* z, void* h, int dtype, int M, int ff, DropCfg drop, cudaStream_t st) {
     const int64_t n = (int64_t)M * ff;
     if (n <= 0) return;
-    if (dtype == DT_F32) gated_gelu_fwd_kernel<float><<<ew_grid(n, 1), 256, 0, st>>>((const float*)z, (float*)h, M, ff, drop);
-    else gated_gelu_fwd_kernel<bf16><<<ew_grid(n, 1), 256, 0, st>>>((const bf16*)z, (bf16*)h, M, ff, drop);
+    if (dtype == DT_F32) launch_k(gated_gelu_fwd_kernel<float>, ew_grid(n, 1), 256, 0, st, (const float*)z, (float*)h, M, ff, drop);
+    else launch_k(gated_gelu_fwd_kernel<bf16>, ew_grid(n, 1), 256, 0, st, (const bf16*)z, (bf16*)h, M, ff, drop);
     LAUNCHED();
 }
 void gated_gelu_bwd(const void* z, const void* dh, void* dz, int dtype, int M, int ff, DropCfg drop, cudaStream_t st) {
     const int64_t n = (int64_t)M * ff;
     if (n <= 0) return;
     if (dtype == DT_F32)
-        gated_gelu_bwd_kernel<float><<<ew_grid(n, 1), 256, 0, st>>>((const float*)z, (const float*)dh, (float*)dz, M, ff, drop);
+        launch_k(gated_gelu_bwd_kernel<float>, ew_grid(n, 1), 256, 0, st, (const float*)z, (const float*)dh, (float*)dz, M, ff, drop);
     else
-        gated_gelu_bwd_kernel<bf16><<<ew_grid(n, 1), 256, 0, st>>>((const bf16*)z, (const bf16*)dh, (bf16*)dz, M, ff, drop);
+        launch_k(gated_gelu_bwd_kernel<bf16>, ew_grid(n, 1), 256, 0, st, (const bf16*)z, (const bf16*)dh, (bf16*)dz, M, ff, drop);
     LAUNCHED();
 }
 
@@ -525,6 +553,8 @@ void gated_gelu_bwd(const void* z, const void* dh, void* dz, int dtype, int M, i
 __global__ void __launch_bounds__(256)
 ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int* __restrict__ labels, float* __restrict__ loss,
               float* __restrict__ lse, int V) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ float sh[32];
     const int row = blockIdx.x;
     const float* l = logits + (int64_t)row * ld;
@@ -544,7 +574,7 @@ ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int* __restric
 void ce_fwd(const float* logits, int64_t ld, const int* labels, float* loss_tok, float* lse, int M, int V,
             cudaStream_t st) {
     if (M <= 0) return;
-    ce_fwd_kernel<<<M, 256, 0, st>>>(logits, ld, labels, loss_tok, lse, V);
+    launch_k(ce_fwd_kernel, M, 256, 0, st, logits, ld, labels, loss_tok, lse, V);
     LAUNCHED();
 }
 template <typename T>
@@ -552,6 +582,8 @@ __global__ void __launch_bounds__(256)
 ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restrict__ lse,
               const int* __restrict__ labels, const float* __restrict__ dloss, T* __restrict__ dlogits, int V,
               int Vpad) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int row = blockIdx.x;
     const float* l = logits + (int64_t)row * ld;
     T* o = dlogits + (int64_t)row * Vpad;
@@ -567,14 +599,16 @@ ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restr
 void ce_bwd(const float* logits, int64_t ld, const float* lse, const int* labels, const float* dloss, void* dlogits,
             int d_dtype, int M, int V, int Vpad, cudaStream_t st) {
     if (M <= 0) return;
-    if (d_dtype == DT_F32) ce_bwd_kernel<float><<<M, 256, 0, st>>>(logits, ld, lse, labels, dloss, (float*)dlogits, V, Vpad);
-    else ce_bwd_kernel<bf16><<<M, 256, 0, st>>>(logits, ld, lse, labels, dloss, (bf16*)dlogits, V, Vpad);
+    if (d_dtype == DT_F32) launch_k(ce_bwd_kernel<float>, M, 256, 0, st, logits, ld, lse, labels, dloss, (float*)dlogits, V, Vpad);
+    else launch_k(ce_bwd_kernel<bf16>, M, 256, 0, st, logits, ld, lse, labels, dloss, (bf16*)dlogits, V, Vpad);
     LAUNCHED();
 }
 
 // one block; B*Ld is small (<= 64K)
 __global__ void runner_loss_kernel(const float* __restrict__ loss_tok, const int* __restrict__ mask, int B, int Ld,
                                    float* __restrict__ loss_out, float* __restrict__ dloss) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ float sh[32];
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -594,7 +628,7 @@ __global__ void runner_loss_kernel(const float* __restrict__ loss_tok, const int
 }
 void runner_loss_fwd_bwd(const float* loss_tok, const int* labels_mask, int B, int Ld, float* loss_out,
                          float* dloss_tok, cudaStream_t st) {
-    runner_loss_kernel<<<1, 256, 0, st>>>(loss_tok, labels_mask, B, Ld, loss_out, dloss_tok);
+    launch_k(runner_loss_kernel, 1, 256, 0, st, loss_tok, labels_mask, B, Ld, loss_out, dloss_tok);
     LAUNCHED();
 }
 
@@ -603,17 +637,21 @@ void runner_loss_fwd_bwd(const float* loss_tok, const int* labels_mask, int B, i
 // =================================================================================================================
 __global__ void relbias_build_kernel(const float* __restrict__ table, const int* __restrict__ lut,
                                      float* __restrict__ bias_rel, int H, int n_delta) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H * n_delta) return;
     const int h = i / n_delta, dlt = i % n_delta;
     bias_rel[i] = table[lut[dlt] * H + h];
 }
 void relbias_build(const float* table, const int* bucket_lut, float* bias_rel, int H, int n_delta, cudaStream_t st) {
-    relbias_build_kernel<<<(unsigned)cdiv(H * n_delta, 256), 256, 0, st>>>(table, bucket_lut, bias_rel, H, n_delta);
+    launch_k(relbias_build_kernel, (unsigned)cdiv(H * n_delta, 256), 256, 0, st, table, bucket_lut, bias_rel, H, n_delta);
     LAUNCHED();
 }
 __global__ void relbias_scatter_kernel(const float* __restrict__ dbias_rel, const int* __restrict__ lut,
                                        float* __restrict__ dtable, int H, int n_delta) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H * n_delta) return;
     const int h = i / n_delta, dlt = i % n_delta;
@@ -622,7 +660,7 @@ __global__ void relbias_scatter_kernel(const float* __restrict__ dbias_rel, cons
 }
 void relbias_scatter_grad(const float* dbias_rel, const int* bucket_lut, float* dtable, int H, int n_delta,
                           cudaStream_t st) {
-    relbias_scatter_kernel<<<(unsigned)cdiv(H * n_delta, 256), 256, 0, st>>>(dbias_rel, bucket_lut, dtable, H, n_delta);
+    launch_k(relbias_scatter_kernel, (unsigned)cdiv(H * n_delta, 256), 256, 0, st, dbias_rel, bucket_lut, dtable, H, n_delta);
     LAUNCHED();
 }
 

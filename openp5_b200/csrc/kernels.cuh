@@ -107,16 +107,18 @@ void softmax_fwd(const float* S, const float* bias_rel, const int* key_mask, voi
                  int H, int Lq, int Lk, int causal, DropCfg drop, cudaStream_t st);
 //   dP_in = gradient wrt Pd (fp32); dS = P * (mask(dP) - rowsum(mask(dP) * P)) -> dS (dtype);  Pd regenerated
 // lens (optional, packed training): rows / columns >= lens[b] hold no probabilities -> dS and Pd are written as zeros
+// row_scale (optional, [B,H,Lq]): P holds un-normalised probabilities, the true P is P * row_scale[row] (fattn_fwd)
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
-                 int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens = nullptr);
+                 int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens = nullptr, const float* row_scale = nullptr);
 
-// fused tcgen05 encoder self-attention forward (fattn.cu): qkv [B*L, 3A] bf16 -> ctx [B*L, A] bf16 (+ P_save bf16
-// [B,H,L,L] normalised un-dropped probabilities for the backward).  Returns false when the shape is unsupported.
+// fused tcgen05 encoder self-attention forward (fattn.cu): qkv [B*L, 3A] bf16 -> ctx [B*L, A] bf16.  For the backward
+// it saves P_save bf16 [B,H,L,L] = UN-normalised un-dropped probabilities 2^(s2 - m2) and row_scale fp32 [B,H,L] =
+// 1 / row sum (P = P_save * row_scale; softmax_bwd takes the pair).  Returns false when the shape is unsupported.
 // packed mode (offs/lens non-null): qkv / ctx are [packed_rows, .] with sequence b at rows offs[b] .. offs[b]+lens[b];
 // P_save keeps the padded [B,H,L,L] geometry (rows/cols < lens[b] written).
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
-               void* P_save, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st, const int* offs = nullptr,
-               const int* lens = nullptr, int64_t packed_rows = 0);
+               void* P_save, float* row_scale, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st,
+               const int* offs = nullptr, const int* lens = nullptr, int64_t packed_rows = 0);
 
 // dbias_rel[h, j - i + Lq - 1] += sum_{b,i} dS[b,h,i,j]   (dS [B,H,Lq,Lk], register accumulation per diagonal)
 void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H, int Lq, int Lk, cudaStream_t st);

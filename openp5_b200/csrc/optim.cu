@@ -10,6 +10,8 @@ extern int g_launches;
 #define LAUNCHED() do { P5_CUDA(cudaGetLastError()); ++g_launches; } while (0)
 
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ float sh[32];
     float s = 0.f;
     const int64_t n4 = n >> 2;
@@ -24,6 +26,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partial, int np, float* __restrict__ out) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     __shared__ float sh[32];
     // accumulate the per-block partials in double: 1e3 partials of ~1e5 elements each
     double s = 0.0;
@@ -35,19 +39,21 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restric
 }
 void sumsq_norm(const float* g, int64_t n, float* partial, float* out_norm, cudaStream_t st) {
     const int np = 1024;
-    sumsq_partial_kernel<<<np, 256, 0, st>>>(g, n, partial);
+    launch_k(sumsq_partial_kernel, np, 256, 0, st, g, n, partial);
     LAUNCHED();
-    sumsq_final_kernel<<<1, 256, 0, st>>>(partial, np, out_norm);
+    launch_k(sumsq_final_kernel, 1, 256, 0, st, partial, np, out_norm);
     LAUNCHED();
 }
 
 __global__ void scale_kernel(float* __restrict__ g, int64_t n, float s) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] *= s;
 }
 void scale_f32(float* g, int64_t n, float s, cudaStream_t st) {
     if (n <= 0) return;
-    scale_kernel<<<148 * 8, 256, 0, st>>>(g, n, s);
+    launch_k(scale_kernel, 148 * 8, 256, 0, st, g, n, s);
     LAUNCHED();
 }
 
@@ -56,6 +62,8 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, int64_t n, float lr, float b1, float b2, float eps, float wd, float step_size,
              float clip, const float* __restrict__ norm_ptr, float grad_div) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
     float gs = grad_div;
     if (clip > 0.f && norm_ptr) {
         // clip_grad_norm_: coef = clip / (norm + 1e-6), clamped to 1; the norm is of the (already averaged) gradient
@@ -108,7 +116,7 @@ void adamw_flat(float* p, const float* g, float* m, float* v, bf16* p16, int64_t
     const double bc1 = 1.0 - pow((double)b1, (double)step);
     const double bc2 = 1.0 - pow((double)b2, (double)step);
     const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-    adamw_kernel<<<148 * 8, 256, 0, st>>>(p, g, m, v, p16, n, lr, b1, b2, eps, wd, step_size, clip, norm_ptr, grad_div);
+    launch_k(adamw_kernel, 148 * 8, 256, 0, st, p, g, m, v, p16, n, lr, b1, b2, eps, wd, step_size, clip, norm_ptr, grad_div);
     LAUNCHED();
 }
 

