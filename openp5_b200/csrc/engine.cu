@@ -118,7 +118,7 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     for (auto& p : ne) p = dalloc(Mem * d * e);
     enc_out = dalloc(Mem * d * e);
     qkv_e.resize(NE); ctx_e.resize(NE); h_e.resize(NE); z_e.assign(NE, nullptr); P_e.assign(NE, nullptr);
-    lse_e.assign(NE, nullptr); p_unnorm.assign(NE, false);
+    lse_e.assign(NE, nullptr); p_unnorm.assign(NE, false); p_fbwd.assign(NE, false);
     const int64_t SS = (int64_t)Bm * H * Lem * Lem;
     for (int i = 0; i < NE; ++i) {
         qkv_e[i] = dalloc(Mem * 3 * A * e);
@@ -408,10 +408,15 @@ void Engine::enc_attention_fwd(int l) {
     if (fused < 0) { const char* e = getenv("P5_ATTN"); fused = (e && strcmp(e, "unfused") == 0) ? 0 : 1; }
     const DropCfg dc = drop(S_ENC_P, l);
     if (dt == DT_BF16 && (fused || packed)) {
-        const bool ok = fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, P_e[l], lse_e[l], ctx_e[l], A, dc, st,
+        // Le <= 256: the fused backward recomputes P from the row statistic, nothing of size L^2 is saved
+        static const bool no_fbwd = getenv("P5_NO_FATTN_BWD") != nullptr;
+        const bool fbwd = Le <= 256 && !no_fbwd;
+        const bool ok = fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, fbwd ? nullptr : P_e[l],
+                                  fbwd ? nullptr : lse_e[l], fbwd ? lse_e[l] : nullptr, ctx_e[l], A, dc, st,
                                   packed ? offs_d : nullptr, packed ? lens_d : nullptr, Mt);
         P5_CHECK(ok || !packed, "packed encoder attention needs the fused kernel (Le <= 512)");
-        p_unnorm[l] = ok;     // P_e[l] holds un-normalised probabilities, lse_e[l] the 1 / row-sum factors
+        p_unnorm[l] = ok && !fbwd;     // P_e[l] holds un-normalised probabilities, lse_e[l] the 1 / row-sum factors
+        p_fbwd[l] = ok && fbwd;        // lse_e[l] holds lse2 for fattn_bwd
         if (ok) return;
     }
     const void* qkv = qkv_e[l];
@@ -455,6 +460,14 @@ void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
     const void* dctx = dctx_in;
     void* dqkv = dqkv_out;
     const void* ctx_fwd = ctx_e[l];
+    if (dt == DT_BF16 && p_fbwd[l]) {
+        const bool ok = fattn_bwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, lse_e[l], ctx_e[l], A, dctx_in, A, dqkv_out, 3 * A,
+                                  dbias_enc, dc, st, packed ? offs_d : nullptr, packed ? lens_d : nullptr, Mt);
+        P5_CHECK(ok, "fused attention backward refused a shape its forward accepted");
+        if (packed && Mt > Mt_true)   // filler rows carry zero gradient
+            P5_CUDA(cudaMemsetAsync((char*)dqkv_out + Mt_true * 3 * A * esz(), 0, (Mt - Mt_true) * 3 * A * esz(), st));
+        return;
+    }
     if (packed) {
         unpack_rows(qkv_e[l], qkv_pad, offs_d, lens_d, B, Le, (int64_t)3 * A * esz(), st);
         unpack_rows(dctx_in, ctx_pad, offs_d, lens_d, B, Le, (int64_t)A * esz(), st);

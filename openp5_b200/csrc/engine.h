@@ -82,6 +82,7 @@ struct Engine {
     std::vector<void*> ne;              // [2*NE] normed inputs (dt)
     void* enc_out = nullptr;            // dt [Me, d]
     std::vector<void*> qkv_e, ctx_e, h_e, z_e, P_e;
+    std::vector<bool> p_fbwd;     // per encoder layer: lse_e holds lse2, the fused attention backward applies
     std::vector<bool> p_unnorm;   // per encoder layer: P_e holds un-normalised probabilities (fused attention forward)
     std::vector<float*> lse_e;
     float* S_scr = nullptr;             // fp32 [B,H,Le,Le] scores / dP

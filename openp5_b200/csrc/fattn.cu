@@ -39,6 +39,7 @@ struct FaParams {
     const int* key_mask;     // [B, Lk]
     bf16* P_save;            // [B, H, Lq, Lk] UN-normalised probabilities 2^(s2 - m2) (un-dropped)
     float* row_scale;        // [B, H, Lq] 1 / row sum: P = P_save * row_scale
+    float* row_lse2;         // [B, H, Lq] m2 + log2(row sum): P = 2^(s2 - lse2), all the fused backward needs
     uint32_t bias_cs;        // stride (floats) between the four shifted copies of the bias row
     bf16* ctx;               // [B*Lq, ld_ctx]
     int64_t ld_ctx;
@@ -370,6 +371,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 for (int g2 = 0; g2 < NWG; ++g2) l += statl_s[g2 * QT + r];
                 const float inv_l = l > 0.f ? 1.f / l : 0.f;
                 if (wg == 0 && row_ok && P.row_scale) P.row_scale[((int64_t)b * P.H + h) * Lq + i] = inv_l;
+                if (wg == 1 && row_ok && P.row_lse2) P.row_lse2[((int64_t)b * P.H + h) * Lq + i] = m2 + __log2f(l);
                 // ---------------- O -> ctx (this warpgroup writes 16 of the 64 head columns)
                 mbar_wait(o_full, of_ph);
                 of_ph ^= 1;
@@ -411,8 +413,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // qkv: [B*L, 3A] bf16 (q | k | v column blocks, heads 64 wide).  Returns false if the shape is not supported.
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
-               void* P_save, float* row_scale, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st, const int* offs,
-               const int* lens, int64_t packed_rows) {
+               void* P_save, float* row_scale, float* row_lse2, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st,
+               const int* offs, const int* lens, int64_t packed_rows) {
     if (L > 512 || L % 8 != 0 || ld_qkv % 8 != 0) return false;
     static int num_sms = 0;
     if (!num_sms) {
@@ -426,7 +428,7 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     const uint32_t kv_bytes = (uint32_t)P.nkb * KB * 128;
     P.nq_buf = (kv_bytes <= 48 * 1024) ? 2 : 1;
     P.sK = 0; P.sV = kv_bytes; P.sQ = 2 * kv_bytes; P.sP = P.sQ + P.nq_buf * QT * 128;
-    P.np_buf = (kv_bytes <= 96 * 1024) ? 2 : 1;       // L = 512: K + V take 128 KB, one P tile is all that fits
+    P.np_buf = (kv_bytes <= 48 * 1024) ? 2 : 1;       // L = 512: K + V take 128 KB, one P tile is all that fits
     P.sBias = P.sP + P.np_buf * QT * KB * 2;
     P.bias_cs = (uint32_t)(((L + P.nkb * KB + 4 + 31) & ~31) + 8);   // copies land in different bank groups
     P.sMask = P.sBias + (uint32_t)round_up(4 * P.bias_cs * 4, 16);
@@ -434,7 +436,7 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.sBar = P.sStat + NWG * QT * 8;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
-    P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.row_scale = row_scale; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
+    P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.row_scale = row_scale; P.row_lse2 = row_lse2; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
     P.offs = offs; P.lens = lens;
     P.drop = drop;
     static size_t max_set = 0;

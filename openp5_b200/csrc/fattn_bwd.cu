@@ -1,0 +1,477 @@
+// Fused encoder self-attention BACKWARD on tcgen05 (bf16 operands, fp32 softmax math): neither S, P, dP nor dS ever
+// touch HBM.   HF:models/t5/modeling_t5.py:308-344 differentiated by hand:
+//     S = Q K^T + bias + mask,  P = softmax(S),  Pd = dropout(P),  O = Pd V
+//     dPd = dO V^T,  dP = dropout'(dPd),  dS = P o (dP - delta),  delta_i = sum_c dO_ic O_ic
+//     dV = Pd^T dO,  dK = dS^T Q,  dQ = dS K,  d(bias)[h, j-i] += dS
+// It replaces, per layer, unpack x2 + (dP GEMM -> fp32 S buffer) + softmax_bwd + three batched GEMMs + pack
+// (265 us at T5-base B=64 Le=256) and makes the forward's P_save write unnecessary (P is recomputed from the row
+// statistic lse2 = m2 + log2(l) that the forward stores: 4 B per row instead of 2 B per score).
+//
+// One persistent CTA per SM walks (batch, head) pairs (sequence length <= 256: two 128-row query tiles, two 128-key
+// blocks).  Q, K, V, dO of the pair are TMA-loaded once into 128B-swizzled smem (128 KB) and serve as K-major AND
+// MN-major UMMA operands in place (the same bytes are A of S = Q K^T and B of dK = dS^T Q).
+//   warp 0    : TMA producer
+//   warp 1    : MMA issuer.  per (key block j, query tile i):  S = Q_i K_j^T, dPd = dO_i V_j^T  (128x128x64 each)
+//               then dV_j += Pd^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j  (128x64x128 each, Pd / dS read from smem)
+//   warp 2    : TMEM allocator: S 128 + dPd 128 + dV 64 + dK 64 + dQ 2 x 64 = 512 columns
+//   warp 3    : bias (log2 domain, four shifted copies for LDS.128) and key-mask tables per pair
+//   warps 4-19: four softmax warpgroups; thread = (query row, 32 of the 128 key columns).  P = 2^(s2 - lse2), dropout
+//               mask regenerated from the counter hash, dS, bf16 Pd / dS tiles written to swizzled smem (the same
+//               physical tile is the MN-major A of dV / dK and the K-major A of dQ); the relative-bias gradient is
+//               summed along diagonals with a systolic shuffle (one accumulator per lane slides down the rows, so
+//               j - i stays constant) and lands in shared memory with 2 atomics per lane per 32x32 block.
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+#include <float.h>
+
+namespace p5 {
+extern int g_launches;
+
+namespace {
+
+constexpr int NWG = 4;
+constexpr int FB_THREADS = 128 + NWG * 128;
+constexpr int QT = 128, KB = 128;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+struct FbParams {
+    int B, H, L;
+    const float* bias_rel;     // [H, 2L-1]
+    const int* key_mask;       // [B, L] or null
+    const float* row_lse2;     // [B, H, L]  m2 + log2(l) of the forward (log2 domain)
+    const bf16* ctx;           // forward output O, rows as qkv
+    const bf16* dctx;          // dO
+    int64_t ld_ctx, ld_dctx;
+    bf16* dqkv;                // dQ | dK | dV column blocks (A wide each), rows as qkv
+    int64_t ld_dqkv;
+    int A;
+    float* dbias_rel;          // [H, 2L-1] accumulated atomically, may be null
+    const int* offs;           // packed rows: first row of batch b; null = padded [B, L]
+    const int* lens;
+    uint32_t sQ, sdO, sK, sV, sPd, sdS, sBias, sMask, sStat, sDb, sBar, bias_cs;
+    DropCfg drop;
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                 const __grid_constant__ FbParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base + P.sQ, sdO = base + P.sdO, sK = base + P.sK, sV = base + P.sV, sPd = base + P.sPd,
+                   sdS = base + P.sdS, bar = base + P.sBar;
+    float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
+    float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
+    float* stat_s = reinterpret_cast<float*>(gbase + P.sStat);     // [NWG][2][128] partial delta
+    float* sdb = reinterpret_cast<float*>(gbase + P.sDb);          // [2L] relative-bias gradient of the current pair
+    const uint32_t ld_full = bar, ld_empty = bar + 8, bm_full = bar + 16, bm_empty = bar + 24, sdp_full = bar + 32,
+                   sdp_free = bar + 40, pds_full = bar + 48, pds_free = bar + 56, dvk_full = bar + 64, dvk_free = bar + 72,
+                   dq_full = bar + 80, dq_free = bar + 88, tmem_holder = bar + 96;
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 96);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_pairs = P.B * P.H, L = P.L;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO); }
+    if (warp == 1 && lane == 0) {
+        mbar_init(ld_full, 1); mbar_init(ld_empty, 1);
+        mbar_init(bm_full, 1); mbar_init(bm_empty, 4 * NWG);
+        mbar_init(sdp_full, 1); mbar_init(sdp_free, 4 * NWG);
+        mbar_init(pds_full, 4 * NWG); mbar_init(pds_free, 1);
+        mbar_init(dvk_full, 1); mbar_init(dvk_free, 4 * NWG);
+        mbar_init(dq_full, 1); mbar_init(dq_free, 4 * NWG);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_holder, 512);
+    if (warp >= 4)
+        for (int e = threadIdx.x - 128; e < 2 * L; e += NWG * 128) sdb[e] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder_ptr;
+    pdl_wait();               // PDL: the set-up above overlaps the previous kernel's tail (see common.cuh)
+    pdl_launch_dependents();
+    const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+    auto tdQ = [&](int i) { return tmem + 384u + 64u * (uint32_t)i; };
+
+    if (warp == 0) {
+        // ========================= TMA producer =========================
+        if (lane == 0) {
+            uint32_t ph = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const int b = pair / P.H, h = pair % P.H;
+                const int len = P.lens ? P.lens[b] : L;
+                const int row0 = P.offs ? P.offs[b] : 0, bc = P.offs ? 0 : b;
+                const int nt = (len + QT - 1) / QT;
+                mbar_wait(ld_empty, ph ^ 1);
+                mbar_expect_tx(ld_full, (uint32_t)(4 * nt * QT * 128));
+                for (int t = 0; t < nt; ++t) {
+                    tma_load_4d(sQ + t * (QT * 128), &tmQ, ld_full, 0, row0 + t * QT, h, bc);
+                    tma_load_4d(sdO + t * (QT * 128), &tmdO, ld_full, 0, row0 + t * QT, h, bc);
+                    tma_load_4d(sK + t * (KB * 128), &tmK, ld_full, 0, row0 + t * KB, h, bc);
+                    tma_load_4d(sV + t * (KB * 128), &tmV, ld_full, 0, row0 + t * KB, h, bc);
+                }
+                ph ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ========================= MMA issuer =========================
+        if (lane == 0) {
+            const uint32_t f32bf16 = (1u << 4) | (1u << 7) | (1u << 10);
+            const uint32_t idesc_s = f32bf16 | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                       // K-major x K-major
+            const uint32_t idesc_g = f32bf16 | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // MN x MN
+            const uint32_t idesc_q = f32bf16 | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);              // K x MN
+            uint32_t ld_ph = 0, sdpf_ph = 0, pdsf_ph = 0, dvkf_ph = 0, dqf_ph = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const int len = P.lens ? P.lens[pair / P.H] : L;
+                const int nt = (len + QT - 1) / QT, T = nt * nt;
+                mbar_wait(ld_full, ld_ph);
+                ld_ph ^= 1;
+                tc_fence_after();
+                auto issue_sdp = [&](int t) {
+                    const int j = t / nt, i = t % nt;
+                    mbar_wait(sdp_free, sdpf_ph ^ 1);       // the softmax warps have read the previous S / dPd out of TMEM
+                    sdpf_ph ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tS, make_smem_desc(sQ + i * (QT * 128) + k * 32, 16, 1024),
+                                  make_smem_desc(sK + j * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tdP, make_smem_desc(sdO + i * (QT * 128) + k * 32, 16, 1024),
+                                  make_smem_desc(sV + j * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
+                    umma_commit(sdp_full);
+                };
+                issue_sdp(0);
+                for (int t = 0; t < T; ++t) {
+                    const int j = t / nt, i = t % nt;
+                    if (t + 1 < T) issue_sdp(t + 1);
+                    mbar_wait(pds_full, pdsf_ph);           // Pd / dS tiles of (j, i) are in smem
+                    pdsf_ph ^= 1;
+                    if (i == 0) { mbar_wait(dvk_free, dvkf_ph ^ 1); dvkf_ph ^= 1; }      // previous dV / dK read out
+                    if (t == 0) { mbar_wait(dq_free, dqf_ph ^ 1); dqf_ph ^= 1; }         // previous pair's dQ read out
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)       // dV_j += Pd^T dO_i : A = Pd tile MN-major (k = query row), B = dO_i MN-major
+                        umma_bf16(tdV, make_smem_desc(sPd + k * 2048, 16384, 1024),
+                                  make_smem_desc(sdO + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)       // dK_j += dS^T Q_i
+                        umma_bf16(tdK, make_smem_desc(sdS + k * 2048, 16384, 1024),
+                                  make_smem_desc(sQ + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)       // dQ_i += dS K_j : A = dS tile K-major (k = key), B = K_j MN-major
+                        umma_bf16(tdQ(i), make_smem_desc(sdS + (k >> 2) * (QT * 128) + (k & 3) * 32, 16, 1024),
+                                  make_smem_desc(sK + j * (KB * 128) + k * 2048, 8192, 1024), idesc_q, (j | k) != 0);
+                    umma_commit(pds_free);
+                    if (i == nt - 1) umma_commit(dvk_full);
+                }
+                umma_commit(dq_full);
+                umma_commit(ld_empty);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ========================= bias / mask tables per (batch, head): see fattn.cu =========================
+        uint32_t bm_ph = 0;
+        const int n_delta = 2 * L - 1;
+        const int cs = (int)P.bias_cs;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const int b = pair / P.H, h = pair % P.H;
+            const int len = P.lens ? P.lens[b] : L;
+            const int nt = (len + KB - 1) / KB;
+            mbar_wait(bm_empty, bm_ph ^ 1);
+            for (int e = lane; e < L + nt * KB + 4; e += 32) {
+                const float v = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] * LOG2E_F : 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (e >= c) bias_s[c * cs + e - c] = v;
+            }
+            for (int j = lane; j < nt * KB; j += 32)
+                mask_s[j] = (j < len && (!P.key_mask || P.key_mask[b * L + j] != 0)) ? 0.f : -INFINITY;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bm_full);
+            bm_ph ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ========================= softmax warps =========================
+        const int wg = (warp - 4) >> 2, sw = warp & 3;
+        const int r = sw * 32 + lane;                     // row inside a 128-row tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
+        const int st_tid = threadIdx.x - 128;             // 0 .. 511
+        uint32_t bm_ph = 0, sdp_ph = 0, pdsf_ph = 0, dvk_ph = 0, dq_ph = 0;
+        const uint32_t t16 = P.drop.thr >> 16;
+        const float ik = P.drop.inv_keep;
+        const int cs = (int)P.bias_cs;
+        const int n_delta = 2 * L - 1;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const int b = pair / P.H, h = pair % P.H;
+            const int len = P.lens ? P.lens[b] : L;
+            const int nt = (len + QT - 1) / QT;
+            const int64_t row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * L;
+            mbar_wait(bm_full, bm_ph);
+            bm_ph ^= 1;
+            // ---- delta_i = sum_c dO_ic O_ic (this warpgroup: 16 of the 64 columns), lse2_i
+            float delta[2] = {0.f, 0.f}, lse[2] = {0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int gi = i * QT + r;
+                float part = 0.f;
+                if (i < nt && gi < len) {
+                    const uint4* po = reinterpret_cast<const uint4*>(P.ctx + (row0 + gi) * P.ld_ctx + h * 64 + wg * 16);
+                    const uint4* pg = reinterpret_cast<const uint4*>(P.dctx + (row0 + gi) * P.ld_dctx + h * 64 + wg * 16);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const uint4 o = po[q], g = pg[q];
+                        part += bf_lo(o.x) * bf_lo(g.x) + bf_hi(o.x) * bf_hi(g.x) + bf_lo(o.y) * bf_lo(g.y) + bf_hi(o.y) * bf_hi(g.y);
+                        part += bf_lo(o.z) * bf_lo(g.z) + bf_hi(o.z) * bf_hi(g.z) + bf_lo(o.w) * bf_lo(g.w) + bf_hi(o.w) * bf_hi(g.w);
+                    }
+                    lse[i] = P.row_lse2[((int64_t)b * P.H + h) * L + gi];
+                }
+                stat_s[(wg * 2 + i) * QT + r] = part;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int g2 = 0; g2 < NWG; ++g2) delta[i] += stat_s[(g2 * 2 + i) * QT + r];
+
+            for (int j = 0; j < nt; ++j) {
+                for (int i = 0; i < nt; ++i) {
+                    const int gi = i * QT + r;
+                    const bool row_ok = gi < len;
+                    const int j0 = j * KB + wg * 32;
+                    const int o = (row_ok ? (L - 1 - gi) : 0) + j0;
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
+                    const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
+                    const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
+                    const uint32_t pair0 = (uint32_t)((uint64_t)((((int64_t)b * P.H + h) * L + gi) * L + j0) >> 1);
+                    const float my_lse = i ? lse[1] : lse[0], my_delta = i ? delta[1] : delta[0];
+                    // diagonal index of (row of lane 0, column j0): entry + (t - lane) is the bias slot of element (lane, t)
+                    const int diag0 = (j0 - (i * QT + sw * 32)) + (L - 1);
+                    float dacc = 0.f;
+                    mbar_wait(sdp_full, sdp_ph);
+                    sdp_ph ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t vs[16], vd[16];
+                        tmem_ld16(tS + lane_off + wg * 32 + hf * 16, vs);
+                        tmem_ld16(tdP + lane_off + wg * 32 + hf * 16, vd);
+                        tmem_ld_wait();
+                        if (hf == 1) {           // S / dPd fully read: the MMA warp may overwrite them
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(sdp_free);
+                        } else {                 // the MMAs that read the previous Pd / dS tiles have retired
+                            mbar_wait(pds_free, pdsf_ph ^ 1);
+                            pdsf_ph ^= 1;
+                        }
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; ++q2) {
+                            const int q = 2 * hf + q2;               // 8-column group of this thread's 32 columns
+                            float pd[8], ds[8];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const float4 bb = b4[2 * q + u];
+                                float x[4];
+                                x[0] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u]), LOG2E_F, bb.x);
+                                x[1] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u + 1]), LOG2E_F, bb.y);
+                                x[2] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u + 2]), LOG2E_F, bb.z);
+                                x[3] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u + 3]), LOG2E_F, bb.w);
+                                if (!full) {
+                                    const float4 mm = m4[2 * q + u];
+                                    x[0] += mm.x; x[1] += mm.y; x[2] += mm.z; x[3] += mm.w;
+                                }
+#pragma unroll
+                                for (int e2 = 0; e2 < 2; ++e2) {       // one hash per aligned pair of columns
+                                    float p0 = row_ok ? ex2_approx(x[2 * e2] - my_lse) : 0.f;
+                                    float p1 = row_ok ? ex2_approx(x[2 * e2 + 1] - my_lse) : 0.f;
+                                    float g0 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2]), g1 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2 + 1]);
+                                    float d0 = p0, d1 = p1;
+                                    if (P.drop.thr) {
+                                        const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + 2 * u + e2));
+                                        const bool k0 = (hsh & 0xffffu) >= t16, k1 = (hsh >> 16) >= t16;
+                                        d0 = k0 ? p0 * ik : 0.f; d1 = k1 ? p1 * ik : 0.f;
+                                        g0 = k0 ? g0 * ik : 0.f; g1 = k1 ? g1 * ik : 0.f;
+                                    }
+                                    pd[4 * u + 2 * e2] = d0; pd[4 * u + 2 * e2 + 1] = d1;
+                                    ds[4 * u + 2 * e2] = p0 * (g0 - my_delta);
+                                    ds[4 * u + 2 * e2 + 1] = p1 * (g1 - my_delta);
+                                }
+                            }
+                            // bf16 tiles: [64-key chunk (wg >> 1)][128 rows][128 B], 16-byte units XOR (row & 7)
+                            const uint32_t off = (uint32_t)((wg >> 1) * (QT * 128) + r * 128 + ((((wg & 1) * 4 + q) ^ (r & 7)) << 4));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPd + off), "r"(pack2(pd[0], pd[1])),
+                                         "r"(pack2(pd[2], pd[3])), "r"(pack2(pd[4], pd[5])), "r"(pack2(pd[6], pd[7])) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off), "r"(pack2(ds[0], ds[1])),
+                                         "r"(pack2(ds[2], ds[3])), "r"(pack2(ds[4], ds[5])), "r"(pack2(ds[6], ds[7])) : "memory");
+                            if (P.dbias_rel) {
+                                // systolic diagonal sum: the accumulator that sits on lane l after column t holds diagonal t - l
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int t = 8 * q + e;
+                                    if (t > 0 && lane == 31 && dacc != 0.f) atomicAdd(&sdb[diag0 + (t - 1) - 31], dacc);
+                                    dacc = __shfl_up_sync(0xffffffffu, dacc, 1);
+                                    if (lane == 0) dacc = 0.f;
+                                    dacc += ds[e];
+                                }
+                            }
+                        }
+                    }
+                    // Pd / dS tiles complete: make the generic-proxy smem writes visible to the tensor core
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pds_full);
+                    if (P.dbias_rel && dacc != 0.f) atomicAdd(&sdb[diag0 + 31 - lane], dacc);
+                    if (i == nt - 1) {
+                        // ---- dV_j, dK_j complete: rows = keys of block j, this warpgroup writes 16 of the 64 columns
+                        mbar_wait(dvk_full, dvk_ph);
+                        dvk_ph ^= 1;
+                        tc_fence_after();
+                        uint32_t v[16], w[16];
+                        tmem_ld16(tdV + lane_off + wg * 16, v);
+                        tmem_ld16(tdK + lane_off + wg * 16, w);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(dvk_free);
+                        const int gj = j * KB + r;
+                        if (gj < len) {
+                            bf16* dst = P.dqkv + (row0 + gj) * P.ld_dqkv + h * 64 + wg * 16;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                uint4 a, c;
+                                a.x = pack2(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1]));
+                                a.y = pack2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                                a.z = pack2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                                a.w = pack2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                                c.x = pack2(__uint_as_float(w[8 * q]), __uint_as_float(w[8 * q + 1]));
+                                c.y = pack2(__uint_as_float(w[8 * q + 2]), __uint_as_float(w[8 * q + 3]));
+                                c.z = pack2(__uint_as_float(w[8 * q + 4]), __uint_as_float(w[8 * q + 5]));
+                                c.w = pack2(__uint_as_float(w[8 * q + 6]), __uint_as_float(w[8 * q + 7]));
+                                *reinterpret_cast<uint4*>(dst + 2 * P.A + 8 * q) = a;     // dV
+                                *reinterpret_cast<uint4*>(dst + P.A + 8 * q) = c;         // dK
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- dQ tiles of the pair
+            mbar_wait(dq_full, dq_ph);
+            dq_ph ^= 1;
+            tc_fence_after();
+            for (int i = 0; i < nt; ++i) {
+                uint32_t v[16];
+                tmem_ld16(tdQ(i) + lane_off + wg * 16, v);
+                tmem_ld_wait();
+                const int gi = i * QT + r;
+                if (gi < len) {
+                    bf16* dst = P.dqkv + (row0 + gi) * P.ld_dqkv + h * 64 + wg * 16;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint4 a;
+                        a.x = pack2(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1]));
+                        a.y = pack2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                        a.z = pack2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                        a.w = pack2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                        *reinterpret_cast<uint4*>(dst + 8 * q) = a;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);
+            // ---- relative-bias gradient of this pair -> global, table cleared for the next pair
+            if (P.dbias_rel) {
+                asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+                for (int e = st_tid; e < n_delta; e += NWG * 128) {
+                    const float v = sdb[e];
+                    if (v != 0.f) { atomicAdd(P.dbias_rel + h * n_delta + e, v); sdb[e] = 0.f; }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bm_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace
+
+bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
+               const float* row_lse2, const void* ctx, int64_t ld_ctx, const void* dctx, int64_t ld_dctx, void* dqkv,
+               int64_t ld_dqkv, float* dbias_rel, DropCfg drop, cudaStream_t st, const int* offs, const int* lens,
+               int64_t packed_rows) {
+    static const bool off = getenv("P5_NO_FATTN_BWD") != nullptr;
+    if (off || L > 256 || L % 8 != 0 || ld_qkv % 8 != 0 || ld_ctx % 8 != 0 || ld_dctx % 8 != 0 || ld_dqkv % 8 != 0 || !row_lse2)
+        return false;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        P5_CUDA(cudaGetDevice(&dev));
+        P5_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    FbParams P;
+    P.B = B; P.H = H; P.L = L;
+    const uint32_t tile = QT * 128;                      // 16 KB: 128 rows x 64 bf16
+    P.sQ = 0; P.sdO = 2 * tile; P.sK = 4 * tile; P.sV = 6 * tile; P.sPd = 8 * tile; P.sdS = 10 * tile;
+    P.sBias = 12 * tile;
+    P.bias_cs = (uint32_t)(((2 * L + 4 + 31) & ~31) + 8);
+    P.sMask = P.sBias + (uint32_t)round_up(4 * P.bias_cs * 4, 16);
+    P.sStat = P.sMask + 2 * KB * 4;
+    P.sDb = P.sStat + NWG * 2 * QT * 4;
+    P.sBar = P.sDb + (uint32_t)round_up(2 * L * 4, 16);
+    const size_t smem = P.sBar + 256 + 1024;
+    P5_CHECK(smem <= 232448, "fattn_bwd: shared memory budget exceeded");
+    P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.row_lse2 = row_lse2;
+    P.ctx = (const bf16*)ctx; P.dctx = (const bf16*)dctx; P.ld_ctx = ld_ctx; P.ld_dctx = ld_dctx;
+    P.dqkv = (bf16*)dqkv; P.ld_dqkv = ld_dqkv; P.A = A; P.dbias_rel = dbias_rel;
+    P.offs = offs; P.lens = lens; P.drop = drop;
+    static size_t max_set = 0;
+    if (smem > max_set) {
+        P5_CUDA(cudaFuncSetAttribute(fattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = smem;
+    }
+    const uint64_t rows = (uint64_t)(offs ? packed_rows : L);
+    const uint64_t dims[4] = {64, rows, (uint64_t)H, (uint64_t)(offs ? 1 : B)};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    const uint64_t strides[3] = {(uint64_t)ld_qkv * 2, 128, rows * (uint64_t)ld_qkv * 2};
+    const uint64_t strides_g[3] = {(uint64_t)ld_dctx * 2, 128, rows * (uint64_t)ld_dctx * 2};
+    const bf16* base = (const bf16*)qkv;
+    CUtensorMap tmQ = tmap_bf16_4d(base, dims, strides, box);
+    CUtensorMap tmK = tmap_bf16_4d(base + A, dims, strides, box);
+    CUtensorMap tmV = tmap_bf16_4d(base + 2 * A, dims, strides, box);
+    CUtensorMap tmdO = tmap_bf16_4d((const bf16*)dctx, dims, strides_g, box);
+    const int n_pairs = B * H;
+    const int grid = n_pairs < num_sms ? n_pairs : num_sms;
+    launch_k(fattn_bwd_kernel, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
+    P5_CUDA(cudaGetLastError());
+    ++g_launches;
+    return true;
+}
+
+}  // namespace p5

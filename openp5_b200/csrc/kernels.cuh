@@ -113,12 +113,20 @@ void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dt
 
 // fused tcgen05 encoder self-attention forward (fattn.cu): qkv [B*L, 3A] bf16 -> ctx [B*L, A] bf16.  For the backward
 // it saves P_save bf16 [B,H,L,L] = UN-normalised un-dropped probabilities 2^(s2 - m2) and row_scale fp32 [B,H,L] =
-// 1 / row sum (P = P_save * row_scale; softmax_bwd takes the pair).  Returns false when the shape is unsupported.
+// 1 / row sum (P = P_save * row_scale; softmax_bwd takes the pair), and/or row_lse2 fp32 [B,H,L] for the fused backward
+// (each output is skipped when its pointer is null).  Returns false when the shape is unsupported.
 // packed mode (offs/lens non-null): qkv / ctx are [packed_rows, .] with sequence b at rows offs[b] .. offs[b]+lens[b];
 // P_save keeps the padded [B,H,L,L] geometry (rows/cols < lens[b] written).
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
-               void* P_save, float* row_scale, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st,
+               void* P_save, float* row_scale, float* row_lse2, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st,
                const int* offs = nullptr, const int* lens = nullptr, int64_t packed_rows = 0);
+// fused tcgen05 backward of the same attention (fattn_bwd.cu), L <= 256: recomputes P from row_lse2 (= m2 + log2 l,
+// written by fattn_fwd; P_save / row_scale may then be null), writes dQ | dK | dV as bf16 into dqkv (rows as qkv) and
+// accumulates d(bias_rel).  Returns false when the shape is unsupported (caller falls back to the GEMM chain).
+bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
+               const float* row_lse2, const void* ctx, int64_t ld_ctx, const void* dctx, int64_t ld_dctx, void* dqkv,
+               int64_t ld_dqkv, float* dbias_rel, DropCfg drop, cudaStream_t st, const int* offs = nullptr,
+               const int* lens = nullptr, int64_t packed_rows = 0);
 
 // dbias_rel[h, j - i + Lq - 1] += sum_{b,i} dS[b,h,i,j]   (dS [B,H,Lq,Lk], register accumulation per diagonal)
 void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H, int Lq, int Lk, cudaStream_t st);

@@ -15,7 +15,8 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256", "bwd_bf16_small_le512", "bwd_fp32_small_le300",
          "bwd_fp32_tiny_packed", "bwd_fp32_small_packed", "bwd_bf16_small_packed", "bwd_bf16_base_le256_packed",
          "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed", "bwd_bf16_small_ld12", "bwd_fp32_small_ld12",
-         "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed"]
+         "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed", "xcheck_fbwd_dropout_small",
+         "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256"]
 
 
 def setup(case):
@@ -157,8 +158,9 @@ def run_case(case):
         else:
             res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
     elif case.startswith("xcheck"):
-        # decoder attention: mma.sync kernels (dattn.cu) vs the fp32-math SIMT kernels at the SAME dropout seed.
-        # Both regenerate the mask from the same counter hash, so gradients must agree to bf16 rounding.
+        # decoder attention: mma.sync kernels (dattn.cu) vs the fp32-math SIMT kernels at the SAME dropout seed; or
+        # ("fbwd") the fused tcgen05 attention backward vs the GEMM chain + softmax_bwd.  Both sides regenerate the
+        # mask from the same counter hash, so gradients must agree to bf16 rounding.
         dump = os.environ.get("P5_XCHECK_DUMP")
         if dump:
             m = make_model(cfg, w, prec, dropout=0.1).train()
@@ -172,7 +174,8 @@ def run_case(case):
             res["ok"] = True
             return res
         outs = []
-        for tag, extra in (("dattn", {}), ("simt", {"P5_NO_DATTN": "1"})):
+        ref_env = {"P5_NO_FATTN_BWD": "1"} if "fbwd" in case else {"P5_NO_DATTN": "1"}
+        for tag, extra in (("new", {}), ("ref", ref_env)):
             path = "/tmp/p5_xcheck_%s_%s.pt" % (case, tag)
             env = dict(os.environ, P5_XCHECK_DUMP=path, **extra)
             p = subprocess.run([sys.executable, __file__, "--case", case], capture_output=True, text=True, timeout=280, env=env)
@@ -186,8 +189,10 @@ def run_case(case):
         res["worst5"] = [(round(e, 4), k) for e, k in errs[:5]]
         # the tensors fed directly by the decoder attention kernels: a forward/backward mask mismatch would put O(1)
         # errors here; bf16 rounding differences between the two kernels stay at the percent level
-        att = [(e, k) for e, k in errs if k.startswith("decoder") and ("Attention.q" in k or "Attention.k" in k or "Attention.v" in k)]
-        res["worst_dec_attn_qkv"] = [(round(e, 4), k) for e, k in att[:3]]
+        side = "encoder" if "fbwd" in case else "decoder"
+        att = [(e, k) for e, k in errs if k.startswith(side) and ("Attention.q" in k or "Attention.k" in k or "Attention.v" in k
+                                                                  or "relative_attention_bias" in k)]
+        res["worst_attn_qkv_bias"] = [(round(e, 4), k) for e, k in att[:4]]
         res["worst_rel"] = errs[0][0]
         res["loss_rel"] = relerr(outs[0]["loss"], outs[1]["loss"])
         res["ok"] = errs[0][0] < 0.25 and att[0][0] < 0.1 and res["loss_rel"] < 0.02
