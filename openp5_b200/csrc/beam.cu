@@ -211,45 +211,52 @@ __global__ void gen_init_kernel(int* seq, int* fin_seq, int* src, int* node, flo
 
 // decode self-attention for ONE new position per row, with KV append and row indirection.
 // grid (H, R), 64 threads.  K/V cache layout [R, T, A].
+template <typename T> __device__ __forceinline__ float2 ld2(const T* p);
+template <> __device__ __forceinline__ float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld2<bf16>(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+template <typename T> __device__ __forceinline__ void st2(T* p, float2 v);
+template <> __device__ __forceinline__ void st2<float>(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+template <> __device__ __forceinline__ void st2<bf16>(bf16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+
+// one warp per (beam row, head): lane owns two of the 64 head columns; the <= max_length cached positions are walked
+// once with an online softmax (running max / sum / weighted V), scores reduced with warp shuffles
 template <typename T>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 decode_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ Kc, T* __restrict__ Vc, const int* __restrict__ src,
                         const float* __restrict__ bias_rel, int n_delta, int bias_off, T* __restrict__ ctx, int A, int Tm,
-                        int pos) {
+                        int pos, int R, int H) {
     pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
     pdl_launch_dependents();
-    extern __shared__ float sm[];
-    float* q = sm;            // [64]
-    float* p = sm + 64;       // [pos+1]
-    const int h = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
-    const T* row = qkv + (int64_t)r * 3 * A + h * 64;
-    q[c] = to_f32(row[c]);
-    const T kc = row[A + c], vc = row[2 * A + c];
-    Kc[((int64_t)r * Tm + pos) * A + h * 64 + c] = kc;
-    Vc[((int64_t)r * Tm + pos) * A + h * 64 + c] = vc;
-    __syncthreads();
-    for (int j = c; j <= pos; j += 64) {
-        const T* kp = (j == pos) ? (row + A) : (Kc + ((int64_t)src[r * Tm + j] * Tm + j) * A + h * 64);
-        float s = 0.f;
-#pragma unroll 16
-        for (int k = 0; k < 64; ++k) s = fmaf(q[k], to_f32(kp[k]), s);
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gw >= R * H) return;
+    const int r = gw / H, h = gw % H, c = 2 * lane;
+    const T* row = qkv + (int64_t)r * 3 * A + h * 64 + c;
+    const float2 q = ld2<T>(row), kc = ld2<T>(row + A), vc = ld2<T>(row + 2 * A);
+    st2<T>(Kc + ((int64_t)r * Tm + pos) * A + h * 64 + c, kc);
+    st2<T>(Vc + ((int64_t)r * Tm + pos) * A + h * 64 + c, vc);
+    float m = -INFINITY, l = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = 0; j <= pos; ++j) {
+        float2 k = kc, v = vc;
+        if (j < pos) {
+            const int64_t o = ((int64_t)src[r * Tm + j] * Tm + j) * A + h * 64 + c;
+            k = ld2<T>(Kc + o);
+            v = ld2<T>(Vc + o);
+        }
+        float sc = warp_sum(fmaf(q.x, k.x, q.y * k.y));
         int di = j - pos + bias_off;
         di = di < 0 ? 0 : (di >= n_delta ? n_delta - 1 : di);
-        p[j] = s + bias_rel[h * n_delta + di];
+        sc += bias_rel[h * n_delta + di];
+        const float mn = fmaxf(m, sc);
+        const float scale = __expf(m - mn), p = __expf(sc - mn);     // first step: exp(-inf) = 0
+        l = l * scale + p;
+        acc.x = fmaf(acc.x, scale, p * v.x);
+        acc.y = fmaf(acc.y, scale, p * v.y);
+        m = mn;
     }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int j = 0; j <= pos; ++j) mx = fmaxf(mx, p[j]);
-    float sum = 0.f;
-    for (int j = 0; j <= pos; ++j) sum += __expf(p[j] - mx);
-    const float inv = 1.f / sum;
-    float acc = 0.f;
-    for (int j = 0; j <= pos; ++j) {
-        const float w = __expf(p[j] - mx) * inv;
-        const float v = (j == pos) ? to_f32(vc) : to_f32(Vc[((int64_t)src[r * Tm + j] * Tm + j) * A + h * 64 + c]);
-        acc = fmaf(w, v, acc);
-    }
-    ctx[(int64_t)r * A + h * 64 + c] = from_f32<T>(acc);
+    const float inv = 1.f / l;
+    st2<T>(ctx + (int64_t)r * A + h * 64 + c, make_float2(acc.x * inv, acc.y * inv));
 }
 
 // row-wise max and log(sum(exp(x - max))) over the vocabulary (torch log_softmax = (x - max) - logsum)
@@ -596,20 +603,28 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
             const DecLayerOff& w = e->dec[l];
             rmsnorm_fwd(g->y, e->P + w.ln0, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
             e->linear_fwd(g->n, d, w.sa.q, 3 * A, d, R, g->qkv, dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
-            const size_t sm = (64 + pos + 1) * sizeof(float);
+            const unsigned sa_grid = (unsigned)cdiv((int64_t)R * H, 4);
             if (dt == DT_F32)
-                launch_k(decode_self_attn_kernel<float>, dim3(H, R), 64, sm, st, (const float*)g->qkv, (float*)g->Kc[l], (float*)g->Vc[l],
-                                                                         g->src[cur], e->bias_dec, n_delta, bias_off,
-                                                                         (float*)g->ctx, A, T, pos);
+                launch_k(decode_self_attn_kernel<float>, sa_grid, 128, 0, st, (const float*)g->qkv, (float*)g->Kc[l], (float*)g->Vc[l],
+                         g->src[cur], e->bias_dec, n_delta, bias_off, (float*)g->ctx, A, T, pos, R, H);
             else
-                launch_k(decode_self_attn_kernel<bf16>, dim3(H, R), 64, sm, st, (const bf16*)g->qkv, (bf16*)g->Kc[l], (bf16*)g->Vc[l],
-                                                                        g->src[cur], e->bias_dec, n_delta, bias_off,
-                                                                        (bf16*)g->ctx, A, T, pos);
+                launch_k(decode_self_attn_kernel<bf16>, sa_grid, 128, 0, st, (const bf16*)g->qkv, (bf16*)g->Kc[l], (bf16*)g->Vc[l],
+                         g->src[cur], e->bias_dec, n_delta, bias_off, (bf16*)g->ctx, A, T, pos, R, H);
             LAUNCHED();
             resid_gemm(g->ctx, A, w.sa.o, d, A);
             rmsnorm_fwd(g->y, e->P + w.ln1, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);
             e->linear_fwd(g->n, d, w.ca.q, A, d, R, g->cq, dt, A, 0, 1.f, nullptr, nullptr, none);
-            if (dt == DT_BF16) {
+            AttnArgs xa;   // the K beams of a user are the query rows against that user's cross K/V
+            xa.B = B; xa.H = H; xa.Lq = K; xa.Lk = Le;
+            xa.q = {g->cq, dt, A, (int64_t)K * A};
+            xa.k = {e->ckv[l], dt, 2 * A, (int64_t)Le * 2 * A};
+            xa.v = {(const char*)e->ckv[l] + (size_t)A * e->esz(), dt, 2 * A, (int64_t)Le * 2 * A};
+            xa.bias_rel = nullptr; xa.bias_off = 0; xa.n_delta = 0; xa.key_mask = e->mask_e; xa.causal = 0; xa.q_pos_offset = 0;
+            xa.row_map = nullptr;
+            if (dt == DT_BF16 && dattn_infer_supported(xa)) {
+                // one mma.sync kernel per layer: S, softmax and P V of a (user, head) pair stay in registers
+                dattn_fwd(xa, g->ctx, A, (int64_t)K * A, nullptr, st);
+            } else if (dt == DT_BF16) {
                 // cross-attention on the tensor cores: the K beams of a user are the M rows of one batched GEMM per
                 // (user, head) against that user's cross K/V (stored once per user): S = Q K^T -> softmax -> P V
                 const int64_t KL = (int64_t)K * Le;
@@ -628,14 +643,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
                 pv.epi.C = g->ctx; pv.epi.c_dtype = dt; pv.epi.ldc = A; pv.epi.cs1 = 64; pv.epi.cs2 = (int64_t)K * A;
                 e->gemm(pv);
             } else {
-            AttnArgs a;   // the K beams of a user are the query rows against that user's cross K/V
-            a.B = B; a.H = H; a.Lq = K; a.Lk = Le;
-            a.q = {g->cq, dt, A, (int64_t)K * A};
-            a.k = {e->ckv[l], dt, 2 * A, (int64_t)Le * 2 * A};
-            a.v = {(const char*)e->ckv[l] + (size_t)A * e->esz(), dt, 2 * A, (int64_t)Le * 2 * A};
-            a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0; a.key_mask = e->mask_e; a.causal = 0; a.q_pos_offset = 0;
-            a.row_map = nullptr;
-            attn_simt_fwd(a, g->ctx, dt, A, (int64_t)K * A, nullptr, st);
+                attn_simt_fwd(xa, g->ctx, dt, A, (int64_t)K * A, nullptr, st);
             }
             resid_gemm(g->ctx, A, w.ca.o, d, A);
             rmsnorm_fwd(g->y, e->P + w.ln2, g->n, dt, nullptr, R, d, e->cfg.ln_eps, none, st);

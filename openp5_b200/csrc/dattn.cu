@@ -278,6 +278,155 @@ dattn_fwd_kernel(DAttnDev a, bf16* __restrict__ O, int64_t ld_o, int64_t bs_o, f
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// forward for 17..32 query rows (two m16 tiles): the decode-step cross-attention, where the num_beams (20) running
+// beams of a user are the query rows against that user's cross K/V.  Inference only: no dropout, no LSE.
+// K fragments are loaded once and feed both row tiles.
+// ------------------------------------------------------------------------------------------------------------
+template <int NT, int NW>
+__global__ void __launch_bounds__(NW * 32)
+dattn_fwd32_kernel(DAttnDev a, bf16* __restrict__ O, int64_t ld_o, int64_t bs_o) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
+    using C = DCfg<NT, NW>;
+    constexpr int PART = NW * 32 * 64 * 4;
+    constexpr int REGION = C::TILE > PART ? C::TILE : PART;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* Vs = smem;
+    float* red = reinterpret_cast<float*>(smem + REGION);            // [2][NW][32]
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int Lk = a.kv_len ? a.kv_len[b] : a.Lk;
+    const int64_t k_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.k_ld : (int64_t)b * a.k_bs;
+    const int64_t v_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.v_ld : (int64_t)b * a.v_bs;
+    const int kpw = min(C::KW, (((Lk + NW - 1) / NW) + 15) & ~15);
+    const int key0 = warp * kpw, ntw = kpw >> 3;
+    const bf16* kb = a.k + k_boff + h * 64;
+    const bf16* vb = a.v + v_boff + h * 64;
+    stage_rows(Vs, warp * C::KW, vb, a.v_ld, key0, kpw, Lk, lane);
+
+    uint32_t q[2][2][8];
+    const bf16* qb = a.q + (int64_t)b * a.q_bs + h * 64 + 16 * t;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+            const int r = 16 * mt + 8 * hi + g;
+            ld_row16(q[mt][hi], qb + (int64_t)r * a.q_ld, r < a.Lq);
+        }
+    float s[2][NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+        if (nt < ntw) {
+            const int j = key0 + 8 * nt + g;
+            uint32_t kr[8];
+            ld_row16(kr, kb + (int64_t)j * a.k_ld + 16 * t, j < Lk);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    mma16816(s[mt][nt], q[mt][0][2 * k4], q[mt][1][2 * k4], q[mt][0][2 * k4 + 1], q[mt][1][2 * k4 + 1], kr[2 * k4],
+                             kr[2 * k4 + 1]);
+        }
+    }
+    ScoreCtx sc{a.Lq, Lk, a.Lk, a.causal, a.bias_off, a.n_delta, a.bias_rel ? a.bias_rel + h * a.n_delta : nullptr,
+                a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr};
+    float mx[2][2], sum[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        mx[mt][0] = mx[mt][1] = -FLT_MAX;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = 16 * mt + g + 8 * (e >> 1), j = key0 + 8 * nt + 2 * t + (e & 1);
+                float v = -FLT_MAX;
+                if (nt < ntw && score_valid(sc, r, j)) v = s[mt][nt][e] + (sc.bias ? sc.bias[bias_index(sc, r, j)] : 0.f);
+                s[mt][nt][e] = v;
+                mx[mt][e >> 1] = fmaxf(mx[mt][e >> 1], v);
+            }
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            mx[mt][q2] = fmaxf(mx[mt][q2], __shfl_xor_sync(0xffffffffu, mx[mt][q2], 1));
+            mx[mt][q2] = fmaxf(mx[mt][q2], __shfl_xor_sync(0xffffffffu, mx[mt][q2], 2));
+        }
+    }
+    if (t == 0)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { red[warp * 32 + 16 * mt + g] = mx[mt][0]; red[warp * 32 + 16 * mt + g + 8] = mx[mt][1]; }
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            mx[mt][0] = fmaxf(mx[mt][0], red[w * 32 + 16 * mt + g]);
+            mx[mt][1] = fmaxf(mx[mt][1], red[w * 32 + 16 * mt + g + 8]);
+        }
+    float* red2 = red + NW * 32;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        sum[mt][0] = sum[mt][1] = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = (s[mt][nt][e] == -FLT_MAX) ? 0.f : __expf(s[mt][nt][e] - mx[mt][e >> 1]);
+                s[mt][nt][e] = p;
+                sum[mt][e >> 1] += p;
+            }
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            sum[mt][q2] += __shfl_xor_sync(0xffffffffu, sum[mt][q2], 1);
+            sum[mt][q2] += __shfl_xor_sync(0xffffffffu, sum[mt][q2], 2);
+        }
+        if (t == 0) { red2[warp * 32 + 16 * mt + g] = sum[mt][0]; red2[warp * 32 + 16 * mt + g + 8] = sum[mt][1]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        float tot[2] = {0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { tot[0] += red2[w * 32 + 16 * mt + g]; tot[1] += red2[w * 32 + 16 * mt + g + 8]; }
+        const float inv0 = tot[0] > 0.f ? 1.f / tot[0] : 0.f, inv1 = tot[1] > 0.f ? 1.f / tot[1] : 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { s[mt][nt][0] *= inv0; s[mt][nt][1] *= inv0; s[mt][nt][2] *= inv1; s[mt][nt][3] *= inv1; }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    float o[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[mt][c][0] = o[mt][c][1] = o[mt][c][2] = o[mt][c][3] = 0.f;
+        pv_tiles<NT>(o[mt], s[mt], Vs, warp * C::KW, ntw, lane);
+    }
+    __syncthreads();                       // every warp is done with its V rows: reuse the region for the partial sums
+    float* part = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<float2*>(part + (warp * 32 + 16 * mt + g) * 64 + 8 * c + 2 * t) = make_float2(o[mt][c][0], o[mt][c][1]);
+            *reinterpret_cast<float2*>(part + (warp * 32 + 16 * mt + g + 8) * 64 + 8 * c + 2 * t) = make_float2(o[mt][c][2], o[mt][c][3]);
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 8; e += NW * 32) {      // (row, 8-column chunk)
+        const int r = e >> 3, c8 = (e & 7) * 8;
+        if (r >= a.Lq) continue;
+        float v[8];
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2) v[q2] = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int q2 = 0; q2 < 8; ++q2) v[q2] += part[(w * 32 + r) * 64 + c8 + q2];
+        uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *reinterpret_cast<uint4*>(O + (int64_t)b * bs_o + (int64_t)r * ld_o + h * 64 + c8) = pk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // backward: P recomputed from LSE; dQ, dK, dV written as bf16; d(bias_rel) accumulated atomically (self-attention)
 // ------------------------------------------------------------------------------------------------------------
 template <int NT, int NW, bool LQ16>
@@ -501,6 +650,16 @@ void launch_bwd(const AttnArgs& a, const void* dO, int64_t ld_do, int64_t bs_do,
     LAUNCHED();
 }
 
+template <int NT, int NW>
+void launch_fwd32(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, cudaStream_t st) {
+    constexpr int part = NW * 32 * 64 * 4;
+    constexpr int sm = (DCfg<NT, NW>::TILE > part ? DCfg<NT, NW>::TILE : part) + NW * 32 * 2 * 4;
+    static bool set = false;
+    if (!set) { P5_CUDA(cudaFuncSetAttribute(dattn_fwd32_kernel<NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); set = true; }
+    launch_k(dattn_fwd32_kernel<NT, NW>, (unsigned)(a.B * a.H), NW * 32, sm, st, to_dev(a), (bf16*)O, ld_o, bs_o);
+    LAUNCHED();
+}
+
 }  // namespace
 
 bool dattn_supported(const AttnArgs& a) {
@@ -520,8 +679,23 @@ bool dattn_supported(const AttnArgs& a) {
         else { if (hi) FN<8, 8, true>(__VA_ARGS__); else FN<8, 8, false>(__VA_ARGS__); }                     \
     } while (0)
 
+bool dattn_infer_supported(const AttnArgs& a) {
+    if (a.Lq <= 16) return dattn_supported(a) && a.drop.thr == 0;
+    AttnArgs c = a;
+    c.Lq = 16;
+    return a.Lq <= 32 && dattn_supported(c) && a.drop.thr == 0;
+}
+
 void dattn_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st) {
     if (a.B <= 0) return;
+    if (a.Lq > 16) {     // inference-only two-tile variant
+        P5_CHECK(dattn_infer_supported(a) && lse == nullptr, "dattn_fwd: 17..32 query rows are supported without dropout / LSE only");
+        P5_CHECK((ld_o % 8) == 0 && (bs_o % 8) == 0, "dattn_fwd: output rows must be 16-byte aligned");
+        if (a.Lk <= 64) launch_fwd32<2, 4>(a, O, ld_o, bs_o, st);
+        else if (a.Lk <= 256) launch_fwd32<8, 4>(a, O, ld_o, bs_o, st);
+        else launch_fwd32<8, 8>(a, O, ld_o, bs_o, st);
+        return;
+    }
     P5_CHECK(dattn_supported(a), "dattn_fwd: unsupported geometry");
     P5_CHECK((ld_o % 8) == 0 && (bs_o % 8) == 0, "dattn_fwd: output rows must be 16-byte aligned");
     P5_DATTN_DISPATCH(launch_fwd, a, O, ld_o, bs_o, lse, st);

@@ -96,6 +96,7 @@ void attn_simt_bwd(const AttnArgs& a, const void* O, const void* dO, int o_dtype
 // 16-byte aligned rows.  Same semantics / dropout stream as attn_simt_*; gradients are written as bf16 in place
 // (every (key row, head) slice is owned by exactly one CTA: no zero-fill, no fp32 staging).
 bool dattn_supported(const AttnArgs& a);
+bool dattn_infer_supported(const AttnArgs& a);   // forward without dropout / LSE: up to 32 query rows (decode-step beams)
 void dattn_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* lse, cudaStream_t st);
 void dattn_bwd(const AttnArgs& a, const void* dO, int64_t ld_do, int64_t bs_do, const float* lse, void* dQ, int64_t ld_dq,
                int64_t bs_dq, void* dK, void* dV, int64_t ld_dkv, int64_t bs_dkv, float* dbias_rel, cudaStream_t st);
