@@ -60,7 +60,7 @@ struct FbParams {
     float* dbias_rel;          // [H, 2L-1] accumulated atomically, may be null
     const int* offs;           // packed rows: first row of batch b; null = padded [B, L]
     const int* lens;
-    uint32_t sQ, sdO, sK, sV, sPd, sdS, sBias, sMask, sStat, sDb, sBar, bias_cs;
+    uint32_t sQ, sdO, sK, sV, sPd, sdS, sBias, sMask, sStat, sDb, sScr, sBar, bias_cs;
     DropCfg drop;
 };
 
@@ -75,12 +75,15 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                    sdS = base + P.sdS, bar = base + P.sBar;
     float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
     float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
-    float* stat_s = reinterpret_cast<float*>(gbase + P.sStat);     // [NWG][2][128] partial delta
+    float* rows_s = reinterpret_cast<float*>(gbase + P.sStat);     // [2 buffers][delta 256 | lse2 256]
     float* sdb = reinterpret_cast<float*>(gbase + P.sDb);          // [2L] relative-bias gradient of the current pair
-    const uint32_t ld_full = bar, ld_empty = bar + 8, bm_full = bar + 16, bm_empty = bar + 24, sdp_full = bar + 32,
-                   sdp_free = bar + 40, pds_full = bar + 48, pds_free = bar + 56, dvk_full = bar + 64, dvk_free = bar + 72,
-                   dq_full = bar + 80, dq_free = bar + 88, tmem_holder = bar + 96;
-    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 96);
+    float* scr_all = reinterpret_cast<float*>(gbase + P.sScr);     // [16 warps][32] parked diagonal sums
+    const uint32_t ld_full = bar, ld_empty = bar + 8, sdp_full = bar + 32, sdp_free = bar + 40, pds_full = bar + 48,
+                   pds_free = bar + 56, dvk_full = bar + 64, dvk_free = bar + 72, dq_full = bar + 80, dq_free = bar + 88,
+                   tmem_holder = bar + 128;
+    auto bm_full = [&](int i) { return bar + 96 + 8 * i; };      // two table buffers: warp 3 works one pair ahead
+    auto bm_empty = [&](int i) { return bar + 112 + 8 * i; };
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pairs = P.B * P.H, L = P.L;
@@ -88,7 +91,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO); }
     if (warp == 1 && lane == 0) {
         mbar_init(ld_full, 1); mbar_init(ld_empty, 1);
-        mbar_init(bm_full, 1); mbar_init(bm_empty, 4 * NWG);
+        for (int i = 0; i < 2; ++i) { mbar_init(bm_full(i), 1); mbar_init(bm_empty(i), 4 * NWG); }
         mbar_init(sdp_full, 1); mbar_init(sdp_free, 4 * NWG);
         mbar_init(pds_full, 4 * NWG); mbar_init(pds_free, 1);
         mbar_init(dvk_full, 1); mbar_init(dvk_free, 4 * NWG);
@@ -188,26 +191,61 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 3) {
-        // ========================= bias / mask tables per (batch, head): see fattn.cu =========================
+        // ========================= per-pair tables, one pair AHEAD of the softmax warps (double buffered) ==========
+        //  * bias (log2 domain, four shifted copies for LDS.128) and key mask: see fattn.cu
+        //  * rows_s[0][i] = delta_i = sum_c dO_ic O_ic, rows_s[1][i] = lse2_i (+inf for rows past the sequence end, so
+        //    that P = 2^(x - lse2) is an exact 0 there without a select).  The global-load latency is off the softmax
+        //    warps' critical path.
         uint32_t bm_ph = 0;
         const int n_delta = 2 * L - 1;
         const int cs = (int)P.bias_cs;
+        int buf = 0;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
             const int len = P.lens ? P.lens[b] : L;
             const int nt = (len + KB - 1) / KB;
-            mbar_wait(bm_empty, bm_ph ^ 1);
+            const int64_t row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * L;
+            float* bias_b = bias_s + buf * 4 * cs;
+            float* mask_b = mask_s + buf * 2 * KB;
+            float* rows_b = rows_s + buf * 4 * QT;
+            mbar_wait(bm_empty(buf), ((bm_ph >> buf) & 1u) ^ 1u);
+#pragma unroll 4
             for (int e = lane; e < L + nt * KB + 4; e += 32) {
                 const float v = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] * LOG2E_F : 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    if (e >= c) bias_s[c * cs + e - c] = v;
+                    if (e >= c) bias_b[c * cs + e - c] = v;
             }
             for (int j = lane; j < nt * KB; j += 32)
-                mask_s[j] = (j < len && (!P.key_mask || P.key_mask[b * L + j] != 0)) ? 0.f : -INFINITY;
+                mask_b[j] = (j < len && (!P.key_mask || P.key_mask[b * L + j] != 0)) ? 0.f : -INFINITY;
+            // one row per lane (128 contiguous bytes of O and of dO each): 8 independent 16-byte loads in flight per
+            // tensor and lane, 32 rows per step -> the whole pair costs a handful of memory round trips
+            for (int i0 = 0; i0 < nt * QT; i0 += 32) {
+                const int gi = i0 + lane;
+                float part = 0.f, lse_v = INFINITY;
+                if (gi < len) {
+                    const uint4* po = reinterpret_cast<const uint4*>(P.ctx + (row0 + gi) * P.ld_ctx + h * 64);
+                    const uint4* pg = reinterpret_cast<const uint4*>(P.dctx + (row0 + gi) * P.ld_dctx + h * 64);
+                    lse_v = P.row_lse2[((int64_t)b * P.H + h) * L + gi];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 o[4], g[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { o[q] = po[4 * hh + q]; g[q] = pg[4 * hh + q]; }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            part += bf_lo(o[q].x) * bf_lo(g[q].x) + bf_hi(o[q].x) * bf_hi(g[q].x) + bf_lo(o[q].y) * bf_lo(g[q].y) +
+                                    bf_hi(o[q].y) * bf_hi(g[q].y) + bf_lo(o[q].z) * bf_lo(g[q].z) + bf_hi(o[q].z) * bf_hi(g[q].z) +
+                                    bf_lo(o[q].w) * bf_lo(g[q].w) + bf_hi(o[q].w) * bf_hi(g[q].w);
+                    }
+                }
+                rows_b[gi] = part;
+                rows_b[2 * QT + gi] = lse_v;
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bm_full);
-            bm_ph ^= 1;
+            if (lane == 0) mbar_arrive(bm_full(buf));
+            bm_ph ^= 1u << buf;
+            buf ^= 1;
         }
     } else if (warp >= 4) {
         // ========================= softmax warps =========================
@@ -215,42 +253,24 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int r = sw * 32 + lane;                     // row inside a 128-row tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
         const int st_tid = threadIdx.x - 128;             // 0 .. 511
+        float* scr = scr_all + (warp - 4) * 32;
         uint32_t bm_ph = 0, sdp_ph = 0, pdsf_ph = 0, dvk_ph = 0, dq_ph = 0;
-        const uint32_t t16 = P.drop.thr >> 16;
+        const uint32_t thr_hi = P.drop.thr & 0xffff0000u;       // keep iff 16-bit field >= thr16, compared in place
         const float ik = P.drop.inv_keep;
         const int cs = (int)P.bias_cs;
         const int n_delta = 2 * L - 1;
+        int buf = 0;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
             const int len = P.lens ? P.lens[b] : L;
             const int nt = (len + QT - 1) / QT;
             const int64_t row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * L;
-            mbar_wait(bm_full, bm_ph);
-            bm_ph ^= 1;
-            // ---- delta_i = sum_c dO_ic O_ic (this warpgroup: 16 of the 64 columns), lse2_i
-            float delta[2] = {0.f, 0.f}, lse[2] = {0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int gi = i * QT + r;
-                float part = 0.f;
-                if (i < nt && gi < len) {
-                    const uint4* po = reinterpret_cast<const uint4*>(P.ctx + (row0 + gi) * P.ld_ctx + h * 64 + wg * 16);
-                    const uint4* pg = reinterpret_cast<const uint4*>(P.dctx + (row0 + gi) * P.ld_dctx + h * 64 + wg * 16);
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const uint4 o = po[q], g = pg[q];
-                        part += bf_lo(o.x) * bf_lo(g.x) + bf_hi(o.x) * bf_hi(g.x) + bf_lo(o.y) * bf_lo(g.y) + bf_hi(o.y) * bf_hi(g.y);
-                        part += bf_lo(o.z) * bf_lo(g.z) + bf_hi(o.z) * bf_hi(g.z) + bf_lo(o.w) * bf_lo(g.w) + bf_hi(o.w) * bf_hi(g.w);
-                    }
-                    lse[i] = P.row_lse2[((int64_t)b * P.H + h) * L + gi];
-                }
-                stat_s[(wg * 2 + i) * QT + r] = part;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int g2 = 0; g2 < NWG; ++g2) delta[i] += stat_s[(g2 * 2 + i) * QT + r];
+            const float* bias_b = bias_s + buf * 4 * cs;
+            const float* mask_b = mask_s + buf * 2 * KB;
+            const float* rows_b = rows_s + buf * 4 * QT;
+            mbar_wait(bm_full(buf), (bm_ph >> buf) & 1u);
+            bm_ph ^= 1u << buf;
+            const float delta0 = rows_b[r], delta1 = rows_b[QT + r], lse0 = rows_b[2 * QT + r], lse1 = rows_b[3 * QT + r];
 
             for (int j = 0; j < nt; ++j) {
                 for (int i = 0; i < nt; ++i) {
@@ -258,14 +278,14 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     const bool row_ok = gi < len;
                     const int j0 = j * KB + wg * 32;
                     const int o = (row_ok ? (L - 1 - gi) : 0) + j0;
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
-                    const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_b + (o & 3) * cs + (o & ~3));
+                    const float4* m4 = reinterpret_cast<const float4*>(mask_b + j0);
                     const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
                     const uint32_t pair0 = (uint32_t)((uint64_t)((((int64_t)b * P.H + h) * L + gi) * L + j0) >> 1);
-                    const float my_lse = i ? lse[1] : lse[0], my_delta = i ? delta[1] : delta[0];
+                    const float my_lse = i ? lse1 : lse0, my_delta = i ? delta1 : delta0;
                     // diagonal index of (row of lane 0, column j0): entry + (t - lane) is the bias slot of element (lane, t)
                     const int diag0 = (j0 - (i * QT + sw * 32)) + (L - 1);
-                    float dacc = 0.f;
+                    float dacc[2] = {0.f, 0.f};
                     mbar_wait(sdp_full, sdp_ph);
                     sdp_ph ^= 1;
                     tc_fence_after();
@@ -279,14 +299,12 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sdp_free);
-                        } else {                 // the MMAs that read the previous Pd / dS tiles have retired
-                            mbar_wait(pds_free, pdsf_ph ^ 1);
-                            pdsf_ph ^= 1;
                         }
+                        uint32_t pk[2][8];       // [8-column group][Pd x4 | dS x4] packed bf16 pairs
 #pragma unroll
                         for (int q2 = 0; q2 < 2; ++q2) {
                             const int q = 2 * hf + q2;               // 8-column group of this thread's 32 columns
-                            float pd[8], ds[8];
+                            float ds[8];
 #pragma unroll
                             for (int u = 0; u < 2; ++u) {
                                 const float4 bb = b4[2 * q + u];
@@ -301,45 +319,68 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                 }
 #pragma unroll
                                 for (int e2 = 0; e2 < 2; ++e2) {       // one hash per aligned pair of columns
-                                    float p0 = row_ok ? ex2_approx(x[2 * e2] - my_lse) : 0.f;
-                                    float p1 = row_ok ? ex2_approx(x[2 * e2 + 1] - my_lse) : 0.f;
-                                    float g0 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2]), g1 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2 + 1]);
-                                    float d0 = p0, d1 = p1;
+                                    const float p0 = ex2_approx(x[2 * e2] - my_lse), p1 = ex2_approx(x[2 * e2 + 1] - my_lse);
+                                    const float g0 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2]), g1 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2 + 1]);
+                                    float m0 = 1.f, m1 = 1.f;          // dropout multiplier: 1 / keep or 0
                                     if (P.drop.thr) {
                                         const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + 2 * u + e2));
-                                        const bool k0 = (hsh & 0xffffu) >= t16, k1 = (hsh >> 16) >= t16;
-                                        d0 = k0 ? p0 * ik : 0.f; d1 = k1 ? p1 * ik : 0.f;
-                                        g0 = k0 ? g0 * ik : 0.f; g1 = k1 ? g1 * ik : 0.f;
+                                        m0 = (hsh << 16) >= thr_hi ? ik : 0.f;
+                                        m1 = hsh >= thr_hi ? ik : 0.f;
                                     }
-                                    pd[4 * u + 2 * e2] = d0; pd[4 * u + 2 * e2 + 1] = d1;
-                                    ds[4 * u + 2 * e2] = p0 * (g0 - my_delta);
-                                    ds[4 * u + 2 * e2 + 1] = p1 * (g1 - my_delta);
+                                    const float d0 = p0 * m0, d1 = p1 * m1;
+                                    ds[4 * u + 2 * e2] = p0 * fmaf(g0, m0, -my_delta);
+                                    ds[4 * u + 2 * e2 + 1] = p1 * fmaf(g1, m1, -my_delta);
+                                    pk[q2][2 * u + e2] = pack2(d0, d1);
                                 }
                             }
-                            // bf16 tiles: [64-key chunk (wg >> 1)][128 rows][128 B], 16-byte units XOR (row & 7)
-                            const uint32_t off = (uint32_t)((wg >> 1) * (QT * 128) + r * 128 + ((((wg & 1) * 4 + q) ^ (r & 7)) << 4));
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPd + off), "r"(pack2(pd[0], pd[1])),
-                                         "r"(pack2(pd[2], pd[3])), "r"(pack2(pd[4], pd[5])), "r"(pack2(pd[6], pd[7])) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off), "r"(pack2(ds[0], ds[1])),
-                                         "r"(pack2(ds[2], ds[3])), "r"(pack2(ds[4], ds[5])), "r"(pack2(ds[6], ds[7])) : "memory");
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) pk[q2][4 + u] = pack2(ds[2 * u], ds[2 * u + 1]);
                             if (P.dbias_rel) {
-                                // systolic diagonal sum: the accumulator that sits on lane l after column t holds diagonal t - l
+                                // systolic diagonal sum over this half's 32 rows x 16 columns: the accumulator that sits
+                                // on lane l after local column t holds diagonal t - l.  What falls off lane 31 is parked in
+                                // a per-warp scratch row with a plain store (no atomics on the shuffle chain).
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    const int t = 8 * q + e;
-                                    if (t > 0 && lane == 31 && dacc != 0.f) atomicAdd(&sdb[diag0 + (t - 1) - 31], dacc);
-                                    dacc = __shfl_up_sync(0xffffffffu, dacc, 1);
-                                    if (lane == 0) dacc = 0.f;
-                                    dacc += ds[e];
+                                    const int t = 8 * q2 + e;                   // column inside the half
+                                    if (t > 0 && lane == 31) scr[hf * 16 + t - 1] = dacc[hf];   // diagonal (t - 1) - 31
+                                    dacc[hf] = __shfl_up_sync(0xffffffffu, dacc[hf], 1);
+                                    if (lane == 0) dacc[hf] = 0.f;
+                                    dacc[hf] += ds[e];
                                 }
                             }
+                        }
+                        if (hf == 0) {           // all the arithmetic above overlapped the MMAs that still read the previous tiles
+                            mbar_wait(pds_free, pdsf_ph ^ 1);
+                            pdsf_ph ^= 1;
+                        }
+                        // bf16 tiles: [64-key chunk (wg >> 1)][128 rows][128 B], 16-byte units XOR (row & 7)
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; ++q2) {
+                            const int q = 2 * hf + q2;
+                            const uint32_t off = (uint32_t)((wg >> 1) * (QT * 128) + r * 128 + ((((wg & 1) * 4 + q) ^ (r & 7)) << 4));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPd + off), "r"(pk[q2][0]), "r"(pk[q2][1]),
+                                         "r"(pk[q2][2]), "r"(pk[q2][3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off), "r"(pk[q2][4]), "r"(pk[q2][5]),
+                                         "r"(pk[q2][6]), "r"(pk[q2][7]) : "memory");
                         }
                     }
                     // Pd / dS tiles complete: make the generic-proxy smem writes visible to the tensor core
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(pds_full);
-                    if (P.dbias_rel && dacc != 0.f) atomicAdd(&sdb[diag0 + 31 - lane], dacc);
+                    if (P.dbias_rel) {
+                        // half hf covers columns 16 hf .. 16 hf + 15: lane l ends on diagonal 15 - l (+ 16 hf); the parked
+                        // values are diagonals (t - 1) - 31 for t = 1 .. 15
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            if (dacc[hf] != 0.f) atomicAdd(&sdb[diag0 + 16 * hf + 15 - lane], dacc[hf]);
+                            if (lane < 15) {
+                                const float v = scr[hf * 16 + lane];
+                                if (v != 0.f) atomicAdd(&sdb[diag0 + 16 * hf + lane - 31], v);
+                            }
+                        }
+                        __syncwarp();
+                    }
                     if (i == nt - 1) {
                         // ---- dV_j, dK_j complete: rows = keys of block j, this warpgroup writes 16 of the 64 columns
                         mbar_wait(dvk_full, dvk_ph);
@@ -397,7 +438,8 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(dq_free);
+            if (lane == 0) { mbar_arrive(dq_free); mbar_arrive(bm_empty(buf)); }
+            buf ^= 1;
             // ---- relative-bias gradient of this pair -> global, table cleared for the next pair
             if (P.dbias_rel) {
                 asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
@@ -407,8 +449,6 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bm_empty);
         }
     }
 
@@ -441,10 +481,11 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.sQ = 0; P.sdO = 2 * tile; P.sK = 4 * tile; P.sV = 6 * tile; P.sPd = 8 * tile; P.sdS = 10 * tile;
     P.sBias = 12 * tile;
     P.bias_cs = (uint32_t)(((2 * L + 4 + 31) & ~31) + 8);
-    P.sMask = P.sBias + (uint32_t)round_up(4 * P.bias_cs * 4, 16);
-    P.sStat = P.sMask + 2 * KB * 4;
-    P.sDb = P.sStat + NWG * 2 * QT * 4;
-    P.sBar = P.sDb + (uint32_t)round_up(2 * L * 4, 16);
+    P.sMask = P.sBias + 2 * (uint32_t)round_up(4 * P.bias_cs * 4, 16);     // two table buffers
+    P.sStat = P.sMask + 2 * 2 * KB * 4;
+    P.sDb = P.sStat + 2 * 4 * QT * 4;
+    P.sScr = P.sDb + (uint32_t)round_up(2 * L * 4, 16);
+    P.sBar = P.sScr + NWG * 4 * 32 * 4;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_bwd: shared memory budget exceeded");
     P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.row_lse2 = row_lse2;
