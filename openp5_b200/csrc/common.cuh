@@ -220,6 +220,10 @@ struct GemmProblem {
     int M = 0, N = 0, K = 0;
     int nb1 = 1, nb2 = 1;
     int prefer_bn = 0;   // tcgen05 path: 0 = heuristic, else force BLOCK_N (256 / 128 / 64)
+    // The kernel launched immediately before this one on the stream neither produces an input of this GEMM nor reads
+    // its output: the PDL wait moves to the END of the kernel, so this GEMM's CTAs fill the SMs that idle during the
+    // partial last wave of its predecessor (completion order along the stream stays transitive).
+    bool indep_of_prev = false;
     GemmOperand A, B;
     GemmEpilogue epi;
 };

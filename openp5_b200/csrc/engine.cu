@@ -202,6 +202,7 @@ void Engine::refresh_shadow() {
 // GEMM helpers
 // ------------------------------------------------------------------------------------------------------------
 void Engine::gemm(GemmProblem& p) {
+    if (next_gemm_indep) { p.indep_of_prev = true; next_gemm_indep = false; }   // one-shot flag set by the caller
     if (dt == DT_BF16 && gemm_tc_supported(p, mn)) gemm_tc(p, st);
     else { gemm_simt(p, st); ++g_launches; }
 }
@@ -234,9 +235,13 @@ void Engine::linear_dgrad(const void* dY, int64_t lddy, int64_t w_off, int N, in
 }
 
 // G[w_off : N x K] += alpha * dY[M,N]^T * X[M,K]     (both operands read in place as MN-major, split-K over M)
+// after_own_dgrad: the kernel launched just before this one is the dgrad of the same linear layer (reads dY and W,
+// writes dX) — independent of the weight gradient, so the wgrad may start in the SM slots that idle during the dgrad's
+// partial last wave (GemmProblem::indep_of_prev).
 void Engine::linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t w_off, int N, int K, int M,
-                          float alpha) {
+                          float alpha, bool after_own_dgrad) {
     GemmProblem p;
+    p.indep_of_prev = after_own_dgrad;
     p.M = N; p.N = K; p.K = M;
     // split-K over the token dimension with 128 x 256 tiles: pick the split count (a divisor of M, >= 256 rows per
     // split) that minimises  rounds(tiles * splits / #SM) * (k-blocks per split + fixed tile overhead)
@@ -382,18 +387,20 @@ void Engine::ffn_fwd(const void* n, int64_t M, const FfnOff& w, void* z, void* h
 void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void* n, const void* z, const void* h,
                      void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer) {
     // g_d = dropout-cast(dx_out) was already produced by the rmsnorm_bwd that computed dx_out
-    linear_wgrad(g_d, d, h, ff, w.wo, d, ff, (int)M, 1.f);
+    // every linear: dgrad first, then its wgrad (independent of the dgrad -> fills the dgrad's partial last wave)
     if (!gated) {
         const DropCfg da = drop(kind_act, layer);
         linear_dgrad(g_d, d, w.wo, d, ff, (int)M, g_ff, dt, ff, EPI_MULPOS, da.inv_keep, h, false);
-        linear_wgrad(g_ff, ff, n, d, w.wi, ff, d, (int)M, 1.f);
+        linear_wgrad(g_d, d, h, ff, w.wo, d, ff, (int)M, 1.f, true);
         linear_dgrad(g_ff, ff, w.wi, ff, d, (int)M, dn_out, dt, d, 0, 1.f, nullptr, false);
+        linear_wgrad(g_ff, ff, n, d, w.wi, ff, d, (int)M, 1.f, true);
     } else {
         void* dh = poff(g_ff, (int64_t)M * 2 * ff, dt);   // g_ff = [dz (M x 2ff) | dh (M x ff)]
         linear_dgrad(g_d, d, w.wo, d, ff, (int)M, dh, dt, ff, 0, 1.f, nullptr, false);
+        linear_wgrad(g_d, d, h, ff, w.wo, d, ff, (int)M, 1.f, true);
         gated_gelu_bwd(z, dh, g_ff, dt, (int)M, ff, drop(kind_act, layer), st);
-        linear_wgrad(g_ff, 2 * ff, n, d, w.wi, 2 * ff, d, (int)M, 1.f);
         linear_dgrad(g_ff, 2 * ff, w.wi, 2 * ff, d, (int)M, dn_out, dt, d, 0, 1.f, nullptr, false);
+        linear_wgrad(g_ff, 2 * ff, n, d, w.wi, 2 * ff, d, (int)M, 1.f, true);
     }
 }
 
@@ -599,6 +606,7 @@ void Engine::decoder_forward() {
                    drop(S_DEC_SO, l));
         rmsnorm_fwd(y1, P + w.ln1, nd[3 * l + 1], dt, rstd_d[3 * l + 1], (int)Md, d, cfg.ln_eps, none, st);
         linear_fwd(nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, cq[l], dt, A, 0, 1.f, nullptr, nullptr, none);
+        next_gemm_indep = true;   // cross K|V projection: needs enc_out only, not the (small) cross-Q GEMM just before it
         linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Mt, ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
         {
             const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
@@ -649,8 +657,8 @@ void Engine::backward() {
     };
     // ---- head
     ce_bwd(logits, Vpad, lse_ce, labels, dloss, dlogits, dt, (int)Md, V, Vpad, st);
-    linear_wgrad(dlogits, Vpad, dec_out, d, off_shared, V, d, (int)Md, hs);
     linear_dgrad(dlogits, Vpad, off_shared, V, d, (int)Md, g_d2, dt, d, 0, hs, nullptr, false);
+    linear_wgrad(dlogits, Vpad, dec_out, d, off_shared, V, d, (int)Md, hs, true);
     float* dy = dx_a;
     rmsnorm_bwd(g_d2, dt, yd[3 * ND], rstd_d[3 * ND], P + off_dec_final, nullptr, dy, G + off_dec_final, (int)Md, d,
                 drop(S_DEC_FINAL, 0), st, g_d, dt, drop(S_DEC_WO, ND - 1));
@@ -665,8 +673,8 @@ void Engine::backward() {
         rmsnorm_bwd(g_d2, dt, y2, rstd_d[3 * l + 2], P + w.ln2, dy, dy, G + w.ln2, (int)Md, d, none, st, g_d, dt,
                     drop(S_DEC_CO, l));
         // cross attention (g_d = dropout-cast(dy))
-        linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f, true);
         void *gq, *gkv;
         const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
         if (dattn_supported(ca)) {   // bf16: tensor-core kernel writes dQ and dK|dV as bf16 in place
@@ -685,15 +693,16 @@ void Engine::backward() {
             gq = as_T(f_qkv, g_qkv, Md * A);
             gkv = as_T(f_ckv, g_ckv, Mt * 2 * A);
         }
-        linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f);
         linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Mt, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
-        linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f);
+        linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f, true);
+        next_gemm_indep = true;   // reads gq and W only: independent of the cross-K|V dgrad / wgrad before it
         linear_dgrad(gq, A, w.ca.q, A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
+        linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f, true);
         rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st, g_d, dt,
                     drop(S_DEC_SO, l));
         // self attention (g_d = dropout-cast(dy))
-        linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f);
         linear_dgrad(g_d, d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f, true);
         void* gqkv;
         const AttnArgs sa = dec_self_args(*this, l, drop(S_DEC_SP, l));
         if (dattn_supported(sa)) {
@@ -706,8 +715,8 @@ void Engine::backward() {
                           f_qkv + 2 * A, 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
             gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
         }
-        linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f);
         linear_dgrad(gqkv, 3 * A, w.sa.q, 3 * A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
+        linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f, true);
         rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st, l > 0 ? g_d : nullptr, dt,
                     drop(S_DEC_WO, l > 0 ? l - 1 : 0));
     }
@@ -727,12 +736,12 @@ void Engine::backward() {
         ffn_bwd(dx, Mt, w.ff, ne[2 * l + 1], z_e[l], h_e[l], g_d2, S_ENC_ACT, S_ENC_WO, l);
         rmsnorm_bwd(g_d2, dt, x_mid, rstd_e[2 * l + 1], P + w.ln1, dx, dx, G + w.ln1, (int)Mt, d, none, st, g_d, dt,
                     drop(S_ENC_O, l));
-        linear_wgrad(g_d, d, ctx_e[l], A, w.sa.o, d, A, (int)Mt, 1.f);
         linear_dgrad(g_d, d, w.sa.o, d, A, (int)Mt, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        linear_wgrad(g_d, d, ctx_e[l], A, w.sa.o, d, A, (int)Mt, 1.f, true);
         void* dqkv = dt == DT_F32 ? (void*)f_qkv : g_qkv;
         enc_attention_bwd(l, g_ctx, dqkv);
-        linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Mt, 1.f);
         linear_dgrad(dqkv, 3 * A, w.sa.q, 3 * A, d, (int)Mt, g_d2, dt, d, 0, 1.f, nullptr, false);
+        linear_wgrad(dqkv, 3 * A, ne[2 * l], d, w.sa.q, 3 * A, d, (int)Mt, 1.f, true);
         rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Mt, d, none, st, l > 0 ? g_d : nullptr, dt,
                     drop(S_ENC_WO, l > 0 ? l - 1 : 0));
         // block l >= 1 is final (block 0 also holds the shared relative bias, reduced with the embeddings at the end)

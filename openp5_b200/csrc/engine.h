@@ -82,6 +82,7 @@ struct Engine {
     std::vector<void*> ne;              // [2*NE] normed inputs (dt)
     void* enc_out = nullptr;            // dt [Me, d]
     std::vector<void*> qkv_e, ctx_e, h_e, z_e, P_e;
+    bool next_gemm_indep = false; // one-shot: the next gemm() neither consumes nor clobbers the kernel launched before it
     std::vector<bool> p_fbwd;     // per encoder layer: lse_e holds lse2, the fused attention backward applies
     std::vector<bool> p_unnorm;   // per encoder layer: P_e holds un-normalised probabilities (fused attention forward)
     std::vector<float*> lse_e;
@@ -138,7 +139,7 @@ struct Engine {
     void linear_dgrad(const void* dY, int64_t lddy, int64_t w_off, int N, int K, int M, void* dX, int dx_dtype,
                       int64_t lddx, int flags, float alpha, const void* aux, bool accum_f32);
     void linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t w_off, int N, int K, int M,
-                      float alpha);
+                      float alpha, bool after_own_dgrad = false);
 
     void encoder_forward();
     void decoder_forward();

@@ -38,6 +38,7 @@ struct TcParams {
     int nb1, nb2;
     int a_major, b_major;
     int dbg;   // perf-debug only (P5_GEMM_DBG): 1 = no global stores, 2 = no smem staging either, 4 = no TMEM loads
+    int late_wait;   // GemmProblem::indep_of_prev: griddepcontrol.wait at the end instead of the start
     GemmEpilogue epi;
 };
 
@@ -45,8 +46,8 @@ template <int BLOCK_N>
 struct TcCfg {
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    static constexpr int STAGES = (BLOCK_N >= 192) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);   // power of two >= 2 accumulators
     static constexpr int EPI_STRIDE = 66;                       // floats per staged row (64 + 2 pad: conflict-free 8-byte accesses)
     static constexpr int EPI_BYTES = 4 * 32 * EPI_STRIDE * 4;   // one 32x64 fp32 tile per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
@@ -230,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_holder_ptr;
     // PDL: barrier init, TMEM allocation and tensor-map prefetch above overlap the tail of the previous kernel; nothing
     // below touches global memory before the previous grid has completed
-    pdl_wait();
+    if (!P.late_wait) pdl_wait();
     pdl_launch_dependents();
 
     if (warp == 0) {
@@ -479,6 +480,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+    // independent-of-predecessor GEMM: the dependency wait happens here, so that "this grid completed" still implies
+    // "everything before it on the stream completed" for the kernels that follow
+    if (P.late_wait) pdl_wait();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -620,7 +624,7 @@ std::string gemm_tc_prof_summary() {
     for (auto& r : g_prof) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
-        const int c = r.bn == 256 ? 0 : (r.bn == 128 ? 1 : 2);
+        const int c = r.bn >= 192 ? 0 : (r.bn == 128 ? 1 : 2);
         ms[c] += t; fl[c] += r.flops; n[c] += 1;
     }
     char b[512];
@@ -652,6 +656,7 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("P5_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     P.dbg = dbg;
+    P.late_wait = (p.indep_of_prev && pdl_enabled()) ? 1 : 0;
     const long long tiles = (long long)cdiv(p.M, BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     ProfRec rec;
@@ -669,6 +674,7 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
 template <int EPI>
 static void launch_bn(int bn, const GemmProblem& p, cudaStream_t stream) {
     if (bn == 256) launch_tc<256, EPI>(p, stream);
+    else if (bn == 192) launch_tc<192, EPI>(p, stream);
     else if (bn == 128) launch_tc<128, EPI>(p, stream);
     else launch_tc<64, EPI>(p, stream);
 }
@@ -684,7 +690,17 @@ void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     if (!bn) {
         const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
         // largest tile that still gives every SM a tile; narrow outputs use a narrow tile
-        if (p.N > 128 && mt * cdiv(p.N, 256) >= g_num_sms) bn = 256;
+        if (p.N > 128 && mt * cdiv(p.N, 256) >= g_num_sms) {
+            // persistent waves: time ~ rounds x (bytes a CTA pulls per k-block ~ 128 + bn, plus a fixed part).  A 192-wide
+            // tile wins when it removes a mostly empty last wave (N = 768 with ~100 row tiles: 300 tiles = 2.03 waves
+            // of 256-wide tiles, but 400 tiles = 2.7 waves of 192-wide ones)
+            const double c256 = (double)cdiv(mt * cdiv(p.N, 256), g_num_sms) * (128 + 256 + 24);
+            const double c192 = (double)cdiv(mt * cdiv(p.N, 192), g_num_sms) * (128 + 192 + 24);
+            // measured on B200 (T5-base step): no gain over 256 once the wgrads fill the dgrad tails (17.34 vs 17.27
+            // ms/step), so the 192-wide tile is opt-in (P5_BN192=1); kept for shapes where the tail is not filled
+            static const bool use192 = getenv("P5_BN192") != nullptr;
+            bn = (c192 < 0.95 * c256 && use192) ? 192 : 256;
+        }
         else if (p.N > 64 && mt * cdiv(p.N, 128) >= g_num_sms) bn = 128;
         else bn = 64;
         if (p.N <= 64) bn = 64;

@@ -31,6 +31,12 @@ CASES = [
     ("epi_resid_f32", 256, 512, 128, 0, 0, 1, 1, 0, 8),
     ("epi_accum_f32", 256, 512, 128, 0, 0, 1, 1, 0, 16),
     ("vocab_head", 512, 32100, 768, 0, 0, 1, 1, 0, 0),
+    ("kk_bn192", 512, 768, 256, 0, 0, 1, 1, 192, 0),
+    ("kk_bn192_ragged", 200, 700, 136, 0, 0, 1, 1, 192, 0),
+    ("mnAB_bn192", 256, 576, 192, 1, 1, 1, 1, 192, 0),
+    ("epi_resid_bn192", 384, 768, 128, 0, 0, 1, 1, 192, 8),
+    ("epi_dropout_bn192", 384, 768, 128, 0, 0, 1, 1, 192, 4),
+    ("auto_bn192_n768", 12800, 768, 768, 0, 0, 1, 1, 0, 0),
 ]
 
 
