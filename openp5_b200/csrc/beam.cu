@@ -298,37 +298,73 @@ topk_candidates_kernel(const float* __restrict__ logits, int64_t ld, int V, cons
                        float* __restrict__ cand_lp, int* __restrict__ cand_beam, int* __restrict__ cand_tok) {
     pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
     pdl_launch_dependents();
-    __shared__ int s_count;
+    constexpr int MAXK = 64, NS = 1024;
+    __shared__ int s_off[MAXK + 1], s_nd[MAXK];
+    __shared__ float s_sc[NS];
+    __shared__ int s_fl[NS];
     __shared__ float s_best[8];
     __shared__ int s_besti[8], s_bestf[8];
     const int b = blockIdx.x;
     float* sc = scr_score + (int64_t)b * scr_cap;
     int* fl = scr_flat + (int64_t)b * scr_cap;
-    if (threadIdx.x == 0) s_count = 0;
+    // children of every running beam: counts -> exclusive offsets (K <= 64: one thread adds them up)
+    if (threadIdx.x < K) s_nd[threadIdx.x] = node[b * K + threadIdx.x];
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < K; ++k) {
+            s_off[k] = acc;
+            const int nd = s_nd[k];
+            if (nd >= 0) acc += t_off[nd + 1] - t_off[nd];
+        }
+        s_off[K] = acc;
+    }
+    __syncthreads();
+    const int n = min(s_off[K], scr_cap);
+    const bool in_smem = n <= NS;         // the usual case (a few children per beam): no global scratch, no selection loop
+    float* vsc = in_smem ? s_sc : sc;
+    int* vfl = in_smem ? s_fl : fl;
     for (int k = 0; k < K; ++k) {
-        const int r = b * K + k;
-        const int nd = node[r];
+        const int nd = s_nd[k];
         if (nd < 0) continue;
-        const int e0 = t_off[nd], e1 = t_off[nd + 1];
-        __shared__ int s_base;
-        if (threadIdx.x == 0) { s_base = s_count; s_count += e1 - e0; }
-        __syncthreads();
-        const int base = s_base;
-        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-            const int tok = t_tok[e];
-            const int slot = base + (e - e0);
+        const int r = b * K + k, e0 = t_off[nd], cnt = s_off[k + 1] - s_off[k], base = s_off[k];
+        const float rs = run_score[r], nrm = rowmax[r], ls = logsum[r];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+            const int tok = t_tok[e0 + e];
+            const int slot = base + e;
             if (slot < scr_cap && tok >= 0 && tok < V) {
-                const float lp = (logits[(int64_t)r * ld + tok] - rowmax[r]) - logsum[r];
-                sc[slot] = lp + run_score[r];
-                fl[slot] = k * V + tok;
+                const float lp = (logits[(int64_t)r * ld + tok] - nrm) - ls;
+                vsc[slot] = lp + rs;
+                vfl[slot] = k * V + tok;
             } else if (slot < scr_cap) {
-                sc[slot] = -INFINITY; fl[slot] = 0x7fffffff;
+                vsc[slot] = -INFINITY; vfl[slot] = 0x7fffffff;
             }
         }
-        __syncthreads();
     }
-    const int n = min(s_count, scr_cap);
+    // fewer than 2K continuations: HF's remaining top-k slots hold -inf entries
+    for (int sel = threadIdx.x; sel < 2 * K; sel += blockDim.x) {
+        const int o = b * 2 * K + sel;
+        cand_lp[o] = -INFINITY; cand_beam[o] = 0; cand_tok[o] = 0;
+    }
+    __syncthreads();
+    if (in_smem) {
+        // rank of a candidate in the order (score desc, flat index asc) == the slot torch.topk would give it
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float v = s_sc[i];
+            const int f = s_fl[i];
+            if (!(v > -INFINITY)) continue;
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const float vj = s_sc[j];
+                rank += (vj > v || (vj == v && s_fl[j] < f)) ? 1 : 0;
+            }
+            if (rank < 2 * K) {
+                const int o = b * 2 * K + rank;
+                cand_lp[o] = v; cand_beam[o] = f / V; cand_tok[o] = f % V;
+            }
+        }
+        return;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int sel = 0; sel < 2 * K; ++sel) {
         float best = -INFINITY; int bi = -1, bf = 0x7fffffff;
@@ -353,8 +389,6 @@ topk_candidates_kernel(const float* __restrict__ logits, int64_t ld, int V, cons
             if (ii >= 0 && bb > -INFINITY) {
                 cand_lp[o] = bb; cand_beam[o] = ff / V; cand_tok[o] = ff % V;
                 sc[ii] = -INFINITY;
-            } else {   // fewer than 2K continuations: HF's remaining top-k slots hold -inf entries
-                cand_lp[o] = -INFINITY; cand_beam[o] = 0; cand_tok[o] = 0;
             }
         }
         __syncthreads();
@@ -377,140 +411,104 @@ beam_update_kernel(const float* __restrict__ cand_lp, const int* __restrict__ ca
     extern __shared__ int smi[];
     int* run_sel = smi;              // [K]   candidate index chosen for running slot k
     int* fin_sel = smi + K;          // [K]   merged index chosen for finished slot k
-    float* s_lp = reinterpret_cast<float*>(smi + 2 * K);   // [2K] candidates staged in smem (the selection is serial)
+    float* s_lp = reinterpret_cast<float*>(smi + 2 * K);   // [2K] candidates
     int* s_cb = smi + 4 * K;
     int* s_ct = smi + 6 * K;
+    float* s_rv = reinterpret_cast<float*>(smi + 8 * K);   // [2K] running-beam keys
+    float* s_fv = reinterpret_cast<float*>(smi + 10 * K);  // [3K] finished-beam keys: old finished (K) | candidates (2K)
+    int* s_fin = smi + 13 * K;       // [K]   is_finished of the selected finished slots
+    float* s_misc = reinterpret_cast<float*>(smi + 14 * K);   // [0] best running score, [1] worst kept finished score
     const int b = blockIdx.x;
+    const bool at_max = (cur_len + 1 >= max_len);
+    const bool us = unsat[b] != 0;
     for (int c = threadIdx.x; c < 2 * K; c += blockDim.x) {
-        s_lp[c] = cand_lp[b * 2 * K + c]; s_cb[c] = cand_beam[b * 2 * K + c]; s_ct[c] = cand_tok[b * 2 * K + c];
+        const float l = cand_lp[b * 2 * K + c];
+        const int tk = cand_tok[b * 2 * K + c];
+        s_lp[c] = l; s_cb[c] = cand_beam[b * 2 * K + c]; s_ct[c] = tk;
+        const bool hit = (tk == eos) || at_max;
+        s_rv[c] = l + (hit ? NEG_BIG : -0.0f);                 // running beams: top-K of lp + hits * -1e9
+        float v = l / denom_fin;                                // finished beams: candidates that hit EOS inside the top K
+        v += us ? -0.0f : NEG_BIG;
+        v += (hit && c < K) ? -0.0f : NEG_BIG;
+        s_fv[K + c] = v;
     }
+    for (int m = threadIdx.x; m < K; m += blockDim.x) s_fv[m] = fscore_in[b * K + m];
     __syncthreads();
     const float* lp = s_lp;
     const int* cb = s_cb;
     const int* ct = s_ct;
-    // selection is done by warp 0: candidates live in registers (index c = lane + 32*q), every pick is a warp argmax
-    // with ties broken by the lowest index (the order torch.topk yields on distinct values; SURVEY §7 tie-break)
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const bool at_max = (cur_len + 1 >= max_len);
-        const bool us = unsat[b] != 0;
-        auto warp_argmax = [&](float v, int idx, float& bv, int& bi) {
-            bv = v; bi = idx;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-            }
-        };
-        // ---- running beams: top-K of lp + hits * -1e9
-        float rv[4]; bool ru[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = lane + 32 * q;
-            ru[q] = c >= 2 * K;                     // slots past 2K never compete
-            rv[q] = 0.f;
-            if (c < 2 * K) {
-                const bool hit = (ct[c] == eos) || at_max;
-                rv[q] = lp[c] + (hit ? NEG_BIG : -0.0f);
-            }
+    // Selection by RANK instead of K serial arg-max rounds: an element's rank in the order (value desc, index asc) is
+    // the round in which the serial selection (ties -> lowest index, the order torch.topk yields; SURVEY 7 tie-break)
+    // would have picked it.
+    for (int c = threadIdx.x; c < 2 * K; c += blockDim.x) {
+        const float v = s_rv[c];
+        int rank = 0;
+        for (int j = 0; j < 2 * K; ++j) rank += (s_rv[j] > v || (s_rv[j] == v && j < c)) ? 1 : 0;
+        if (rank < K) {
+            run_sel[rank] = c;
+            run_out[b * K + rank] = v;
+            if (rank == 0) s_misc[0] = v;
         }
-        for (int k = 0; k < K; ++k) {
-            float lv = 0.f; int li = -1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (!ru[q] && (li < 0 || rv[q] > lv)) { lv = rv[q]; li = lane + 32 * q; }
-            float bv; int bi;
-            warp_argmax(lv, li, bv, bi);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (lane + 32 * q == bi) ru[q] = true;
-            if (lane == 0) { run_sel[k] = bi; run_out[b * K + k] = bv; }
-        }
-        // ---- finished beams: merge [old finished (K), new candidates (2K)] -> index m = lane + 32*q, q < 6
-        float fv[6]; bool fu[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int m = lane + 32 * q;
-            fu[q] = m >= 3 * K;
-            fv[q] = 0.f;
-            if (m < K) fv[q] = fscore_in[b * K + m];
-            else if (m < 3 * K) {
+    }
+    for (int m = threadIdx.x; m < 3 * K; m += blockDim.x) {
+        const float v = s_fv[m];
+        int rank = 0;
+        for (int j = 0; j < 3 * K; ++j) rank += (s_fv[j] > v || (s_fv[j] == v && j < m)) ? 1 : 0;
+        if (rank < K) {
+            fin_sel[rank] = m;
+            fscore_out[b * K + rank] = v;
+            int fin, gl;
+            if (m < K) { fin = isfin_in[b * K + m]; gl = glen_in[b * K + m]; }
+            else {
                 const int c = m - K;
                 const bool hit = (ct[c] == eos) || at_max;
-                float v = lp[c] / denom_fin;
-                v += us ? -0.0f : NEG_BIG;
-                v += (hit && c < K) ? -0.0f : NEG_BIG;
-                fv[q] = v;
+                fin = (hit && c < K) ? 1 : 0;
+                gl = cur_len;   // cur_len + 1 - prompt_len(=1)
             }
-        }
-        float min_fs = INFINITY;
-        int all_fin_bits = 0;   // unused; finished flags are re-read below
-        for (int k = 0; k < K; ++k) {
-            float lv = 0.f; int li = -1;
-#pragma unroll
-            for (int q = 0; q < 6; ++q)
-                if (!fu[q] && (li < 0 || fv[q] > lv)) { lv = fv[q]; li = lane + 32 * q; }
-            float bv; int bi;
-            warp_argmax(lv, li, bv, bi);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) if (lane + 32 * q == bi) fu[q] = true;
-            if (lane == 0) {
-                fin_sel[k] = bi;
-                fscore_out[b * K + k] = bv;
-                int fin, gl;
-                if (bi < K) { fin = isfin_in[b * K + bi]; gl = glen_in[b * K + bi]; }
-                else {
-                    const int c = bi - K;
-                    const bool hit = (ct[c] == eos) || at_max;
-                    fin = (hit && c < K) ? 1 : 0;
-                    gl = cur_len;   // cur_len + 1 - prompt_len(=1)
-                }
-                isfin_out[b * K + k] = fin; glen_out[b * K + k] = gl;
-            }
-            min_fs = fminf(min_fs, bv);
-        }
-        (void)all_fin_bits;
-        __syncwarp();
-        // ---- early-stop heuristic with cur_len already incremented
-        if (lane == 0) {
-            const float best_running = run_out[b * K] / denom_next;
-            bool any = false;
-            for (int k = 0; k < K; ++k) {
-                const float worst = isfin_out[b * K + k] ? min_fs : NEG_BIG;
-                if (best_running > worst) any = true;
-            }
-            unsat[b] = (us && any) ? 1 : 0;
+            isfin_out[b * K + rank] = fin; glen_out[b * K + rank] = gl;
+            s_fin[rank] = fin;
+            if (rank == K - 1) s_misc[1] = v;      // min over the kept finished scores
         }
     }
     __syncthreads();
+    // ---- early-stop heuristic with cur_len already incremented
+    if (threadIdx.x == 0) {
+        const float best_running = s_misc[0] / denom_next, min_fs = s_misc[1];
+        bool any = false;
+        for (int k = 0; k < K; ++k) {
+            const float worst = s_fin[k] ? min_fs : NEG_BIG;
+            if (best_running > worst) any = true;
+        }
+        unsat[b] = (us && any) ? 1 : 0;
+    }
     // ---- materialise the selected rows (all threads)
-    for (int k = 0; k < K; ++k) {
+    for (int idx = threadIdx.x; idx < K * T; idx += blockDim.x) {
+        const int k = idx / T, t = idx - k * T;
         const int c = run_sel[k];
         const int parent = b * K + cb[c];
         const int r = b * K + k;
-        for (int t = threadIdx.x; t < T; t += blockDim.x) {
-            int v = seq_in[parent * T + t];
-            if (t == cur_len) v = ct[c];
-            seq_out[r * T + t] = v;
-            int s = src_in[parent * T + t];
-            if (t >= cur_len) s = r;
-            src_out[r * T + t] = s;
-        }
-        if (threadIdx.x == 0) {
-            cur_tok[r] = ct[c];
-            node_out[r] = (lp[c] > -INFINITY) ? trie_child(t_off, t_tok, t_node, node_in[parent], ct[c]) : -1;
-        }
+        int v = seq_in[parent * T + t];
+        if (t == cur_len) v = ct[c];
+        seq_out[r * T + t] = v;
+        int sr = src_in[parent * T + t];
+        if (t >= cur_len) sr = r;
+        src_out[r * T + t] = sr;
         const int m = fin_sel[k];
-        for (int t = threadIdx.x; t < T; t += blockDim.x) {
-            int v;
-            if (m < K) v = fin_in[(b * K + m) * T + t];
-            else {
-                const int c2 = m - K;
-                v = seq_in[(b * K + cb[c2]) * T + t];
-                if (t == cur_len) v = ct[c2];
-            }
-            fin_out[r * T + t] = v;
+        int fv;
+        if (m < K) fv = fin_in[(b * K + m) * T + t];
+        else {
+            const int c2 = m - K;
+            fv = seq_in[(b * K + cb[c2]) * T + t];
+            if (t == cur_len) fv = ct[c2];
         }
+        fin_out[r * T + t] = fv;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int c = run_sel[k];
+        const int parent = b * K + cb[c];
+        const int r = b * K + k;
+        cur_tok[r] = ct[c];
+        node_out[r] = (lp[c] > -INFINITY) ? trie_child(t_off, t_tok, t_node, node_in[parent], ct[c]) : -1;
     }
 }
 
@@ -667,7 +665,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         const int nxt = cur ^ 1;
         const float denom_fin = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
         const float denom_next = (float)pow((double)(cur_len + 1 - 1), (double)length_penalty);
-        launch_k(beam_update_kernel, B, 128, 8 * K * sizeof(int), st, g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
+        launch_k(beam_update_kernel, B, 128, (14 * K + 4) * sizeof(int), st, g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
             g->src[nxt], g->node[cur], g->node[nxt], g->run_score[nxt], g->fin_score[cur], g->fin_score[nxt], g->is_fin[cur],
             g->is_fin[nxt], g->gen_len[cur], g->gen_len[nxt], g->cur_tok, g->unsat, trie->d_off, trie->d_tok, trie->d_node, K,
             T, cur_len, max_len, 1 /*eos*/, denom_fin, denom_next);

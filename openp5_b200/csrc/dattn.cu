@@ -670,11 +670,17 @@ bool dattn_supported(const AttnArgs& a) {
            a.q_pos_offset == 0;
 }
 
+// Lk <= 256: eight warps with 32 keys each instead of four with 64 (shorter per-warp chain, A/B switch P5_DATTN_NW4=1)
+static bool dattn_wide() {
+    static const bool narrow = getenv("P5_DATTN_NW4") != nullptr;
+    return !narrow;
+}
 #define P5_DATTN_DISPATCH(FN, ...)                                                              \
     do {                                                                                        \
         const bool hi = a.Lq > 8;                                                               \
         if (a.Lk <= 16) { if (hi) FN<2, 1, true>(__VA_ARGS__); else FN<2, 1, false>(__VA_ARGS__); }          \
         else if (a.Lk <= 64) { if (hi) FN<2, 4, true>(__VA_ARGS__); else FN<2, 4, false>(__VA_ARGS__); }     \
+        else if (a.Lk <= 256 && dattn_wide()) { if (hi) FN<4, 8, true>(__VA_ARGS__); else FN<4, 8, false>(__VA_ARGS__); }  \
         else if (a.Lk <= 256) { if (hi) FN<8, 4, true>(__VA_ARGS__); else FN<8, 4, false>(__VA_ARGS__); }    \
         else { if (hi) FN<8, 8, true>(__VA_ARGS__); else FN<8, 8, false>(__VA_ARGS__); }                     \
     } while (0)
@@ -692,6 +698,7 @@ void dattn_fwd(const AttnArgs& a, void* O, int64_t ld_o, int64_t bs_o, float* ls
         P5_CHECK(dattn_infer_supported(a) && lse == nullptr, "dattn_fwd: 17..32 query rows are supported without dropout / LSE only");
         P5_CHECK((ld_o % 8) == 0 && (bs_o % 8) == 0, "dattn_fwd: output rows must be 16-byte aligned");
         if (a.Lk <= 64) launch_fwd32<2, 4>(a, O, ld_o, bs_o, st);
+        else if (a.Lk <= 256 && dattn_wide()) launch_fwd32<4, 8>(a, O, ld_o, bs_o, st);
         else if (a.Lk <= 256) launch_fwd32<8, 4>(a, O, ld_o, bs_o, st);
         else launch_fwd32<8, 8>(a, O, ld_o, bs_o, st);
         return;

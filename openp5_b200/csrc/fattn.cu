@@ -41,6 +41,7 @@ struct FaParams {
     float* row_scale;        // [B, H, Lq] 1 / row sum: P = P_save * row_scale
     float* row_lse2;         // [B, H, Lq] m2 + log2(row sum): P = 2^(s2 - lse2), all the fused backward needs
     uint32_t bias_cs;        // stride (floats) between the four shifted copies of the bias row
+    uint32_t ntbl, tbl_stride;   // table buffers (2 when they fit: the table warp runs one pair ahead), floats per bias buffer
     bf16* ctx;               // [B*Lq, ld_ctx]
     int64_t ld_ctx;
     uint32_t sK, sV, sQ, sP, sBias, sMask, sStat, sBar;   // smem offsets from the 1024-aligned base
@@ -61,8 +62,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sK = base + P.sK, sV = base + P.sV, sQ = base + P.sQ, sP = base + P.sP, bar = base + P.sBar;
-    float* bias_s = reinterpret_cast<float*>(gbase + P.sBias);
-    float* mask_s = reinterpret_cast<float*>(gbase + P.sMask);
+    float* bias_all = reinterpret_cast<float*>(gbase + P.sBias);    // [ntbl][4 copies][bias_cs]
+    float* mask_all = reinterpret_cast<float*>(gbase + P.sMask);    // [ntbl][nkb * KB]
     float* statm_s = reinterpret_cast<float*>(gbase + P.sStat);    // [NWG][128] row max per warpgroup (log2 domain)
     float* statl_s = statm_s + NWG * QT;                           // [NWG][128] row sum per warpgroup
     // barriers (8 bytes each)
@@ -73,9 +74,11 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto s_empty = [&](int i) { return bar + 72 + 8 * i; };
     auto p_full = [&](int i) { return bar + 96 + 8 * i; };
     auto p_empty = [&](int i) { return bar + 112 + 8 * i; };
-    const uint32_t o_full = bar + 128, o_empty = bar + 136, bm_full = bar + 144, bm_empty = bar + 152;
-    const uint32_t tmem_holder = bar + 160;
-    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 160);
+    const uint32_t o_full = bar + 128, o_empty = bar + 136;
+    auto bm_full = [&](int i) { return bar + 144 + 8 * i; };     // table buffers: the table warp works one pair ahead
+    auto bm_empty = [&](int i) { return bar + 160 + 8 * i; };
+    const uint32_t tmem_holder = bar + 176;
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 176);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pairs = P.B * P.H;
@@ -90,7 +93,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         for (int i = 0; i < NSB; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4 * NWG); }
         mbar_init(o_full, 1); mbar_init(o_empty, 4 * NWG);
-        mbar_init(bm_full, 1); mbar_init(bm_empty, 4 * NWG);
+        for (int i = 0; i < 2; ++i) { mbar_init(bm_full(i), 1); mbar_init(bm_empty(i), 4 * NWG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -199,11 +202,14 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t bm_ph = 0;
         const int n_delta = Lq + Lk - 1;
         const int cs = (int)P.bias_cs;
+        int buf = 0;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
             const int len = P.lens ? P.lens[b] : Lk;
             const int nkb = (len + KB - 1) / KB;
-            mbar_wait(bm_empty, bm_ph ^ 1);
+            float* bias_s = bias_all + buf * P.tbl_stride;
+            float* mask_s = mask_all + buf * (P.nkb * KB);
+            mbar_wait(bm_empty(buf), ((bm_ph >> buf) & 1u) ^ 1u);
             // entries past n_delta are only touched for padded keys (masked with -inf): keep them finite
             for (int e = lane; e < Lq + nkb * KB + 4; e += 32) {
                 const float v = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] * LOG2E : 0.f;
@@ -214,8 +220,9 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int j = lane; j < nkb * KB; j += 32)
                 mask_s[j] = (j < len && (!P.key_mask || P.key_mask[b * Lk + j] != 0)) ? 0.f : -INFINITY;
             __syncwarp();
-            if (lane == 0) mbar_arrive(bm_full);
-            bm_ph ^= 1;
+            if (lane == 0) mbar_arrive(bm_full(buf));
+            bm_ph ^= 1u << buf;
+            buf = (buf + 1 == (int)P.ntbl) ? 0 : buf + 1;
         }
     } else if (warp >= 4) {
         // ========================= softmax warps =========================
@@ -224,7 +231,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int r = sw * 32 + lane;                     // row of the query tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
         uint32_t sf_ph = 0, pe_ph = 0, of_ph = 0, bm_ph = 0;   // phase bits per buffer
-        int sb = 0, pb = 0;
+        int sb = 0, pb = 0, buf = 0;
         const uint32_t t16 = P.drop.thr >> 16;
         const int cs = (int)P.bias_cs;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -232,8 +239,10 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int len = P.lens ? P.lens[b] : Lq;
             const int nkb = (len + KB - 1) / KB, nqt = (len + QT - 1) / QT;
             const int64_t ctx_row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * Lq;
-            mbar_wait(bm_full, bm_ph);
-            bm_ph ^= 1;
+            const float* bias_s = bias_all + buf * P.tbl_stride;
+            const float* mask_s = mask_all + buf * (P.nkb * KB);
+            mbar_wait(bm_full(buf), (bm_ph >> buf) & 1u);
+            bm_ph ^= 1u << buf;
             for (int qt = 0; qt < nqt; ++qt) {
                 const int i = qt * QT + r;                // query position
                 const bool row_ok = i < len;
@@ -399,7 +408,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             // bias/mask tables of this pair no longer needed
             __syncwarp();
-            if (lane == 0) mbar_arrive(bm_empty);
+            if (lane == 0) mbar_arrive(bm_empty(buf));
+            buf = (buf + 1 == (int)P.ntbl) ? 0 : buf + 1;
         }
     }
 
@@ -431,8 +441,13 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.np_buf = (kv_bytes <= 48 * 1024) ? 2 : 1;       // L = 512: K + V take 128 KB, one P tile is all that fits
     P.sBias = P.sP + P.np_buf * QT * KB * 2;
     P.bias_cs = (uint32_t)(((L + P.nkb * KB + 4 + 31) & ~31) + 8);   // copies land in different bank groups
-    P.sMask = P.sBias + (uint32_t)round_up(4 * P.bias_cs * 4, 16);
-    P.sStat = P.sMask + (uint32_t)round_up(P.nkb * KB * 4, 16);
+    P.tbl_stride = 4 * P.bias_cs;
+    {   // two table buffers when shared memory allows (L <= 384)
+        const size_t one = (size_t)P.sBias + P.tbl_stride * 4 + (size_t)P.nkb * KB * 4 + NWG * QT * 8 + 256 + 1024;
+        P.ntbl = (one + P.tbl_stride * 4 + (size_t)P.nkb * KB * 4 <= 232448) ? 2 : 1;
+    }
+    P.sMask = P.sBias + P.ntbl * P.tbl_stride * 4;
+    P.sStat = P.sMask + P.ntbl * (uint32_t)(P.nkb * KB * 4);
     P.sBar = P.sStat + NWG * QT * 8;
     const size_t smem = P.sBar + 256 + 1024;
     P5_CHECK(smem <= 232448, "fattn_fwd: shared memory budget exceeded");
