@@ -56,6 +56,29 @@ def ncu_summary(rep, dst):
     return True
 
 
+def gemm_traffic(rep, dst):
+    """DRAM bytes of the first captured gemm_tc_kernel<256, .> launch -> profiles/<tag>_gemm_traffic.json (bench.py reads it)."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return
+    h, u = rows[0], rows[1]
+    for v in rows[2:]:
+        d = dict(zip(h, v))
+        if "gemm_tc_kernel<256" not in d.get("Kernel Name", ""):
+            continue
+
+        def to_bytes(name):
+            val = float(d[name].replace(",", ""))
+            unit = u[h.index(name)].lower()
+            return val * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+        out = {"kernel": d["Kernel Name"][:120], "launch": "grid %s block %s" % (d.get("Grid Size"), d.get("Block Size")),
+               "dram_bytes": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+               "duration_us_under_ncu": float(d["gpu__time_duration.sum"].replace(",", ""))}
+        json.dump(out, open(dst, "w"), indent=1)
+        return
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
@@ -73,6 +96,8 @@ def main():
         rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, name))
         if os.path.exists(rep):
             ncu_summary(rep, os.path.join(PROF, "%s_%s_ncu_full_summary.txt" % (tag, name)))
+            if name == "gemm":
+                gemm_traffic(rep, os.path.join(PROF, "%s_gemm_traffic.json" % tag))
 
 
 if __name__ == "__main__":
