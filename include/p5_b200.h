@@ -95,6 +95,11 @@ int p5_zero_grad(p5_handle h);
  * computed on device (no host sync).  step is 1-based. */
 int p5_adamw_step(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float clip);
+/* replaces: optimizer.step() immediately followed by model.zero_grad() (DistributedRunner.py:85-87) in ONE pass over
+ * the flat buffers: identical update to p5_adamw_step, the gradient is cleared while it is read (saves the separate
+ * 4 B/parameter memset of p5_zero_grad). */
+int p5_adamw_step_zero_grad(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                            float clip);
 
 /* ---- data-parallel gradient exchange (the DDP all-reduce the reference constructs, DistributedRunner.py:26) ---- */
 int p5_comm_unique_id(void* id128_host);                      /* 128-byte ncclUniqueId */

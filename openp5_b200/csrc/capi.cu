@@ -161,6 +161,14 @@ int p5_adamw_step(p5_handle h, float lr, float beta1, float beta2, float eps, fl
     P5_API_END
 }
 
+int p5_adamw_step_zero_grad(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                            float clip) {
+    P5_API_BEGIN
+    P5_CHECK(step >= 1, "AdamW step is 1-based");
+    E(h)->adamw(lr, beta1, beta2, eps, weight_decay, step, clip, true);
+    P5_API_END
+}
+
 int p5_comm_unique_id(void* id128_host) {
     P5_API_BEGIN
     comm_unique_id(id128_host);

@@ -224,6 +224,7 @@ struct GemmProblem {
     // its output: the PDL wait moves to the END of the kernel, so this GEMM's CTAs fill the SMs that idle during the
     // partial last wave of its predecessor (completion order along the stream stays transitive).
     bool indep_of_prev = false;
+    bool tail_filled = false;   // an independent kernel follows and fills this GEMM's partial last wave: keep the 256-wide tile
     GemmOperand A, B;
     GemmEpilogue epi;
 };

@@ -225,6 +225,7 @@ void Engine::linear_fwd(const void* X, int64_t ldx, int64_t w_off, int N, int K,
 void Engine::linear_dgrad(const void* dY, int64_t lddy, int64_t w_off, int N, int K, int M, void* dX, int dx_dtype,
                           int64_t lddx, int flags, float alpha, const void* aux, bool accum_f32) {
     GemmProblem p;
+    p.tail_filled = true;   // every dgrad is followed by its (independent, late-wait) wgrad
     p.M = M; p.N = K; p.K = N;
     p.A.ptr = dY; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = lddy;
     p.B.ptr = W(w_off); p.B.dtype = dt; p.B.major = MAJOR_MN; p.B.ld = K;
@@ -766,10 +767,12 @@ void Engine::zero_grad() {
     P5_CUDA(cudaMemsetAsync(G, 0, n_flat * sizeof(float), st));
     norm_valid = false;
 }
-void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip) {
+void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip, bool zero_grad_after) {
     if (clip > 0.f && !norm_valid) grad_norm();
-    adamw_flat(P, G, M1, V2, P16, n_flat, lr, b1, b2, eps, wd, step, clip, clip > 0.f ? norm_out : nullptr, 1.f, st);
+    adamw_flat(P, G, M1, V2, P16, n_flat, lr, b1, b2, eps, wd, step, clip, clip > 0.f ? norm_out : nullptr, 1.f, st,
+               zero_grad_after);
     shadow_stale = false;
+    if (zero_grad_after) norm_valid = false;
 }
 
 }  // namespace p5

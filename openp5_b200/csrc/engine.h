@@ -155,7 +155,7 @@ struct Engine {
                  void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer);
 
     void grad_norm();
-    void adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip);
+    void adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip, bool zero_grad_after = false);
     void zero_grad();
 };
 

@@ -696,10 +696,9 @@ void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
             // of 256-wide tiles, but 400 tiles = 2.7 waves of 192-wide ones)
             const double c256 = (double)cdiv(mt * cdiv(p.N, 256), g_num_sms) * (128 + 256 + 24);
             const double c192 = (double)cdiv(mt * cdiv(p.N, 192), g_num_sms) * (128 + 192 + 24);
-            // measured on B200 (T5-base step): no gain over 256 once the wgrads fill the dgrad tails (17.34 vs 17.27
-            // ms/step), so the 192-wide tile is opt-in (P5_BN192=1); kept for shapes where the tail is not filled
-            static const bool use192 = getenv("P5_BN192") != nullptr;
-            bn = (c192 < 0.95 * c256 && use192) ? 192 : 256;
+            // (the backward's dgrads pass prefer_bn = 256: their partial last wave is filled by the wgrad that follows)
+            static const bool use192 = getenv("P5_NO_BN192") == nullptr;
+            bn = (c192 < 0.95 * c256 && use192 && !p.tail_filled) ? 192 : 256;
         }
         else if (p.N > 64 && mt * cdiv(p.N, 128) >= g_num_sms) bn = 128;
         else bn = 64;

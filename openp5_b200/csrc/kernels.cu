@@ -222,7 +222,7 @@ rmsnorm_bwd_kernel(const T* __restrict__ dn, const float* __restrict__ x, const 
 // vectorised form for d = NV * 128: each lane owns NV float4 column groups, the whole row lives in registers
 // (x, dn, dres are each read exactly once: 2+4+4 B in, 4 B out per element), dw partials stay in registers per warp
 template <typename T, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ rstd,
                        const float* __restrict__ w, const float* dres, float* dx, float* __restrict__ dw, int M,
                        DropCfg drop, bf16* __restrict__ dx_cast, DropCfg cast_drop) {
@@ -233,17 +233,14 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < d; c += 256) sdw[c] = 0.f;
     __syncthreads();
-    float wv[NV][4], acc[NV][4];
+    float acc[NV][4];     // the norm weight (3 KB) is re-read from L1 per row instead of pinning NV*4 registers
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        ldv<4>(w + 4 * (lane + 32 * k), wv[k]);
+    for (int k = 0; k < NV; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
-    }
-    const int r0 = blockIdx.x * RMS_BWD_ROWS;
-    for (int rr = warp; rr < RMS_BWD_ROWS; rr += 8) {
-        const int row = r0 + rr;
-        if (row >= M) break;
+    // persistent rows: the grid is sized to the resident CTAs (2 per SM) and every warp strides over the rows, so the
+    // last wave is as full as the first (400 x 32-row CTAs on 148 SMs were 2.7 waves)
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
         const int64_t base = (int64_t)row * d;
         float xv[NV][4], gv[NV][4], rv[NV][4];
 #pragma unroll
@@ -258,13 +255,15 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int c = 4 * (lane + 32 * k);
+            float wk[4];
+            ldv<4>(w + c, wk);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float g = gv[k][j];
                 if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)(base + c + j), drop.thr) ? g * drop.inv_keep : 0.f;
                 gv[k][j] = g;
                 xv[k][j] *= r;                  // xhat
-                dot += g * wv[k][j] * xv[k][j];
+                dot += g * wk[j] * xv[k][j];
                 acc[k][j] += g * xv[k][j];
             }
         }
@@ -272,10 +271,11 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int c = 4 * (lane + 32 * k);
-            float o[4];
+            float o[4], wk[4];
+            ldv<4>(w + c, wk);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                o[j] = r * (gv[k][j] * wv[k][j] - xv[k][j] * dot);
+                o[j] = r * (gv[k][j] * wk[j] - xv[k][j] * dot);
                 if (dres) o[j] += rv[k][j];
             }
             stv<4>(dx + base + c, o);
@@ -306,7 +306,10 @@ template <typename T>
 static bool launch_rms_bwd_vec(const void* dn, const float* x, const float* rstd, const float* w, const float* dres,
                                float* dx, float* dw, int M, int d, DropCfg drop, bf16* dx_cast, DropCfg cast_drop,
                                cudaStream_t st) {
-    dim3 grid((unsigned)cdiv(M, RMS_BWD_ROWS));
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int64_t want = cdiv(M, 8);
+    dim3 grid((unsigned)(want < 2 * sms ? want : 2 * sms));
     switch (d) {
         case 512: launch_k(rmsnorm_bwd_vec_kernel<T, 4>, grid, 256, 0, st, (const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;
         case 768: launch_k(rmsnorm_bwd_vec_kernel<T, 6>, grid, 256, 0, st, (const T*)dn, x, rstd, w, dres, dx, dw, M, drop, dx_cast, cast_drop); return true;

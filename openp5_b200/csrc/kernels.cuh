@@ -136,7 +136,8 @@ void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H,
 void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
 void scale_f32(float* g, int64_t n, float s, cudaStream_t st);
 // transformers-4.26 AdamW on the flat parameter buffer; clip_norm_ptr (device) optional
-void adamw_flat(float* p, const float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
-                float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st);
+void adamw_flat(float* p, float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
+                float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st,
+                bool zero_grad_after = false);
 
 }  // namespace p5

@@ -57,11 +57,12 @@ void scale_f32(float* g, int64_t n, float s, cudaStream_t st) {
     LAUNCHED();
 }
 
-// p, g, m, v fp32 (16 B read + 12 B write per parameter) + 2 B bf16 shadow write.
+// p, g, m, v fp32 (16 B read + 12 B write per parameter) + 2 B bf16 shadow write (+ 4 B when the gradient is
+// cleared in the same pass: the fused zero_grad replaces a separate 4 B/param memset).
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, int64_t n, float lr, float b1, float b2, float eps, float wd, float step_size,
-             float clip, const float* __restrict__ norm_ptr, float grad_div) {
+             float clip, const float* __restrict__ norm_ptr, float grad_div, int zero_g) {
     pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
     pdl_launch_dependents();
     float gs = grad_div;
@@ -88,6 +89,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
             pa[j] = pa[j] - lr * wd * pa[j];                // decoupled decay AFTER the update, un-corrected lr
         }
         reinterpret_cast<float4*>(p)[i] = pp;
+        if (zero_g) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // fused model.zero_grad()
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
         if (p16) {
@@ -105,18 +107,20 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
         float pj = p[i] - step_size * (mj / (sqrtf(vj) + eps));
         pj = pj - lr * wd * pj;
         p[i] = pj; m[i] = mj; v[i] = vj;
+        if (zero_g) g[i] = 0.f;
         if (p16) p16[i] = __float2bfloat16_rn(pj);
     }
 }
 
-void adamw_flat(float* p, const float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
-                float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st) {
+void adamw_flat(float* p, float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
+                float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st,
+                bool zero_grad_after) {
     if (n <= 0) return;
     // step_size = lr * sqrt(1 - b2^t) / (1 - b1^t)   (correct_bias=True)
     const double bc1 = 1.0 - pow((double)b1, (double)step);
     const double bc2 = 1.0 - pow((double)b2, (double)step);
     const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-    launch_k(adamw_kernel, 148 * 8, 256, 0, st, p, g, m, v, p16, n, lr, b1, b2, eps, wd, step_size, clip, norm_ptr, grad_div);
+    launch_k(adamw_kernel, 148 * 8, 256, 0, st, p, g, m, v, p16, n, lr, b1, b2, eps, wd, step_size, clip, norm_ptr, grad_div, zero_grad_after ? 1 : 0);
     LAUNCHED();
 }
 

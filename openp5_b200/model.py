@@ -299,8 +299,8 @@ class P5B200:
         if self.world_size > 1:
             _lib.check(self.lib.p5_allreduce_grads(self.handle))
         self._opt_step = step if step is not None else self._opt_step + 1
-        _lib.check(self.lib.p5_adamw_step(self.handle, lr, betas[0], betas[1], eps, weight_decay, self._opt_step, clip))
-        _lib.check(self.lib.p5_zero_grad(self.handle))
+        # optimizer.step() + model.zero_grad() (DistributedRunner.py:85-87) in one pass over the flat buffers
+        _lib.check(self.lib.p5_adamw_step_zero_grad(self.handle, lr, betas[0], betas[1], eps, weight_decay, self._opt_step, clip))
         self._versions = self._version_sum()
         return loss
 
