@@ -42,11 +42,13 @@ struct TcParams {
     GemmEpilogue epi;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CTA2 = false>
 struct TcCfg {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    // CTA2: a CTA pair shares one 256 x BLOCK_N tile; each CTA stages its 128 rows of A and HALF of B
+    static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
+    static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BLOCK_N >= 192) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int STAGES = CTA2 ? 6 : ((BLOCK_N >= 192) ? 4 : (BLOCK_N == 128 ? 6 : 8));
     static constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);   // power of two >= 2 accumulators
     static constexpr int EPI_STRIDE = 66;                       // floats per staged row (64 + 2 pad: conflict-free 8-byte accesses)
     static constexpr int EPI_BYTES = 4 * 32 * EPI_STRIDE * 4;   // one 32x64 fp32 tile per epilogue warp
@@ -179,11 +181,11 @@ __device__ __forceinline__ void epi_store2(const GemmEpilogue& e, float a0, floa
     }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
-    using Cfg = TcCfg<BLOCK_N>;
+    using Cfg = TcCfg<BLOCK_N, CTA2>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -201,7 +203,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int m_tiles = (P.M + BLOCK_M - 1) / BLOCK_M;
+    // CTA2: the scheduling unit is the CTA pair (cluster of 2); it owns 256 rows of which this CTA takes 128
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const long long unit = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const long long unit_stride = CTA2 ? (gridDim.x >> 1) : gridDim.x;
+    constexpr int UNIT_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+    const int m_tiles = (P.M + UNIT_M - 1) / UNIT_M;
     const int n_tiles = (P.N + BLOCK_N - 1) / BLOCK_N;
     const int k_blocks = (P.K + BLOCK_K - 1) / BLOCK_K;
     const long long total_tiles = (long long)m_tiles * n_tiles * P.nb1 * P.nb2;
@@ -217,16 +225,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+        if constexpr (CTA2) tmem_alloc_2cta(tmem_holder, Cfg::TMEM_COLS);
+        else tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder_ptr;
     // PDL: barrier init, TMEM allocation and tensor-map prefetch above overlap the tail of the previous kernel; nothing
@@ -239,32 +249,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (long long t = unit; t < total_tiles; t += unit_stride) {
                 const int n_blk = (int)(t % n_tiles);
                 const long long t2 = t / n_tiles;
-                const int m_blk = (int)(t2 % m_tiles);
+                const int m_blk = (int)(t2 % m_tiles) * (CTA2 ? 2 : 1) + (int)cta_rank;   // 128-row block of this CTA
                 const int b = (int)(t2 / m_tiles);
                 const int b1 = b % P.nb1, b2 = b / P.nb1;
+                const int n0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::B_ROWS;            // first B row staged by this CTA
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    // pair mode: only the leader arms its barrier, with the bytes of BOTH CTAs' loads
+                    if (!CTA2 || leader) mbar_expect_tx(full_bar(stage), (CTA2 ? 2 : 1) * Cfg::STAGE_BYTES);
+                    auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
+                        if constexpr (CTA2) tma_load_4d_2cta(dst, tm, full_bar(stage), c0, c1, b1, b2);
+                        else tma_load_4d(dst, tm, full_bar(stage), c0, c1, b1, b2);
+                    };
                     if (P.a_major == MAJOR_K) {
-                        tma_load_4d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M, b1, b2);
+                        load(sa, &tmA, kb * BLOCK_K, m_blk * BLOCK_M);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < BLOCK_M / 64; ++c)
-                            tma_load_4d(sa + c * 8192, &tmA, full_bar(stage), m_blk * BLOCK_M + c * 64, kb * BLOCK_K,
-                                        b1, b2);
+                        for (int c = 0; c < BLOCK_M / 64; ++c) load(sa + c * 8192, &tmA, m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
                     }
                     if (P.b_major == MAJOR_K) {
-                        tma_load_4d(sb, &tmB, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N, b1, b2);
+                        load(sb, &tmB, kb * BLOCK_K, n0);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < BLOCK_N / 64; ++c)
-                            tma_load_4d(sb + c * 8192, &tmB, full_bar(stage), n_blk * BLOCK_N + c * 64, kb * BLOCK_K,
-                                        b1, b2);
+                        for (int c = 0; c < Cfg::B_ROWS / 64; ++c) load(sb + c * 8192, &tmB, n0 + c * 64, kb * BLOCK_K);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -273,17 +285,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
-            // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+            // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)   (pair mode: M = 256 across the two CTAs)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.a_major & 1) << 15) |
                                    ((uint32_t)(P.b_major & 1) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)(UNIT_M >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (long long t = unit; t < total_tiles; t += unit_stride) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -300,12 +312,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                                    : make_smem_desc(sa + k * 2048, 8192, 1024);
                         const uint64_t db = (P.b_major == MAJOR_K) ? make_smem_desc(sb + k * 32, 16, 1024)
                                                                    : make_smem_desc(sb + k * 2048, 8192, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CTA2) umma_bf16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+                    if constexpr (CTA2) umma_commit_2cta(empty_bar(stage)); else umma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if constexpr (CTA2) umma_commit_2cta(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -315,10 +330,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp & 3;  // TMEM lane quarter owned by this warp
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (long long t = unit; t < total_tiles; t += unit_stride) {
             const int n_blk = (int)(t % n_tiles);
             const long long t2 = t / n_tiles;
-            const int m_blk = (int)(t2 % m_tiles);
+            const int m_blk = (int)(t2 % m_tiles) * (CTA2 ? 2 : 1) + (int)cta_rank;
             const int b = (int)(t2 / m_tiles);
             const int b1 = b % P.nb1, b2 = b / P.nb1;
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -373,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (c == BLOCK_N / 64 - 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        if (lane == 0) { if (CTA2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
                     }
                     if (P.dbg & 2) {
                         uint32_t x = 0;
@@ -452,7 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) { if (CTA2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
                 }
                 const int col0 = n_blk * BLOCK_N + c * 32;
                 if (row_ok && col0 < P.N) {
@@ -475,10 +490,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();     // neither CTA frees TMEM / exits while its peer still reads or signals it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
     // independent-of-predecessor GEMM: the dependency wait happens here, so that "this grid completed" still implies
     // "everything before it on the stream completed" for the kernels that follow
@@ -671,9 +688,63 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     ++g_tc_launches;
 }
 
+// CTA-pair (cta_group::2) launch of the 256-wide tile: clusters of two CTAs, each pair owns a 256 x 256 tile.  Per
+// k-block a CTA pulls 16 KB of A + 16 KB of B from L2 instead of 16 + 32 KB: the single-CTA kernel moves ~94 B/clk/SM
+// at full tensor rate, which is what caps it below the cuBLAS rate.
+template <int EPI>
+static void launch_tc_pair(const GemmProblem& p, cudaStream_t stream) {
+    constexpr int BN = 256;
+    using Cfg = TcCfg<BN, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        P5_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA = make_tmap(p.A, p.M, p.K, p.nb1, p.nb2, BLOCK_M);
+    CUtensorMap tmB = make_tmap(p.B, p.N, p.K, p.nb1, p.nb2, Cfg::B_ROWS);
+    TcParams P;
+    P.M = p.M; P.N = p.N; P.K = p.K; P.nb1 = p.nb1; P.nb2 = p.nb2;
+    P.a_major = p.A.major; P.b_major = p.B.major;
+    P.epi = p.epi;
+    P.dbg = 0;
+    P.late_wait = (p.indep_of_prev && pdl_enabled()) ? 1 : 0;
+    const long long units = (long long)cdiv(p.M, 2 * BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
+    const int pairs = (int)(units < g_num_sms / 2 ? units : g_num_sms / 2);
+    ProfRec rec;
+    if (g_prof_on) {
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+        rec.flops = 2.0 * p.M * p.N * (double)p.K * p.nb1 * p.nb2; rec.bn = BN;
+        cudaEventRecord(rec.e0, stream);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    P5_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true>, tmA, tmB, P));
+    P5_CUDA(cudaGetLastError());
+    if (g_prof_on) { cudaEventRecord(rec.e1, stream); g_prof.push_back(rec); }
+    ++g_tc_launches;
+}
+
+// Pair mode is OPT-IN (P5_GEMM_PAIR=1): measured on B200 it is parity-green but not faster (T5-base step 16.91 vs
+// 16.86 ms; 128x256x16 MMAs retire every ~245 cycles in both modes), i.e. the kernel is bound by operand delivery
+// from shared memory into the tensor core (SS mode: 12 KB per MMA), not by L2 -> SM traffic, which pair mode cuts
+// by a third.  The next step for the GEMM is therefore A-from-TMEM (TS mode), not wider operand sharing.
+static bool use_pair(const GemmProblem& p) {
+    static const int mode = [] { const char* e = getenv("P5_GEMM_PAIR"); return e ? atoi(e) : 0; }();
+    if (!mode) return false;
+    const long long units = (long long)cdiv(p.M, 2 * BLOCK_M) * cdiv(p.N, 256) * p.nb1 * p.nb2;
+    return units >= g_num_sms / 2;
+}
+
 template <int EPI>
 static void launch_bn(int bn, const GemmProblem& p, cudaStream_t stream) {
-    if (bn == 256) launch_tc<256, EPI>(p, stream);
+    if (bn == 256 && use_pair(p)) launch_tc_pair<EPI>(p, stream);
+    else if (bn == 256) launch_tc<256, EPI>(p, stream);
     else if (bn == 192) launch_tc<192, EPI>(p, stream);
     else if (bn == 128) launch_tc<128, EPI>(p, stream);
     else launch_tc<64, EPI>(p, stream);

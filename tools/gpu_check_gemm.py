@@ -37,6 +37,17 @@ CASES = [
     ("epi_resid_bn192", 384, 768, 128, 0, 0, 1, 1, 192, 8),
     ("epi_dropout_bn192", 384, 768, 128, 0, 0, 1, 1, 192, 4),
     ("auto_bn192_n768", 12800, 768, 768, 0, 0, 1, 1, 0, 0),
+    # big enough for the CTA-pair (cta_group::2) path when P5_GEMM_PAIR=1 (>= 74 units of 256 x 256)
+    ("pair_kk", 4096, 2304, 768, 0, 0, 1, 1, 256, 0),
+    ("pair_mnAB", 2304, 3072, 4096, 1, 1, 1, 1, 256, 0),
+    ("pair_mnB", 4096, 2304, 768, 0, 1, 1, 1, 256, 0),
+    ("pair_ragged", 4000, 2500, 520, 0, 0, 1, 1, 256, 0),
+    ("pair_odd_blocks", 3968, 2304, 256, 0, 0, 1, 1, 256, 0),
+    ("pair_batched", 2048, 1536, 256, 0, 0, 2, 1, 256, 0),
+    ("pair_epi_resid", 4096, 2304, 256, 0, 0, 1, 1, 256, 8),
+    ("pair_epi_mulpos", 4096, 2304, 256, 0, 0, 1, 1, 256, 2),
+    ("pair_epi_dropout", 4096, 2304, 256, 0, 0, 1, 1, 256, 4),
+    ("pair_epi_accum", 4096, 2304, 256, 0, 0, 1, 1, 256, 16),
 ]
 
 
