@@ -100,6 +100,15 @@ int p5_adamw_step(p5_handle h, float lr, float beta1, float beta2, float eps, fl
  * 4 B/parameter memset of p5_zero_grad). */
 int p5_adamw_step_zero_grad(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                             float clip);
+/* Same update and gradient clearing as p5_adamw_step_zero_grad, but issued range by range (embeddings, encoder layer
+ * 0.., decoder layer 0..) on an engine-owned side stream: the HBM-bound optimiser pass overlaps the tensor-bound
+ * forward of the NEXT step, which waits for each range right before it first reads it (the training loop of
+ * DistributedRunner.py:59-87 never touches the parameters between optimizer.step() and the next forward).  Every
+ * other entry point of this library joins the pending update first; code that reads the parameter buffers directly
+ * (torch views) must call p5_optimizer_join before doing so. */
+int p5_adamw_step_zero_grad_async(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  int step, float clip);
+int p5_optimizer_join(p5_handle h);
 
 /* ---- data-parallel gradient exchange (the DDP all-reduce the reference constructs, DistributedRunner.py:26) ---- */
 int p5_comm_unique_id(void* id128_host);                      /* 128-byte ncclUniqueId */

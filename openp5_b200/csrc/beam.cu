@@ -542,6 +542,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
     P5_CHECK(max_len >= 2 && max_len <= 256, "max_length must be in [2, 256]");
     P5_CHECK(ids && mask, "null input");
     P5_CUDA(cudaSetDevice(e->device));
+    e->join_optimizer();          // an asynchronous AdamW of the last train step must have updated every weight
     cudaStream_t st = e->st;
     const int dt = e->dt, d = e->d, A = e->A, H = e->H, ff = e->ff, V = e->V, Vpad = e->Vpad;
     const int R = B * K, T = max_len;

@@ -144,6 +144,7 @@ int p5_grad_norm(p5_handle h, float* out) {
 int p5_grad_scale(p5_handle h, float s) {
     P5_API_BEGIN
     Engine* e = E(h);
+    e->join_optimizer();
     scale_f32(e->G, e->n_flat, s, e->st);
     e->norm_valid = false;
     P5_API_END
@@ -169,6 +170,19 @@ int p5_adamw_step_zero_grad(p5_handle h, float lr, float beta1, float beta2, flo
     P5_API_END
 }
 
+int p5_adamw_step_zero_grad_async(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                  float clip) {
+    P5_API_BEGIN
+    P5_CHECK(step >= 1, "AdamW step is 1-based");
+    E(h)->adamw_async(lr, beta1, beta2, eps, weight_decay, step, clip);
+    P5_API_END
+}
+int p5_optimizer_join(p5_handle h) {
+    P5_API_BEGIN
+    E(h)->join_optimizer();
+    P5_API_END
+}
+
 int p5_comm_unique_id(void* id128_host) {
     P5_API_BEGIN
     comm_unique_id(id128_host);
@@ -181,6 +195,7 @@ int p5_comm_init(p5_handle h, const void* id128_host, int rank, int world) {
 }
 int p5_allreduce_grads(p5_handle h) {
     P5_API_BEGIN
+    E(h)->join_optimizer();
     comm_allreduce_grads(E(h));
     P5_API_END
 }

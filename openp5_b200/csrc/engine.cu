@@ -178,7 +178,11 @@ void free_gen_ws(struct GenWs* g);
 
 Engine::~Engine() {
     cudaSetDevice(device);
+    if (st_opt) cudaStreamSynchronize(st_opt);
     cudaStreamSynchronize(st);
+    for (auto e : ev_opt) cudaEventDestroy(e);
+    if (ev_opt_start) cudaEventDestroy(ev_opt_start);
+    if (st_opt) cudaStreamDestroy(st_opt);
     if (gen) free_gen_ws(gen);
     for (void* p : allocs) cudaFree(p);
     gemm_tc_clear_cache();
@@ -194,6 +198,7 @@ DropCfg Engine::drop(uint32_t kind, int layer) const {
 }
 
 void Engine::refresh_shadow() {
+    join_optimizer();
     if (dt == DT_BF16) cast_f32_to(P, P16, DT_BF16, n_flat, st);
     shadow_stale = false;
 }
@@ -544,6 +549,8 @@ void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
 // forward
 // ------------------------------------------------------------------------------------------------------------
 void Engine::encoder_forward() {
+    wait_opt(0);                 // embeddings
+    if (NE > 0) wait_opt(1);     // encoder layer 0 holds the shared relative-bias table
     build_bias(true, Le);
     const int* ids_in = packed ? ids_p : ids_e;
     const int* ww_in = packed ? ww_p : ww_e;
@@ -551,6 +558,7 @@ void Engine::encoder_forward() {
     DropCfg none;
     for (int l = 0; l < NE; ++l) {
         const EncLayerOff& w = enc[l];
+        wait_opt(1 + l);          // asynchronous AdamW: this layer's range must be updated before its first GEMM
         float *x_in = xe[2 * l], *x_mid = xe[2 * l + 1], *x_out = xe[2 * l + 2];
         rmsnorm_fwd(x_in, P + w.ln0, ne[2 * l], dt, rstd_e[2 * l], (int)Mt, d, cfg.ln_eps, none, st);
         linear_fwd(ne[2 * l], d, w.sa.q, 3 * A, d, (int)Mt, qkv_e[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
@@ -590,11 +598,14 @@ static AttnArgs dec_cross_args(Engine& e, int l, DropCfg dc) {
 }
 
 void Engine::decoder_forward() {
+    wait_opt(0);
+    if (ND > 0) wait_opt(1 + NE);
     build_bias(false, Ld);
     embed_fwd(P + off_shared, nullptr, dec_ids, nullptr, yd[0], (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
     DropCfg none;
     for (int l = 0; l < ND; ++l) {
         const DecLayerOff& w = dec[l];
+        wait_opt(1 + NE + l);
         float *y0 = yd[3 * l], *y1 = yd[3 * l + 1], *y2 = yd[3 * l + 2], *y3 = yd[3 * l + 3];
         rmsnorm_fwd(y0, P + w.ln0, nd[3 * l], dt, rstd_d[3 * l], (int)Md, d, cfg.ln_eps, none, st);
         linear_fwd(nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, sqkv[l], dt, 3 * A, 0, 1.f, nullptr, nullptr, none);
@@ -640,6 +651,7 @@ void Engine::forward(const int32_t* ids, const int32_t* mask, const int32_t* ww,
     encoder_forward();
     decoder_forward();
     head_forward();
+    opt_pending = false;      // every optimiser range has been waited for by now
     have_fwd = true;
 }
 
@@ -649,6 +661,7 @@ void Engine::forward(const int32_t* ids, const int32_t* mask, const int32_t* ww,
 void Engine::backward() {
     P5_CHECK(have_fwd, "p5_backward called without a preceding p5_forward");
     P5_CUDA(cudaSetDevice(device));
+    join_optimizer();
     norm_valid = false;
     const float hs = 1.f / sqrtf((float)d);
     auto as_T = [&](float* src, void* dst, int64_t n) -> void* {
@@ -760,14 +773,57 @@ void Engine::backward() {
 // optimiser
 // ------------------------------------------------------------------------------------------------------------
 void Engine::grad_norm() {
+    join_optimizer();
     sumsq_norm(G, n_flat, norm_partial, norm_out, st);
     norm_valid = true;
 }
 void Engine::zero_grad() {
+    join_optimizer();
     P5_CUDA(cudaMemsetAsync(G, 0, n_flat * sizeof(float), st));
     norm_valid = false;
 }
+void Engine::wait_opt(int r) {
+    if (opt_pending) P5_CUDA(cudaStreamWaitEvent(st, ev_opt[r], 0));
+}
+void Engine::join_optimizer() {
+    if (!opt_pending) return;
+    for (auto e : ev_opt) P5_CUDA(cudaStreamWaitEvent(st, e, 0));
+    opt_pending = false;
+}
+void Engine::adamw_async(float lr, float b1, float b2, float eps, float wd, int step, float clip) {
+    join_optimizer();
+    if (clip > 0.f && !norm_valid) grad_norm();
+    if (!st_opt) {
+        P5_CUDA(cudaStreamCreateWithFlags(&st_opt, cudaStreamNonBlocking));
+        P5_CUDA(cudaEventCreateWithFlags(&ev_opt_start, cudaEventDisableTiming));
+        // ranges in the order the forward first touches them: [embeddings] [encoder layer l (+ final norm)] [decoder layer l]
+        std::vector<int64_t> cuts;
+        cuts.push_back(0);
+        for (int l = 0; l < NE; ++l) cuts.push_back(enc[l].sa.q);
+        for (int l = 0; l < ND; ++l) cuts.push_back(dec[l].sa.q);
+        cuts.push_back(n_flat);
+        for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+            P5_CHECK(cuts[i + 1] > cuts[i], "optimizer ranges must be increasing");
+            opt_ranges.push_back({cuts[i], cuts[i + 1] - cuts[i]});
+            cudaEvent_t e;
+            P5_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev_opt.push_back(e);
+        }
+    }
+    P5_CUDA(cudaEventRecord(ev_opt_start, st));
+    P5_CUDA(cudaStreamWaitEvent(st_opt, ev_opt_start, 0));
+    for (size_t r = 0; r < opt_ranges.size(); ++r) {
+        const int64_t o = opt_ranges[r].first, n = opt_ranges[r].second;
+        adamw_flat(P + o, G + o, M1 + o, V2 + o, P16 ? P16 + o : nullptr, n, lr, b1, b2, eps, wd, step, clip,
+                   clip > 0.f ? norm_out : nullptr, 1.f, st_opt, true);
+        P5_CUDA(cudaEventRecord(ev_opt[r], st_opt));
+    }
+    opt_pending = true;
+    shadow_stale = false;
+    norm_valid = false;
+}
 void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip, bool zero_grad_after) {
+    join_optimizer();
     if (clip > 0.f && !norm_valid) grad_norm();
     adamw_flat(P, G, M1, V2, P16, n_flat, lr, b1, b2, eps, wd, step, clip, clip > 0.f ? norm_out : nullptr, 1.f, st,
                zero_grad_after);

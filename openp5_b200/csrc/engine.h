@@ -7,6 +7,7 @@
 #include "../../include/p5_b200.h"
 #include <string>
 #include <vector>
+#include <utility>
 
 namespace p5 {
 extern int g_launches;
@@ -113,6 +114,17 @@ struct Engine {
     // comm
     void* nccl_comm = nullptr;
     int world = 1, rank = 0;
+    // ---- asynchronous optimiser (p5_adamw_step_zero_grad_async): AdamW runs range by range (embeddings, encoder layer
+    // 0..NE-1, decoder layer 0..ND-1) on a side stream; the NEXT forward waits for a range just before it first reads
+    // it, every other entry point joins all ranges first.  HBM-bound AdamW then overlaps the tensor-bound forward.
+    cudaStream_t st_opt = nullptr;
+    cudaEvent_t ev_opt_start = nullptr;
+    std::vector<cudaEvent_t> ev_opt;
+    std::vector<std::pair<int64_t, int64_t>> opt_ranges;   // (offset, count) in forward-use order
+    bool opt_pending = false;
+    void adamw_async(float lr, float b1, float b2, float eps, float wd, int step, float clip);
+    void wait_opt(int range);      // st waits for one range (no-op when nothing is pending)
+    void join_optimizer();         // st waits for every range
     bool overlap_comm = false;   // set for the fused train step: ranges are all-reduced as backward completes them
 
     // ---- generate workspace (beam.cu) ----

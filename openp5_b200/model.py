@@ -156,10 +156,17 @@ class P5B200:
         self.world_size, self.rank = 1, 0
 
     # ---------------------------------------------------------------- module protocol
+    def _join_optimizer(self):
+        """an asynchronous AdamW (train_step(..., overlap_optimizer=True)) may still be updating the buffers behind the
+        torch views: order it before anything else that is enqueued on this stream"""
+        _lib.check(self.lib.p5_optimizer_join(self.handle))
+
     def named_parameters(self):
+        self._join_optimizer()
         return iter(self._params.items())
 
     def parameters(self):
+        self._join_optimizer()
         return iter(self._params.values())
 
     def num_parameters(self) -> int:
@@ -179,6 +186,7 @@ class P5B200:
         _lib.check(self.lib.p5_zero_grad(self.handle))
 
     def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        self._join_optimizer()
         """HF T5 key names incl. the tied aliases (ref DistributedRunner.py:155,169)."""
         sd = OrderedDict((k, v.detach().clone()) for k, v in self._params.items())
         sd["encoder.embed_tokens.weight"] = sd["shared.weight"]
@@ -187,6 +195,7 @@ class P5B200:
         return sd
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        self._join_optimizer()
         aliases = {"encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight"}
         missing = [k for k in self._params if k not in sd]
         unexpected = [k for k in sd if k not in self._params and k not in aliases]
@@ -277,10 +286,17 @@ class P5B200:
     # ---------------------------------------------------------------- fused training step (fast path)
     def train_step(self, input_ids, whole_word_ids, attention_mask, labels, labels_attention, *, lr: float,
                    clip: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.01,
-                   seed: Optional[int] = None, step: Optional[int] = None, enc_lengths=None) -> torch.Tensor:
+                   seed: Optional[int] = None, step: Optional[int] = None, enc_lengths=None,
+                   overlap_optimizer: bool = False) -> torch.Tensor:
         """One optimisation step = ref DistributedRunner.py:63-87 (forward, runner loss, backward, clip, AdamW,
         zero_grad) + the gradient all-reduce DDP was meant to do.  Returns the scalar loss as a device tensor
-        (no host sync)."""
+        (no host sync).
+
+        overlap_optimizer=True issues AdamW range by range on an engine-owned side stream so that it overlaps the
+        forward of the NEXT train_step (which waits per layer).  Same arithmetic, same results; the only contract is
+        that parameter tensors obtained earlier (`p = model.shared.weight`) are not read by the caller until the next
+        call into this object (state_dict / named_parameters / generate / ... all join first) — which is how the
+        reference's training loop behaves."""
         self._on_stream()
         self._sync_params(fast_path=True)
         self._set_enc_lengths(enc_lengths, attention_mask)
@@ -300,7 +316,8 @@ class P5B200:
             _lib.check(self.lib.p5_allreduce_grads(self.handle))
         self._opt_step = step if step is not None else self._opt_step + 1
         # optimizer.step() + model.zero_grad() (DistributedRunner.py:85-87) in one pass over the flat buffers
-        _lib.check(self.lib.p5_adamw_step_zero_grad(self.handle, lr, betas[0], betas[1], eps, weight_decay, self._opt_step, clip))
+        step_fn = self.lib.p5_adamw_step_zero_grad_async if overlap_optimizer else self.lib.p5_adamw_step_zero_grad
+        _lib.check(step_fn(self.handle, lr, betas[0], betas[1], eps, weight_decay, self._opt_step, clip))
         self._versions = self._version_sum()
         return loss
 

@@ -122,7 +122,8 @@ class B200Runner:
         a = self.args
         loss = self.model.train_step(batch[0], batch[2], batch[1], batch[3], batch[4], lr=self._lr(),
                                      clip=getattr(a, "clip", 1.0), eps=getattr(a, "adam_eps", 1e-6),
-                                     weight_decay=getattr(a, "weight_decay", 0.01))
+                                     weight_decay=getattr(a, "weight_decay", 0.01),
+                                     overlap_optimizer=True)   # the loop never reads parameters between steps
         self.global_step += 1
         return loss
 

@@ -16,7 +16,8 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "bwd_fp32_tiny_packed", "bwd_fp32_small_packed", "bwd_bf16_small_packed", "bwd_bf16_base_le256_packed",
          "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed", "bwd_bf16_small_ld12", "bwd_fp32_small_ld12",
          "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed", "xcheck_fbwd_dropout_small",
-         "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256"]
+         "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256", "adamw_fp32_tiny_async",
+         "asyncopt_bf16_small_bitwise"]
 
 
 def setup(case):
@@ -127,7 +128,7 @@ def run_case(case):
                 po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, lr, eps=1e-6, weight_decay=0.01)
             m.training = False
             loss = m.train_step(ids.to(dev), ww.to(dev), attn.to(dev), labels.to(dev), oattn.to(dev), lr=lr, clip=1.0, step=step,
-                                enc_lengths=attn.sum(1) if "packed" in case else None)
+                                enc_lengths=attn.sum(1) if "packed" in case else None, overlap_optimizer="async" in case)
             losses.append((loss.item(), l_o.item()))
         worst = max(relerr(p.detach().cpu(), wo[k]) for k, p in m.named_parameters())
         res["losses"] = losses
@@ -157,6 +158,25 @@ def run_case(case):
             res["ok"] = same and res["score_err"] < 1e-4 and res["trie_get_ok"]
         else:
             res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
+    elif case.startswith("asyncopt"):
+        # AdamW on the side stream under the next forward must be the same computation as AdamW in stream order:
+        # 5 train steps (dropout on, bf16) from identical weights / seeds -> bit-identical losses and parameters
+        outs = []
+        for ov in (False, True):
+            m = make_model(cfg, w, prec, dropout=0.1).train()
+            a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+            losses = []
+            for step in range(1, 6):
+                losses.append(m.train_step(a[0], a[1], a[2], a[3], a[4], lr=1e-3, clip=1.0, step=step, seed=100 + step,
+                                           enc_lengths=attn.sum(1), overlap_optimizer=ov))
+            torch.cuda.synchronize()
+            outs.append(([l.item() for l in losses], {k: p.detach().clone() for k, p in m.named_parameters()}))
+        res["losses"] = [outs[0][0], outs[1][0]]
+        res["losses_equal"] = outs[0][0] == outs[1][0]
+        # split-K wgrads accumulate with fp32 atomics (order-dependent rounding), so parameters agree to rounding, not bitwise
+        worst = max(relerr(outs[1][1][k].float(), outs[0][1][k].float()) for k in outs[0][1])
+        res["worst_param_rel"] = worst
+        res["ok"] = worst < 2e-3 and all(abs(x - y) < 2e-3 * abs(x) for x, y in zip(*res["losses"]))
     elif case.startswith("xcheck"):
         # decoder attention: mma.sync kernels (dattn.cu) vs the fp32-math SIMT kernels at the SAME dropout seed; or
         # ("fbwd") the fused tcgen05 attention backward vs the GEMM chain + softmax_bwd.  Both sides regenerate the
