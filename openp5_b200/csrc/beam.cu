@@ -564,8 +564,12 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
     e->have_fwd = false;   // training activations are not valid for backward any more
     const int Le = e->Le;
     DropCfg none;
-    for (int l = 0; l < e->ND; ++l)
-        e->linear_fwd(e->enc_out, d, e->dec[l].ca.k, 2 * A, d, (int)e->Me, e->ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
+    if (e->batched_ckv) {
+        e->project_cross_kv_all(e->Me);
+    } else {
+        for (int l = 0; l < e->ND; ++l)
+            e->linear_fwd(e->enc_out, d, e->dec[l].ca.k, 2 * A, d, (int)e->Me, e->ckv[l], dt, e->ckv_ld, 0, 1.f, nullptr, nullptr, none);
+    }
     e->build_bias(false, T);   // decoder relative bias for positions 0..T-1: [H, 2T-1], offset T-1
     const int n_delta = 2 * T - 1, bias_off = T - 1;
 
@@ -616,8 +620,8 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
             AttnArgs xa;   // the K beams of a user are the query rows against that user's cross K/V
             xa.B = B; xa.H = H; xa.Lq = K; xa.Lk = Le;
             xa.q = {g->cq, dt, A, (int64_t)K * A};
-            xa.k = {e->ckv[l], dt, 2 * A, (int64_t)Le * 2 * A};
-            xa.v = {(const char*)e->ckv[l] + (size_t)A * e->esz(), dt, 2 * A, (int64_t)Le * 2 * A};
+            xa.k = {e->ckv[l], dt, e->ckv_ld, (int64_t)Le * e->ckv_ld};
+            xa.v = {(const char*)e->ckv[l] + (size_t)A * e->esz(), dt, e->ckv_ld, (int64_t)Le * e->ckv_ld};
             xa.bias_rel = nullptr; xa.bias_off = 0; xa.n_delta = 0; xa.key_mask = e->mask_e; xa.causal = 0; xa.q_pos_offset = 0;
             xa.row_map = nullptr;
             if (dt == DT_BF16 && dattn_infer_supported(xa)) {
@@ -630,15 +634,15 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
                 GemmProblem sp;
                 sp.M = K; sp.N = Le; sp.K = 64; sp.nb1 = H; sp.nb2 = B;
                 sp.A.ptr = g->cq; sp.A.dtype = dt; sp.A.major = MAJOR_K; sp.A.ld = A; sp.A.bs1 = 64; sp.A.bs2 = (int64_t)K * A;
-                sp.B.ptr = e->ckv[l]; sp.B.dtype = dt; sp.B.major = MAJOR_K; sp.B.ld = 2 * A; sp.B.bs1 = 64; sp.B.bs2 = (int64_t)Le * 2 * A;
+                sp.B.ptr = e->ckv[l]; sp.B.dtype = dt; sp.B.major = MAJOR_K; sp.B.ld = e->ckv_ld; sp.B.bs1 = 64; sp.B.bs2 = (int64_t)Le * e->ckv_ld;
                 sp.epi.C = g->xS; sp.epi.c_dtype = DT_F32; sp.epi.ldc = Le; sp.epi.cs1 = KL; sp.epi.cs2 = KL * H;
                 e->gemm(sp);
                 softmax_fwd(g->xS, nullptr, e->mask_e, g->xP, nullptr, dt, B, H, K, Le, 0, none, st);
                 GemmProblem pv;
                 pv.M = K; pv.N = 64; pv.K = Le; pv.nb1 = H; pv.nb2 = B;
                 pv.A.ptr = g->xP; pv.A.dtype = dt; pv.A.major = MAJOR_K; pv.A.ld = Le; pv.A.bs1 = KL; pv.A.bs2 = KL * H;
-                pv.B.ptr = (const char*)e->ckv[l] + (size_t)A * e->esz(); pv.B.dtype = dt; pv.B.major = MAJOR_MN; pv.B.ld = 2 * A;
-                pv.B.bs1 = 64; pv.B.bs2 = (int64_t)Le * 2 * A;
+                pv.B.ptr = (const char*)e->ckv[l] + (size_t)A * e->esz(); pv.B.dtype = dt; pv.B.major = MAJOR_MN; pv.B.ld = e->ckv_ld;
+                pv.B.bs1 = 64; pv.B.bs2 = (int64_t)Le * e->ckv_ld;
                 pv.epi.C = g->ctx; pv.epi.c_dtype = dt; pv.epi.ldc = A; pv.epi.cs1 = 64; pv.epi.cs2 = (int64_t)K * A;
                 e->gemm(pv);
             } else {

@@ -189,6 +189,7 @@ struct GemmOperand {
     int major = MAJOR_K;
     int64_t ld = 0;
     int64_t bs1 = 0, bs2 = 0;  // batch strides in elements
+    bool bcast1 = false, bcast2 = false;   // the operand is shared by every index of batch dimension 1 / 2 (stride 0)
 };
 
 enum EpiFlags : int {

@@ -140,11 +140,20 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     dec_out = dalloc(Mdm * d * e);
     sqkv.resize(ND); sctx.resize(ND); cq.resize(ND); ckv.resize(ND); cctx.resize(ND); h_d.resize(ND);
     z_d.assign(ND, nullptr); slse.resize(ND); clse.resize(ND);
+    ckv_ld = (int64_t)ND * 2 * A;
+    if (ND > 0) ckv_all = dalloc(Mem * ckv_ld * e);
+    dec_layer_stride = ND > 1 ? dec[1].ca.k - dec[0].ca.k : 0;
+    {
+        static const bool off = getenv("P5_NO_BATCHED_CKV") != nullptr;
+        batched_ckv = dt == DT_BF16 && ND > 1 && !off;
+        for (int i = 1; i < ND; ++i) batched_ckv = batched_ckv && (dec[i].ca.k - dec[0].ca.k == i * dec_layer_stride);
+        if (batched_ckv) g_ckv_all = dalloc(Mem * ckv_ld * e);
+    }
     for (int i = 0; i < ND; ++i) {
         sqkv[i] = dalloc(Mdm * 3 * A * e);
         sctx[i] = dalloc(Mdm * A * e);
         cq[i] = dalloc(Mdm * A * e);
-        ckv[i] = dalloc(Mem * 2 * A * e);
+        ckv[i] = poff(ckv_all, (int64_t)i * 2 * A, dt);
         cctx[i] = dalloc(Mdm * A * e);
         h_d[i] = dalloc(Mdm * ff * e);
         if (gated) z_d[i] = dalloc(Mdm * 2 * ff * e);
@@ -587,8 +596,8 @@ static AttnArgs dec_cross_args(Engine& e, int l, DropCfg dc) {
     const int A = e.A, Ld = e.Ld, Le = e.Le;
     a.B = e.B; a.H = e.H; a.Lq = Ld; a.Lk = Le;
     a.q = {e.cq[l], e.dt, A, (int64_t)Ld * A};
-    a.k = {e.ckv[l], e.dt, 2 * A, (int64_t)Le * 2 * A};
-    a.v = {poff(e.ckv[l], A, e.dt), e.dt, 2 * A, (int64_t)Le * 2 * A};
+    a.k = {e.ckv[l], e.dt, e.ckv_ld, (int64_t)Le * e.ckv_ld};
+    a.v = {poff(e.ckv[l], A, e.dt), e.dt, e.ckv_ld, (int64_t)Le * e.ckv_ld};
     a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0;   // cross-attention position bias is zero (HF:...:317-322)
     a.key_mask = e.mask_e; a.causal = 0; a.q_pos_offset = 0; a.row_map = nullptr; a.drop = dc;
     if (e.packed) {   // encoder rows are packed: per-user row offset + key count replace (batch stride, key mask)
@@ -597,9 +606,25 @@ static AttnArgs dec_cross_args(Engine& e, int l, DropCfg dc) {
     return a;
 }
 
+// cross K|V of every decoder layer in ONE batched GEMM: C[:, l*2A : (l+1)*2A] = enc_out . W_l^T  (batch dim 2 = layer:
+// A broadcast, B strided by the per-layer parameter stride, C strided by 2A columns).  7200 tiles instead of 12 x 600:
+// no per-layer wave quantisation (600 tiles = 4.05 waves on 148 SMs).
+void Engine::project_cross_kv_all(int64_t rows) {
+    GemmProblem p;
+    p.M = (int)rows; p.N = 2 * A; p.K = d; p.nb1 = 1; p.nb2 = ND;
+    p.A.ptr = enc_out; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = d; p.A.bcast2 = true;
+    p.B.ptr = W(dec[0].ca.k); p.B.dtype = dt; p.B.major = MAJOR_K; p.B.ld = d; p.B.bs2 = dec_layer_stride;
+    p.epi.C = ckv_all; p.epi.c_dtype = dt; p.epi.ldc = ckv_ld; p.epi.cs2 = 2 * A; p.epi.alpha = 1.f; p.epi.flags = 0;
+    gemm(p);
+}
+
 void Engine::decoder_forward() {
     wait_opt(0);
     if (ND > 0) wait_opt(1 + NE);
+    if (batched_ckv) {
+        for (int l = 1; l < ND; ++l) wait_opt(1 + NE + l);
+        project_cross_kv_all(Mt);
+    }
     build_bias(false, Ld);
     embed_fwd(P + off_shared, nullptr, dec_ids, nullptr, yd[0], (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
     DropCfg none;
@@ -618,8 +643,10 @@ void Engine::decoder_forward() {
                    drop(S_DEC_SO, l));
         rmsnorm_fwd(y1, P + w.ln1, nd[3 * l + 1], dt, rstd_d[3 * l + 1], (int)Md, d, cfg.ln_eps, none, st);
         linear_fwd(nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, cq[l], dt, A, 0, 1.f, nullptr, nullptr, none);
-        next_gemm_indep = true;   // cross K|V projection: needs enc_out only, not the (small) cross-Q GEMM just before it
-        linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Mt, ckv[l], dt, 2 * A, 0, 1.f, nullptr, nullptr, none);
+        if (!batched_ckv) {
+            next_gemm_indep = true;   // cross K|V projection: needs enc_out only, not the (small) cross-Q GEMM just before it
+            linear_fwd(enc_out, d, w.ca.k, 2 * A, d, (int)Mt, ckv[l], dt, ckv_ld, 0, 1.f, nullptr, nullptr, none);
+        }
         {
             const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
             if (dattn_supported(ca)) dattn_fwd(ca, cctx[l], A, (int64_t)Ld * A, clse[l], st);
@@ -689,12 +716,15 @@ void Engine::backward() {
         // cross attention (g_d = dropout-cast(dy))
         linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
         linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f, true);
-        void *gq, *gkv;
+        void *gq, *gkv = nullptr;
         const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
+        const bool batch_kv = batched_ckv && dattn_supported(ca);     // dK|dV of all layers -> one wgrad / dgrad after the loop
         if (dattn_supported(ca)) {   // bf16: tensor-core kernel writes dQ and dK|dV as bf16 in place
-            dattn_bwd(ca, g_ctx, A, (int64_t)Ld * A, clse[l], g_qkv, A, (int64_t)Ld * A, g_ckv, poff(g_ckv, A, dt), 2 * A,
-                      (int64_t)Le * 2 * A, nullptr, st);
-            if (packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
+            void* dk = batch_kv ? poff(g_ckv_all, (int64_t)l * 2 * A, dt) : g_ckv;
+            const int64_t ldkv = batch_kv ? ckv_ld : 2 * A;
+            dattn_bwd(ca, g_ctx, A, (int64_t)Ld * A, clse[l], g_qkv, A, (int64_t)Ld * A, dk, poff(dk, A, dt), ldkv,
+                      (int64_t)Le * ldkv, nullptr, st);
+            if (!batch_kv && packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
                 P5_CUDA(cudaMemsetAsync(poff(g_ckv, Mt_true * 2 * A, dt), 0, (Mt - Mt_true) * 2 * A * dtype_size(dt), st));
             gq = g_qkv;
             gkv = g_ckv;
@@ -707,9 +737,11 @@ void Engine::backward() {
             gq = as_T(f_qkv, g_qkv, Md * A);
             gkv = as_T(f_ckv, g_ckv, Mt * 2 * A);
         }
-        linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Mt, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
-        linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f, true);
-        next_gemm_indep = true;   // reads gq and W only: independent of the cross-K|V dgrad / wgrad before it
+        if (!batch_kv) {
+            linear_dgrad(gkv, 2 * A, w.ca.k, 2 * A, d, (int)Mt, d_encout, DT_F32, d, 0, 1.f, nullptr, true);
+            linear_wgrad(gkv, 2 * A, enc_out, d, w.ca.k, 2 * A, d, (int)Mt, 1.f, true);
+            next_gemm_indep = true;   // reads gq and W only: independent of the cross-K|V dgrad / wgrad before it
+        }
         linear_dgrad(gq, A, w.ca.q, A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
         linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f, true);
         rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st, g_d, dt,
@@ -733,6 +765,42 @@ void Engine::backward() {
         linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f, true);
         rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st, l > 0 ? g_d : nullptr, dt,
                     drop(S_DEC_WO, l > 0 ? l - 1 : 0));
+    }
+    if (batched_ckv && ND > 0 && dattn_supported(dec_cross_args(*this, 0, none))) {
+        if (packed && Mt > Mt_true)   // filler rows of every layer's dK|dV: zero gradient
+            P5_CUDA(cudaMemsetAsync(poff(g_ckv_all, Mt_true * ckv_ld, dt), 0, (Mt - Mt_true) * ckv_ld * dtype_size(dt), st));
+        {   // d_encout += sum_l gkv_l . W_l : the layers are batch dimension 2, all accumulating into the same (zeroed) C
+            GemmProblem p;
+            p.tail_filled = true;
+            p.M = (int)Mt; p.N = d; p.K = 2 * A; p.nb1 = 1; p.nb2 = ND;
+            p.A.ptr = g_ckv_all; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = ckv_ld; p.A.bs2 = 2 * A;
+            p.B.ptr = W(dec[0].ca.k); p.B.dtype = dt; p.B.major = MAJOR_MN; p.B.ld = d; p.B.bs2 = dec_layer_stride;
+            p.epi.C = d_encout; p.epi.c_dtype = DT_F32; p.epi.ldc = d; p.epi.cs2 = 0; p.epi.alpha = 1.f; p.epi.flags = EPI_ATOMIC;
+            gemm(p);
+        }
+        {   // dW_l = gkv_l^T . enc_out for every layer: batch dim 2 = layer (B broadcast), batch dim 1 = split-K
+            GemmProblem p;
+            p.indep_of_prev = true;
+            p.M = 2 * A; p.N = d;
+            int splits = 1;
+            {
+                const int64_t t256 = cdiv(2 * A, 128) * cdiv(d, 256) * ND;
+                double best = 1e30;
+                for (int sp = 1; sp <= 32; sp *= 2) {
+                    if (Mt % sp != 0 || Mt / sp < 256) break;
+                    const double rounds = (double)cdiv(t256 * sp, 148);
+                    const double cost = rounds * ((double)(Mt / sp) / 64.0 + 16.0);
+                    if (cost < best) { best = cost; splits = sp; }
+                }
+            }
+            const int64_t Ks = Mt / splits;
+            p.K = (int)Ks; p.nb1 = splits; p.nb2 = ND; p.prefer_bn = 256;
+            p.A.ptr = g_ckv_all; p.A.dtype = dt; p.A.major = MAJOR_MN; p.A.ld = ckv_ld; p.A.bs1 = Ks * ckv_ld; p.A.bs2 = 2 * A;
+            p.B.ptr = enc_out; p.B.dtype = dt; p.B.major = MAJOR_MN; p.B.ld = d; p.B.bs1 = Ks * d; p.B.bcast2 = true;
+            p.epi.C = G + dec[0].ca.k; p.epi.c_dtype = DT_F32; p.epi.ldc = d; p.epi.cs1 = 0; p.epi.cs2 = dec_layer_stride;
+            p.epi.alpha = 1.f; p.epi.flags = EPI_ATOMIC;
+            gemm(p);
+        }
     }
     embed_bwd(dy, dec_ids, nullptr, G + off_shared, nullptr, (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
     relbias_scatter_grad(dbias_dec, lut_dec, G + off_dec_rel, H, 2 * Ld - 1, st);

@@ -96,6 +96,13 @@ struct Engine {
     std::vector<void*> nd;              // [3*ND]
     void* dec_out = nullptr;
     std::vector<void*> sqkv, sctx, cq, ckv, cctx, h_d, z_d;
+    // cross K|V of ALL decoder layers live in one [rows, ND * 2A] matrix (ckv[l] = column block l, row stride ckv_ld):
+    // the ND projections of enc_out are ONE batched GEMM (no per-layer wave quantisation), and so are their weight /
+    // input gradients (g_ckv_all holds dK|dV of every layer until the decoder backward is done)
+    void *ckv_all = nullptr, *g_ckv_all = nullptr;
+    int64_t ckv_ld = 0, dec_layer_stride = 0;
+    bool batched_ckv = false;
+    void project_cross_kv_all(int64_t rows);
     std::vector<float*> slse, clse;
     // head
     float *logits = nullptr, *lse_ce = nullptr, *loss_tok = nullptr, *dloss = nullptr, *loss_scalar = nullptr;

@@ -81,8 +81,8 @@ static void launch_simt(const GemmProblem& p, cudaStream_t stream) {
     dim3 grid((unsigned)cdiv(p.N, ST), (unsigned)cdiv(p.M, ST), (unsigned)(p.nb1 * p.nb2));
     int64_t a_rs = p.A.major == MAJOR_K ? p.A.ld : 1, a_ks = p.A.major == MAJOR_K ? 1 : p.A.ld;
     int64_t b_rs = p.B.major == MAJOR_K ? p.B.ld : 1, b_ks = p.B.major == MAJOR_K ? 1 : p.B.ld;
-    launch_k(gemm_simt_kernel<TA, TB>, grid, 256, 0, stream, p.M, p.N, p.K, p.nb1, (const TA*)p.A.ptr, a_rs, a_ks, p.A.bs1,
-                                                        p.A.bs2, (const TB*)p.B.ptr, b_rs, b_ks, p.B.bs1, p.B.bs2,
+    launch_k(gemm_simt_kernel<TA, TB>, grid, 256, 0, stream, p.M, p.N, p.K, p.nb1, (const TA*)p.A.ptr, a_rs, a_ks, p.A.bcast1 ? 0 : p.A.bs1,
+                                                        p.A.bcast2 ? 0 : p.A.bs2, (const TB*)p.B.ptr, b_rs, b_ks, p.B.bcast1 ? 0 : p.B.bs1, p.B.bcast2 ? 0 : p.B.bs2,
                                                         p.epi);
     P5_CUDA(cudaGetLastError());
 }

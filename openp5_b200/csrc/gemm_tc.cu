@@ -39,6 +39,7 @@ struct TcParams {
     int a_major, b_major;
     int dbg;   // perf-debug only (P5_GEMM_DBG): 1 = no global stores, 2 = no smem staging either, 4 = no TMEM loads
     int late_wait;   // GemmProblem::indep_of_prev: griddepcontrol.wait at the end instead of the start
+    int a_m1, a_m2, b_m1, b_m2;   // batch-coordinate multipliers (0 = the operand is broadcast over that batch dimension)
     GemmEpilogue epi;
 };
 
@@ -263,8 +264,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // pair mode: only the leader arms its barrier, with the bytes of BOTH CTAs' loads
                     if (!CTA2 || leader) mbar_expect_tx(full_bar(stage), (CTA2 ? 2 : 1) * Cfg::STAGE_BYTES);
                     auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
-                        if constexpr (CTA2) tma_load_4d_2cta(dst, tm, full_bar(stage), c0, c1, b1, b2);
-                        else tma_load_4d(dst, tm, full_bar(stage), c0, c1, b1, b2);
+                        const bool is_a = tm == &tmA;
+                        const int c2 = b1 * (is_a ? P.a_m1 : P.b_m1), c3 = b2 * (is_a ? P.a_m2 : P.b_m2);
+                        if constexpr (CTA2) tma_load_4d_2cta(dst, tm, full_bar(stage), c0, c1, c2, c3);
+                        else tma_load_4d(dst, tm, full_bar(stage), c0, c1, c2, c3);
                     };
                     if (P.a_major == MAJOR_K) {
                         load(sa, &tmA, kb * BLOCK_K, m_blk * BLOCK_M);
@@ -591,6 +594,8 @@ static CUtensorMap make_tmap(const GemmOperand& op, int rows, int K, int nb1, in
         dims[0] = (uint64_t)rows; dims[1] = (uint64_t)K;
         box[0] = 64; box[1] = BLOCK_K;
     }
+    if (op.bcast1) nb1 = 1;     // broadcast operand: the kernel always passes coordinate 0 for that dimension
+    if (op.bcast2) nb2 = 1;
     dims[2] = (uint64_t)nb1; dims[3] = (uint64_t)nb2;
     box[2] = 1; box[3] = 1;
     strides[0] = ld_b;
@@ -604,8 +609,8 @@ static bool operand_ok(const GemmOperand& o, int nb1, int nb2, bool allow_mn) {
     if (o.major == MAJOR_MN && !allow_mn) return false;
     if (((uintptr_t)o.ptr & 15) != 0) return false;
     if (o.ld % 8 != 0 || o.ld <= 0) return false;
-    if (nb1 > 1 && (o.bs1 % 8 != 0 || o.bs1 <= 0)) return false;
-    if (nb2 > 1 && (o.bs2 % 8 != 0 || o.bs2 <= 0)) return false;
+    if (nb1 > 1 && !o.bcast1 && (o.bs1 % 8 != 0 || o.bs1 <= 0)) return false;
+    if (nb2 > 1 && !o.bcast2 && (o.bs2 % 8 != 0 || o.bs2 <= 0)) return false;
     return true;
 }
 
@@ -674,6 +679,7 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     if (dbg < 0) { const char* e = getenv("P5_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     P.dbg = dbg;
     P.late_wait = (p.indep_of_prev && pdl_enabled()) ? 1 : 0;
+    P.a_m1 = p.A.bcast1 ? 0 : 1; P.a_m2 = p.A.bcast2 ? 0 : 1; P.b_m1 = p.B.bcast1 ? 0 : 1; P.b_m2 = p.B.bcast2 ? 0 : 1;
     const long long tiles = (long long)cdiv(p.M, BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     ProfRec rec;
@@ -708,6 +714,7 @@ static void launch_tc_pair(const GemmProblem& p, cudaStream_t stream) {
     P.epi = p.epi;
     P.dbg = 0;
     P.late_wait = (p.indep_of_prev && pdl_enabled()) ? 1 : 0;
+    P.a_m1 = p.A.bcast1 ? 0 : 1; P.a_m2 = p.A.bcast2 ? 0 : 1; P.b_m1 = p.B.bcast1 ? 0 : 1; P.b_m2 = p.B.bcast2 ? 0 : 1;
     const long long units = (long long)cdiv(p.M, 2 * BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
     const int pairs = (int)(units < g_num_sms / 2 ? units : g_num_sms / 2);
     ProfRec rec;
