@@ -553,7 +553,8 @@ void gated_gelu_bwd(const void* z, const void* dh, void* dz, int dtype, int M, i
 // =================================================================================================================
 // cross entropy over the item-token vocabulary (one CTA per decoder position)
 // =================================================================================================================
-__global__ void __launch_bounds__(256)
+// one CTA per target position: ONE pass over the row with 16-byte loads and an online (max, sum) per thread
+__global__ void __launch_bounds__(512)
 ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int* __restrict__ labels, float* __restrict__ loss,
               float* __restrict__ lse, int V) {
     pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
@@ -561,14 +562,25 @@ ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int* __restric
     __shared__ float sh[32];
     const int row = blockIdx.x;
     const float* l = logits + (int64_t)row * ld;
-    float mx = -INFINITY;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, l[c]);
-    mx = block_max(mx, sh);
-    float s = 0.f;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) s += __expf(l[c] - mx);
+    float mx = -INFINITY, s = 0.f;
+    const int V4 = V >> 2;
+    const float4* l4 = reinterpret_cast<const float4*>(l);       // rows start 16-byte aligned (ld % 4 == 0)
+    for (int c = threadIdx.x; c < V4; c += blockDim.x) {
+        const float4 v = l4[c];
+        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (m4 > mx) { s *= __expf(mx - m4); mx = m4; }
+        s += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+    }
+    for (int c = (V4 << 2) + threadIdx.x; c < V; c += blockDim.x) {
+        const float v = l[c];
+        if (v > mx) { s *= __expf(mx - v); mx = v; }
+        s += __expf(v - mx);
+    }
+    const float bm = block_max(mx, sh);
+    s = (mx > -INFINITY) ? s * __expf(mx - bm) : 0.f;
     s = block_sum(s, sh);
     if (threadIdx.x == 0) {
-        const float z = mx + logf(s);
+        const float z = bm + logf(s);
         lse[row] = z;
         const int y = labels[row];
         loss[row] = (y >= 0 && y < V) ? z - l[y] : 0.f;  // ignore_index = -100 (never produced by the collator)
@@ -577,11 +589,12 @@ ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int* __restric
 void ce_fwd(const float* logits, int64_t ld, const int* labels, float* loss_tok, float* lse, int M, int V,
             cudaStream_t st) {
     if (M <= 0) return;
-    launch_k(ce_fwd_kernel, M, 256, 0, st, logits, ld, labels, loss_tok, lse, V);
+    P5_CHECK(ld % 4 == 0, "ce_fwd: logits rows must be 16-byte aligned");
+    launch_k(ce_fwd_kernel, M, 512, 0, st, logits, ld, labels, loss_tok, lse, V);
     LAUNCHED();
 }
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restrict__ lse,
               const int* __restrict__ labels, const float* __restrict__ dloss, T* __restrict__ dlogits, int V,
               int Vpad) {
@@ -593,17 +606,27 @@ ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restr
     const int y = labels[row];
     const float g = (y >= 0 && y < V) ? dloss[row] : 0.f;
     const float z = lse[row];
-    for (int c = threadIdx.x; c < Vpad; c += blockDim.x) {
-        float v = 0.f;
-        if (c < V) v = g * (__expf(l[c] - z) - (c == y ? 1.f : 0.f));
-        o[c] = from_f32<T>(v);
+    // four columns per thread and iteration: 16-byte loads, 8- / 16-byte stores (Vpad % 4 == 0, rows 16-byte aligned)
+    for (int c = 4 * threadIdx.x; c < Vpad; c += 4 * blockDim.x) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c + 4 <= V) {
+            const float4 x = *reinterpret_cast<const float4*>(l + c);
+            v[0] = g * __expf(x.x - z); v[1] = g * __expf(x.y - z); v[2] = g * __expf(x.z - z); v[3] = g * __expf(x.w - z);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < V) v[j] = g * __expf(l[c + j] - z);
+        }
+        if (y >= c && y < c + 4) v[y - c] -= g;
+        stv<4>(o + c, v);
     }
 }
 void ce_bwd(const float* logits, int64_t ld, const float* lse, const int* labels, const float* dloss, void* dlogits,
             int d_dtype, int M, int V, int Vpad, cudaStream_t st) {
     if (M <= 0) return;
-    if (d_dtype == DT_F32) launch_k(ce_bwd_kernel<float>, M, 256, 0, st, logits, ld, lse, labels, dloss, (float*)dlogits, V, Vpad);
-    else launch_k(ce_bwd_kernel<bf16>, M, 256, 0, st, logits, ld, lse, labels, dloss, (bf16*)dlogits, V, Vpad);
+    P5_CHECK(ld % 4 == 0 && Vpad % 4 == 0, "ce_bwd: rows must be 16-byte aligned");
+    if (d_dtype == DT_F32) launch_k(ce_bwd_kernel<float>, M, 512, 0, st, logits, ld, lse, labels, dloss, (float*)dlogits, V, Vpad);
+    else launch_k(ce_bwd_kernel<bf16>, M, 512, 0, st, logits, ld, lse, labels, dloss, (bf16*)dlogits, V, Vpad);
     LAUNCHED();
 }
 
