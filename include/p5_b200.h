@@ -63,6 +63,12 @@ int p5_destroy(p5_handle h);
  * Names are the HF T5 keys ("shared.weight", "encoder.block.0.layer.0.SelfAttention.q.weight", ...). */
 int p5_param_count(p5_handle h, int* n);
 int p5_param_info(p5_handle h, int i, const char** name, int* ndim, int64_t shape[2], float** data, float** grad);
+/* replaces: model.resize_token_embeddings(len(tokenizer)) (main.py:193; HF:modeling_utils.py resize_token_embeddings):
+ * the engine is rebuilt for the new vocabulary size in place (same handle); every tensor other than shared.weight is
+ * kept, shared.weight keeps its first min(old, new) rows (and Adam moments), new rows are drawn from N(0, 1) as HF's
+ * T5 initialiser does (the reference then overwrites them in utils/initialization.py:27).  All pointers returned by
+ * p5_param_info are invalidated: query them again. */
+int p5_resize_vocab(p5_handle h, int new_vocab);
 /* call after writing parameter data from the host side (refreshes the bf16 GEMM shadows) */
 int p5_params_changed(p5_handle h);
 

@@ -85,6 +85,11 @@ int p5_param_info(p5_handle h, int i, const char** name, int* ndim, int64_t shap
     if (grad) *grad = e->G + p.off;
     P5_API_END
 }
+int p5_resize_vocab(p5_handle h, int new_vocab) {
+    P5_API_BEGIN
+    E(h)->resize_vocab(new_vocab);
+    P5_API_END
+}
 int p5_params_changed(p5_handle h) {
     P5_API_BEGIN
     E(h)->shadow_stale = true;

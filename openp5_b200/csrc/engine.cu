@@ -197,6 +197,57 @@ Engine::~Engine() {
     gemm_tc_clear_cache();
 }
 
+__global__ void init_normal_rows_kernel(float* __restrict__ w, int64_t n, uint64_t seed) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // Box-Muller on two counter hashes: N(0, 1) (HF T5 `_init_weights`: shared.weight ~ N(0, factor * 1.0))
+        const uint32_t a = drop_hash(seed, 1u, (uint64_t)(2 * i)), b = drop_hash(seed, 2u, (uint64_t)(2 * i + 1));
+        const float u1 = ((float)a + 1.f) * (1.f / 4294967296.f), u2 = (float)b * (1.f / 4294967296.f);
+        w[i] = sqrtf(-2.f * logf(u1)) * cosf(6.2831853f * u2);
+    }
+}
+
+void Engine::resize_vocab(int new_vocab) {
+    P5_CHECK(new_vocab >= 2 && new_vocab < (1 << 24), "resize_vocab: vocabulary size out of range");
+    if (new_vocab == V) return;
+    P5_CUDA(cudaSetDevice(device));
+    join_optimizer();
+    P5_CUDA(cudaStreamSynchronize(st));
+    P5Config c2 = cfg;
+    c2.vocab_size = new_vocab;
+    Engine* ne = new Engine(c2, device, st);
+    try {
+        P5_CHECK(ne->params.size() == params.size(), "resize_vocab: parameter lists differ");
+        for (size_t i = 0; i < params.size(); ++i) {
+            const ParamInfo &o = params[i], &n = ne->params[i];
+            P5_CHECK(o.name == n.name, "resize_vocab: parameter order differs");
+            const int64_t cnt = o.numel < n.numel ? o.numel : n.numel;    // row-major: common leading rows
+            P5_CUDA(cudaMemcpyAsync(ne->P + n.off, P + o.off, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            P5_CUDA(cudaMemcpyAsync(ne->M1 + n.off, M1 + o.off, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            P5_CUDA(cudaMemcpyAsync(ne->V2 + n.off, V2 + o.off, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (n.numel > cnt) {
+                launch_k(init_normal_rows_kernel, 256, 256, 0, st, ne->P + n.off + cnt, n.numel - cnt, (uint64_t)0x5eed0000 + i);
+                P5_CUDA(cudaGetLastError());
+            }
+        }
+        ne->training = training;
+        ne->shadow_stale = true;
+        P5_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete ne;
+        throw;
+    }
+    // exchange the two objects wholesale (every member is a scalar, a raw pointer or a std::vector: bytewise
+    // relocatable); the temporary then owns the old buffers and frees them
+    alignas(Engine) unsigned char tmp[sizeof(Engine)];
+    memcpy(tmp, (void*)this, sizeof(Engine));
+    memcpy((void*)this, (void*)ne, sizeof(Engine));
+    memcpy((void*)ne, tmp, sizeof(Engine));
+    delete ne;
+}
+
 DropCfg Engine::drop(uint32_t kind, int layer) const {
     DropCfg c;
     if (training && p_drop > 0.f) {

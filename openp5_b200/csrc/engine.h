@@ -103,6 +103,9 @@ struct Engine {
     int64_t ckv_ld = 0, dec_layer_stride = 0;
     bool batched_ckv = false;
     void project_cross_kv_all(int64_t rows);
+    // model.resize_token_embeddings(n) (main.py:193): rebuilds the flat buffers for the new vocabulary, keeps every other
+    // tensor and the first min(V, n) embedding rows (and their Adam moments); new rows ~ N(0, 1) like HF's T5 init
+    void resize_vocab(int new_vocab);
     std::vector<float*> slse, clse;
     // head
     float *logits = nullptr, *lse_ce = nullptr, *loss_tok = nullptr, *dloss = nullptr, *loss_scalar = nullptr;

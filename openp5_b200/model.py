@@ -132,6 +132,18 @@ class P5B200:
             self.stream = torch.cuda.current_stream()
             _lib.check(self.lib.p5_create(C.byref(cfg), self.device_index, C.c_void_p(self.stream.cuda_stream),
                                           C.byref(self.handle)))
+        self._build_param_views()
+        self.module = self                                                      # DDP `.module` alias (SURVEY §8b)
+        self.training = True
+        self._versions = self._version_sum()
+        self._shadow_trusted = False
+        self._anchor = torch.zeros((), device=self.device, requires_grad=True)
+        self._step_seed = 0
+        self._opt_step = 0
+        self.world_size, self.rank = 1, 0
+
+    def _build_param_views(self):
+        """torch views (zero-copy, `.grad` attached) over the engine's flat parameter / gradient buffers"""
         self._params: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         n = C.c_int()
         _lib.check(self.lib.p5_param_count(self.handle, C.byref(n)))
@@ -146,14 +158,22 @@ class P5B200:
             p.grad = torch.as_tensor(_DevArray(grad.value, shp), device=self.device)
             self._params[name.value.decode()] = p
         self.shared = SimpleNamespace(weight=self._params["shared.weight"])   # ref utils/initialization.py:27
-        self.module = self                                                      # DDP `.module` alias (SURVEY §8b)
-        self.training = True
+
+    def resize_token_embeddings(self, new_num_tokens: int):
+        """ref main.py:193 `model.resize_token_embeddings(len(tokenizer))`: the engine is rebuilt in place for the new
+        vocabulary (tied embedding / LM head rows kept, new rows ~ N(0, 1) as HF's T5 initialiser draws them); every
+        parameter tensor obtained before this call is invalid afterwards."""
+        new_num_tokens = int(new_num_tokens)
+        if new_num_tokens == self.cfg.vocab_size:
+            return self.shared
+        self._on_stream()
+        _lib.check(self.lib.p5_resize_vocab(self.handle, new_num_tokens))
+        self.cfg.vocab_size = new_num_tokens
+        self.config.vocab_size = new_num_tokens
+        self._build_param_views()
         self._versions = self._version_sum()
         self._shadow_trusted = False
-        self._anchor = torch.zeros((), device=self.device, requires_grad=True)
-        self._step_seed = 0
-        self._opt_step = 0
-        self.world_size, self.rank = 1, 0
+        return self.shared
 
     # ---------------------------------------------------------------- module protocol
     def _join_optimizer(self):
@@ -186,8 +206,8 @@ class P5B200:
         _lib.check(self.lib.p5_zero_grad(self.handle))
 
     def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
-        self._join_optimizer()
         """HF T5 key names incl. the tied aliases (ref DistributedRunner.py:155,169)."""
+        self._join_optimizer()
         sd = OrderedDict((k, v.detach().clone()) for k, v in self._params.items())
         sd["encoder.embed_tokens.weight"] = sd["shared.weight"]
         sd["decoder.embed_tokens.weight"] = sd["shared.weight"]

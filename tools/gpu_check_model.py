@@ -17,7 +17,7 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed", "bwd_bf16_small_ld12", "bwd_fp32_small_ld12",
          "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed", "xcheck_fbwd_dropout_small",
          "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256", "adamw_fp32_tiny_async",
-         "asyncopt_bf16_small_bitwise"]
+         "asyncopt_bf16_small_bitwise", "resize_vocab_fp32_tiny", "resize_vocab_bf16_tiny"]
 
 
 def setup(case):
@@ -158,6 +158,38 @@ def run_case(case):
             res["ok"] = same and res["score_err"] < 1e-4 and res["trie_get_ok"]
         else:
             res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
+    elif case.startswith("resize_vocab"):
+        # model.resize_token_embeddings(n) (ref main.py:193): old rows / all other tensors kept, logits of the old
+        # vocabulary unchanged, the resized engine trains and generates
+        m = make_model(cfg, w, prec).eval()
+        a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+        with torch.no_grad():
+            lg0 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["logits"].float().clone()
+        V0, V1 = cfg.vocab_size, cfg.vocab_size + 100
+        m.resize_token_embeddings(V1)
+        sd = m.state_dict()
+        res["shape_ok"] = tuple(sd["shared.weight"].shape) == (V1, cfg.d_model)
+        same = all(torch.equal(v.cpu()[:V0] if k in ("shared.weight", "encoder.embed_tokens.weight", "decoder.embed_tokens.weight",
+                                                     "lm_head.weight") else v.cpu(), w[k]) for k, v in sd.items() if k in w)
+        res["old_params_kept"] = bool(same)
+        new_rows = sd["shared.weight"][V0:].float()
+        res["new_rows_std"] = new_rows.std().item()
+        with torch.no_grad():
+            lg1 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["logits"].float()
+        res["logits_shape"] = list(lg1.shape)
+        res["old_logits_rel"] = relerr(lg1[..., :V0].cpu(), lg0.cpu())
+        m.train()
+        l1 = m.train_step(a[0], a[1], a[2], a[3], a[4], lr=1e-3, clip=1.0, step=1)
+        l2 = m.train_step(a[0], a[1], a[2], a[3], a[4], lr=1e-3, clip=1.0, step=2)
+        res["losses"] = [l1.item(), l2.item()]
+        m.eval()
+        trie = m.build_trie(items)
+        out = m.generate(input_ids=a[0], attention_mask=a[2], whole_word_ids=a[1], max_length=20, trie=trie, num_beams=5,
+                         num_return_sequences=5)
+        res["gen_shape"] = list(out["sequences"].shape)
+        res["ok"] = (res["shape_ok"] and res["old_params_kept"] and 0.8 < res["new_rows_std"] < 1.2 and lg1.shape[-1] == V1 and
+                     res["old_logits_rel"] < (1e-5 if prec == "fp32" else 2e-2) and l2.item() < l1.item() and
+                     torch.isfinite(out["sequences_scores"]).all().item())
     elif case.startswith("asyncopt"):
         # AdamW on the side stream under the next forward must be the same computation as AdamW in stream order:
         # 5 train steps (dropout on, bf16) from identical weights / seeds -> bit-identical losses and parameters
