@@ -17,7 +17,9 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed", "bwd_bf16_small_ld12", "bwd_fp32_small_ld12",
          "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed", "xcheck_fbwd_dropout_small",
          "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256", "adamw_fp32_tiny_async",
-         "asyncopt_bf16_small_bitwise", "resize_vocab_fp32_tiny", "resize_vocab_bf16_tiny"]
+         "asyncopt_bf16_small_bitwise", "resize_vocab_fp32_tiny", "resize_vocab_bf16_tiny",
+         # edge geometries: a single sequence, the shortest encoder input the engine accepts, two beams
+         "bwd_bf16_tiny_b1", "bwd_fp32_tiny_b1_packed", "bwd_bf16_tiny_le8", "gen_fp32_tiny_k2", "gen_bf16_tiny_b1"]
 
 
 def setup(case):
@@ -37,6 +39,10 @@ def setup(case):
         B, Le, Ld, n_items = 3, 21, 8, 60
     if "ld12" in case:
         Ld = 12          # second half of the 16-row query tile of the decoder attention kernels
+    if "_b1" in case:
+        B = 1
+    if "le8" in case:
+        Le = 8
     if "gated" in case:
         cfg.ffn_gated_gelu = True
     w = po.init_weights(cfg, seed=1)
@@ -136,7 +142,7 @@ def run_case(case):
         res["ok"] = worst < 1e-3 and all(abs(a - b) < 1e-3 * abs(b) for a, b in losses)
     elif case.startswith("gen"):
         m = make_model(cfg, w, prec).eval()
-        K = 5 if "tiny" in case else 10
+        K = 2 if "_k2" in case else (5 if "tiny" in case else 10)
         trie_o = po.Trie(items)
         t0 = time.time()
         s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, trie_o, K, K, 20)
