@@ -764,37 +764,6 @@ softmax_bwd_sq_kernel(const float* __restrict__ dPd, const T* __restrict__ P, T*
     }
 }
 
-// d(bias_rel)[h, j - i + Lq - 1] += sum_{b, i} dS[b, h, i, j]: thread = diagonal, rows streamed with coalesced loads,
-// register accumulation, one global atomic per (CTA, diagonal).  (Doing this with shared-memory atomics inside
-// softmax_bwd cost more than the softmax itself: 8 ATOMS per lane per row.)
-template <typename T>
-__global__ void __launch_bounds__(512)
-relbias_diag_sum_kernel(const T* __restrict__ dS, float* __restrict__ dbias_rel, int B, int H, int Lq, int Lk, int b_per_cta) {
-    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
-    pdl_launch_dependents();
-    const int h = blockIdx.x, b0 = blockIdx.y * b_per_cta;
-    const int n_delta = Lq + Lk - 1;
-    for (int dl = threadIdx.x; dl < n_delta; dl += blockDim.x) {
-        const int delta = dl - (Lq - 1);                 // j - i
-        const int i_lo = max(0, -delta), i_hi = min(Lq, Lk - delta);   // rows with 0 <= i + delta < Lk
-        float acc = 0.f;
-        for (int b = b0; b < min(B, b0 + b_per_cta); ++b) {
-            const T* base = dS + ((int64_t)b * H + h) * Lq * Lk;
-#pragma unroll 8
-            for (int i = i_lo; i < i_hi; ++i) acc += to_f32(base[(int64_t)i * Lk + i + delta]);
-        }
-        if (acc != 0.f) atomicAdd(dbias_rel + h * n_delta + dl, acc);
-    }
-}
-void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H, int Lq, int Lk, cudaStream_t st) {
-    if (B <= 0) return;
-    const int b_per_cta = 1;
-    dim3 grid((unsigned)H, (unsigned)cdiv(B, b_per_cta));
-    if (dtype == DT_F32) launch_k(relbias_diag_sum_kernel<float>, grid, 512, 0, st, (const float*)dS, dbias_rel, B, H, Lq, Lk, b_per_cta);
-    else launch_k(relbias_diag_sum_kernel<bf16>, grid, 512, 0, st, (const bf16*)dS, dbias_rel, B, H, Lq, Lk, b_per_cta);
-    LAUNCHED();
-}
-
 void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dtype, float* dbias_rel, int B, int H,
                  int Lq, int Lk, DropCfg drop, cudaStream_t st, const int* lens, const float* row_scale) {
     if (B <= 0) return;

@@ -129,8 +129,6 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
                int64_t ld_dqkv, float* dbias_rel, DropCfg drop, cudaStream_t st, const int* offs = nullptr,
                const int* lens = nullptr, int64_t packed_rows = 0);
 
-// dbias_rel[h, j - i + Lq - 1] += sum_{b,i} dS[b,h,i,j]   (dS [B,H,Lq,Lk], register accumulation per diagonal)
-void relbias_diag_sum(const void* dS, int dtype, float* dbias_rel, int B, int H, int Lq, int Lk, cudaStream_t st);
 
 // ---- optimiser (optim.cu) ---------------------------------------------------------------------------------------
 void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
