@@ -116,6 +116,15 @@ int p5_adamw_step_zero_grad_async(p5_handle h, float lr, float beta1, float beta
                                   int step, float clip);
 int p5_optimizer_join(p5_handle h);
 
+/* replaces: utils/evaluate.py:37-92 (rel_results + hit@k / ndcg@k) and the per-batch accumulation of
+ * DistributedRunner.py:376-393, on token-id paths and on the device: seqs [B*K, T] / scores [B*K] as returned by
+ * p5_generate, gold [B, Tg] the tokenised target items, ks_dev [n_k] the cut-offs (device).  Pad (0) and eos (1) are
+ * ignored in the comparison (== batch_decode(skip_special_tokens=True) as a key).  out_sums (device, 2*n_k floats,
+ * NOT cleared): [hit@ks[0..n_k) | ndcg@ks[0..n_k)] summed over the B users; the caller divides by the (all-reduced)
+ * user count as the reference does. */
+int p5_eval_metrics(p5_handle h, const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg,
+                    const int32_t* ks_dev, int n_k, float* out_sums);
+
 /* ---- data-parallel gradient exchange (the DDP all-reduce the reference constructs, DistributedRunner.py:26) ---- */
 int p5_comm_unique_id(void* id128_host);                      /* 128-byte ncclUniqueId */
 int p5_comm_init(p5_handle h, const void* id128_host, int rank, int world);

@@ -533,6 +533,61 @@ __global__ void gen_finalize_kernel(const int* __restrict__ fin_seq, const float
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// ranking metrics on the device (ref utils/evaluate.py:37-92, DistributedRunner.py:376-393): per user, the K generated
+// rows are ordered by score (desc, stable), marked 1 where their token path (pad 0 / eos 1 stripped ==
+// batch_decode(skip_special_tokens=True) as a key) equals the gold item's; hit@k = any(rel[:k]),
+// ndcg@k = sum_r rel[r] / log2(r + 2).  Sums over users are accumulated into out[0 .. n_k) (hit) and out[n_k .. 2 n_k).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+eval_metrics_kernel(const int32_t* __restrict__ seqs, const float* __restrict__ scores, int K, int T,
+                    const int32_t* __restrict__ gold, int Tg, const int32_t* __restrict__ ks, int n_k, float* __restrict__ out) {
+    pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
+    pdl_launch_dependents();
+    __shared__ int rel[64];
+    const int b = blockIdx.x, i = threadIdx.x;
+    if (i < 64) rel[i] = 0;
+    __syncthreads();
+    if (i < K) {
+        const int32_t* p = seqs + (int64_t)(b * K + i) * T;
+        const int32_t* g = gold + (int64_t)b * Tg;
+        int a = 0, c = 0;
+        bool same = true;
+        while (true) {     // two cursors over the rows, skipping pad (0) and eos (1)
+            while (a < T && (p[a] == 0 || p[a] == 1)) ++a;
+            while (c < Tg && (g[c] == 0 || g[c] == 1)) ++c;
+            if (a >= T || c >= Tg) { same = (a >= T) && (c >= Tg); break; }
+            if (p[a] != g[c]) { same = false; break; }
+            ++a; ++c;
+        }
+        const float sc = scores[b * K + i];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+            const float sj = scores[b * K + j];
+            rank += (sj > sc || (sj == sc && j < i)) ? 1 : 0;
+        }
+        rel[rank] = same ? 1 : 0;
+    }
+    __syncthreads();
+    if (i < n_k) {
+        const int k = min(ks[i], K);
+        bool hit = false;
+        float ndcg = 0.f;
+        for (int r = 0; r < k; ++r)
+            if (rel[r]) { hit = true; ndcg += 1.f / log2f((float)r + 2.f); }
+        if (hit) atomicAdd(out + i, 1.f);
+        if (ndcg != 0.f) atomicAdd(out + n_k + i, ndcg);
+    }
+}
+
+void eval_metrics(const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg, const int32_t* ks_dev,
+                  int n_k, float* out_sums, cudaStream_t st) {
+    if (B <= 0) return;
+    P5_CHECK(K >= 1 && K <= 64 && n_k >= 1 && n_k <= 64 && T >= 1 && Tg >= 1, "eval_metrics: K and the number of cut-offs must be in [1, 64]");
+    launch_k(eval_metrics_kernel, (unsigned)B, 64, 0, st, seqs, scores, K, T, gold, Tg, ks_dev, n_k, out_sums);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------------------
 void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t* ww, int B, int Le_user, Trie* trie,

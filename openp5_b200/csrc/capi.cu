@@ -188,6 +188,15 @@ int p5_optimizer_join(p5_handle h) {
     P5_API_END
 }
 
+int p5_eval_metrics(p5_handle h, const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg,
+                    const int32_t* ks_dev, int n_k, float* out_sums) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CUDA(cudaSetDevice(e->device));
+    eval_metrics(seqs, scores, B, K, T, gold, Tg, ks_dev, n_k, out_sums, e->st);
+    P5_API_END
+}
+
 int p5_comm_unique_id(void* id128_host) {
     P5_API_BEGIN
     comm_unique_id(id128_host);

@@ -138,4 +138,8 @@ void adamw_flat(float* p, float* g, float* m, float* v, bf16* p16, int64_t n, fl
                 float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st,
                 bool zero_grad_after = false);
 
+// ranking metrics of one eval batch on the device (beam.cu)
+void eval_metrics(const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg, const int32_t* ks_dev,
+                  int n_k, float* out_sums, cudaStream_t st);
+
 }  // namespace p5

@@ -404,6 +404,24 @@ class P5B200:
             return {"sequences": sequences, "sequences_scores": scores if output_scores else None}
         return sequences
 
+    def eval_metric_sums(self, sequences: torch.Tensor, sequences_scores: torch.Tensor, gold: torch.Tensor, num_beams: int,
+                         ks: Sequence[int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """hit@k / ndcg@k SUMMED over the users of one eval batch, on the device (ref utils/evaluate.py:37-92 and
+        DistributedRunner.py:376-393 on token-id paths).  Returns / accumulates into a float32 tensor
+        [hit@ks..., ndcg@ks...]; no host synchronisation."""
+        self._on_stream()
+        seqs = _i32(sequences, self.device)
+        sc = sequences_scores.to(self.device, torch.float32).contiguous()
+        g = _i32(gold, self.device)
+        B = g.shape[0]
+        assert seqs.shape[0] == B * num_beams and sc.numel() == B * num_beams
+        kd = torch.tensor([int(k) for k in ks], dtype=torch.int32, device=self.device)
+        if out is None:
+            out = torch.zeros(2 * len(ks), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.p5_eval_metrics(self.handle, seqs.data_ptr(), sc.data_ptr(), B, num_beams, seqs.shape[1], g.data_ptr(),
+                                            g.shape[1], kd.data_ptr(), len(ks), out.data_ptr()))
+        return out
+
     def _trie_from_callback(self, fn) -> Trie:
         if fn is None:
             raise ValueError("generate() needs trie= or a prefix_allowed_tokens_fn built from a Trie")

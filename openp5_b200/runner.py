@@ -194,12 +194,18 @@ class B200Runner:
         sums = [0.0] * len(self.metrics)
         total = 0
         K = self.generate_num
+        # metrics on the device: the generated sequences never leave the GPU, one small D2H read at the very end
+        kinds = [m.lower().split("@") for m in self.metrics]
+        ks = sorted({int(k) for _, k in kinds})
+        dev_sums = None
         for batch in testloader:
             pred = self.model.generate(input_ids=batch[0], attention_mask=batch[1], whole_word_ids=batch[2], max_length=50,
                                        trie=trie, num_beams=K, num_return_sequences=K)
-            rel = rel_results(pred["sequences"].tolist(), pred["sequences_scores"].tolist(), batch[3].tolist(), K)
-            total += len(rel)
-            sums = [s + x for s, x in zip(sums, metric_sums(rel, self.metrics))]
+            dev_sums = self.model.eval_metric_sums(pred["sequences"], pred["sequences_scores"], batch[3], K, ks, out=dev_sums)
+            total += int(batch[3].shape[0])
+        if dev_sums is not None:
+            host = dev_sums.tolist()
+            sums = [host[(0 if kind.startswith("hit") else len(ks)) + ks.index(int(k))] for kind, k in kinds]
         res, n = allreduce_metrics(sums, total, device=self.device)
         if self.rank == 0:
             for name, v in zip(self.metrics, res):

@@ -130,3 +130,31 @@ def test_full_size_properties_t5_base(built_lib):
     losses = [m.train_step(ids, ww, attn, labels, oattn, lr=1e-3, clip=1.0, step=s + 1).item() for s in range(4)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
     assert torch.isfinite(m.grad_norm()).item()
+
+
+def test_device_metrics_match_host_metrics(built_lib):
+    """p5_eval_metrics (device hit@k / ndcg@k sums) vs the host restatement of utils/evaluate.py that is pinned on the
+    reference's own goldens (tests/test_host_cpu.py): random beams with planted gold items, ties in the scores, pad / eos
+    noise inside the rows."""
+    import random
+    from openp5_b200 import runner as R
+    from openp5_b200.model import P5B200
+    m = P5B200(backbone="custom", vocab_size=1200, precision="fp32", dropout=0.0, max_batch=4, max_enc_len=32, max_dec_len=8,
+               d_model=64, d_ff=128, num_layers=1, num_decoder_layers=1, num_heads=2)
+    rng = random.Random(7)
+    B, K, T, Tg = 37, 20, 12, 8
+    seqs, scores, gold = [], [], []
+    for b in range(B):
+        g = [rng.randrange(2, 1000) for _ in range(rng.randrange(2, 6))]
+        gold.append((g + [1] + [0] * Tg)[:Tg])
+        hit_at = rng.choice([None, None, 0, 1, 4, 9, 19])
+        for i in range(K):
+            row = g if i == hit_at else [rng.randrange(2, 1000) for _ in range(rng.randrange(1, 7))]
+            seqs.append(([0] + row + [1] + [0] * T)[:T])
+            scores.append(round(-0.5 * (i // 2), 3))          # pairs of equal scores: the stable order decides
+    names = ["hit@1", "hit@5", "hit@10", "hit@20", "ndcg@1", "ndcg@5", "ndcg@10", "ndcg@20"]
+    want = R.metric_sums(R.rel_results(seqs, scores, gold, K), names)
+    out = m.eval_metric_sums(torch.tensor(seqs), torch.tensor(scores), torch.tensor(gold), K, [1, 5, 10, 20])
+    out = m.eval_metric_sums(torch.tensor(seqs), torch.tensor(scores), torch.tensor(gold), K, [1, 5, 10, 20], out=out)
+    got = (out / 2).tolist()                                    # accumulated twice
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-5), (got, want)
