@@ -5,15 +5,19 @@
 // One persistent CTA per SM walks (batch, head) pairs; K and V of the pair ([Lk, 64] each, Lk <= 512) are loaded once
 // into 128B-swizzled smem by TMA and reused by every 128-row query tile.
 //   warp 0    : TMA producer (K, V per pair; Q per tile)
-//   warp 1    : MMA issuer.  pass 1: S_blk = Q K_blk^T (128x128x64) per 128-key block -> TMEM (double buffered)
+//   warp 1    : MMA issuer.  pass 1: S_blk = Q K_blk^T (128x128x64) per 128-key block -> TMEM (three score buffers)
 //               pass 2: S_blk again, then O += P_blk V_blk (128x64x128) with P_blk read from smem
 //   warp 2    : TMEM allocator (3 x 128 columns S + 64 columns O)
+//   warp 3    : per-pair tables, one pair ahead (double buffered): relative bias x log2(e) in four shifted copies (every
+//               thread reads its 32 entries with LDS.128), key mask
 //   warps 4-19: softmax, four warpgroups.  thread = (query row, 32 of the 128 key columns of a block); four warps per
-//               scheduler hide the ALU / MUFU / LDS latencies of the softmax arithmetic.
-//               pass 1: row max / sum (online over blocks; the two halves are combined through smem);
-//               pass 2: p = exp(s - m) / l -> P_save (bf16, for the backward), dropout -> bf16 -> swizzled smem A tile
-// Two passes over the key blocks (QK^T is recomputed: K = 64, cheap) make the written P exactly normalised and avoid
-// rescaling the O accumulator in TMEM.
+//               scheduler hide the ALU / MUFU / LDS latencies of the softmax arithmetic.  Log2 domain throughout:
+//               pass 1: row max only (FFMA + FMNMX per score; the four column slices are combined through smem);
+//               pass 2: p~ = 2^(s2 - m2) UN-normalised (FFMA + EX2), row sum, dropout -> bf16 -> swizzled smem A tile;
+//               O is scaled by 1 / l when it is read out of TMEM.
+// Two passes over the key blocks (QK^T is recomputed: K = 64, cheap) avoid rescaling the O accumulator in TMEM.  For the
+// backward the kernel stores either lse2 = m2 + log2(l) per row (Le <= 256: fattn_bwd recomputes P, nothing of size
+// L^2 is written) or the un-normalised P plus 1 / l (materialised backward for 256 < Le <= 512).
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 #include <float.h>

@@ -8,8 +8,11 @@
 //   warp 0   : TMA producer      cp.async.bulk.tensor.4d -> 128B-swizzled smem ring (STAGES deep)
 //   warp 1   : MMA issuer        one lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16
 //   warp 2   : TMEM allocator    2 accumulator stages x BLOCK_N fp32 columns
-//   warps 4-7: epilogue          tcgen05.ld 32x32b -> registers -> fused epilogue -> global
-// Three mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue).
+//   warps 4-7: epilogue          tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> fused epilogue (one
+//                                compile-time variant per flag set, operands prefetched 32 rows ahead) -> coalesced stores
+// Two mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue).  Tile widths 64 / 128 / 192 / 256;
+// an opt-in CTA-pair variant (cta_group::2, cluster of two, 256 x 256 tile per pair); batch operands may be broadcast;
+// programmatic dependent launch with the wait at the start or (for GEMMs independent of their predecessor) at the end.
 //
 // Operands may be K-major (reduction index contiguous) or MN-major (row index contiguous); the latter lets
 // dgrad/wgrad read the forward tensors in place (no transposes): TMA loads [64k x 64mn] boxes and the smem
