@@ -74,3 +74,6 @@ def test_sass_contains_blackwell_instructions(built_lib):
     assert "UTCHMMA" in out, "tcgen05.mma missing from SASS"
     assert "UTMALDG" in out, "TMA loads missing from SASS"
     assert "LDTM" in out, "tcgen05.ld missing from SASS"
+    assert "UTCHMMA.2CTA" in out and "UTMALDG.4D.2CTA" in out, "cta_group::2 GEMM variant missing from SASS"
+    assert "HMMA.16816.F32.BF16" in out and "LDSM" in out, "mma.sync / ldmatrix decoder attention missing from SASS"
+    assert "ACQBULK" in out and "PREEXIT" in out, "programmatic dependent launch (griddepcontrol) missing from SASS"
