@@ -1,0 +1,302 @@
+"""Engine-vs-oracle parity cases on the GPU (each case in its own process): the parametrised cases of
+tests/test_model_gpu.py and, through tools/gpu_check_model.py, a stand-alone check under gpurun.
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fused_fp32_tiny", "adamw_fp32_tiny",
+         "gen_fp32_tiny", "gen_bf16_tiny", "fwd_fp32_small", "bwd_fp32_small", "bwd_bf16_small", "gated_fp32_tiny",
+         "dropout_bf16_small", "gen_fp32_small", "bwd_bf16_base_le256", "bwd_bf16_small_le512", "bwd_fp32_small_le300",
+         "bwd_fp32_tiny_packed", "bwd_fp32_small_packed", "bwd_bf16_small_packed", "bwd_bf16_base_le256_packed",
+         "bwd_bf16_small_le512_packed", "adamw_fp32_tiny_packed", "bwd_bf16_small_ld12", "bwd_fp32_small_ld12",
+         "xcheck_dattn_dropout_small", "xcheck_dattn_dropout_base_le256_packed", "xcheck_fbwd_dropout_small",
+         "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256", "adamw_fp32_tiny_async",
+         "asyncopt_bf16_small_bitwise", "resize_vocab_fp32_tiny", "resize_vocab_bf16_tiny",
+         # edge geometries: a single sequence, the shortest encoder input the engine accepts, two beams
+         "bwd_bf16_tiny_b1", "bwd_fp32_tiny_b1_packed", "bwd_bf16_tiny_le8", "gen_fp32_tiny_k2", "gen_bf16_tiny_b1"]
+
+
+def setup(case):
+    import torch
+    from oracle import p5_oracle as po
+    if "base" in case:
+        cfg = po.t5_cfg("t5-base", vocab_size=32100, num_layers=2, num_decoder_layers=2)
+        B, Le, Ld, n_items = 8, 256, 8, 200
+    elif "le512" in case or "le300" in case:
+        cfg = po.t5_cfg("t5-small", vocab_size=2100, num_layers=1, num_decoder_layers=1)
+        B, Le, Ld, n_items = 2, (512 if "le512" in case else 300), 8, 300
+    elif "small" in case:
+        cfg = po.t5_cfg("t5-small", vocab_size=2100, num_layers=2, num_decoder_layers=2)
+        B, Le, Ld, n_items = 4, 64, 8, 300
+    else:
+        cfg = po.t5_cfg("t5-tiny", vocab_size=1200)
+        B, Le, Ld, n_items = 3, 21, 8, 60
+    if "ld12" in case:
+        Ld = 12          # second half of the 16-row query tile of the decoder attention kernels
+    if "_b1" in case:
+        B = 1
+    if "le8" in case:
+        Le = 8
+    if "gated" in case:
+        cfg.ffn_gated_gelu = True
+    w = po.init_weights(cfg, seed=1)
+    items = po.synth_items(n_items, seed=3)
+    batch = po.synth_batch(B, Le, Ld, cfg.vocab_size, items, seed=5)
+    return po, cfg, w, items, batch
+
+
+def make_model(cfg, w, precision, dropout=0.0, **kw):
+    from openp5_b200.model import P5B200
+    m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, precision=precision, dropout=dropout, max_batch=8,
+               max_enc_len=512, max_dec_len=16, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
+               num_decoder_layers=cfg.num_decoder_layers, num_heads=cfg.num_heads, ffn_gated_gelu=cfg.ffn_gated_gelu, **kw)
+    m.load_state_dict(w, strict=True)
+    return m
+
+
+def relerr(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def run_case(case):
+    import torch
+    po, cfg, w, items, (ids, attn, ww, labels, oattn) = setup(case)
+    prec = "bf16" if ("bf16" in case or case.startswith("xcheck")) else "fp32"
+    tol = 6e-2 if prec == "bf16" else 2e-4
+    dev = "cuda"
+    res = dict(name=case)
+    if case.startswith("fwd"):
+        m = make_model(cfg, w, prec).eval()
+        with torch.no_grad():
+            out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev))
+        lt_o, lg_o = po.forward(w, cfg, ids, ww, attn, labels)
+        res["logits_rel"] = relerr(out["logits"].cpu(), lg_o)
+        res["loss_rel"] = relerr(out["loss"].cpu(), lt_o)
+        res["ok"] = res["logits_rel"] < tol and res["loss_rel"] < tol
+    elif case.startswith("bwd") or case.startswith("gated") or case.startswith("fused"):
+        m = make_model(cfg, w, prec).eval()   # eval => dropout off; gradients still flow
+        l_o, lt_o, lg_o, g_o = po.loss_and_grads(w, cfg, ids, ww, attn, labels, oattn)
+        m.zero_grad()
+        if case.startswith("fused"):
+            import ctypes as C
+            from openp5_b200 import _lib
+            i32 = lambda t: t.to(dev).to(torch.int32).contiguous()
+            a = [i32(t) for t in (ids, attn, ww, labels, oattn)]
+            loss = torch.empty(1, device=dev)
+            m.training = False
+            m.cfg.dropout = 0.0
+            _lib.check(m.lib.p5_train_fwd_bwd(m.handle, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
+                                              a[4].data_ptr(), ids.shape[0], ids.shape[1], labels.shape[1], loss.data_ptr(),
+                                              C.c_uint64(1)))
+            loss = loss[0]
+        else:
+            lens = attn.sum(1) if "packed" in case else None
+            out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev),
+                    enc_lengths=lens)
+            B, Ld = labels.shape
+            lm = (oattn.to(dev) != 0).float()
+            loss = ((out["loss"].view(B, Ld) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
+            loss.backward()
+        torch.cuda.synchronize()
+        res["loss"] = loss.item()
+        res["loss_ref"] = l_o.item()
+        worst, worst_name = 0.0, ""
+        bad = []
+        for k, p in m.named_parameters():
+            g = p.grad.cpu()
+            e = ((g - g_o[k]).abs().max() / g_o[k].abs().max().clamp_min(1e-9)).item()
+            if e > worst:
+                worst, worst_name = e, k
+            if e > (0.25 if prec == "bf16" else 5 * tol):   # bf16: few-token decoder sums carry ~0.2 max-norm noise
+                bad.append((k, round(e, 5)))
+        res["worst_grad_rel"] = worst
+        res["worst_grad_name"] = worst_name
+        res["bad"] = bad[:8]
+        res["n_bad"] = len(bad)
+        res["ok"] = abs(res["loss"] - res["loss_ref"]) < tol * abs(res["loss_ref"]) and not bad
+    elif case.startswith("adamw"):
+        m = make_model(cfg, w, prec).eval()
+        wo = {k: v.clone() for k, v in w.items()}
+        mo = {k: torch.zeros_like(v) for k, v in w.items()}
+        vo = {k: torch.zeros_like(v) for k, v in w.items()}
+        losses = []
+        for step in range(1, 4):
+            lr = 1e-3
+            l_o, _, _, g = po.loss_and_grads(wo, cfg, ids, ww, attn, labels, oattn)
+            po.clip_grad_norm(g, 1.0)
+            for k in wo:
+                po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, lr, eps=1e-6, weight_decay=0.01)
+            m.training = False
+            loss = m.train_step(ids.to(dev), ww.to(dev), attn.to(dev), labels.to(dev), oattn.to(dev), lr=lr, clip=1.0, step=step,
+                                enc_lengths=attn.sum(1) if "packed" in case else None, overlap_optimizer="async" in case)
+            losses.append((loss.item(), l_o.item()))
+        worst = max(relerr(p.detach().cpu(), wo[k]) for k, p in m.named_parameters())
+        res["losses"] = losses
+        res["worst_param_rel"] = worst
+        res["ok"] = worst < 1e-3 and all(abs(a - b) < 1e-3 * abs(b) for a, b in losses)
+    elif case.startswith("gen"):
+        m = make_model(cfg, w, prec).eval()
+        K = 2 if "_k2" in case else (5 if "tiny" in case else 10)
+        trie_o = po.Trie(items)
+        t0 = time.time()
+        s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, trie_o, K, K, 20)
+        res["oracle_s"] = time.time() - t0
+        trie = m.build_trie(items)
+        res["trie"] = trie.stats()
+        res["trie_get_ok"] = sorted(trie.get(items[0][:6])) == sorted(trie_o.get(items[0][:6]))
+        out = m.generate(input_ids=ids.to(dev), attention_mask=attn.to(dev), whole_word_ids=ww.to(dev), max_length=20,
+                         trie=trie, num_beams=K, num_return_sequences=K)
+        s, sc = out["sequences"].cpu(), out["sequences_scores"].cpu()
+        res["shape"] = [list(s.shape), list(s_o.shape)]
+        same = s.shape == s_o.shape and bool((s == s_o).all())
+        res["seq_equal"] = same
+        res["score_err"] = (sc - sc_o).abs().max().item()
+        if not same and s.shape == s_o.shape:
+            res["rows_equal_frac"] = (s == s_o).all(dim=1).float().mean().item()
+            res["top1_equal_frac"] = (s.view(ids.shape[0], K, -1)[:, 0] == s_o.view(ids.shape[0], K, -1)[:, 0]).all(dim=1).float().mean().item()
+        if prec == "fp32":
+            res["ok"] = same and res["score_err"] < 1e-4 and res["trie_get_ok"]
+        else:
+            res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
+    elif case.startswith("resize_vocab"):
+        # model.resize_token_embeddings(n) (ref main.py:193): old rows / all other tensors kept, logits of the old
+        # vocabulary unchanged, the resized engine trains and generates
+        m = make_model(cfg, w, prec).eval()
+        a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+        with torch.no_grad():
+            lg0 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["logits"].float().clone()
+        V0, V1 = cfg.vocab_size, cfg.vocab_size + 100
+        m.resize_token_embeddings(V1)
+        sd = m.state_dict()
+        res["shape_ok"] = tuple(sd["shared.weight"].shape) == (V1, cfg.d_model)
+        same = all(torch.equal(v.cpu()[:V0] if k in ("shared.weight", "encoder.embed_tokens.weight", "decoder.embed_tokens.weight",
+                                                     "lm_head.weight") else v.cpu(), w[k]) for k, v in sd.items() if k in w)
+        res["old_params_kept"] = bool(same)
+        new_rows = sd["shared.weight"][V0:].float()
+        res["new_rows_std"] = new_rows.std().item()
+        with torch.no_grad():
+            lg1 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["logits"].float()
+        res["logits_shape"] = list(lg1.shape)
+        res["old_logits_rel"] = relerr(lg1[..., :V0].cpu(), lg0.cpu())
+        m.train()
+        l1 = m.train_step(a[0], a[1], a[2], a[3], a[4], lr=1e-3, clip=1.0, step=1)
+        l2 = m.train_step(a[0], a[1], a[2], a[3], a[4], lr=1e-3, clip=1.0, step=2)
+        res["losses"] = [l1.item(), l2.item()]
+        m.eval()
+        trie = m.build_trie(items)
+        out = m.generate(input_ids=a[0], attention_mask=a[2], whole_word_ids=a[1], max_length=20, trie=trie, num_beams=5,
+                         num_return_sequences=5)
+        res["gen_shape"] = list(out["sequences"].shape)
+        res["ok"] = (res["shape_ok"] and res["old_params_kept"] and 0.8 < res["new_rows_std"] < 1.2 and lg1.shape[-1] == V1 and
+                     res["old_logits_rel"] < (1e-5 if prec == "fp32" else 2e-2) and l2.item() < l1.item() and
+                     torch.isfinite(out["sequences_scores"]).all().item())
+    elif case.startswith("asyncopt"):
+        # AdamW on the side stream under the next forward must be the same computation as AdamW in stream order:
+        # 5 train steps (dropout on, bf16) from identical weights / seeds -> bit-identical losses and parameters
+        outs = []
+        for ov in (False, True):
+            m = make_model(cfg, w, prec, dropout=0.1).train()
+            a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+            losses = []
+            for step in range(1, 6):
+                losses.append(m.train_step(a[0], a[1], a[2], a[3], a[4], lr=1e-3, clip=1.0, step=step, seed=100 + step,
+                                           enc_lengths=attn.sum(1), overlap_optimizer=ov))
+            torch.cuda.synchronize()
+            outs.append(([l.item() for l in losses], {k: p.detach().clone() for k, p in m.named_parameters()}))
+        res["losses"] = [outs[0][0], outs[1][0]]
+        res["losses_equal"] = outs[0][0] == outs[1][0]
+        # split-K wgrads accumulate with fp32 atomics (order-dependent rounding), so parameters agree to rounding, not bitwise
+        worst = max(relerr(outs[1][1][k].float(), outs[0][1][k].float()) for k in outs[0][1])
+        res["worst_param_rel"] = worst
+        res["ok"] = worst < 2e-3 and all(abs(x - y) < 2e-3 * abs(x) for x, y in zip(*res["losses"]))
+    elif case.startswith("xcheck"):
+        # decoder attention: mma.sync kernels (dattn.cu) vs the fp32-math SIMT kernels at the SAME dropout seed; or
+        # ("fbwd") the fused tcgen05 attention backward vs the GEMM chain + softmax_bwd.  Both sides regenerate the
+        # mask from the same counter hash, so gradients must agree to bf16 rounding.
+        dump = os.environ.get("P5_XCHECK_DUMP")
+        if dump:
+            m = make_model(cfg, w, prec, dropout=0.1).train()
+            m._step_seed = 1234
+            a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+            m.zero_grad()
+            lens = attn.sum(1) if "packed" in case else None
+            out = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3], enc_lengths=lens)
+            out["loss"].mean().backward()
+            torch.save({"loss": out["loss"].detach().cpu(), **{k: p.grad.detach().cpu() for k, p in m.named_parameters()}}, dump)
+            res["ok"] = True
+            return res
+        outs = []
+        ref_env = {"P5_NO_FATTN_BWD": "1"} if "fbwd" in case else {"P5_NO_DATTN": "1"}
+        for tag, extra in (("new", {}), ("ref", ref_env)):
+            path = "/tmp/p5_xcheck_%s_%s.pt" % (case, tag)
+            env = dict(os.environ, P5_XCHECK_DUMP=path, **extra)
+            p = subprocess.run([sys.executable, __file__, "--case", case], capture_output=True, text=True, timeout=280, env=env)
+            if not os.path.exists(path):
+                res["ok"] = False
+                res["error"] = (p.stdout[-400:] + p.stderr[-600:])
+                return res
+            outs.append(torch.load(path))
+            os.remove(path)
+        errs = sorted(((relerr(outs[0][k].float(), outs[1][k].float()), k) for k in outs[0]), reverse=True)
+        res["worst5"] = [(round(e, 4), k) for e, k in errs[:5]]
+        # the tensors fed directly by the decoder attention kernels: a forward/backward mask mismatch would put O(1)
+        # errors here; bf16 rounding differences between the two kernels stay at the percent level
+        side = "encoder" if "fbwd" in case else "decoder"
+        att = [(e, k) for e, k in errs if k.startswith(side) and ("Attention.q" in k or "Attention.k" in k or "Attention.v" in k
+                                                                  or "relative_attention_bias" in k)]
+        res["worst_attn_qkv_bias"] = [(round(e, 4), k) for e, k in att[:4]]
+        res["worst_rel"] = errs[0][0]
+        res["loss_rel"] = relerr(outs[0]["loss"], outs[1]["loss"])
+        res["ok"] = errs[0][0] < 0.25 and att[0][0] < 0.1 and res["loss_rel"] < 0.02
+    elif case.startswith("dropout"):
+        m = make_model(cfg, w, prec, dropout=0.1).train()
+        a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+        m.zero_grad()
+        out1 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])
+        l1 = out1["loss"].detach().clone()
+        out1["loss"].mean().backward()
+        g1 = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        finite = all(torch.isfinite(g).all().item() for g in g1.values())
+        m._step_seed -= 1            # same seed -> identical masks -> identical loss
+        with torch.no_grad():
+            l2 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["loss"]
+        l3 = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["loss"].detach()
+        m.eval()
+        with torch.no_grad():
+            l_eval = m(input_ids=a[0], whole_word_ids=a[1], attention_mask=a[2], labels=a[3])["loss"]
+        res["same_seed_equal"] = bool((l1 == l2).all())
+        res["diff_seed_differs"] = bool((l1 != l3).any())
+        res["train_vs_eval_rel"] = relerr(l1, l_eval)
+        res["finite"] = finite
+        res["ok"] = finite and res["same_seed_equal"] and res["diff_seed_differs"] and 0.0 < res["train_vs_eval_rel"] < 0.8
+    return res
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--case":
+        try:
+            print("RESULT " + json.dumps(run_case(sys.argv[2])))
+        except Exception as e:  # noqa
+            import traceback
+            print("RESULT " + json.dumps(dict(name=sys.argv[2], ok=False, error=repr(e)[:500], tb=traceback.format_exc()[-900:])))
+        sys.exit(0)
+    cases = sys.argv[1:] or CASES
+    results = []
+    for c in cases:
+        try:
+            p = subprocess.run([sys.executable, __file__, "--case", c], capture_output=True, text=True, timeout=300)
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            if line:
+                results.append(json.loads(line[-1][7:]))
+            else:
+                results.append(dict(name=c, ok=False, rc=p.returncode, stdout=p.stdout[-800:], stderr=p.stderr[-1500:]))
+        except subprocess.TimeoutExpired:
+            results.append(dict(name=c, ok=False, error="timeout"))
+        print(json.dumps(results[-1]), flush=True)
+    print("SUMMARY passed %d / %d" % (sum(1 for r in results if r.get("ok")), len(results)))

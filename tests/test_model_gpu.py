@@ -8,13 +8,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _cases():
-    import tools.gpu_check_model as M
+    import gpu_cases_model as M
     return M.CASES
 
 
 @pytest.mark.parametrize("name", _cases())
 def test_model_case(name, built_lib):
-    import tools.gpu_check_model as M
+    import gpu_cases_model as M
     res = M.run_case(name)
     assert res["ok"], res
 
