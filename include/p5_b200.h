@@ -41,7 +41,8 @@ typedef struct {
     int32_t whole_word_rows;   /* 512, P5_T5.py:64-66 */
     float   dropout;           /* dropout_rate */
     float   ln_eps;            /* layer_norm_epsilon */
-    int32_t precision;         /* 0 = fp32 parity path (SIMT fp32), 1 = bf16 tensor-core path */
+    int32_t precision;         /* 0 = fp32 parity path (SIMT fp32), 1 = bf16 tensor-core path, 2 = bf16x3 tensor-core parity
+                                  path (fp32 storage; every linear layer is the tcgen05 kernel over hi/lo-split operands) */
     int32_t max_batch;         /* workspace sizing: largest B the handle will see */
     int32_t max_enc_len;       /* largest Le (<= 512, Collator.py:13) */
     int32_t max_dec_len;       /* largest Ld for training / max_length for generate */
@@ -98,7 +99,8 @@ int p5_grad_scale(p5_handle h, float s);
 int p5_zero_grad(p5_handle h);
 /* replaces: transformers(4.26).AdamW.step (SingleRunner.py:214): m,v update, eps outside bias correction,
  * decoupled decay after the update.  clip > 0 folds clip_grad_norm_(clip) into the same pass using the norm
- * computed on device (no host sync).  step is 1-based. */
+ * computed on device (no host sync).  step is 1-based.  Parameter groups as the reference builds them
+ * (SingleRunner.py:186-205): names containing "bias" — the two relative_attention_bias tables — take weight_decay 0. */
 int p5_adamw_step(p5_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float clip);
 /* replaces: optimizer.step() immediately followed by model.zero_grad() (DistributedRunner.py:85-87) in ONE pass over
@@ -124,6 +126,19 @@ int p5_optimizer_join(p5_handle h);
  * user count as the reference does. */
 int p5_eval_metrics(p5_handle h, const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg,
                     const int32_t* ks_dev, int n_k, float* out_sums);
+
+/* Filtered variant — replaces: utils/evaluate.py:6-35 (rel_results_filtered) as driven by DistributedRunner.py:204-265:
+ * the R (= generate_num + max_positive) returned rows of a user are ordered by score, rows that equal one of the user's
+ * positive (already interacted) items pos [B, Pmax, Tp] (npos [B] valid rows per user; device pointers) are skipped, the
+ * first k_cut remaining rows form the relevance list the hit@k / ndcg@k sums are taken over. */
+int p5_eval_metrics_filtered(p5_handle h, const int32_t* seqs, const float* scores, int B, int R, int T, const int32_t* gold,
+                             int Tg, const int32_t* pos, const int32_t* npos, int Pmax, int Tp, const int32_t* ks_dev, int n_k,
+                             int k_cut, float* out_sums);
+
+/* Optimiser state of parameter i (same index / shape as p5_param_info): device pointers to the fp32 Adam moments
+ * exp_avg / exp_avg_sq.  With the step count (kept by the host) this is what a resumable checkpoint adds to the
+ * reference's plain state_dict (DistributedRunner.py:155,169 saves weights only). */
+int p5_opt_state_info(p5_handle h, int i, float** exp_avg, float** exp_avg_sq);
 
 /* ---- data-parallel gradient exchange (the DDP all-reduce the reference constructs, DistributedRunner.py:26) ---- */
 int p5_comm_unique_id(void* id128_host);                      /* 128-byte ncclUniqueId */

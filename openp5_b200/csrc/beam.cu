@@ -579,6 +579,76 @@ eval_metrics_kernel(const int32_t* __restrict__ seqs, const float* __restrict__ 
     }
 }
 
+// two token rows are the same item iff they agree after dropping pad (0) and eos (1)
+__device__ __forceinline__ bool same_path(const int32_t* p, int T, const int32_t* g, int Tg) {
+    int a = 0, c = 0;
+    while (true) {
+        while (a < T && (p[a] == 0 || p[a] == 1)) ++a;
+        while (c < Tg && (g[c] == 0 || g[c] == 1)) ++c;
+        if (a >= T || c >= Tg) return (a >= T) && (c >= Tg);
+        if (p[a] != g[c]) return false;
+        ++a; ++c;
+    }
+}
+
+// filtered variant (ref utils/evaluate.py:6-35 rel_results_filtered, DistributedRunner.py:204-265): the R returned rows of a
+// user are ordered by score (desc, stable); rows equal to one of the user's POSITIVE (already interacted) items are
+// skipped; the first k_cut remaining rows form the relevance list.  pos [B, Pmax, Tp] token paths, npos [B] valid counts.
+__global__ void __launch_bounds__(64)
+eval_metrics_filtered_kernel(const int32_t* __restrict__ seqs, const float* __restrict__ scores, int R, int T,
+                             const int32_t* __restrict__ gold, int Tg, const int32_t* __restrict__ pos,
+                             const int32_t* __restrict__ npos, int Pmax, int Tp, const int32_t* __restrict__ ks, int n_k,
+                             int k_cut, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ int s_gold[64], s_pos[64], rel[64];
+    __shared__ int n_rel;
+    const int b = blockIdx.x, i = threadIdx.x;
+    if (i < R) {
+        const int32_t* p = seqs + (int64_t)(b * R + i) * T;
+        const bool is_gold = same_path(p, T, gold + (int64_t)b * Tg, Tg);
+        bool is_pos = false;
+        const int np = min(npos[b], Pmax);
+        for (int j = 0; j < np && !is_pos; ++j) is_pos = same_path(p, T, pos + ((int64_t)b * Pmax + j) * Tp, Tp);
+        const float sc = scores[b * R + i];
+        int rank = 0;
+        for (int j = 0; j < R; ++j) {
+            const float sj = scores[b * R + j];
+            rank += (sj > sc || (sj == sc && j < i)) ? 1 : 0;
+        }
+        s_gold[rank] = is_gold ? 1 : 0;
+        s_pos[rank] = is_pos ? 1 : 0;
+    }
+    __syncthreads();
+    if (i == 0) {
+        int n = 0;
+        for (int r = 0; r < R && n < k_cut; ++r)
+            if (!s_pos[r]) rel[n++] = s_gold[r];
+        n_rel = n;
+    }
+    __syncthreads();
+    if (i < n_k) {
+        const int k = min(ks[i], n_rel);
+        bool hit = false;
+        float ndcg = 0.f;
+        for (int r = 0; r < k; ++r)
+            if (rel[r]) { hit = true; ndcg += 1.f / log2f((float)r + 2.f); }
+        if (hit) atomicAdd(out + i, 1.f);
+        if (ndcg != 0.f) atomicAdd(out + n_k + i, ndcg);
+    }
+}
+
+void eval_metrics_filtered(const int32_t* seqs, const float* scores, int B, int R, int T, const int32_t* gold, int Tg,
+                           const int32_t* pos, const int32_t* npos, int Pmax, int Tp, const int32_t* ks_dev, int n_k, int k_cut,
+                           float* out_sums, cudaStream_t st) {
+    if (B <= 0) return;
+    P5_CHECK(R >= 1 && R <= 64 && n_k >= 1 && n_k <= 64 && T >= 1 && Tg >= 1 && k_cut >= 1 && k_cut <= 64 && Pmax >= 0 && Tp >= 1,
+             "eval_metrics_filtered: rows per user, cut-offs and k must be in [1, 64]");
+    launch_k(eval_metrics_filtered_kernel, (unsigned)B, 64, 0, st, seqs, scores, R, T, gold, Tg, pos, npos, Pmax, Tp, ks_dev, n_k, k_cut,
+             out_sums);
+    LAUNCHED();
+}
+
 void eval_metrics(const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg, const int32_t* ks_dev,
                   int n_k, float* out_sums, cudaStream_t st) {
     if (B <= 0) return;
@@ -642,7 +712,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         const int64_t tiles = cdiv(R, 128) * cdiv(N, 64);
         int splits = 1;
         for (int s2 = 1; s2 <= kb; ++s2)
-            if (kb % s2 == 0 && (K % 64 == 0)) { splits = s2; if (tiles * s2 >= 140) break; }
+            if (kb % s2 == 0 && (K % 64 == 0) && !e->x3) { splits = s2; if (tiles * s2 >= 140) break; }
         const int Ks = K / splits;
         p.K = Ks; p.nb1 = splits; p.prefer_bn = 64;
         p.A.ptr = X; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = ldx; p.A.bs1 = Ks;
@@ -651,6 +721,10 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         e->gemm(p);
     };
     const int n_steps = std::min(max_len - 1, trie->max_depth - 1);
+    // A trie shallower than max_length: every path has ended by step n_steps, a beam that sits on a leaf without EOS has no
+    // allowed continuation (transformers 4.26: an all -inf row; 5.x raises).  The last executed step is then the
+    // MaxLengthCriteria step, so such hypotheses are finalised instead of being dropped with a -1e9 score.
+    const int max_len_eff = std::min(max_len, n_steps + 1);
     int cur = 0;
     const float hs = 1.f / sqrtf((float)d);
     for (int step = 0; step < n_steps; ++step) {
@@ -728,7 +802,7 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         launch_k(beam_update_kernel, B, 128, (14 * K + 4) * sizeof(int), st, g->cand_lp, g->cand_beam, g->cand_tok, g->seq[cur], g->seq[nxt], g->fin_seq[cur], g->fin_seq[nxt], g->src[cur],
             g->src[nxt], g->node[cur], g->node[nxt], g->run_score[nxt], g->fin_score[cur], g->fin_score[nxt], g->is_fin[cur],
             g->is_fin[nxt], g->gen_len[cur], g->gen_len[nxt], g->cur_tok, g->unsat, trie->d_off, trie->d_tok, trie->d_node, K,
-            T, cur_len, max_len, 1 /*eos*/, denom_fin, denom_next);
+            T, cur_len, max_len_eff, 1 /*eos*/, denom_fin, denom_next);
         LAUNCHED();
         cur = nxt;
     }

@@ -21,9 +21,11 @@ namespace p5 { int g_launches = 0; }
     }                                                         \
     return 0;
 
+// the handle is a box around the engine pointer: p5_resize_vocab replaces the engine behind an unchanged handle
+struct p5_engine { Engine* e; };
 static Engine* E(p5_handle h) {
-    P5_CHECK(h != nullptr, "null engine handle");
-    return reinterpret_cast<Engine*>(h);
+    P5_CHECK(h != nullptr && h->e != nullptr, "null engine handle");
+    return h->e;
 }
 
 namespace p5 {
@@ -57,14 +59,15 @@ int p5_create(const P5Config* cfg, int device, void* cuda_stream, p5_handle* out
     if (ce != cudaSuccess || ndev <= 0)
         throw P5Error(4, "p5_create: no CUDA device available — the B200 engine has no CPU fallback");
     P5_CHECK(device >= 0 && device < ndev, "invalid device index");
-    *out = reinterpret_cast<p5_handle>(new Engine(*cfg, device, (cudaStream_t)cuda_stream));
+    Engine* e = new Engine(*cfg, device, (cudaStream_t)cuda_stream);
+    *out = new p5_engine{e};
     P5_API_END
 }
 int p5_destroy(p5_handle h) {
     P5_API_BEGIN
     if (h) {
-        comm_destroy(E(h));
-        delete E(h);
+        if (h->e) { comm_destroy(h->e); delete h->e; }
+        delete h;
     }
     P5_API_END
 }
@@ -87,7 +90,11 @@ int p5_param_info(p5_handle h, int i, const char** name, int* ndim, int64_t shap
 }
 int p5_resize_vocab(p5_handle h, int new_vocab) {
     P5_API_BEGIN
-    E(h)->resize_vocab(new_vocab);
+    Engine* old = E(h);
+    if (new_vocab != old->V) {
+        h->e = old->resized(new_vocab);
+        delete old;
+    }
     P5_API_END
 }
 int p5_params_changed(p5_handle h) {
@@ -194,6 +201,27 @@ int p5_eval_metrics(p5_handle h, const int32_t* seqs, const float* scores, int B
     Engine* e = E(h);
     P5_CUDA(cudaSetDevice(e->device));
     eval_metrics(seqs, scores, B, K, T, gold, Tg, ks_dev, n_k, out_sums, e->st);
+    P5_API_END
+}
+
+int p5_eval_metrics_filtered(p5_handle h, const int32_t* seqs, const float* scores, int B, int R, int T, const int32_t* gold,
+                             int Tg, const int32_t* pos, const int32_t* npos, int Pmax, int Tp, const int32_t* ks_dev, int n_k,
+                             int k_cut, float* out_sums) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CUDA(cudaSetDevice(e->device));
+    P5_CHECK(seqs && scores && gold && npos && ks_dev && out_sums && (pos || Pmax == 0), "null argument");
+    eval_metrics_filtered(seqs, scores, B, R, T, gold, Tg, pos, npos, Pmax, Tp, ks_dev, n_k, k_cut, out_sums, e->st);
+    P5_API_END
+}
+
+int p5_opt_state_info(p5_handle h, int i, float** exp_avg, float** exp_avg_sq) {
+    P5_API_BEGIN
+    Engine* e = E(h);
+    P5_CHECK(i >= 0 && i < (int)e->params.size(), "parameter index out of range");
+    e->join_optimizer();
+    if (exp_avg) *exp_avg = e->M1 + e->params[i].off;
+    if (exp_avg_sq) *exp_avg_sq = e->V2 + e->params[i].off;
     P5_API_END
 }
 

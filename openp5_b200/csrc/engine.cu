@@ -40,7 +40,9 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     P5_CHECK(c.max_enc_len >= 1 && c.max_enc_len <= 512, "max_enc_len must be in [1, 512] (Collator.py:13)");
     P5_CHECK(c.max_batch >= 1 && c.max_dec_len >= 1, "max_batch / max_dec_len");
     P5_CUDA(cudaSetDevice(dev));
-    dt = c.precision == 0 ? DT_F32 : DT_BF16;
+    P5_CHECK(c.precision >= 0 && c.precision <= 2, "precision must be 0 (fp32 SIMT), 1 (bf16 tcgen05) or 2 (bf16x3 tcgen05 parity)");
+    dt = c.precision == 1 ? DT_BF16 : DT_F32;
+    x3 = c.precision == 2;
     mn = c.use_mn_major != 0;
     d = c.d_model; H = c.num_heads; A = H * 64; ff = c.d_ff; V = c.vocab_size; Vpad = (int)round_up(V, 64);
     NE = c.num_layers; ND = c.num_decoder_layers; gated = c.ffn_gated_gelu != 0; p_drop = c.dropout;
@@ -209,9 +211,12 @@ __global__ void init_normal_rows_kernel(float* __restrict__ w, int64_t n, uint64
     }
 }
 
-void Engine::resize_vocab(int new_vocab) {
+// model.resize_token_embeddings(n) (ref main.py:193): a NEW engine for the new vocabulary that keeps every tensor other
+// than shared.weight, the first min(V, n) embedding rows (with their Adam moments), the data-parallel communicator and
+// the mode flags; new rows ~ N(0, 1) as HF's T5 initialiser draws them.  The C-ABI handle is a box around the Engine
+// pointer (capi.cu), so the caller swaps the pointer and deletes the old engine — no object is relocated bytewise.
+Engine* Engine::resized(int new_vocab) {
     P5_CHECK(new_vocab >= 2 && new_vocab < (1 << 24), "resize_vocab: vocabulary size out of range");
-    if (new_vocab == V) return;
     P5_CUDA(cudaSetDevice(device));
     join_optimizer();
     P5_CUDA(cudaStreamSynchronize(st));
@@ -239,13 +244,10 @@ void Engine::resize_vocab(int new_vocab) {
         delete ne;
         throw;
     }
-    // exchange the two objects wholesale (every member is a scalar, a raw pointer or a std::vector: bytewise
-    // relocatable); the temporary then owns the old buffers and frees them
-    alignas(Engine) unsigned char tmp[sizeof(Engine)];
-    memcpy(tmp, (void*)this, sizeof(Engine));
-    memcpy((void*)this, (void*)ne, sizeof(Engine));
-    memcpy((void*)ne, tmp, sizeof(Engine));
-    delete ne;
+    // the communicator (own stream / events, addresses the gradient buffer through the engine it is called with) moves over
+    ne->nccl_comm = nccl_comm; ne->world = world; ne->rank = rank;
+    nccl_comm = nullptr; world = 1; rank = 0;
+    return ne;
 }
 
 DropCfg Engine::drop(uint32_t kind, int layer) const {
@@ -269,6 +271,7 @@ void Engine::refresh_shadow() {
 void Engine::gemm(GemmProblem& p) {
     if (next_gemm_indep) { p.indep_of_prev = true; next_gemm_indep = false; }   // one-shot flag set by the caller
     if (dt == DT_BF16 && gemm_tc_supported(p, mn)) gemm_tc(p, st);
+    else if (x3 && gemm_x3_supported(p)) gemm_bf16x3(p, st);   // fp32 storage, tcgen05 arithmetic at fp32-class accuracy
     else { gemm_simt(p, st); ++g_launches; }
 }
 
@@ -322,6 +325,7 @@ void Engine::linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t l
             if (cost < best) { best = cost; splits = s; }
         }
     }
+    if (x3) splits = 1;   // the bf16x3 parity GEMM takes non-batched operands
     p.prefer_bn = K > 128 ? 256 : (K > 64 ? 128 : 64);
     const int Ks = M / splits;
     p.K = Ks; p.nb1 = splits;
@@ -891,6 +895,17 @@ void Engine::backward() {
 // ------------------------------------------------------------------------------------------------------------
 // optimiser
 // ------------------------------------------------------------------------------------------------------------
+// the reference's optimizer groups (SingleRunner.py:186-205): `no_decay = ["bias", "LayerNorm.weight"]` is matched by
+// substring against the parameter names; T5 names its norms "layer_norm" (no match) but "bias" matches the two
+// `relative_attention_bias.weight` tables, which therefore take weight_decay = 0.  Ranges relative to `base`.
+NoDecay Engine::no_decay(int64_t base) const {
+    NoDecay nd;
+    const int64_t n = (int64_t)cfg.rel_buckets * H;
+    if (NE > 0) { nd.lo0 = off_enc_rel - base; nd.hi0 = nd.lo0 + n; }
+    if (ND > 0) { nd.lo1 = off_dec_rel - base; nd.hi1 = nd.lo1 + n; }
+    return nd;
+}
+
 void Engine::grad_norm() {
     join_optimizer();
     sumsq_norm(G, n_flat, norm_partial, norm_out, st);
@@ -934,7 +949,7 @@ void Engine::adamw_async(float lr, float b1, float b2, float eps, float wd, int 
     for (size_t r = 0; r < opt_ranges.size(); ++r) {
         const int64_t o = opt_ranges[r].first, n = opt_ranges[r].second;
         adamw_flat(P + o, G + o, M1 + o, V2 + o, P16 ? P16 + o : nullptr, n, lr, b1, b2, eps, wd, step, clip,
-                   clip > 0.f ? norm_out : nullptr, 1.f, st_opt, true);
+                   clip > 0.f ? norm_out : nullptr, 1.f, st_opt, true, no_decay(o));
         P5_CUDA(cudaEventRecord(ev_opt[r], st_opt));
     }
     opt_pending = true;
@@ -945,7 +960,7 @@ void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, 
     join_optimizer();
     if (clip > 0.f && !norm_valid) grad_norm();
     adamw_flat(P, G, M1, V2, P16, n_flat, lr, b1, b2, eps, wd, step, clip, clip > 0.f ? norm_out : nullptr, 1.f, st,
-               zero_grad_after);
+               zero_grad_after, no_decay(0));
     shadow_stale = false;
     if (zero_grad_after) norm_valid = false;
 }

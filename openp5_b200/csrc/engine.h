@@ -14,6 +14,10 @@ extern int g_launches;
 void gemm_tc_force_block_n(int bn);
 // tcgen05 when the problem qualifies (bf16 operands, aligned), SIMT otherwise
 void gemm_auto(const GemmProblem& p, cudaStream_t stream, bool allow_mn_major);
+// gemm_x3.cu: fp32 operands split into bf16 hi/lo pairs, three products in ONE tcgen05 GEMM (K-concatenated operands)
+bool gemm_x3_supported(const GemmProblem& p);
+void gemm_bf16x3(const GemmProblem& p, cudaStream_t st);
+void gemm_x3_release();
 
 struct ParamInfo {
     std::string name;
@@ -41,6 +45,7 @@ struct Engine {
     int device = 0;
     cudaStream_t st = nullptr;
     int dt = DT_BF16;          // activation / GEMM operand dtype
+    bool x3 = false;           // precision 2: fp32 storage, every linear layer through the tcgen05 kernel as a bf16x3 product
     bool mn = true;            // MN-major operands allowed on the tcgen05 path
     int d = 0, A = 0, H = 0, ff = 0, V = 0, Vpad = 0, NE = 0, ND = 0;
     bool gated = false;
@@ -105,7 +110,7 @@ struct Engine {
     void project_cross_kv_all(int64_t rows);
     // model.resize_token_embeddings(n) (main.py:193): rebuilds the flat buffers for the new vocabulary, keeps every other
     // tensor and the first min(V, n) embedding rows (and their Adam moments); new rows ~ N(0, 1) like HF's T5 init
-    void resize_vocab(int new_vocab);
+    Engine* resized(int new_vocab);
     std::vector<float*> slse, clse;
     // head
     float *logits = nullptr, *lse_ce = nullptr, *loss_tok = nullptr, *dloss = nullptr, *loss_scalar = nullptr;
@@ -176,6 +181,7 @@ struct Engine {
     void ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void* n, const void* z, const void* h,
                  void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer);
 
+    NoDecay no_decay(int64_t base) const;
     void grad_norm();
     void adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip, bool zero_grad_after = false);
     void zero_grad();

@@ -582,6 +582,9 @@ CUtensorMap tmap_bf16_4d(const void* ptr, const uint64_t dims[4], const uint64_t
         throw P5Error(3, b);
     }
     std::lock_guard<std::mutex> g(g_tmap_mu);
+    // bounded: pad-to-longest batches change Le (hence the activation shapes) from step to step, so an epoch can create
+    // thousands of distinct keys; an encode costs ~1 us, so the cache is simply restarted when it is full
+    if (g_tmap_cache.size() >= 4096) g_tmap_cache.clear();
     g_tmap_cache[key] = m;
     return m;
 }

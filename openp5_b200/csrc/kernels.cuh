@@ -133,13 +133,20 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
 // ---- optimiser (optim.cu) ---------------------------------------------------------------------------------------
 void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
 void scale_f32(float* g, int64_t n, float s, cudaStream_t st);
+// element ranges [lo, hi) (relative to the pointers passed to adamw_flat) that take weight_decay = 0: the reference's
+// no_decay group (SingleRunner.py:186-205, names containing "bias" -> the two relative_attention_bias tables)
+struct NoDecay { int64_t lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0; };
 // transformers-4.26 AdamW on the flat parameter buffer; clip_norm_ptr (device) optional
 void adamw_flat(float* p, float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
                 float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st,
-                bool zero_grad_after = false);
+                bool zero_grad_after = false, NoDecay nd = NoDecay());
 
 // ranking metrics of one eval batch on the device (beam.cu)
 void eval_metrics(const int32_t* seqs, const float* scores, int B, int K, int T, const int32_t* gold, int Tg, const int32_t* ks_dev,
                   int n_k, float* out_sums, cudaStream_t st);
+
+void eval_metrics_filtered(const int32_t* seqs, const float* scores, int B, int R, int T, const int32_t* gold, int Tg,
+                           const int32_t* pos, const int32_t* npos, int Pmax, int Tp, const int32_t* ks_dev, int n_k, int k_cut,
+                           float* out_sums, cudaStream_t st);
 
 }  // namespace p5

@@ -62,7 +62,7 @@ void scale_f32(float* g, int64_t n, float s, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, int64_t n, float lr, float b1, float b2, float eps, float wd, float step_size,
-             float clip, const float* __restrict__ norm_ptr, float grad_div, int zero_g) {
+             float clip, const float* __restrict__ norm_ptr, float grad_div, int zero_g, NoDecay nd) {
     pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
     pdl_launch_dependents();
     float gs = grad_div;
@@ -79,6 +79,10 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
         float4 mm = reinterpret_cast<float4*>(m)[i];
         float4 vv = reinterpret_cast<float4*>(v)[i];
         float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+        // parameter groups of ref SingleRunner.py:186-205: names containing "bias" (= the two relative_attention_bias
+        // tables) take weight_decay 0; the ranges are 4-aligned, so a float4 never straddles a boundary
+        const int64_t e0 = i << 2;
+        const float lwd = ((e0 >= nd.lo0 && e0 < nd.hi0) || (e0 >= nd.lo1 && e0 < nd.hi1)) ? 0.f : lr * wd;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float gj = ga[j] * gs;
@@ -86,7 +90,7 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
             va[j] = va[j] * b2 + gj * gj * (1.f - b2);
             const float denom = sqrtf(va[j]) + eps;         // eps OUTSIDE the bias correction (HF 4.26)
             pa[j] = pa[j] - step_size * (ma[j] / denom);
-            pa[j] = pa[j] - lr * wd * pa[j];                // decoupled decay AFTER the update, un-corrected lr
+            pa[j] = pa[j] - lwd * pa[j];                    // decoupled decay AFTER the update, un-corrected lr
         }
         reinterpret_cast<float4*>(p)[i] = pp;
         if (zero_g) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // fused model.zero_grad()
@@ -105,7 +109,8 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
         const float mj = m[i] * b1 + gj * (1.f - b1);
         const float vj = v[i] * b2 + gj * gj * (1.f - b2);
         float pj = p[i] - step_size * (mj / (sqrtf(vj) + eps));
-        pj = pj - lr * wd * pj;
+        const float lwd = ((i >= nd.lo0 && i < nd.hi0) || (i >= nd.lo1 && i < nd.hi1)) ? 0.f : lr * wd;
+        pj = pj - lwd * pj;
         p[i] = pj; m[i] = mj; v[i] = vj;
         if (zero_g) g[i] = 0.f;
         if (p16) p16[i] = __float2bfloat16_rn(pj);
@@ -114,13 +119,13 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
 
 void adamw_flat(float* p, float* g, float* m, float* v, bf16* p16, int64_t n, float lr, float b1, float b2,
                 float eps, float wd, int step, float clip, const float* norm_ptr, float grad_div, cudaStream_t st,
-                bool zero_grad_after) {
+                bool zero_grad_after, NoDecay nd) {
     if (n <= 0) return;
     // step_size = lr * sqrt(1 - b2^t) / (1 - b1^t)   (correct_bias=True)
     const double bc1 = 1.0 - pow((double)b1, (double)step);
     const double bc2 = 1.0 - pow((double)b2, (double)step);
     const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-    launch_k(adamw_kernel, 148 * 8, 256, 0, st, p, g, m, v, p16, n, lr, b1, b2, eps, wd, step_size, clip, norm_ptr, grad_div, zero_grad_after ? 1 : 0);
+    launch_k(adamw_kernel, 148 * 8, 256, 0, st, p, g, m, v, p16, n, lr, b1, b2, eps, wd, step_size, clip, norm_ptr, grad_div, zero_grad_after ? 1 : 0, nd);
     LAUNCHED();
 }
 

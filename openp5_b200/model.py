@@ -99,7 +99,9 @@ class Trie:
 
 
 class P5B200:
-    """P5 T5 encoder-decoder on one B200.  `precision`: "bf16" (tcgen05 tensor-core path) or "fp32" (exact parity path)."""
+    """P5 T5 encoder-decoder on one B200.  `precision`: "bf16" (tcgen05 tensor-core path, the benchmarked mode), "fp32"
+    (SIMT fp32 parity path) or "bf16x3" (fp32 storage, every linear layer through the tcgen05 kernel as a hi/lo-split
+    three-product GEMM: the tensor-core path at fp32-class accuracy, gated at the north star's 1e-3)."""
 
     def __init__(self, backbone: str = "t5-small", vocab_size: int = 32100, device: Optional[int] = None,
                  precision: str = "bf16", dropout: float = 0.1, max_batch: int = 64, max_enc_len: int = 512,
@@ -120,7 +122,7 @@ class P5B200:
         cfg.ffn_gated_gelu = int(ffn_gated_gelu)
         cfg.whole_word_rows = 512
         cfg.dropout, cfg.ln_eps = float(dropout), 1e-6
-        cfg.precision = {"fp32": 0, "bf16": 1}[precision]
+        cfg.precision = {"fp32": 0, "bf16": 1, "bf16x3": 2}[precision]
         cfg.max_batch, cfg.max_enc_len, cfg.max_dec_len, cfg.max_beams = max_batch, max_enc_len, max_dec_len, max_beams
         cfg.use_mn_major = int(use_mn_major)
         self.cfg = cfg
@@ -231,8 +233,38 @@ class P5B200:
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     def mark_params_changed(self):
+        """call after writing parameters through `.data` / raw pointers BETWEEN fused train_step() calls: such writes do
+        not bump tensor versions, and train_step trusts the engine's own bf16 shadows otherwise"""
         _lib.check(self.lib.p5_params_changed(self.handle))
         self._versions = self._version_sum()
+
+    # ---------------------------------------------------------------- optimiser state (checkpoint / resume, SURVEY §8f-3)
+    def _opt_views(self):
+        views = OrderedDict()
+        for i, (name, p) in enumerate(self._params.items()):
+            m, v = C.c_void_p(), C.c_void_p()
+            _lib.check(self.lib.p5_opt_state_info(self.handle, i, C.byref(m), C.byref(v)))
+            views[name] = (torch.as_tensor(_DevArray(m.value, p.shape), device=self.device),
+                           torch.as_tensor(_DevArray(v.value, p.shape), device=self.device))
+        return views
+
+    def optimizer_state_dict(self):
+        """AdamW state in torch.optim layout keyed by parameter NAME: {"state": {name: {"step", "exp_avg", "exp_avg_sq"}},
+        "step": n}.  The reference saves weights only (DistributedRunner.py:155,169), so its runs cannot resume."""
+        self._join_optimizer()
+        return {"step": int(self._opt_step),
+                "state": OrderedDict((k, {"step": int(self._opt_step), "exp_avg": m.detach().clone().cpu(),
+                                          "exp_avg_sq": v.detach().clone().cpu()}) for k, (m, v) in self._opt_views().items())}
+
+    def load_optimizer_state_dict(self, sd):
+        self._join_optimizer()
+        views = self._opt_views()
+        with torch.no_grad():
+            for k, (m, v) in views.items():
+                st = sd["state"][k]
+                m.copy_(st["exp_avg"].to(self.device, torch.float32))
+                v.copy_(st["exp_avg_sq"].to(self.device, torch.float32))
+        self._opt_step = int(sd["step"])
 
     def _version_sum(self) -> int:
         return sum(p._version for p in self._params.values())
@@ -257,7 +289,13 @@ class P5B200:
         rows instead of B*Le.  Lengths come from the caller, or for free from a HOST attention mask (the collator's
         tensors start on the CPU, ref Collator.py:8-34); a device-resident mask without lengths keeps the padded path."""
         if enc_lengths is None and attention_mask is not None and not attention_mask.is_cuda:
-            enc_lengths = attention_mask.sum(dim=1)
+            # the packed layout needs CONTIGUOUS right padding with >= 1 token per row (what the collator produces,
+            # Collator.py:12-21); any other mask keeps the padded layout, where the mask itself is applied
+            m = attention_mask != 0
+            lens = m.sum(dim=1)
+            prefix = torch.arange(m.shape[1])[None, :] < lens[:, None]
+            if bool((m == prefix).all()) and bool((lens >= 1).all()):
+                enc_lengths = lens
         if enc_lengths is None:
             return
         if torch.is_tensor(enc_lengths):
@@ -420,6 +458,27 @@ class P5B200:
             out = torch.zeros(2 * len(ks), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.p5_eval_metrics(self.handle, seqs.data_ptr(), sc.data_ptr(), B, num_beams, seqs.shape[1], g.data_ptr(),
                                             g.shape[1], kd.data_ptr(), len(ks), out.data_ptr()))
+        return out
+
+    def eval_metric_sums_filtered(self, sequences, sequences_scores, gold, rows_per_user: int, ks: Sequence[int], positives,
+                                  n_positives, k_cut: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """filtered hit@k / ndcg@k sums (ref utils/evaluate.py:6-35 via DistributedRunner.py:204-265): `positives`
+        [B, Pmax, Tp] token paths of each user's already-interacted items, `n_positives` [B]; rows equal to a positive
+        are skipped, the first `k_cut` remaining rows (by score) form the relevance list."""
+        self._on_stream()
+        seqs = _i32(sequences, self.device)
+        sc = sequences_scores.to(self.device, torch.float32).contiguous()
+        g = _i32(gold, self.device)
+        pos = _i32(positives, self.device)
+        npos = _i32(n_positives, self.device)
+        B = g.shape[0]
+        assert seqs.shape[0] == B * rows_per_user and pos.dim() == 3 and pos.shape[0] == B
+        kd = torch.tensor([int(k) for k in ks], dtype=torch.int32, device=self.device)
+        if out is None:
+            out = torch.zeros(2 * len(ks), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.p5_eval_metrics_filtered(self.handle, seqs.data_ptr(), sc.data_ptr(), B, rows_per_user, seqs.shape[1],
+                                                     g.data_ptr(), g.shape[1], pos.data_ptr(), npos.data_ptr(), pos.shape[1],
+                                                     pos.shape[2], kd.data_ptr(), len(ks), int(k_cut), out.data_ptr()))
         return out
 
     def _trie_from_callback(self, fn) -> Trie:

@@ -53,12 +53,16 @@ def hf_vectors():
         g = {k: g[k] for k in wo}
         po.clip_grad_norm(g, 1.0)
         for k in wo:
-            po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, 1e-3, eps=1e-6, weight_decay=0.01)
+            # the reference's two parameter groups (SingleRunner.py:186-205): no decay for names containing "bias"
+            po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, 1e-3, eps=1e-6, weight_decay=po.adamw_weight_decay_for(k, 0.01))
         losses.append(l.item())
     out["adamw_losses"] = np.array(losses, dtype=np.float64)
     out["adamw::shared.weight[:8]"] = wo["shared.weight"][:8].numpy()
     out["adamw::encoder.block.0.layer.0.SelfAttention.q.weight"] = wo["encoder.block.0.layer.0.SelfAttention.q.weight"].numpy()
     out["adamw::decoder.final_layer_norm.weight"] = wo["decoder.final_layer_norm.weight"].numpy()
+    for k in ("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+              "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"):
+        out["adamw::" + k] = wo[k].numpy()        # weight_decay 0 group
     # constrained beam search
     trie = po.Trie(items)
     seqs, scores = hf_pin.hf_generate(m, wwe, ids, ww, attn, trie, 5, 5, 20)
@@ -93,8 +97,15 @@ def reference_helpers():
     targets = ["b", "x", "k"]
     rel = ev.rel_results(preds, targets, scores, 4)
     metrics = ev.get_metrics_results(rel, ["hit@1", "hit@3", "ndcg@3", "ndcg@4"]).tolist()
+    # filtered variant (evaluate.py:6-35): 3 users x 4 returned rows, top-2 after removing each user's positives
+    positive = {"u1": {"q", "a"}, "u2": {"e"}, "u3": set()}
+    id2user = {0: "u1", 1: "u2", 2: "u3"}
+    rel_f = ev.rel_results_filtered(positive, id2user, [0, 1, 2], 4, preds, targets, scores, 2)
+    metrics_f = ev.get_metrics_results(rel_f, ["hit@1", "hit@2", "ndcg@2"]).tolist()
     json.dump(dict(items=items, probes=probes, trie_get=trie_get, tokens=toks, whole_word_ids=wwids, tokens2=toks2,
-                   whole_word_ids2=wwids2, preds=preds, scores=scores, targets=targets, rel=rel, metrics=metrics),
+                   whole_word_ids2=wwids2, preds=preds, scores=scores, targets=targets, rel=rel, metrics=metrics,
+                   positive={k: sorted(v) for k, v in positive.items()}, user_order=["u1", "u2", "u3"], rel_filtered=rel_f,
+                   metrics_filtered=metrics_f),
               open(os.path.join(HERE, "reference_helpers.json"), "w"), indent=1, ensure_ascii=False)
     print("reference helper goldens written", metrics)
 

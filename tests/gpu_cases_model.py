@@ -19,13 +19,39 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "xcheck_fbwd_dropout_base_le256_packed", "xcheck_fbwd_dropout_base_le256", "adamw_fp32_tiny_async",
          "asyncopt_bf16_small_bitwise", "resize_vocab_fp32_tiny", "resize_vocab_bf16_tiny",
          # edge geometries: a single sequence, the shortest encoder input the engine accepts, two beams
-         "bwd_bf16_tiny_b1", "bwd_fp32_tiny_b1_packed", "bwd_bf16_tiny_le8", "gen_fp32_tiny_k2", "gen_bf16_tiny_b1"]
+         "bwd_bf16_tiny_b1", "bwd_fp32_tiny_b1_packed", "bwd_bf16_tiny_le8", "gen_fp32_tiny_k2", "gen_bf16_tiny_b1",
+         # ---- round 2: parity on the benchmarked path and shapes
+         # full BASELINE configs[1] geometry (T5-base 12+12, B=64, Le=256, Ld=8, V=32100), bf16 engine vs the bf16-emulating
+         # oracle: logits, per-token loss, every gradient
+         "bwd_bf16_c2full", "bwd_bf16_c2full_packed",
+         # BASELINE configs[4] geometry (T5-base, 20 users x 20 beams, 3416-item trie): fp32 identical, bf16 vs emulation
+         "gen_fp32_c5full", "gen_bf16_c5full",
+         # tensor-core parity GEMM (bf16x3 through the same tcgen05 kernel) gated at the north star's 1e-3
+         "fwd_x3_tiny", "bwd_x3_small", "bwd_x3_base_le256", "bwd_x3_small_packed", "adamw_x3_tiny", "gen_x3_small",
+         # shapes of configs[2] / configs[3] and the gated-GELU FFN on the tensor-core path
+         "bwd_bf16_gated_small", "bwd_bf16_large_le128", "bwd_bf16_large_le512_packed", "bwd_bf16_v32600_packed", "gen_bf16_v32600",
+         # data-parallel semantics on one GPU: mean of two shards' gradients == concatenated-batch oracle gradient
+         "dpaccum_fp32_small", "dpaccum_bf16_small",
+         # optimiser-state checkpoint / resume, no-decay parameter groups
+         "resume_fp32_tiny", "resume_bf16_small", "varlen_bf16_small"]
 
 
 def setup(case):
     import torch
     from oracle import p5_oracle as po
-    if "base" in case:
+    if "c2full" in case:
+        cfg = po.t5_cfg("t5-base", vocab_size=32100)
+        B, Le, Ld, n_items = 64, 256, 8, 3416
+    elif "c5full" in case:
+        cfg = po.t5_cfg("t5-base", vocab_size=32100)
+        B, Le, Ld, n_items = 20, 256, 8, 3416
+    elif "large" in case:      # configs[3] dimensions (d_model 1024, 16 heads, d_ff 4096), two blocks each side
+        cfg = po.t5_cfg("t5-large", vocab_size=32100, num_layers=2, num_decoder_layers=2)
+        B, Le, Ld, n_items = (4, 128, 8, 200) if "le128" in case else (2, 512, 8, 200)
+    elif "v32600" in case:     # configs[2]: collaborative indexing adds <= 500 tokens to the vocabulary (main.py:188-193)
+        cfg = po.t5_cfg("t5-base", vocab_size=32600, num_layers=1, num_decoder_layers=1)
+        B, Le, Ld, n_items = 8, 96, 8, 500
+    elif "base" in case:
         cfg = po.t5_cfg("t5-base", vocab_size=32100, num_layers=2, num_decoder_layers=2)
         B, Le, Ld, n_items = 8, 256, 8, 200
     elif "le512" in case or "le300" in case:
@@ -46,15 +72,26 @@ def setup(case):
     if "gated" in case:
         cfg.ffn_gated_gelu = True
     w = po.init_weights(cfg, seed=1)
-    items = po.synth_items(n_items, seed=3)
+    if "v32600" in case:
+        # collaborative item ids: paths of <CIk> tokens with ids >= 32100, depth 2-4
+        import random
+        rng = random.Random(3)
+        seen, items = set(), []
+        while len(items) < n_items:
+            p = tuple(rng.randrange(32100, 32600) for _ in range(rng.randrange(2, 5)))
+            if p not in seen:
+                seen.add(p)
+                items.append([0, 300, 301] + list(p) + [1])
+    else:
+        items = po.synth_items(n_items, seed=3)
     batch = po.synth_batch(B, Le, Ld, cfg.vocab_size, items, seed=5)
     return po, cfg, w, items, batch
 
 
-def make_model(cfg, w, precision, dropout=0.0, **kw):
+def make_model(cfg, w, precision, dropout=0.0, max_batch=8, max_enc_len=512, **kw):
     from openp5_b200.model import P5B200
-    m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, precision=precision, dropout=dropout, max_batch=8,
-               max_enc_len=512, max_dec_len=16, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
+    m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, precision=precision, dropout=dropout, max_batch=max_batch,
+               max_enc_len=max_enc_len, max_dec_len=16, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
                num_decoder_layers=cfg.num_decoder_layers, num_heads=cfg.num_heads, ffn_gated_gelu=cfg.ffn_gated_gelu, **kw)
     m.load_state_dict(w, strict=True)
     return m
@@ -64,24 +101,84 @@ def relerr(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
+def _precision(case):
+    if "_x3_" in case:
+        return "bf16x3"
+    return "bf16" if ("bf16" in case or case.startswith("xcheck")) else "fp32"
+
+
+# Gates.  fp32 (SIMT) and bf16x3 (tcgen05, hi/lo-split operands) are compared with the fp32 oracle — the reference
+# arithmetic — at the north star's 1e-3 or tighter.  The benchmarked bf16 mode is compared with the bf16-EMULATING oracle
+# (same storage points rounded, oracle/p5_oracle.py:bf16_emulation): what is left is accumulation order, ex2.approx and
+# tie-flips of the bf16 rounding itself, so every tensor is gated at <= 2e-2 of its max-norm (logits / loss at 1e-2).
+# The distance to the fp32 oracle is REPORTED next to it (`*_vs_fp32`): that number is bf16 rounding, not a gate.
+GATE = {"fp32": dict(out=2e-4, grad=1e-3), "bf16x3": dict(out=1e-3, grad=1e-3), "bf16": dict(out=1e-2, grad=2e-2)}
+
+
+def _oracle_grads(po, prec, w, cfg, batch, want_fp32=True):
+    ids, attn, ww, labels, oattn = batch
+    ref32 = po.loss_and_grads(w, cfg, ids, ww, attn, labels, oattn) if (prec != "bf16" or want_fp32) else None
+    if prec != "bf16":
+        return ref32, None
+    with po.bf16_emulation():
+        emu = po.loss_and_grads(w, cfg, ids, ww, attn, labels, oattn)
+    return emu, ref32
+
+
+def _compare_grads(res, named_grads, g_ref, gate, g_fp32=None):
+    worst, worst_name, bad = 0.0, "", []
+    w32, w32_name = 0.0, ""
+    for k, g in named_grads:
+        g = g.cpu()
+        e = ((g - g_ref[k]).abs().max() / g_ref[k].abs().max().clamp_min(1e-9)).item()
+        if e > worst:
+            worst, worst_name = e, k
+        if e > gate:
+            bad.append((k, round(e, 5)))
+        if g_fp32 is not None:
+            e2 = ((g - g_fp32[k]).abs().max() / g_fp32[k].abs().max().clamp_min(1e-9)).item()
+            if e2 > w32:
+                w32, w32_name = e2, k
+    res["worst_grad_rel"], res["worst_grad_name"] = worst, worst_name
+    res["bad"], res["n_bad"] = bad[:8], len(bad)
+    if g_fp32 is not None:
+        res["worst_grad_rel_vs_fp32"], res["worst_grad_name_vs_fp32"] = w32, w32_name
+        # how far the bf16-emulating ORACLE itself is from the fp32 oracle on that tensor: the engine's distance to fp32
+        # is bf16 rounding (ReLU units whose pre-activation changes sign under operand rounding flip whole gradient rows),
+        # not an engine defect
+        res["oracle_emu_vs_fp32_on_that_tensor"] = ((g_ref[w32_name] - g_fp32[w32_name]).abs().max() /
+                                                    g_fp32[w32_name].abs().max().clamp_min(1e-9)).item()
+    return not bad
+
+
 def run_case(case):
     import torch
     po, cfg, w, items, (ids, attn, ww, labels, oattn) = setup(case)
-    prec = "bf16" if ("bf16" in case or case.startswith("xcheck")) else "fp32"
-    tol = 6e-2 if prec == "bf16" else 2e-4
+    prec = _precision(case)
+    gate = GATE[prec]
+    tol = gate["out"]
     dev = "cuda"
-    res = dict(name=case)
+    res = dict(name=case, precision=prec)
+    big = dict(max_batch=max(8, ids.shape[0]))
     if case.startswith("fwd"):
-        m = make_model(cfg, w, prec).eval()
+        m = make_model(cfg, w, prec, **big).eval()
         with torch.no_grad():
             out = m(input_ids=ids.to(dev), whole_word_ids=ww.to(dev), attention_mask=attn.to(dev), labels=labels.to(dev))
-        lt_o, lg_o = po.forward(w, cfg, ids, ww, attn, labels)
+        lt_32, lg_32 = po.forward(w, cfg, ids, ww, attn, labels)
+        lt_o, lg_o = lt_32, lg_32
+        if prec == "bf16":
+            with po.bf16_emulation(), torch.no_grad():
+                lt_o, lg_o = po.forward(w, cfg, ids, ww, attn, labels)
+            res["logits_rel_vs_fp32"] = relerr(out["logits"].cpu(), lg_32)
+            res["loss_rel_vs_fp32"] = relerr(out["loss"].cpu(), lt_32)
         res["logits_rel"] = relerr(out["logits"].cpu(), lg_o)
         res["loss_rel"] = relerr(out["loss"].cpu(), lt_o)
         res["ok"] = res["logits_rel"] < tol and res["loss_rel"] < tol
     elif case.startswith("bwd") or case.startswith("gated") or case.startswith("fused"):
-        m = make_model(cfg, w, prec).eval()   # eval => dropout off; gradients still flow
-        l_o, lt_o, lg_o, g_o = po.loss_and_grads(w, cfg, ids, ww, attn, labels, oattn)
+        m = make_model(cfg, w, prec, **big).eval()   # eval => dropout off; gradients still flow
+        t0 = time.time()
+        (l_o, lt_o, lg_o, g_o), ref32 = _oracle_grads(po, prec, w, cfg, (ids, attn, ww, labels, oattn), want_fp32="c2full" not in case)
+        res["oracle_s"] = round(time.time() - t0, 1)
         m.zero_grad()
         if case.startswith("fused"):
             import ctypes as C
@@ -103,25 +200,44 @@ def run_case(case):
             lm = (oattn.to(dev) != 0).float()
             loss = ((out["loss"].view(B, Ld) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
             loss.backward()
+            res["logits_rel"] = relerr(out["logits"].detach().cpu(), lg_o)
+            res["loss_tok_rel"] = relerr(out["loss"].detach().cpu(), lt_o)
+            if ref32 is not None and prec == "bf16":
+                res["logits_rel_vs_fp32"] = relerr(out["logits"].detach().cpu(), ref32[2])
         torch.cuda.synchronize()
         res["loss"] = loss.item()
         res["loss_ref"] = l_o.item()
-        worst, worst_name = 0.0, ""
-        bad = []
-        for k, p in m.named_parameters():
-            g = p.grad.cpu()
-            e = ((g - g_o[k]).abs().max() / g_o[k].abs().max().clamp_min(1e-9)).item()
-            if e > worst:
-                worst, worst_name = e, k
-            if e > (0.25 if prec == "bf16" else 5 * tol):   # bf16: few-token decoder sums carry ~0.2 max-norm noise
-                bad.append((k, round(e, 5)))
-        res["worst_grad_rel"] = worst
-        res["worst_grad_name"] = worst_name
-        res["bad"] = bad[:8]
-        res["n_bad"] = len(bad)
-        res["ok"] = abs(res["loss"] - res["loss_ref"]) < tol * abs(res["loss_ref"]) and not bad
+        grads_ok = _compare_grads(res, [(k, p.grad) for k, p in m.named_parameters()], g_o, gate["grad"],
+                                  ref32[3] if (ref32 is not None and prec == "bf16") else None)
+        res["ok"] = (abs(res["loss"] - res["loss_ref"]) < tol * abs(res["loss_ref"]) and grads_ok and
+                     res.get("logits_rel", 0.0) < tol and res.get("loss_tok_rel", 0.0) < tol)
+    elif case.startswith("dpaccum"):
+        # data-parallel semantics (ref DistributedRunner.py:26, the DDP mean all-reduce) without a second GPU: the batch is
+        # split into two rank shards, each shard's gradient of ITS runner loss is accumulated in the engine and halved
+        # (= what ncclAvg leaves in every replica); it must equal the oracle gradient of the mean of the two shard
+        # losses, i.e. the concatenated batch (both shards hold B/2 sequences).  The 2-GPU NCCL version of this check is
+        # tests/test_model_gpu.py::test_two_rank_nccl_gradient_matches_concatenated_oracle.
+        m = make_model(cfg, w, prec, **big).eval()
+        (l_o, lt_o, lg_o, g_o), ref32 = _oracle_grads(po, prec, w, cfg, (ids, attn, ww, labels, oattn))
+        m.zero_grad()
+        h = ids.shape[0] // 2
+        losses = []
+        for sl in (slice(0, h), slice(h, 2 * h)):
+            out = m(input_ids=ids[sl].to(dev), whole_word_ids=ww[sl].to(dev), attention_mask=attn[sl].to(dev),
+                    labels=labels[sl].to(dev), return_logits=False)
+            lm = (oattn[sl].to(dev) != 0).float()
+            loss = ((out["loss"].view(h, -1) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
+            loss.backward()        # accumulates into the engine's gradient buffers
+            losses.append(loss.item())
+        from openp5_b200 import _lib
+        _lib.check(m.lib.p5_grad_scale(m.handle, 0.5))
+        torch.cuda.synchronize()
+        res["loss"], res["loss_ref"] = sum(losses) / 2, l_o.item()
+        grads_ok = _compare_grads(res, [(k, p.grad) for k, p in m.named_parameters()], g_o, gate["grad"],
+                                  ref32[3] if (ref32 is not None and prec == "bf16") else None)
+        res["ok"] = abs(res["loss"] - res["loss_ref"]) < tol * abs(res["loss_ref"]) and grads_ok
     elif case.startswith("adamw"):
-        m = make_model(cfg, w, prec).eval()
+        m = make_model(cfg, w, prec, **big).eval()
         wo = {k: v.clone() for k, v in w.items()}
         mo = {k: torch.zeros_like(v) for k, v in w.items()}
         vo = {k: torch.zeros_like(v) for k, v in w.items()}
@@ -130,40 +246,103 @@ def run_case(case):
             lr = 1e-3
             l_o, _, _, g = po.loss_and_grads(wo, cfg, ids, ww, attn, labels, oattn)
             po.clip_grad_norm(g, 1.0)
-            for k in wo:
-                po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, lr, eps=1e-6, weight_decay=0.01)
+            for k in wo:   # the reference's two parameter groups: no decay for names containing "bias" (SingleRunner.py:186-205)
+                po.adamw_hf426(wo[k], g[k], mo[k], vo[k], step, lr, eps=1e-6, weight_decay=po.adamw_weight_decay_for(k, 0.01))
             m.training = False
             loss = m.train_step(ids.to(dev), ww.to(dev), attn.to(dev), labels.to(dev), oattn.to(dev), lr=lr, clip=1.0, step=step,
                                 enc_lengths=attn.sum(1) if "packed" in case else None, overlap_optimizer="async" in case)
             losses.append((loss.item(), l_o.item()))
-        worst = max(relerr(p.detach().cpu(), wo[k]) for k, p in m.named_parameters())
+        errs = {k: relerr(p.detach().cpu(), wo[k]) for k, p in m.named_parameters()}
+        worst = max(errs.values())
         res["losses"] = losses
         res["worst_param_rel"] = worst
+        res["rel_bias_tables_rel"] = max(v for k, v in errs.items() if "relative_attention_bias" in k)
         res["ok"] = worst < 1e-3 and all(abs(a - b) < 1e-3 * abs(b) for a, b in losses)
+    elif case.startswith("resume"):
+        # weights + Adam moments + step round-trip through state dicts; a resumed run continues exactly
+        # like the uninterrupted one (same seeds): 2 steps, save, load into a FRESH engine, 2 more steps
+        a = [t.to(dev) for t in (ids, ww, attn, labels, oattn)]
+        drop = 0.1 if prec == "bf16" else 0.0
+        ref = make_model(cfg, w, prec, dropout=drop, **big).train()
+        ref_losses = [ref.train_step(*a, lr=1e-3, clip=1.0, step=s, seed=50 + s).item() for s in range(1, 5)]
+        m1 = make_model(cfg, w, prec, dropout=drop, **big).train()
+        l12 = [m1.train_step(*a, lr=1e-3, clip=1.0, step=s, seed=50 + s).item() for s in range(1, 3)]
+        import io
+        buf = io.BytesIO()
+        torch.save({"model": m1.state_dict(), "optimizer": m1.optimizer_state_dict()}, buf)
+        del m1
+        buf.seek(0)
+        ck = torch.load(buf, map_location="cpu")
+        m2 = make_model(cfg, w, prec, dropout=drop, **big).train()
+        m2.load_state_dict(ck["model"])
+        m2.load_optimizer_state_dict(ck["optimizer"])
+        l34 = [m2.train_step(*a, lr=1e-3, clip=1.0, seed=50 + s).item() for s in range(3, 5)]   # step continues from the checkpoint
+        worst = max(relerr(p.detach().cpu(), dict(ref.named_parameters())[k].detach().cpu()) for k, p in m2.named_parameters())
+        res["ref_losses"], res["resumed_losses"] = ref_losses, l12 + l34
+        res["worst_param_rel"] = worst
+        res["opt_step"] = m2._opt_step
+        res["ok"] = (m2._opt_step == 4 and worst < (2e-3 if prec == "bf16" else 1e-6) and
+                     all(abs(x - y) <= (2e-3 if prec == "bf16" else 1e-6) * abs(x) for x, y in zip(ref_losses, l12 + l34)))
+    elif case.startswith("varlen"):
+        # pad-to-longest batches change Le from step to step (Collator.py:12): every geometry goes through fresh tensor
+        # maps; the bounded tensor-map cache (gemm_tc.cu) must keep results independent of what was cached before
+        m = make_model(cfg, w, prec, **big).eval()
+        ok, outs = True, []
+        for Le in (64, 40, 57, 64, 33, 40):
+            b = po.synth_batch(ids.shape[0], Le, labels.shape[1], cfg.vocab_size, items, seed=100 + Le)
+            with torch.no_grad():
+                o = m(input_ids=b[0].to(dev), whole_word_ids=b[2].to(dev), attention_mask=b[1].to(dev), labels=b[3].to(dev))
+            with po.bf16_emulation(), torch.no_grad():
+                lt_o, lg_o = po.forward(w, cfg, b[0], b[2], b[1], b[3])
+            e = relerr(o["logits"].cpu(), lg_o)
+            outs.append((Le, round(e, 5)))
+            ok = ok and e < tol
+        res["per_length_logits_rel"] = outs
+        res["ok"] = ok
     elif case.startswith("gen"):
-        m = make_model(cfg, w, prec).eval()
-        K = 2 if "_k2" in case else (5 if "tiny" in case else 10)
+        m = make_model(cfg, w, prec, **big).eval()
+        full = "c5full" in case
+        K = 20 if full else (2 if "_k2" in case else (5 if "tiny" in case else 10))
+        max_len = 50 if full else 20
         trie_o = po.Trie(items)
         t0 = time.time()
-        s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, trie_o, K, K, 20)
-        res["oracle_s"] = time.time() - t0
+        with torch.no_grad():
+            if prec == "bf16":
+                with po.bf16_emulation():
+                    s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, trie_o, K, K, max_len, cached=True)
+            else:
+                s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, trie_o, K, K, max_len, cached=full)
+        res["oracle_s"] = round(time.time() - t0, 1)
         trie = m.build_trie(items)
         res["trie"] = trie.stats()
-        res["trie_get_ok"] = sorted(trie.get(items[0][:6])) == sorted(trie_o.get(items[0][:6]))
-        out = m.generate(input_ids=ids.to(dev), attention_mask=attn.to(dev), whole_word_ids=ww.to(dev), max_length=20,
+        res["trie_get_ok"] = sorted(trie.get(items[0][:4])) == sorted(trie_o.get(items[0][:4]))
+        out = m.generate(input_ids=ids.to(dev), attention_mask=attn.to(dev), whole_word_ids=ww.to(dev), max_length=max_len,
                          trie=trie, num_beams=K, num_return_sequences=K)
         s, sc = out["sequences"].cpu(), out["sequences_scores"].cpu()
         res["shape"] = [list(s.shape), list(s_o.shape)]
         same = s.shape == s_o.shape and bool((s == s_o).all())
         res["seq_equal"] = same
         res["score_err"] = (sc - sc_o).abs().max().item()
-        if not same and s.shape == s_o.shape:
+        B = ids.shape[0]
+        if s.shape == s_o.shape:
+            sv, ov = s.view(B, K, -1), s_o.view(B, K, -1)
             res["rows_equal_frac"] = (s == s_o).all(dim=1).float().mean().item()
-            res["top1_equal_frac"] = (s.view(ids.shape[0], K, -1)[:, 0] == s_o.view(ids.shape[0], K, -1)[:, 0]).all(dim=1).float().mean().item()
-        if prec == "fp32":
+            res["top1_equal_frac"] = (sv[:, 0] == ov[:, 0]).all(dim=1).float().mean().item()
+            # top-K SET overlap per user (order inside the top K may differ where two items score within bf16 noise)
+            ov_frac = []
+            for b in range(B):
+                a_set = {tuple(r.tolist()) for r in sv[b]}
+                o_set = {tuple(r.tolist()) for r in ov[b]}
+                ov_frac.append(len(a_set & o_set) / K)
+            res["topk_set_overlap_mean"] = sum(ov_frac) / B
+            res["topk_set_overlap_min"] = min(ov_frac)
+        if prec != "bf16":
             res["ok"] = same and res["score_err"] < 1e-4 and res["trie_get_ok"]
         else:
-            res["ok"] = s.shape == s_o.shape and res.get("top1_equal_frac", 1.0) >= 0.5 and res["score_err"] < 0.5
+            # identical up to near-ties: the engine and the emulating oracle differ by accumulation order only, so a rank can
+            # move only where two hypotheses score within ~1e-3; top-1 and the returned set must essentially agree
+            res["ok"] = (s.shape == s_o.shape and res["top1_equal_frac"] >= 0.9 and res["topk_set_overlap_mean"] >= 0.95 and
+                         res["score_err"] < 2e-2 and res["trie_get_ok"])
     elif case.startswith("resize_vocab"):
         # model.resize_token_embeddings(n) (ref main.py:193): old rows / all other tensors kept, logits of the old
         # vocabulary unchanged, the resized engine trains and generates

@@ -1,0 +1,129 @@
+"""-m gpu: BASELINE configs[0] through the real engine.  The batches in tests/golden/dropin_ml100k.npz were produced by the
+reference's UNMODIFIED host pipeline (tests/golden/make_dropin_fixture.py: MultiTaskDataset -> DistMultiDataTaskSampler ->
+Collator; TestDataset -> DistributedSampler -> Collator; the candidate item paths of DistributedRunner.py:344-351).  They are
+driven through openp5_b200.runner.B200Runner — train(), validate(), test_dataset_task() — on P5B200 (libp5b200.so) and the
+losses / metrics are compared with the CPU oracle running the same runner (tests/oracle_model.py).  The CPU half of the
+drop-in proof (the reference plumbing itself feeding the runner) is tests/test_dropin_cpu.py."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+
+class _Loader(list):
+    """a list of collator batches with the two attributes B200Runner reads from a DataLoader"""
+
+    def __init__(self, batches, dataset=None):
+        super().__init__(batches)
+        self.dataset = dataset
+
+
+def _batches(fx, name):
+    out = []
+    for i in range(fx[f"{name}_ids"].shape[0]):
+        Le = int(fx[f"{name}_Le"][i])
+        Ld = int(fx[f"{name}_Ld"][i]) if f"{name}_Ld" in fx else fx[f"{name}_labels"].shape[2]
+        t = lambda k, w: torch.from_numpy(fx[f"{name}_{k}"][i][:, :w].astype(np.int64))      # the collator yields int64 CPU tensors
+        out.append((t("ids", Le), t("attn", Le), t("ww", Le), t("labels", Ld), t("oattn", Ld)))
+    return out
+
+
+def _args(**kw):
+    a = dict(epochs=1, lr=1e-3, clip=1.0, warmup_prop=0.05, gradient_accumulation_steps=1, weight_decay=0.01, adam_eps=1e-6,
+             metrics="hit@5,hit@10,ndcg@5,ndcg@10", valid_select=1, test_epoch=0, test_before_train=0, train=1, model_path=None)
+    a.update(kw)
+    return argparse.Namespace(**a)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_b200runner_on_reference_batches(precision, built_lib):
+    from oracle import p5_oracle as po
+    from oracle_model import OracleModel
+    from openp5_b200.model import P5B200
+    from openp5_b200.runner import B200Runner
+    fx = dict(np.load(os.path.join(HERE, "golden", "dropin_ml100k.npz")))
+    cfg = po.t5_cfg("t5-small", vocab_size=32100)                     # configs[0]: T5-small, batch 4, seq_len <= 64
+    w = po.init_weights(cfg, seed=2023)
+    train, valid, test = _batches(fx, "train"), _batches(fx, "valid"), _batches(fx, "test")
+    paths = [fx["item_paths"][i, : fx["item_path_len"][i]].tolist() for i in range(fx["item_paths"].shape[0])]
+    ds = argparse.Namespace(dataset="ML100K", task="sequential", all_items=list(range(len(paths))))
+
+    def run(model):
+        r = B200Runner(model, None, _Loader(train), _Loader(valid), getattr(model, "device", "cpu"), _args())
+        losses = []
+        model.train()
+        for b in train:
+            losses.append(float(r.train_batch(b).reshape(-1)[0]))
+        v = r.validate()
+        metrics, n = r.test_dataset_task(_Loader(test, ds), paths=paths)
+        return losses, v, metrics, n
+
+    want = run(OracleModel(cfg, w))
+    m = P5B200("t5-small", vocab_size=32100, precision=precision, dropout=0.0, max_batch=4, max_enc_len=64, max_dec_len=16,
+               max_beams=10)
+    m.load_state_dict(w)
+    got = run(m)
+    tol = 2e-4 if precision == "fp32" else 3e-2
+    assert len(got[0]) == len(train) == 12
+    for a, b in zip(got[0], want[0]):
+        assert abs(a - b) <= tol * abs(b), (got[0], want[0])
+    assert abs(got[1] - want[1]) <= tol * abs(want[1])
+    assert got[3] == want[3] == 4 * len(test)
+    if precision == "fp32":
+        for k in want[2]:
+            assert abs(got[2][k] - want[2][k]) < 1e-9, (got[2], want[2])
+    else:
+        assert all(np.isfinite(v) for v in got[2].values())
+
+
+def test_generate_accepts_the_reference_callback(built_lib):
+    """the verbatim reference call: model.generate(..., prefix_allowed_tokens_fn=gt.prefix_allowed_tokens_fn(Trie))
+    (DistributedRunner.py:361-371).  The closure's Trie (a `trie_dict` of nested dicts, utils/generation_trie.py:7-97) is
+    recovered and flattened to the device CSR once; results equal the explicit `trie=` path."""
+    from oracle import p5_oracle as po
+    from openp5_b200.model import P5B200
+
+    class RefTrie:                      # the attribute layout of the reference class (utils/generation_trie.py:8-16)
+        def __init__(self, seqs):
+            self.trie_dict = {}
+            for s in seqs:
+                node = self.trie_dict
+                for t in s:
+                    node = node.setdefault(t, {})
+
+        def get(self, prefix):
+            node = self.trie_dict
+            for t in prefix:
+                if t not in node:
+                    return []
+                node = node[t]
+            return list(node.keys())
+
+    def prefix_allowed_tokens_fn(candidate_trie):          # utils/generation_trie.py:91-97 verbatim shape
+        def prefix_allowed_tokens(batch_id, sentence):
+            return candidate_trie.get(sentence.tolist())
+        return prefix_allowed_tokens
+
+    cfg = po.t5_cfg("t5-tiny", vocab_size=1200)
+    w = po.init_weights(cfg, seed=1)
+    items = po.synth_items(60, seed=3)
+    ids, attn, ww, _, _ = po.synth_batch(3, 21, 8, cfg.vocab_size, items, seed=5)
+    m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, precision="fp32", dropout=0.0, max_batch=4, max_enc_len=32,
+               max_dec_len=8, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=2, num_decoder_layers=2, num_heads=2).eval()
+    m.load_state_dict(w)
+    fn = prefix_allowed_tokens_fn(RefTrie(items))
+    kw = dict(input_ids=ids.cuda(), attention_mask=attn.cuda(), whole_word_ids=ww.cuda(), max_length=50, num_beams=5,
+              num_return_sequences=5, output_scores=True, return_dict_in_generate=True)
+    a = m.generate(prefix_allowed_tokens_fn=fn, **kw)
+    b = m.generate(trie=m.build_trie(items), **kw)
+    assert torch.equal(a["sequences"], b["sequences"]) and torch.equal(a["sequences_scores"], b["sequences_scores"])
+    assert getattr(fn, "_p5_device_trie", None) is not None          # flattened once, cached on the callable
+    s_o, sc_o = po.beam_search(w, cfg, ids, ww, attn, po.Trie(items), 5, 5, 50)
+    assert torch.equal(a["sequences"].cpu(), s_o)

@@ -158,3 +158,131 @@ def test_device_metrics_match_host_metrics(built_lib):
     out = m.eval_metric_sums(torch.tensor(seqs), torch.tensor(scores), torch.tensor(gold), K, [1, 5, 10, 20], out=out)
     got = (out / 2).tolist()                                    # accumulated twice
     assert np.allclose(got, want, rtol=1e-5, atol=1e-5), (got, want)
+
+
+def test_bf16x3_tensor_core_engine_matches_hf_golden(golden, built_lib):
+    """north star: "logits/loss within 1e-3 rel fp32 of the reference HF T5 on identical tokenized inputs" — on the
+    tcgen05 path: precision="bf16x3" runs every linear layer through the SAME gemm_tc_kernel the bf16 training path uses
+    (operands split into bf16 hi/lo pairs, three products accumulated in TMEM); gate 1e-3 on logits, loss, gradients,
+    three AdamW steps; beam sequences identical."""
+    m, cfg, w = _golden_model(golden, "bf16x3")
+    t = lambda k: torch.from_numpy(golden[k]).cuda()
+    m.eval()
+    m.zero_grad()
+    out = m(input_ids=t("ids"), whole_word_ids=t("ww"), attention_mask=t("attn"), labels=t("labels"))
+    ref = torch.from_numpy(golden["logits"])
+    assert (out["logits"].detach().cpu() - ref).abs().max() <= 1e-3 * ref.abs().max()
+    assert torch.allclose(out["loss"].detach().cpu(), torch.from_numpy(golden["loss_tok"]), rtol=1e-3, atol=1e-4)
+    B, Ld = golden["labels"].shape
+    lm = (t("oattn") != 0).float()
+    loss = ((out["loss"].view(B, Ld) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
+    assert abs(loss.item() - float(golden["loss"])) < 1e-3 * float(golden["loss"])
+    loss.backward()
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+    for k in golden:
+        if k.startswith("grad::"):
+            r = torch.from_numpy(golden[k])
+            assert (grads[k[6:]] - r).abs().max() <= 1e-3 * r.abs().max() + 1e-8, k
+    meta = golden["meta"]
+    trie = m.build_trie(golden["items"].tolist())
+    gen = m.generate(input_ids=t("ids"), attention_mask=t("attn"), whole_word_ids=t("ww"), max_length=meta["max_length"],
+                     trie=trie, num_beams=meta["K"], num_return_sequences=meta["K"])
+    assert np.array_equal(gen["sequences"].cpu().numpy(), golden["beam_sequences"])
+    assert np.allclose(gen["sequences_scores"].cpu().numpy(), golden["beam_scores"], atol=1e-3)
+    m2, _, _ = _golden_model(golden, "bf16x3")
+    for step in range(1, 4):
+        l = m2.train_step(t("ids"), t("ww"), t("attn"), t("labels"), t("oattn"), lr=1e-3, clip=1.0, step=step)
+        assert abs(l.item() - golden["adamw_losses"][step - 1]) < 1e-3
+    p = dict(m2.named_parameters())
+    for k in golden:
+        if k.startswith("adamw::"):
+            name = k[7:]
+            got = p["shared.weight"][:8] if name == "shared.weight[:8]" else p[name]
+            assert torch.allclose(got.detach().cpu(), torch.from_numpy(golden[k]), rtol=1e-3, atol=1e-5), k
+
+
+def test_device_filtered_metrics_match_host(built_lib):
+    """p5_eval_metrics_filtered vs the host restatement of ref utils/evaluate.py:6-35 (pinned on the reference's own
+    golden in tests/test_oracle_cpu.py): planted gold items, planted positives ABOVE the gold row, score ties"""
+    import random
+    from openp5_b200 import runner as R
+    from openp5_b200.model import P5B200
+    m = P5B200(backbone="custom", vocab_size=1200, precision="fp32", dropout=0.0, max_batch=4, max_enc_len=32, max_dec_len=8,
+               d_model=64, d_ff=128, num_layers=1, num_decoder_layers=1, num_heads=2)
+    rng = random.Random(11)
+    B, Rr, T, Tg, Pmax, Tp, kcut = 29, 14, 12, 8, 5, 7, 10
+    seqs, scores, gold, pos, npos = [], [], [], [], []
+    for b in range(B):
+        g = [rng.randrange(2, 1000) for _ in range(rng.randrange(2, 6))]
+        gold.append((g + [1] + [0] * Tg)[:Tg])
+        rows = [[rng.randrange(2, 1000) for _ in range(rng.randrange(1, 7))] for _ in range(Rr)]
+        hit_at = rng.choice([None, 0, 3, 8, 12])
+        if hit_at is not None:
+            rows[hit_at] = g
+        n = rng.randrange(0, Pmax + 1)
+        mine = [rows[i] for i in rng.sample([i for i in range(Rr) if i != hit_at], n)]   # positives that WERE generated
+        pos.append([(p + [1] + [0] * Tp)[:Tp] for p in mine] + [[0] * Tp] * (Pmax - n))
+        npos.append(n)
+        for i in range(Rr):
+            seqs.append(([0] + rows[i] + [1] + [0] * T)[:T])
+            scores.append(round(-0.5 * (i // 2), 3))
+    names = ["hit@1", "hit@5", "hit@10", "ndcg@1", "ndcg@5", "ndcg@10"]
+    want = R.metric_sums(R.rel_results_filtered(seqs, scores, gold, Rr, pos, npos, kcut), names)
+    out = m.eval_metric_sums_filtered(torch.tensor(seqs), torch.tensor(scores), torch.tensor(gold), Rr, [1, 5, 10],
+                                      torch.tensor(pos), torch.tensor(npos), kcut)
+    assert np.allclose(out.tolist(), want, rtol=1e-5, atol=1e-5), (out.tolist(), want)
+
+
+def _dp_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import ctypes as C
+    from oracle import p5_oracle as po
+    from openp5_b200 import _lib
+    from openp5_b200.model import P5B200
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = po.t5_cfg("t5-small", vocab_size=2100, num_layers=2, num_decoder_layers=2)
+    w = po.init_weights(cfg, seed=1)
+    items = po.synth_items(300, seed=3)
+    ids, attn, ww, labels, oattn = po.synth_batch(8, 64, 8, cfg.vocab_size, items, seed=5)
+    m = P5B200(backbone="custom", vocab_size=cfg.vocab_size, device=rank, precision="fp32", dropout=0.0, max_batch=8, max_enc_len=64,
+               max_dec_len=8, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=2, num_decoder_layers=2, num_heads=cfg.num_heads)
+    m.load_state_dict(w)
+    m.init_data_parallel()
+    sl = slice(rank * 4, rank * 4 + 4)          # rank r's shard (DistMultiDataTaskSampler: list[r::world] of a task-homogeneous stream)
+    i32 = lambda t: t[sl].cuda(rank).to(torch.int32).contiguous()
+    a = [i32(t) for t in (ids, attn, ww, labels, oattn)]
+    loss = torch.empty(1, device="cuda")
+    m.zero_grad()
+    _lib.check(m.lib.p5_train_fwd_bwd(m.handle, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(), a[4].data_ptr(),
+                                      4, 64, 8, loss.data_ptr(), C.c_uint64(1)))
+    m.allreduce_grads()                          # ncclAvg over the two ranks (overlapped ranges + the rest)
+    torch.cuda.synchronize()
+    l_o, _, _, g_o = po.loss_and_grads(w, cfg, ids, ww, attn, labels, oattn)      # the CONCATENATED batch of both ranks
+    worst = max(((p.grad.cpu() - g_o[k]).abs().max() / g_o[k].abs().max().clamp_min(1e-9)).item() for k, p in m.named_parameters())
+    q.put((rank, worst, loss.item(), l_o.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_gradient_matches_concatenated_oracle(built_lib):
+    """a13: the gradient every replica holds after the engine's NCCL mean all-reduce == the oracle gradient of the
+    concatenated global batch (the DDP semantics ref DistributedRunner.py:26 constructs and :63 bypasses)"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = [q.get(timeout=600) for _ in ps]
+    for p in ps:
+        p.join(timeout=120)
+    for rank, worst, loss, l_o in outs:
+        assert worst < 1e-3, outs       # fp32 engine: every gradient tensor within 1e-3 of the concatenated-batch oracle
+    # each rank's loss is its shard's runner loss; their mean is the concatenated-batch loss
+    assert abs(sum(o[2] for o in outs) / 2 - outs[0][3]) < 1e-4 * abs(outs[0][3])

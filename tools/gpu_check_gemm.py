@@ -31,6 +31,12 @@ CASES = [
     ("epi_resid_f32", 256, 512, 128, 0, 0, 1, 1, 0, 8),
     ("epi_accum_f32", 256, 512, 128, 0, 0, 1, 1, 0, 16),
     ("vocab_head", 512, 32100, 768, 0, 0, 1, 1, 0, 0),
+    # split-K weight gradients: EPI_ATOMIC (red.global.add.v2.f32 into ONE fp32 C from every split), both operands
+    # MN-major as linear_wgrad issues them — gemm_tc_kernel<256, EPI_ATOMIC|F32> is the most-launched kernel of a train step
+    ("epi_atomic_splitk_bn256", 2304, 768, 512, 1, 1, 8, 1, 256, 32),
+    ("epi_atomic_splitk_bn128", 768, 768, 256, 1, 1, 4, 1, 128, 32),
+    ("epi_atomic_splitk_bn64", 768, 64, 256, 1, 1, 4, 1, 64, 32),
+    ("epi_atomic_ragged", 200, 328, 136, 1, 1, 3, 2, 0, 32),
     ("kk_bn192", 512, 768, 256, 0, 0, 1, 1, 192, 0),
     ("kk_bn192_ragged", 200, 700, 136, 0, 0, 1, 1, 192, 0),
     ("mnAB_bn192", 256, 576, 192, 1, 1, 1, 1, 192, 0),
@@ -64,7 +70,7 @@ def run_case(name):
     ref = torch.matmul(A.float(), B.float().transpose(1, 2))  # [nb, M, N]
     A_st = A.transpose(1, 2).contiguous() if am else A.contiguous()
     B_st = B.transpose(1, 2).contiguous() if bm else B.contiguous()
-    c_f32 = bool(flags & (8 | 16)) or name == "vocab_head"
+    c_f32 = bool(flags & (8 | 16 | 32)) or name == "vocab_head"
     ldc = ((N + 63) // 64) * 64
     Cout = torch.zeros(nb, M, ldc, device=dev, dtype=torch.float32 if c_f32 else torch.bfloat16)
     aux = resid = None
@@ -83,12 +89,16 @@ def run_case(name):
         ref = ref + Cout[:, :, :N]
     if flags & 4:
         kw = dict(seed=1234, site=7, drop_p=0.25)
+    if flags & 32:
+        # every (b1, b2) batch accumulates into the SAME C (batch strides 0) on top of what is already there
+        Cout = torch.randn(1, M, ldc, device=dev, dtype=torch.float32)
+        ref = (Cout[:, :, :N] + ref.sum(dim=0, keepdim=True)).clone()
     a_rows = A_st.shape[1]
     b_rows = B_st.shape[1]
     common = dict(a_major=am, b_major=bm, M=M, N=N, K=K, nb1=nb1, nb2=nb2,
                   a_bs=(a_rows * A_st.shape[2], a_rows * A_st.shape[2] * nb1),
                   b_bs=(b_rows * B_st.shape[2], b_rows * B_st.shape[2] * nb1),
-                  c_bs=(M * ldc, M * ldc * nb1), lda=A_st.shape[2], ldb=B_st.shape[2], ldc=ldc,
+                  c_bs=(0, 0) if flags & 32 else (M * ldc, M * ldc * nb1), lda=A_st.shape[2], ldb=B_st.shape[2], ldc=ldc,
                   flags=flags, aux=aux, resid=resid, **kw)
     if flags & 4:
         # dropout: the SIMT backend uses the same counter RNG -> masks must agree exactly
@@ -108,7 +118,7 @@ def run_case(name):
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     tol = (2e-2 if not c_f32 else 2e-3) * scale + 1e-3
-    pad_clean = bool((Cout[:, :, N:] == 0).all()) if not (flags & 16) else True
+    pad_clean = bool((Cout[:, :, N:] == 0).all()) if not (flags & (16 | 32)) else True
     res = dict(name=name, ok=bool(err <= tol and pad_clean), max_err=err, ref_scale=scale, pad_clean=pad_clean)
     if not res["ok"]:
         bad = ((got - ref).abs() > tol).nonzero()
