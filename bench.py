@@ -20,9 +20,30 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(backbone="t5-base", vocab=32100, B=64, Le=256, Ld=8, n_items=3416)   # BASELINE.json configs[1]
+# BASELINE.json configs: [1] is the headline (the default `python bench.py`); [2] and [3] are 8-GPU jobs whose per-GPU share
+# is what one rank runs (--workload ...; the driver's scaling run multiplies by N); [4] is the eval leg of every run
+WORKLOADS = {
+    "ml1m_base": dict(backbone="t5-base", vocab=32100, B=64, Le=256, Ld=8, n_items=3416,
+                      name="T5-base train step, ML-1M-shaped synthetic sequences (BASELINE configs[1])"),
+    "beauty_collab": dict(backbone="t5-base", vocab=32600, B=32, Le=256, Ld=8, n_items=12101, collab=True,
+                          name="T5-base train step, Beauty-shaped, collaborative indexing (+500 <CI> tokens), global batch 256 on 8 GPUs "
+                               "= 32 per GPU (BASELINE configs[2])"),
+    "yelp_large": dict(backbone="t5-large", vocab=32100, B=64, Le=512, Ld=8, n_items=112394,
+                       name="T5-large train step, Yelp-shaped random indexing, global batch 512 on 8 GPUs = 64 per GPU, seq_len 512 "
+                            "(BASELINE configs[3])"),
+}
+WORKLOAD = WORKLOADS["ml1m_base"]
 EVAL = dict(B=20, K=20, max_length=50, Le=256)                                       # BASELINE.json configs[4]
-TRAIN_GFLOP_PER_SAMPLE = 165.6     # 3 x 55.2 GFLOP forward, T5-base Le=256 Ld=8
+DIMS = {"t5-base": dict(d=768, ff=3072, H=12, N=12), "t5-large": dict(d=1024, ff=4096, H=16, N=24)}
+
+
+def fwd_flops(backbone, Le, Ld, V):
+    """SURVEY.md §8d algorithmic forward FLOPs of ONE sample with Le encoder tokens (dense, norms / softmax / bias ignored)"""
+    q = DIMS[backbone]
+    d, ff, A, N = q["d"], q["ff"], q["H"] * 64, q["N"]
+    enc = N * (2 * Le * 4 * d * A + 2 * Le * 2 * d * ff + 4 * Le * Le * A)
+    dec = N * (2 * Ld * 4 * d * A + 2 * Ld * 2 * d * A + 2 * Le * 2 * d * A + 2 * Ld * 2 * d * ff + 4 * Ld * Ld * A + 4 * Ld * Le * A)
+    return enc + dec + 2 * Ld * d * V
 # AdamW of step t on a side stream under the forward of step t+1 (what B200Runner.train_batch does; P5_BENCH_SYNC_OPT=1
 # runs the optimiser in stream order instead).  Every step's update completes inside the timed region: the closing
 # torch.cuda.synchronize() waits for the side stream too.
@@ -58,7 +79,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        """keep the samples taken inside [t0, t1] (the timed region); when the region is shorter than nvidia-smi's sampling
+        period, the samples of the warm-up right before it (same load) stand in"""
+        inside = [x for x in self.lines if t0 <= x[0] <= t1]
+        self.lines = inside if len(inside) >= 2 else [x for x in self.lines if x[0] <= t1][-8:]
 
     def stop(self):
         if not self.proc:
@@ -70,7 +97,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for _, l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
                 continue
@@ -134,7 +161,7 @@ def best_threads():
     return best
 
 
-def cpu_reference_train(sample_B, steps, warmup, threads=None, budget_s=90.0):
+def cpu_reference_train(sample_B, steps, warmup, threads=None, budget_s=90.0, w=None):
     """HF T5-base (installed transformers) driven as P5_T5 drives it, fp32, runner loss, clip, HF-4.26 AdamW.
     Stops early (after >= 1 timed step) once `budget_s` seconds have been spent."""
     import torch
@@ -142,7 +169,7 @@ def cpu_reference_train(sample_B, steps, warmup, threads=None, budget_s=90.0):
     from openp5_b200.synth import synth_items
     torch.set_num_threads(threads or best_threads())
     t_start = time.perf_counter()
-    w = WORKLOAD
+    w = w or WORKLOAD
     cfg = po.t5_cfg(w["backbone"], vocab_size=w["vocab"])
     weights = po.init_weights(cfg, seed=2023)
     m, wwe = hf_pin.build_hf(cfg, weights)
@@ -150,7 +177,7 @@ def cpu_reference_train(sample_B, steps, warmup, threads=None, budget_s=90.0):
     params["encoder.whole_word_embeddings.weight"] = wwe.weight
     mom = {k: torch.zeros_like(p) for k, p in params.items()}
     var = {k: torch.zeros_like(p) for k, p in params.items()}
-    items = synth_items(w["n_items"], seed=2023)
+    items = synth_items(min(w["n_items"], 3416), seed=2023)
     batches = make_batches(2, sample_B, w["Le"], w["Ld"], w["vocab"], items, 100)
     times = []
     for s in range(warmup + steps):
@@ -161,7 +188,7 @@ def cpu_reference_train(sample_B, steps, warmup, threads=None, budget_s=90.0):
         po.clip_grad_norm(grads, 1.0)
         with torch.no_grad():
             for k, p in params.items():
-                po.adamw_hf426(p.data, grads[k], mom[k], var[k], s + 1, 1e-3, eps=1e-6, weight_decay=0.01)
+                po.adamw_hf426(p.data, grads[k], mom[k], var[k], s + 1, 1e-3, eps=1e-6, weight_decay=po.adamw_weight_decay_for(k, 0.01))
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -174,28 +201,96 @@ def cpu_reference_train(sample_B, steps, warmup, threads=None, budget_s=90.0):
                 cores=torch.get_num_threads())
 
 
+def cpu_reference_eval(users, K, batches, threads=None):
+    """the reference's eval path on the host: HF generate(num_beams=K, prefix_allowed_tokens_fn=Trie) with the encoder run
+    once with whole-word ids (ref DistributedRunner.py:344-371 through oracle/hf_pin.hf_generate), T5-base fp32, the
+    3416-item ML-1M-shaped trie.  A bounded sample: `users` users per batch."""
+    import torch
+    from oracle import p5_oracle as po, hf_pin   # CPU baseline leg
+    from openp5_b200.synth import synth_items
+    torch.set_num_threads(threads or best_threads())
+    w = WORKLOAD
+    cfg = po.t5_cfg(w["backbone"], vocab_size=w["vocab"])
+    m, wwe = hf_pin.build_hf(cfg, po.init_weights(cfg, seed=2023))
+    items = synth_items(w["n_items"], seed=2023)
+    trie = po.Trie(items)
+    bs = make_batches(batches, users, EVAL["Le"], w["Ld"], w["vocab"], items, 5000)
+    t0 = time.perf_counter()
+    for b in bs:
+        hf_pin.hf_generate(m, wwe, b[0], b[2], b[1], trie, K, K, EVAL["max_length"])
+    dt = time.perf_counter() - t0
+    return dict(items_per_s=users * K * batches / dt, users_per_s=users * batches / dt, s_per_batch=dt / batches, users=users,
+                batches=batches, cores=torch.get_num_threads())
+
+
+def gpu_reference_train(w, steps=3, warmup=2):
+    """SURVEY §8d "the number to beat": the reference's own stack — HuggingFace T5 + PyTorch eager (library kernels: cuBLAS /
+    ATen) — on THIS B200, same shapes, fp32 with TF32 matmuls and bf16 autocast.  Random-init HF model (no oracle involved),
+    whole-word embedding added through inputs_embeds as P5_T5 does, un-reduced CE + runner loss, clip, fused AdamW."""
+    import torch
+    from transformers import T5Config, T5ForConditionalGeneration
+    q = DIMS[w["backbone"]]
+    hc = T5Config(vocab_size=w["vocab"], d_model=q["d"], d_kv=64, d_ff=q["ff"], num_layers=q["N"], num_decoder_layers=q["N"],
+                  num_heads=q["H"], dropout_rate=0.1, feed_forward_proj="relu", tie_word_embeddings=True, pad_token_id=0,
+                  eos_token_id=1, decoder_start_token_id=0)
+    out = {}
+    from openp5_b200.synth import synth_items
+    items = synth_items(min(w["n_items"], 3416), seed=2023)
+    ids, attn, ww, labels, oattn = [t.cuda() for t in make_batches(1, w["B"], w["Le"], w["Ld"], w["vocab"], items, 1000)[0]]
+    for name in ("fp32_tf32", "bf16_autocast"):
+        torch.manual_seed(0)
+        m = T5ForConditionalGeneration(hc).cuda().train()
+        wwe = torch.nn.Embedding(512, q["d"]).cuda()
+        opt = torch.optim.AdamW(list(m.parameters()) + list(wwe.parameters()), lr=1e-3, eps=1e-6, weight_decay=0.01, fused=True)
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(name == "bf16_autocast")):
+                emb = m.shared(ids) + wwe(ww)
+                logits = m(inputs_embeds=emb, attention_mask=attn, labels=labels).logits
+            lt = torch.nn.functional.cross_entropy(logits.float().view(-1, logits.size(-1)), labels.view(-1), reduction="none")
+            lm = (oattn != 0).float()
+            loss = ((lt.view(labels.shape) * lm).sum(1) / lm.sum(1).clamp(min=1)).mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"samples_per_s": w["B"] / (ms / 1e3), "ms_per_step": ms}
+        del m, wwe, opt
+        torch.cuda.empty_cache()
+    out["what"] = ("HuggingFace transformers %s T5ForConditionalGeneration + torch %s eager on this GPU (library kernels), padded "
+                   "batch B=%d Le=%d Ld=%d, dropout 0.1, fused AdamW; %d timed steps" %
+                   (__import__("transformers").__version__, torch.__version__, w["B"], w["Le"], w["Ld"], steps))
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the bounded sample so that (steps + warmup) CPU steps end within a few minutes
-    probe = cpu_reference_train(1, 1, 0, budget_s=60.0)
-    budget = 150.0
-    per_sample = probe["s_per_step"]
-    B = 1
-    for cand in (2, 4, 8):
-        if cand * per_sample * (args.steps + args.warmup) <= budget:
-            B = cand
-    r = cpu_reference_train(B, args.steps, args.warmup, budget_s=180.0)
+    # a FIXED bounded sample (4 rows of the B=64 batch per step) on every box, so that the CPU number does not move with the
+    # host; the step count is what the time budget bounds
+    B = 4
+    w = WORKLOADS[args.workload]
+    r = cpu_reference_train(B, args.steps, args.warmup, budget_s=170.0, w=w)
     out = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": r["samples_per_s"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "T5-base train step, ML-1M-shaped synthetic sequences, Le=256 Ld=8 (BASELINE configs[1])",
-                   "sample": "B=%d rows of the B=64 batch per step" % B},
+        "config": {"workload": w["name"], "sample": "B=%d rows of the B=%d batch per step" % (B, w["B"])},
         "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                         "sample": "HF transformers T5-base fp32 + restated P5 glue (oracle/hf_pin.py), B=%d, %d timed steps"
-                                   % (B, r["steps"])},
+                         "sample": "HF transformers %s fp32 + restated P5 glue (oracle/hf_pin.py), B=%d, %d timed steps"
+                                   % (w["backbone"], B, r["steps"])},
         "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -220,14 +315,26 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOAD
+    w = WORKLOADS[args.workload]
+    headline = args.workload == "ml1m_base"
     B, Le, Ld = w["B"], w["Le"], w["Ld"]
     model = P5B200(w["backbone"], vocab_size=w["vocab"], device=local, precision="bf16", dropout=0.1, max_batch=B,
                    max_enc_len=Le, max_dec_len=Ld, max_beams=EVAL["K"])
     random_init_(model, seed=2023)
     if world > 1:
         model.init_data_parallel()
-    items = synth_items(w["n_items"], seed=2023)
+    if w.get("collab"):
+        # collaborative indexing: item ids are paths of <CIk> tokens appended to the vocabulary (ids >= 32100), depth 2-4
+        import random as _r
+        rng = _r.Random(2023)
+        seen, items = set(), []
+        while len(items) < w["n_items"]:
+            pth = tuple(rng.randrange(32100, w["vocab"]) for _ in range(rng.randrange(2, 5)))
+            if pth not in seen:
+                seen.add(pth)
+                items.append([0, 300, 301] + list(pth) + [1])
+    else:
+        items = synth_items(w["n_items"], seed=2023)
     nb = 4
     host = make_batches(nb, B, Le, Ld, w["vocab"], items, 1000 + 97 * rank)     # a different shard per rank
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
@@ -254,23 +361,29 @@ def run_b200(args):
                                 overlap_optimizer=OVERLAP_OPT)
         return loss.item()      # D2H read of the step's result (4 bytes), synchronises
 
-    # ---------------- device-resident timing
-    for s in range(args.warmup):
-        step_resident(s)
-    barrier()
+    # ---------------- device-resident timing (the clock sampler runs from before the warm-up: nvidia-smi needs ~1 s to start
+    # and the timed region of a short run is shorter than its sampling period)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for s in range(args.warmup):
+        step_resident(s)
+    barrier()
     l0 = _lib.load().p5_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
     e0.record()
     for s in range(args.steps):
         loss = step_resident(args.warmup + s)
     e1.record()
     barrier()
+    t_w1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.load().p5_launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = None
+    if rank == 0:
+        clocks.window(t_w0, t_w1)
+        clk = clocks.stop()
     final_loss = float(loss.item())
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -306,31 +419,67 @@ def run_b200(args):
     # ranks with no data-path collective (ref DistributedSampler in DistributedRunner.py:186): every rank ranks its own
     # users; the whole-job figure is N * users * K / max-over-ranks time.
     ev = EVAL
-    trie = model.build_trie(items)
-    eb = make_batches(2, ev["B"], ev["Le"], Ld, w["vocab"], items, 5000 + 13 * rank)
-    eres = [tuple(t.to(dev) for t in b) for b in eb]
-    model.eval()
-    gen = lambda b: model.generate(input_ids=b[0], attention_mask=b[1], whole_word_ids=b[2], max_length=ev["max_length"],
-                                   trie=trie, num_beams=ev["K"], num_return_sequences=ev["K"])
-    for i in range(2):
-        gen(eres[i % 2])
-    barrier()
-    n_ev = 6
-    e0.record()
-    for i in range(n_ev):
-        gen(eres[i % 2])
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / n_ev], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ev_ms = t.item()
-    model.train()
-    eval_result = {"metric": "eval_items_ranked_per_sec", "value": world * ev["B"] * ev["K"] / (ev_ms / 1e3), "unit": "items/s",
-                   "users_per_sec": world * ev["B"] / (ev_ms / 1e3), "ms_per_batch": ev_ms,
-                   "config": {"workload": "T5-base constrained beam search, ML-1M-shaped 3416-item trie", "users_per_gpu_batch": ev["B"],
-                              "num_beams": ev["K"], "max_length": ev["max_length"], "Le": ev["Le"], "n_gpus": world,
-                              "timed": "host-visible generate() calls incl. the output-length D2H sync per batch, max over ranks"}}
+    eval_result = None
+    if headline:
+        import ctypes as C
+        trie = model.build_trie(items)
+        eb = make_batches(2, ev["B"], ev["Le"], Ld, w["vocab"], items, 5000 + 13 * rank)
+        eres = [tuple(t.to(dev) for t in b) for b in eb]
+        epin = [tuple(t.pin_memory() for t in b) for b in eb]
+        model.eval()
+        gen = lambda b: model.generate(input_ids=b[0], attention_mask=b[1], whole_word_ids=b[2], max_length=ev["max_length"],
+                                       trie=trie, num_beams=ev["K"], num_return_sequences=ev["K"])
+        for i in range(3):
+            gen(eres[i % 2])
+        barrier()
+        n_ev = 8
+        e0.record()
+        for i in range(n_ev):
+            gen(eres[i % 2])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n_ev], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ev_ms = t.item()
+        # roofline of the dominant kernel of the leg: the persistent decode kernel (HBM-bound weight / KV streaming)
+        dms, dby, dst = C.c_float(), C.c_double(), C.c_int()
+        eval_roof = None
+        if _lib.load().p5_decode_last_launch(C.byref(dms), C.byref(dby), C.byref(dst)) == 0 and dms.value > 0:
+            pk_hbm = peaks()["hbm"]
+            gbs = dby.value / (dms.value * 1e-3) / 1e9
+            eval_roof = {"bound": "hbm", "kernel": "p5::decode_persistent_kernel (one cooperative launch per generate(): every decode "
+                                                   "position, grid barriers between phases)",
+                         "achieved": gbs, "peak": pk_hbm, "unit": "GB/s", "frac": gbs / pk_hbm, "traffic": None,
+                         "launch_ms": dms.value, "positions": dst.value, "algorithmic_bytes_per_launch": dby.value,
+                         "share_of_batch": dms.value / ev_ms,
+                         "peak_source": peaks()["source"] + " — of measured",
+                         "measured": "CUDA events on the launch stream around the persistent launch of the last timed batch; algorithmic "
+                                     "bytes = positions x (decoder-block weights used per position + tied LM head, bf16) + every "
+                                     "user's cross K|V once per position (DESIGN.md §3)"}
+        # end to end: pinned host inputs -> generate -> sequences and scores back on the host, every batch
+        barrier()
+        e0.record()
+        for i in range(n_ev):
+            o = gen(epin[i % 2])
+            o["sequences"].cpu(); o["sequences_scores"].cpu()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n_ev], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ev_e2e_ms = t.item()
+        model.train()
+        eval_result = {"metric": "eval_items_ranked_per_sec", "value": world * ev["B"] * ev["K"] / (ev_ms / 1e3), "unit": "items/s",
+                       "users_per_sec": world * ev["B"] / (ev_ms / 1e3), "ms_per_batch": ev_ms,
+                       "e2e": {"value": world * ev["B"] * ev["K"] / (ev_e2e_ms / 1e3), "unit": "items/s", "ms_per_batch": ev_e2e_ms,
+                               "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in epin[0][:3]),
+                               "d2h_bytes_per_step": ev["B"] * ev["K"] * (9 * 8 + 4)},
+                       "roofline": eval_roof,
+                       "config": {"workload": "T5-base constrained beam search, ML-1M-shaped 3416-item trie (BASELINE configs[4])",
+                                  "users_per_gpu_batch": ev["B"], "num_beams": ev["K"], "max_length": ev["max_length"], "Le": ev["Le"],
+                                  "n_gpus": world,
+                                  "timed": "host-visible generate() calls incl. the output-length D2H sync per batch, max over ranks"}}
 
     out = None
     if rank == 0:
@@ -381,26 +530,52 @@ def run_b200(args):
             "measured": "CUDA events on the launch stream around every GEMM launch over %d extra steps (algorithmic FLOPs "
                         "2*M*N*K of the rows actually computed; the event pairs serialise the launches, so PDL overlap is "
                         "off in this leg and the in-step rate is slightly higher)" % nprof,
-            "step_model_flops_frac": (TRAIN_GFLOP_PER_SAMPLE * 1e9 * B / (ms / args.steps / 1e3)) / (pk["tflops"] * 1e12),
         }
+        # whole-step model FLOPs: PADDED = every sequence charged Le tokens (what a padded implementation
+        # computes); VALID = the tokens that exist (the engine skips padding, so this is its algorithmic work and the
+        # honest utilisation figure)
+        step_s = ms / args.steps / 1e3
+        f_pad = 3.0 * fwd_flops(w["backbone"], Le, Ld, w["vocab"]) * B
+        f_valid = sum(3.0 * fwd_flops(w["backbone"], int(n), Ld, w["vocab"]) for lens in lengths for n in lens) / nb
+        roofline["step_model_flops"] = {
+            "padded_gflop_per_sample": f_pad / B / 1e9, "valid_gflop_per_sample": f_valid / B / 1e9,
+            "padded_frac_of_peak": f_pad / step_s / (pk["tflops"] * 1e12),
+            "valid_frac_of_peak": f_valid / step_s / (pk["tflops"] * 1e12),
+            "note": "valid_frac_of_peak is the utilisation figure; padded is reported for comparison with padded baselines"}
         eval_out = eval_result
+        # ---------------- the reference's own stack on THIS GPU (side number)
+        gpu_ref = None
+        if not args.no_gpu_reference and world == 1:
+            try:
+                gpu_ref = gpu_reference_train(w)
+            except Exception as ex:  # noqa
+                gpu_ref = {"failed": repr(ex)[:300]}
         # ---------------- CPU baseline on this box's host cores (bounded sample)
         cpu = None
         if not args.no_cpu_baseline:
+            if eval_out is not None:
+                try:
+                    r = cpu_reference_eval(4, ev["K"], 2)
+                    eval_out["cpu_baseline"] = {
+                        "value": r["items_per_s"], "unit": "items/s", "cores": r["cores"], "kind": "port",
+                        "sample": "HF transformers generate(num_beams=%d, prefix_allowed_tokens_fn=Trie) T5-base fp32 through "
+                                  "oracle/hf_pin.hf_generate, %d users per batch (of the 20-user batch), %d batches, %.1f s per batch"
+                                  % (ev["K"], r["users"], r["batches"], r["s_per_batch"])}
+                except Exception as ex:  # noqa
+                    eval_out["cpu_baseline"] = {"value": None, "unit": "items/s", "kind": "port", "sample": "failed: %r" % (ex,)}
             try:
-                r = cpu_reference_train(4, 2, 1, budget_s=60.0)
+                r = cpu_reference_train(4, 2, 1, budget_s=60.0, w=w)
                 cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                        "sample": "HF transformers T5-base fp32 (oracle/hf_pin.py: the reference's own HF+PyTorch stack with the "
-                                 "P5 glue restated), 4 rows of the B=64 batch, <=1 warm-up + %d timed train steps, %d of %d "
-                                 "usable cores (fastest setting)" % (r["steps"], r["cores"], effective_cores())}
+                                 "P5 glue restated), 4 rows of the B=%d batch, <=1 warm-up + %d timed train steps, %d of %d "
+                                 "usable cores (fastest setting)" % (B, r["steps"], r["cores"], effective_cores())}
             except Exception as ex:  # noqa
                 cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
         out = {
             "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "T5-base train step (fwd+loss+bwd+clip+AdamW%s), ML-1M-shaped synthetic sequences "
-                                   "(BASELINE configs[1])" % ("+NCCL grad all-reduce" if world > 1 else ""),
+            "config": {"workload": w["name"] + " — fwd+loss+bwd+clip+AdamW%s" % ("+NCCL grad all-reduce" if world > 1 else ""),
                        "backbone": w["backbone"], "global_batch": world * B, "per_gpu_batch": B, "seq_len": Le, "dec_len": Ld,
                        "vocab": w["vocab"], "dropout": 0.1, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (4 GB parameters+moments, >5 GB activations) >> 126 MB L2; no flush needed",
@@ -415,6 +590,7 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_reference": gpu_ref,
             "eval": eval_out,
             "final_loss": final_loss,
             "dp_replica_max_rel_diff": dp_diff,
@@ -432,6 +608,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--workload", default="ml1m_base", choices=sorted(WORKLOADS),
+                    help="ml1m_base = BASELINE configs[1] (default, with the configs[4] eval leg); beauty_collab = configs[2]; "
+                         "yelp_large = configs[3] (per-GPU share of the 8-GPU jobs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -162,6 +162,20 @@ int p5_generate(p5_handle h, const int32_t* input_ids, const int32_t* attention_
                 int B, int Le, p5_trie trie, int num_beams, int num_return, int max_len, float length_penalty,
                 int32_t* seqs, float* scores, int* out_len_host);
 
+/* Device time (CUDA events on the launch stream), algorithmic bytes (per position: the decoder-block weights and the tied
+ * LM head once, every user's cross K|V once, all bf16) and number of positions of the LAST persistent decode launch of
+ * p5_generate (bench.py eval roofline).  Synchronises on that launch. */
+int p5_decode_last_launch(float* ms_host, double* bytes_host, int* steps_host);
+
+/* ---- collaborative item indexing: the quadratic part ------------------------------------ */
+/* replaces: the co-occurrence matrix loop of utils/indexing.py:163-180 (generate_collaborative_id): items [sum len] are
+ * the training-prefix item ids (0 .. n_items-1) of every user back to back, offsets [n_users+1]; adj [n_items, n_items]
+ * (fp32 when f64 == 0, else fp64; cleared by the call) receives adj[a][b] += 1, adj[b][a] += 1 for every pair of
+ * positions i < j of a user.  All pointers are device pointers. */
+int p5_cooccurrence(const int32_t* items, const int64_t* offsets, int n_users, int n_items, int f64, void* adj, void* cuda_stream);
+/* replaces: the sub-matrix loop of utils/indexing.py:220-231: out[i][j] = adj[idx[i]][idx[j]] (i != j), 0 on the diagonal */
+int p5_submatrix(const void* adj, int n_items, int f64, const int32_t* idx, int m, void* out, void* cuda_stream);
+
 /* ---- op-level hooks (unit tests / micro-benchmarks of individual kernels) ------------------------------ */
 typedef struct {
     int32_t backend;            /* 0 = SIMT fp32-accumulate kernel, 1 = tcgen05 kernel, 2 = auto */

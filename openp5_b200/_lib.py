@@ -51,6 +51,7 @@ DECLARED_SYMBOLS = [
     "p5_zero_grad", "p5_adamw_step", "p5_adamw_step_zero_grad", "p5_adamw_step_zero_grad_async", "p5_optimizer_join", "p5_eval_metrics", "p5_comm_unique_id", "p5_comm_init", "p5_allreduce_grads",
     "p5_trie_build", "p5_trie_free", "p5_trie_stats", "p5_trie_get", "p5_generate", "p5_op_gemm",
     "p5_launch_count", "p5_prof_enable", "p5_prof_summary", "p5_eval_metrics_filtered", "p5_opt_state_info",
+    "p5_decode_last_launch", "p5_cooccurrence", "p5_submatrix",
 ]
 
 _lib = None
@@ -91,6 +92,9 @@ def load():
     sig("p5_eval_metrics_filtered", vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int,
         C.c_int, vp)
     sig("p5_opt_state_info", vp, C.c_int, C.POINTER(vp), C.POINTER(vp))
+    sig("p5_decode_last_launch", C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int))
+    sig("p5_cooccurrence", vp, vp, C.c_int, C.c_int, C.c_int, vp, vp)
+    sig("p5_submatrix", vp, C.c_int, C.c_int, vp, C.c_int, vp, vp)
     sig("p5_zero_grad", vp)
     sig("p5_adamw_step", vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float)
     sig("p5_adamw_step_zero_grad", vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float)

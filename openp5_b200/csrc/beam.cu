@@ -154,6 +154,12 @@ struct GenWs {
     float* scr_score = nullptr; int* scr_flat = nullptr; int scr_cap = 0;
     std::vector<void*> allocs;
 };
+// decode_persist.cu: the whole search as one persistent cooperative kernel (bf16 mode)
+bool decode_persistent_supported(const Engine* e, int B, int K, int max_len, int Le);
+const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, const int* t_node, int root_child, int max_depth,
+                               int max_fanout, int B, int K, int Rret, int max_len, float length_penalty, int32_t* seqs, float* scores);
+void free_persist_ws();
+
 void free_gen_ws(GenWs* g) {
     for (void* p : g->allocs) cudaFree(p);
     delete g;
@@ -677,7 +683,8 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
         if (trie->h_tok[k] == 0) root_child = trie->h_node[k];
     P5_CHECK(root_child >= 0, "trie paths must start with the decoder start token 0");
     const int cand_cap = K * (trie->max_fanout > 0 ? trie->max_fanout : 1);
-    GenWs* g = get_gen_ws(e, R, T, K, B, cand_cap, (int)round_up(Le_user, 8));
+    const bool persist = decode_persistent_supported(e, B, K, max_len, (int)round_up(Le_user, 8));
+    GenWs* g = persist ? nullptr : get_gen_ws(e, R, T, K, B, cand_cap, (int)round_up(Le_user, 8));
 
     // ---- encoder once per user (eval mode) + cross K/V once per user
     e->set_geometry(B, Le_user, 1);
@@ -697,6 +704,16 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
     }
     e->build_bias(false, T);   // decoder relative bias for positions 0..T-1: [H, 2T-1], offset T-1
     const int n_delta = 2 * T - 1, bias_off = T - 1;
+    if (persist) {
+        // ONE cooperative launch runs every decode position (decode_persist.cu)
+        const int* out_len_dev = generate_persistent(e, trie->d_off, trie->d_tok, trie->d_node, root_child, trie->max_depth,
+                                                     trie->max_fanout, B, K, Rret, max_len, length_penalty, seqs, scores);
+        if (out_len_host) {
+            P5_CUDA(cudaMemcpyAsync(out_len_host, out_len_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+            P5_CUDA(cudaStreamSynchronize(st));
+        }
+        return;
+    }
 
     launch_k(gen_init_kernel, (unsigned)cdiv(R, 128), 128, 0, st, g->seq[0], g->fin_seq[0], g->src[0], g->node[0], g->run_score[0],
                                                            g->fin_score[0], g->is_fin[0], g->gen_len[0], g->cur_tok, g->unsat,

@@ -38,6 +38,9 @@ void trie_stats(Trie* t, int* n_nodes, int* n_edges, int* max_depth);
 int trie_get(Trie* t, const int32_t* prefix, int prefix_len, int32_t* out, int cap);
 void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t* ww, int B, int Le, Trie* trie,
               int K, int R, int max_len, float length_penalty, int32_t* seqs, float* scores, int* out_len);
+int decode_last_launch(float* ms, double* bytes, int* steps);   // decode_persist.cu
+void cooccurrence(const int* items, const long long* offs, int n_users, int n_items, int f64, void* adj, cudaStream_t st);   // indexing.cu
+void submatrix(const void* adj, int n_items, int f64, const int* idx, int m, void* out, cudaStream_t st);
 // comm.cu
 void comm_unique_id(void* id128);
 void comm_init(Engine* e, const void* id128, int rank, int world);
@@ -286,6 +289,25 @@ int p5_prof_summary(char* json_out, int cap) {
     P5_CHECK(json_out && cap > 0, "null buffer");
     const std::string s = gemm_tc_prof_summary();
     snprintf(json_out, (size_t)cap, "%s", s.c_str());
+    P5_API_END
+}
+
+int p5_decode_last_launch(float* ms_host, double* bytes_host, int* steps_host) {
+    P5_API_BEGIN
+    P5_CHECK(decode_last_launch(ms_host, bytes_host, steps_host) == 0, "no persistent decode launch has been timed yet");
+    P5_API_END
+}
+
+int p5_cooccurrence(const int32_t* items, const int64_t* offsets, int n_users, int n_items, int f64, void* adj, void* cuda_stream) {
+    P5_API_BEGIN
+    P5_CHECK(items && offsets && adj, "null argument");
+    cooccurrence(items, (const long long*)offsets, n_users, n_items, f64, adj, (cudaStream_t)cuda_stream);
+    P5_API_END
+}
+int p5_submatrix(const void* adj, int n_items, int f64, const int32_t* idx, int m, void* out, void* cuda_stream) {
+    P5_API_BEGIN
+    P5_CHECK(adj && idx && out, "null argument");
+    submatrix(adj, n_items, f64, idx, m, out, (cudaStream_t)cuda_stream);
     P5_API_END
 }
 

@@ -78,6 +78,20 @@ void comm_init(Engine* e, const void* id128, int rank, int world) {
     CommState* c = new CommState();
     nccl_uid_t id;
     memcpy(&id, id128, 128);
+    // The all-reduce runs UNDER the backward's persistent tcgen05 kernels: give it a fixed, small number of CTAs and
+    // take exactly those SMs out of the persistent grids (common.cuh sm_budget), instead of letting NCCL's default
+    // (up to 32 CTAs) evict GEMM CTAs at random.  P5_COMM_CTAS overrides; an NCCL_MAX_CTAS set by the user wins.
+    int ctas = 8;
+    if (const char* ev = getenv("P5_COMM_CTAS")) ctas = atoi(ev);
+    if (ctas > 0 && world > 1) {
+        char b[16];
+        snprintf(b, sizeof(b), "%d", ctas);
+        setenv("NCCL_MAX_CTAS", b, 0);
+        setenv("NCCL_MIN_CTAS", b, 0);
+        int reserve = ctas;
+        if (const char* ev = getenv("P5_GEMM_RESERVE")) reserve = atoi(ev);
+        sm_reserve(reserve);
+    }
     nccl_check(N.init_rank(&c->comm, world, id, rank), "ncclCommInitRank");
     P5_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     P5_CUDA(cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));

@@ -241,6 +241,14 @@ __device__ __forceinline__ float epilogue_apply(const GemmEpilogue& e, float acc
     return v;
 }
 
+// SMs the persistent kernels (tcgen05 GEMM, fused attention, RMSNorm backward) size their grids to.  During a
+// data-parallel backward the NCCL all-reduce kernels (P5_COMM_CTAS CTAs, comm.cu) run concurrently on a side stream; a
+// persistent grid of one 200 KB-smem CTA per SM cannot share an SM with them, and with a static tile stride the CTAs that
+// find their SM occupied make the whole GEMM wait.  While a communicator is active the persistent grids therefore leave
+// that many SMs to NCCL.  (gemm_tc.cu)
+int sm_budget();
+void sm_reserve(int n_sms);
+
 // launchers (throw P5Error)
 void gemm_simt(const GemmProblem& p, cudaStream_t stream);
 bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major);

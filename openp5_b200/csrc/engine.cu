@@ -186,6 +186,7 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
 }
 
 void free_gen_ws(struct GenWs* g);
+void free_persist_ws();
 
 Engine::~Engine() {
     cudaSetDevice(device);
@@ -195,6 +196,8 @@ Engine::~Engine() {
     if (ev_opt_start) cudaEventDestroy(ev_opt_start);
     if (st_opt) cudaStreamDestroy(st_opt);
     if (gen) free_gen_ws(gen);
+    free_persist_ws();
+    gemm_x3_release();
     for (void* p : allocs) cudaFree(p);
     gemm_tc_clear_cache();
 }

@@ -474,7 +474,8 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     CUtensorMap tmK = tmap_bf16_4d(base + A, dims, strides, box);
     CUtensorMap tmV = tmap_bf16_4d(base + 2 * A, dims, strides, box);
     const int n_pairs = B * H;
-    const int grid = n_pairs < num_sms ? n_pairs : num_sms;
+    const int budget = sm_budget() < num_sms ? sm_budget() : num_sms;     // leaves SMs to a concurrent NCCL all-reduce (common.cuh)
+    const int grid = n_pairs < budget ? n_pairs : budget;
     launch_k(fattn_fwd_kernel, grid, FA_THREADS, smem, st, tmQ, tmK, tmV, P);
     P5_CUDA(cudaGetLastError());
     ++g_launches;

@@ -508,7 +508,8 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     CUtensorMap tmV = tmap_bf16_4d(base + 2 * A, dims, strides, box);
     CUtensorMap tmdO = tmap_bf16_4d((const bf16*)dctx, dims, strides_g, box);
     const int n_pairs = B * H;
-    const int grid = n_pairs < num_sms ? n_pairs : num_sms;
+    const int budget = sm_budget() < num_sms ? sm_budget() : num_sms;     // leaves SMs to a concurrent NCCL all-reduce (common.cuh)
+    const int grid = n_pairs < budget ? n_pairs : budget;
     launch_k(fattn_bwd_kernel, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
     P5_CUDA(cudaGetLastError());
     ++g_launches;

@@ -630,7 +630,20 @@ bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major) {
 }
 
 static int g_num_sms = 0;
+static int g_sm_reserved = 0;
 static int g_force_block_n = 0;  // test hook
+
+void sm_reserve(int n_sms) { g_sm_reserved = n_sms < 0 ? 0 : n_sms; g_num_sms = 0; }
+int sm_budget() {
+    static int total = 0;
+    if (!total) {
+        int dev = 0;
+        P5_CUDA(cudaGetDevice(&dev));
+        P5_CUDA(cudaDeviceGetAttribute(&total, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int n = total - g_sm_reserved;
+    return n < 8 ? 8 : n;
+}
 
 // ---- optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream around every
 //      tcgen05 GEMM launch, with the algorithmic FLOPs of the problem
@@ -718,7 +731,9 @@ static void launch_tc_pair(const GemmProblem& p, cudaStream_t stream) {
     P.M = p.M; P.N = p.N; P.K = p.K; P.nb1 = p.nb1; P.nb2 = p.nb2;
     P.a_major = p.A.major; P.b_major = p.B.major;
     P.epi = p.epi;
-    P.dbg = 0;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("P5_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    P.dbg = dbg;
     P.late_wait = (p.indep_of_prev && pdl_enabled()) ? 1 : 0;
     P.a_m1 = p.A.bcast1 ? 0 : 1; P.a_m2 = p.A.bcast2 ? 0 : 1; P.b_m1 = p.B.bcast1 ? 0 : 1; P.b_m2 = p.B.bcast2 ? 0 : 1;
     const long long units = (long long)cdiv(p.M, 2 * BLOCK_M) * cdiv(p.N, BN) * p.nb1 * p.nb2;
@@ -765,11 +780,7 @@ static void launch_bn(int bn, const GemmProblem& p, cudaStream_t stream) {
 
 void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     P5_CHECK(gemm_tc_supported(p, true), "gemm_tc: unsupported problem");
-    if (!g_num_sms) {
-        int dev = 0;
-        P5_CUDA(cudaGetDevice(&dev));
-        P5_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    if (!g_num_sms) g_num_sms = sm_budget();
     int bn = g_force_block_n ? g_force_block_n : p.prefer_bn;
     if (!bn) {
         const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;

@@ -198,13 +198,22 @@ class B200Runner:
         self.start_epoch = int(ck["epoch"])
 
     # ------------------------------------------------------------------ training
+    def _staged(self, loader):
+        """tokenisation + collation (the reference's Collator, unchanged) run on a background thread, batches
+        arrive through pinned double buffers and one H2D copy each (openp5_b200/pipeline.py); args.stage_batches=0 keeps the
+        reference's inline loop"""
+        if getattr(self.args, "stage_batches", 1) and torch.cuda.is_available() and str(self.device).startswith("cuda"):
+            from .pipeline import BatchStager
+            return BatchStager(loader, self.device)
+        return loader
+
     def train_batch(self, batch):
         """one optimisation step on a collator batch (input_ids, attention, whole_word_ids, output_ids, output_attention):
         ref DistributedRunner.py:56-87"""
         a = self.args
         loss = self.model.train_step(batch[0], batch[2], batch[1], batch[3], batch[4], lr=self._lr(),
                                      clip=getattr(a, "clip", 1.0), eps=getattr(a, "adam_eps", 1e-6),
-                                     weight_decay=getattr(a, "weight_decay", 0.01),
+                                     weight_decay=getattr(a, "weight_decay", 0.01), enc_lengths=getattr(batch, "enc_lengths", None),
                                      overlap_optimizer=True)   # the loop never reads parameters between steps
         self.global_step += 1
         return loss
@@ -244,7 +253,7 @@ class B200Runner:
                 self.train_loader.sampler.set_epoch(epoch)
             self.model.train()
             losses = []
-            for batch in self.train_loader:
+            for batch in self._staged(self.train_loader):
                 losses.append(self.train_batch(batch))
             ep = torch.stack([l.reshape(()) for l in losses]).mean() if losses else torch.zeros((), device=self.device)
             if ddp:

@@ -665,3 +665,116 @@ def calculate_whole_word_ids(tokens: Sequence[str]) -> List[int]:
 # engine dependency) so that bench.py, the tests and this oracle all see identical token ids
 # ----------------------------------------------------------------------------------------------------
 from openp5_b200.synth import DIGIT_BASE, ITEM_PREFIX, synth_items, synth_batch  # noqa: E402,F401
+
+
+# ----------------------------------------------------------------------------------------------------
+# collaborative indexing (ref:src/src_t5/utils/indexing.py:149-282) — restated with the reference's own numpy / Python
+# loops; pinned against the reference function itself in tests/test_dropin_cpu.py (same process, SpectralClustering
+# recorded), and used on the GPU box as the checker of csrc/indexing.cu + openp5_b200/indexing.py
+# ----------------------------------------------------------------------------------------------------
+class collab_helpers:
+    """utils/indexing.py:258-282 (token bookkeeping), verbatim semantics"""
+
+    @staticmethod
+    def add_token_to_indexing(item_map, grouping, index_now, token_size):
+        for group in grouping:
+            index_now = index_now % token_size
+            for (item, idx) in grouping[group]:
+                if item not in item_map:
+                    item_map[item] = ''
+                item_map[item] += f'<CI{index_now}>'
+            index_now += 1
+        return item_map, index_now
+
+    @staticmethod
+    def add_last_token_to_indexing_sequential(item_map, item_list, token_size):
+        for i in range(len(item_list)):
+            item = item_list[i]
+            if item not in item_map:
+                item_map[item] = ''
+            item_map[item] += f'<CI{i}>'
+        return item_map
+
+    @staticmethod
+    def add_last_token_to_indexing_random(item_map, item_list, token_size):
+        import random
+        last_tokens = random.sample([i for i in range(token_size)], len(item_list))
+        for i in range(len(item_list)):
+            item = item_list[i]
+            if item not in item_map:
+                item_map[item] = ''
+            item_map[item] += f'<CI{last_tokens[i]}>'
+        return item_map
+
+
+def collab_item_ids(user_sequence_dict):
+    """utils/indexing.py:153-165: (all_items, train_items, item2id, id2item) — ids follow the iteration order of the set"""
+    all_items, train_items = set(), set()
+    for user in user_sequence_dict:
+        all_items.update(set(user_sequence_dict[user]))
+        train_items.update(set(user_sequence_dict[user][:-2]))
+    item2id, id2item = dict(), dict()
+    for item in train_items:
+        item2id[item] = len(item2id)
+        id2item[len(id2item)] = item
+    return all_items, train_items, item2id, id2item
+
+
+def cooccurrence_matrix_ref(user_sequence_dict, item2id, float32=0):
+    """utils/indexing.py:168-180"""
+    import numpy as np
+    from itertools import combinations
+    adj = np.zeros((len(item2id), len(item2id)), dtype=np.float32 if float32 > 0 else np.float64)
+    for user in user_sequence_dict:
+        for a, b in combinations(user_sequence_dict[user][:-2], 2):
+            adj[item2id[a]][item2id[b]] += 1
+            adj[item2id[b]][item2id[a]] += 1
+    return adj
+
+
+def submatrix_ref(adj, idx):
+    """utils/indexing.py:220-231"""
+    import numpy as np
+    m = len(idx)
+    sub = np.zeros((m, m), dtype=adj.dtype)
+    for i in range(m):
+        for j in range(i + 1, m):
+            sub[i][j] = adj[idx[i]][idx[j]]
+            sub[j][i] = adj[idx[j]][idx[i]]
+    return sub
+
+
+def generate_collaborative_id_ref(user_sequence_dict, token_size, cluster_num, last_token, float32):
+    """utils/indexing.py:149-256 restated"""
+    from collections import defaultdict
+    from sklearn.cluster import SpectralClustering
+    H = collab_helpers
+    all_items, train_items, item2id, id2item = collab_item_ids(user_sequence_dict)
+    adj = cooccurrence_matrix_ref(user_sequence_dict, item2id, float32)
+    sc = lambda m: SpectralClustering(n_clusters=cluster_num, assign_labels="cluster_qr", random_state=0,
+                                      affinity="precomputed").fit(m).labels_.tolist()
+    labels = sc(adj)
+    grouping = defaultdict(list)
+    for i in range(len(labels)):
+        grouping[labels[i]].append((id2item[i], i))
+    item_map, index_now = H.add_token_to_indexing(dict(), grouping, 0, token_size)
+    queue = [grouping[g] for g in grouping]
+    while queue:
+        group_items = queue.pop(0)
+        if len(group_items) <= token_size:
+            item_list = [it[0] for it in group_items]
+            item_map = (H.add_last_token_to_indexing_sequential if last_token == 'sequential' else
+                        H.add_last_token_to_indexing_random)(item_map, item_list, token_size)
+        else:
+            labels = sc(submatrix_ref(adj, [it[1] for it in group_items]))
+            grouping = defaultdict(list)
+            for i in range(len(labels)):
+                grouping[labels[i]].append(group_items[i])
+            item_map, index_now = H.add_token_to_indexing(item_map, grouping, index_now, token_size)
+            for g in grouping:
+                queue.append(grouping[g])
+    remaining = list(all_items - train_items)
+    if remaining:
+        item_map = (H.add_last_token_to_indexing_sequential if last_token == 'sequential' else
+                    H.add_last_token_to_indexing_random)(item_map, remaining, token_size)
+    return item_map

@@ -158,3 +158,41 @@ def test_resume_continues_where_the_checkpoint_stopped(pipeline):
     rb.train()
     for k in m_full.w:
         assert torch.allclose(m_b.w[k], m_full.w[k], rtol=1e-5, atol=1e-7), k
+
+
+def test_collaborative_indexing_restatement_equals_reference(pipeline):
+    """oracle.generate_collaborative_id_ref == the reference's utils/indexing.generate_collaborative_id (same process, so
+    the set iteration order that defines item ids is the same), and the co-occurrence matrix the reference hands to
+    SpectralClustering == oracle.cooccurrence_matrix_ref — the matrices csrc/indexing.cu builds on the GPU are checked
+    against that restatement in tests/test_model_gpu.py."""
+    import random
+    from oracle import p5_oracle as po
+    idx = pipeline["ref"].indexing
+    rng = random.Random(5)
+    seqs = {str(u): [str(1000 + i) for i in rng.sample(range(120), rng.randrange(6, 14))] for u in range(1, 80)}
+    want = idx.generate_collaborative_id(seqs, 20, 4, "sequential", 0)
+    got = po.generate_collaborative_id_ref(seqs, 20, 4, "sequential", 0)
+    assert got == want
+    recorded = []
+
+    class Recorder:
+        def __init__(self, **kw):
+            self.kw = kw
+
+        def fit(self, m):
+            recorded.append(np.array(m))
+            self.labels_ = np.arange(m.shape[0]) % self.kw["n_clusters"]
+            return self
+    orig = idx.SpectralClustering
+    idx.SpectralClustering = Recorder
+    try:
+        idx.generate_collaborative_id(seqs, 20, 4, "sequential", 1)
+    finally:
+        idx.SpectralClustering = orig
+    _, _, item2id, _ = po.collab_item_ids(seqs)
+    adj = po.cooccurrence_matrix_ref(seqs, item2id, 1)
+    assert recorded[0].dtype == np.float32 and np.array_equal(recorded[0], adj)
+    # the first BFS sub-matrix the reference built == the restated extraction for the same group
+    labels = (np.arange(adj.shape[0]) % 4).tolist()
+    group0 = [i for i in range(len(labels)) if labels[i] == 0]
+    assert np.array_equal(recorded[1], po.submatrix_ref(adj, group0))

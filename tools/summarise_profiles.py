@@ -17,7 +17,8 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-           "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+           "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(path, dst, title):
@@ -92,7 +93,8 @@ def main():
         if os.path.exists(src):
             shutil.copy(src, os.path.join(PROF, os.path.basename(src)))
             launches(src, os.path.join(PROF, "%s_%s_kernel_shares.txt" % (tag, kind)), title)
-    for name in ("gemm", "fattn_fwd", "fattn_bwd", "dattn_bwd", "rmsnorm_bwd", "adamw"):
+    for name in ("gemm", "fattn_fwd", "fattn_bwd", "dattn_fwd", "dattn_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "adamw", "ce_fwd", "ce_bwd",
+                 "embed_fwd", "embed_bwd", "sumsq", "decode_persistent", "gemm_qkv", "gemm_wgrad"):
         rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, name))
         if os.path.exists(rep):
             ncu_summary(rep, os.path.join(PROF, "%s_%s_ncu_full_summary.txt" % (tag, name)))
