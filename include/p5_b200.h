@@ -166,6 +166,10 @@ int p5_generate(p5_handle h, const int32_t* input_ids, const int32_t* attention_
  * LM head once, every user's cross K|V once, all bf16) and number of positions of the LAST persistent decode launch of
  * p5_generate (bench.py eval roofline).  Synchronises on that launch. */
 int p5_decode_last_launch(float* ms_host, double* bytes_host, int* steps_host);
+/* per-phase nanoseconds of that launch as CTA 0 saw them (each phase incl. its grid barrier): out32_host[0..15] = positions
+ * run by the weight-streaming GEMM variant (<= 32 live rows), [16..31] = the others; index: 0 qkv, 1 self-attention, 2 o,
+ * 3 cross-q, 4 cross-attention, 5 cross-o, 6 wi, 7 wo, 8 LM head, 9 per-user beam phase, 10 live-list build */
+int p5_decode_phase_ns(uint64_t* out32_host);
 
 /* ---- collaborative item indexing: the quadratic part ------------------------------------ */
 /* replaces: the co-occurrence matrix loop of utils/indexing.py:163-180 (generate_collaborative_id): items [sum len] are
@@ -195,6 +199,8 @@ int p5_launch_count(void);   /* kernels launched by this library since load */
  * {"bn256": {"launches", "ms", "flops"}, "bn128": ..., "bn64": ...} (algorithmic FLOPs = 2*M*N*K per launch) */
 int p5_prof_enable(int on);
 int p5_prof_summary(char* json_out, int cap);
+/* the same profiled launches as a per-shape text table (M N K batches epilogue-flags majors tile : launches, us, TFLOP/s) */
+int p5_prof_shapes(char* text_out, int cap);
 
 #ifdef __cplusplus
 }

@@ -50,8 +50,8 @@ DECLARED_SYMBOLS = [
     "p5_params_changed", "p5_resize_vocab", "p5_forward", "p5_set_enc_lengths", "p5_backward", "p5_train_fwd_bwd", "p5_grad_norm", "p5_grad_scale",
     "p5_zero_grad", "p5_adamw_step", "p5_adamw_step_zero_grad", "p5_adamw_step_zero_grad_async", "p5_optimizer_join", "p5_eval_metrics", "p5_comm_unique_id", "p5_comm_init", "p5_allreduce_grads",
     "p5_trie_build", "p5_trie_free", "p5_trie_stats", "p5_trie_get", "p5_generate", "p5_op_gemm",
-    "p5_launch_count", "p5_prof_enable", "p5_prof_summary", "p5_eval_metrics_filtered", "p5_opt_state_info",
-    "p5_decode_last_launch", "p5_cooccurrence", "p5_submatrix",
+    "p5_launch_count", "p5_prof_enable", "p5_prof_summary", "p5_prof_shapes", "p5_eval_metrics_filtered", "p5_opt_state_info",
+    "p5_decode_last_launch", "p5_decode_phase_ns", "p5_cooccurrence", "p5_submatrix",
 ]
 
 _lib = None
@@ -93,6 +93,7 @@ def load():
         C.c_int, vp)
     sig("p5_opt_state_info", vp, C.c_int, C.POINTER(vp), C.POINTER(vp))
     sig("p5_decode_last_launch", C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int))
+    sig("p5_decode_phase_ns", vp)
     sig("p5_cooccurrence", vp, vp, C.c_int, C.c_int, C.c_int, vp, vp)
     sig("p5_submatrix", vp, C.c_int, C.c_int, vp, C.c_int, vp, vp)
     sig("p5_zero_grad", vp)
@@ -112,6 +113,7 @@ def load():
     sig("p5_op_gemm", C.POINTER(P5GemmDesc), vp)
     sig("p5_prof_enable", C.c_int)
     sig("p5_prof_summary", C.c_char_p, C.c_int)
+    sig("p5_prof_shapes", C.c_char_p, C.c_int)
     lib.p5_version.restype = C.c_int
     lib.p5_launch_count.restype = C.c_int
     _lib = lib

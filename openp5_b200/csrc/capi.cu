@@ -31,6 +31,7 @@ static Engine* E(p5_handle h) {
 namespace p5 {
 void gemm_tc_prof_enable(bool on);
 std::string gemm_tc_prof_summary();
+std::string gemm_tc_prof_shapes();
 // beam.cu
 int trie_build(Engine* e, const int32_t* paths, const int64_t* offsets, int n_paths, Trie** out);
 void trie_free(Trie* t);
@@ -39,6 +40,7 @@ int trie_get(Trie* t, const int32_t* prefix, int prefix_len, int32_t* out, int c
 void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t* ww, int B, int Le, Trie* trie,
               int K, int R, int max_len, float length_penalty, int32_t* seqs, float* scores, int* out_len);
 int decode_last_launch(float* ms, double* bytes, int* steps);   // decode_persist.cu
+int decode_phase_ns(unsigned long long* out32);
 void cooccurrence(const int* items, const long long* offs, int n_users, int n_items, int f64, void* adj, cudaStream_t st);   // indexing.cu
 void submatrix(const void* adj, int n_items, int f64, const int* idx, int m, void* out, cudaStream_t st);
 // comm.cu
@@ -298,6 +300,11 @@ int p5_decode_last_launch(float* ms_host, double* bytes_host, int* steps_host) {
     P5_API_END
 }
 
+int p5_decode_phase_ns(uint64_t* out32_host) {
+    P5_API_BEGIN
+    P5_CHECK(out32_host && decode_phase_ns((unsigned long long*)out32_host) == 0, "no persistent decode launch to report");
+    P5_API_END
+}
 int p5_cooccurrence(const int32_t* items, const int64_t* offsets, int n_users, int n_items, int f64, void* adj, void* cuda_stream) {
     P5_API_BEGIN
     P5_CHECK(items && offsets && adj, "null argument");
@@ -308,6 +315,14 @@ int p5_submatrix(const void* adj, int n_items, int f64, const int32_t* idx, int 
     P5_API_BEGIN
     P5_CHECK(adj && idx && out, "null argument");
     submatrix(adj, n_items, f64, idx, m, out, (cudaStream_t)cuda_stream);
+    P5_API_END
+}
+
+int p5_prof_shapes(char* text_out, int cap) {
+    P5_API_BEGIN
+    P5_CHECK(text_out && cap > 0, "null buffer");
+    const std::string s = gemm_tc_prof_shapes();
+    snprintf(text_out, (size_t)cap, "%s", s.c_str());
     P5_API_END
 }
 

@@ -3,6 +3,7 @@
 // (user, head) pair, shared by the stand-alone kernels (dattn.cu) and the persistent decode kernel (decode_persist.cu).
 #pragma once
 #include "kernels.cuh"
+#include "tc_ptx.cuh"
 #include <float.h>
 
 namespace p5 {
@@ -40,7 +41,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // 16 consecutive bf16 (32 bytes) of one row as 8 packed pairs; zeros when !ok
 __device__ __forceinline__ void ld_row16(uint32_t (&r)[8], const bf16* p, bool ok) {

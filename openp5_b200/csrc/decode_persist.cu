@@ -42,6 +42,19 @@ constexpr int G_TM = 128, G_TN = 64, G_KC = 64, G_STAGES = 4, G_LDS = 72;
 constexpr int G_A_BYTES = G_TM * G_LDS * 2, G_B_BYTES = G_TN * G_LDS * 2, G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_RING_BYTES = G_STAGES * G_STAGE_BYTES;
 
+// ---- GEMM tile (tcgen05, positions with > 32 live rows): 128 rows x 64 columns per tile, TMA -> 128B-swizzled smem ring ->
+//      tcgen05.mma 128x64x16 into two TMEM accumulators -> 4 epilogue warps (thread = row)
+constexpr int T_TM = 128, T_TN = 64, T_KB = 64, T_STAGES = 6;
+constexpr int T_A_BYTES = T_TM * T_KB * 2, T_B_BYTES = T_TN * T_KB * 2, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
+constexpr int T_RING_BYTES = T_STAGES * T_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// tensor-map table (device array): per layer 6 weight maps, then the LM head, then the three activation operands
+enum { TM_QKV = 0, TM_O, TM_CQ, TM_CO, TM_WI, TM_WO, TM_PER_LAYER };
+
+struct TcState {        // pipeline positions that persist across phases (each role keeps its own copy in registers)
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+};
+
 struct PdLayer {
     const bf16 *wqkv, *wo, *wcq, *wco, *wi, *wwo;      // bf16 shadows, [N, K] row-major
     const float *ln0, *ln1, *ln2;                       // RMSNorm weights (fp32)
@@ -70,9 +83,13 @@ struct PdParams {
     int *cur_tok, *unsat, *live_u, *n_u;
     float* scr_score; int* scr_flat; int scr_cap;
     const int *t_off, *t_tok, *t_node;
+    const CUtensorMap* tmaps;  // [6 * ND + 1 + 3]: weights per layer, LM head, then A operands y16 / ctx / h
+    int no_tc;
     unsigned* bar;
+    unsigned long long* prof;      // [2][16] ns per phase kind (CTA 0's view, phase + its barrier), light / heavy positions
     int32_t* out_seqs; float* out_scores; int* out_len;
 };
+enum PdPhase { PH_QKV = 0, PH_SA, PH_O, PH_CQ, PH_CA, PH_CO, PH_WI, PH_WO, PH_LM, PH_USER, PH_LIST, PH_N };
 
 // ------------------------------------------------------------------------------------------------------------
 // small helpers
@@ -104,13 +121,14 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     __syncthreads();
     target += gridDim.x;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to whoever observes the count
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned v;
         uint64_t t0 = 0;
         unsigned spins = 0;
         while (true) {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            // acquire: also invalidates this SM's L1, so the plain loads of the next phase see the other CTAs' writes
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             if ((int)(v - target) >= 0) break;
             if ((++spins & 0xfff) == 0) {
                 const uint64_t now = pd_timer();
@@ -121,7 +139,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
                 }
             }
         }
-        __threadfence();     // acquire side: also drops this SM's L1 lines, so plain loads after the barrier see the other CTAs' writes
     }
     __syncthreads();
 }
@@ -283,6 +300,138 @@ __device__ void gemm_phase(const GemmDesc& g, const int* __restrict__ live, int 
 
 
 // ------------------------------------------------------------------------------------------------------------
+// GEMM phase on the 5th-generation tensor cores (positions with more than 32 live rows: every beam row is computed).
+//   warp 0 lane 0 : TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (6 stages x (128x64 A + 64x64 W))
+//   warp 1 lane 0 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16 128x64x16, two TMEM accumulators (2 x 64 columns)
+//   warps 4-7     : epilogue       tcgen05.ld 32x32b: thread = output row, 64 fp32 columns in registers -> fused epilogue
+// The pipeline barriers and their phase bits live for the whole kernel; `TcState` carries each role's position from one
+// phase to the next.  Activations written by other CTAs in the previous phase were published by the grid barrier
+// (release / acquire at gpu scope); the producer adds the generic -> async proxy fence before its first TMA read.
+// ------------------------------------------------------------------------------------------------------------
+__device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const CUtensorMap* tmB, int rows, uint32_t ring, uint32_t bars,
+                              uint32_t tmem_base, TcState& st) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (rows + T_TM - 1) / T_TM, n_tiles = (g.N + T_TN - 1) / T_TN, k_blocks = g.K / T_KB;
+    const int total = m_tiles * n_tiles;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (T_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * T_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * T_STAGES + 2 + s); };
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int m_blk = t % m_tiles, n_blk = t / m_tiles;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(st.stage), st.phase ^ 1);
+                    const uint32_t sa = ring + st.stage * T_STAGE_BYTES, sb = sa + T_A_BYTES;
+                    mbar_expect_tx(full_bar(st.stage), T_STAGE_BYTES);
+                    tma_load_4d(sa, tmA, full_bar(st.stage), kb * T_KB, m_blk * T_TM, 0, 0);
+                    tma_load_4d(sb, tmB, full_bar(st.stage), kb * T_KB, n_blk * T_TN, 0, 0);
+                    if (++st.stage == T_STAGES) { st.stage = 0; st.phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_TN >> 3) << 17) | ((uint32_t)(T_TM >> 4) << 24);
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                mbar_wait(tempty_bar(st.acc), st.acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(st.acc * T_TN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(st.stage), st.phase);
+                    tc_fence_after();
+                    const uint32_t sa = ring + st.stage * T_STAGE_BYTES, sb = sa + T_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < T_KB / 16; ++k)
+                        umma_bf16(tmem_d, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar(st.stage));
+                    if (++st.stage == T_STAGES) { st.stage = 0; st.phase ^= 1; }
+                }
+                umma_commit(tfull_bar(st.acc));
+                if (++st.acc == 2) { st.acc = 0; st.acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int m_blk = t % m_tiles, n_blk = t / m_tiles;
+            mbar_wait(tfull_bar(st.acc), st.acc_phase);
+            tc_fence_after();
+            uint32_t rr[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(st.acc * T_TN);
+            tmem_ld32(taddr, rr);
+            tmem_ld32(taddr + 32, rr + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(st.acc));          // the accumulator may be overwritten
+            if (++st.acc == 2) { st.acc = 0; st.acc_phase ^= 1; }
+            const int r = m_blk * T_TM + ew * 32 + lane, col0 = n_blk * T_TN;
+            if (r >= rows) continue;
+            if (g.mode == 0) {
+                const float sc = row_scale(g, r);
+                bf16* out = g.out16 + (int64_t)r * g.ldo + col0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { v[e] = __uint_as_float(rr[8 * c + e]) * sc; if (g.relu) v[e] = fmaxf(v[e], 0.f); }
+                    if (col0 + 8 * c < g.N)
+                        *reinterpret_cast<uint4*>(out + 8 * c) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            } else if (g.mode == 1) {
+                float* yp = g.y + (int64_t)r * g.d + col0;
+                bf16* y16 = g.y16 + (int64_t)r * g.d + col0;
+                float ss = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (col0 + 8 * c >= g.N) continue;
+                    float4 a = __ldcg(reinterpret_cast<const float4*>(yp + 8 * c)), b = __ldcg(reinterpret_cast<const float4*>(yp + 8 * c + 4));
+                    const float4 l0 = *reinterpret_cast<const float4*>(g.ln_next + col0 + 8 * c), l1 = *reinterpret_cast<const float4*>(g.ln_next + col0 + 8 * c + 4);
+                    a.x += __uint_as_float(rr[8 * c]); a.y += __uint_as_float(rr[8 * c + 1]); a.z += __uint_as_float(rr[8 * c + 2]); a.w += __uint_as_float(rr[8 * c + 3]);
+                    b.x += __uint_as_float(rr[8 * c + 4]); b.y += __uint_as_float(rr[8 * c + 5]); b.z += __uint_as_float(rr[8 * c + 6]); b.w += __uint_as_float(rr[8 * c + 7]);
+                    *reinterpret_cast<float4*>(yp + 8 * c) = a;
+                    *reinterpret_cast<float4*>(yp + 8 * c + 4) = b;
+                    *reinterpret_cast<uint4*>(y16 + 8 * c) = make_uint4(pack_bf16(a.x * l0.x, a.y * l0.y), pack_bf16(a.z * l0.z, a.w * l0.w),
+                                                                        pack_bf16(b.x * l1.x, b.y * l1.y), pack_bf16(b.z * l1.z, b.w * l1.w));
+                    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+                }
+                atomicAdd(g.rowss_out + r, ss);
+            } else {
+                const float sc = row_scale(g, r);
+                float* lp = g.logits + (int64_t)r * g.ldl + col0;
+                float m = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    float v = __uint_as_float(rr[c]) * sc;
+                    if (col0 + c >= g.V) v = -INFINITY;
+                    rr[c] = __float_as_uint(v);
+                    m = fmaxf(m, v);
+                }
+                float e = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float4 v = make_float4(__uint_as_float(rr[4 * c]), __uint_as_float(rr[4 * c + 1]), __uint_as_float(rr[4 * c + 2]), __uint_as_float(rr[4 * c + 3]));
+                    if (col0 + 4 * c + 3 < g.V) *reinterpret_cast<float4*>(lp + 4 * c) = v;
+                    else {
+                        if (col0 + 4 * c < g.V) lp[4 * c] = v.x;
+                        if (col0 + 4 * c + 1 < g.V) lp[4 * c + 1] = v.y;
+                        if (col0 + 4 * c + 2 < g.V) lp[4 * c + 2] = v.z;
+                    }
+                    if (m > -INFINITY) e += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+                }
+                g.lse_part[(int64_t)r * g.n_ct_total + n_blk] = make_float2(m, e);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // GEMM phase, LIGHT variant (<= 32 live rows: the forced item prefix, where every user has ONE distinct beam).  The phase is
 // pure weight streaming, so it is organised for memory-level parallelism instead of reuse: a tile is (all live rows) x 16
 // output columns, the 8 warps of the CTA split the reduction dimension (64-wide k-blocks round-robin), every warp loads its
@@ -397,38 +546,88 @@ __device__ void gemm_light(const GemmDesc& g, const int* __restrict__ live, int 
 // decoder self-attention of ONE new position per live row, with KV append and row indirection: warp per (row, head)
 // (HF:modeling_t5.py:253-344 with the decoder's unidirectional relative bias; unscaled scores)
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld16_bf(float (&f)[16], const bf16* p) {      // 16 consecutive bf16 (L2 path) -> fp32
+    const uint4 x = __ldcg(reinterpret_cast<const uint4*>(p)), y = __ldcg(reinterpret_cast<const uint4*>(p + 8));
+    const uint32_t u[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[i]));
+        f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+}
+
+// warp per (live row, head).  lane = (position group jg = lane / 4, dim quarter dq = lane % 4): the <= 8 cached positions of
+// the usual item depth are scored IN PARALLEL (one round of independent loads instead of a dependent chain per position);
+// longer prefixes loop in blocks of 8 with an online softmax per lane, merged across the groups with shuffles at the end.
 __device__ void self_attn_phase(const PdParams& P, const PdLayer& L, const int* __restrict__ live, int n_live, const int* __restrict__ src,
                                 int pos) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, jg = lane >> 2, dq = lane & 3;
     const int A = P.A, T = P.T, H = P.H;
     for (int task = blockIdx.x * (PD_THREADS / 32) + warp; task < n_live * H; task += gridDim.x * (PD_THREADS / 32)) {
-        const int i = task / H, h = task - i * H, r = live[i], c = 2 * lane;
-        const bf16* row = P.qkv + (int64_t)r * 3 * A + h * 64 + c;
-        const float2 q = ldcg_bf2(row), kc = ldcg_bf2(row + A), vc = ldcg_bf2(row + 2 * A);
-        st_bf2(L.Kc + ((int64_t)r * T + pos) * A + h * 64 + c, kc.x, kc.y);
-        st_bf2(L.Vc + ((int64_t)r * T + pos) * A + h * 64 + c, vc.x, vc.y);
-        float m = -INFINITY, l = 0.f;
-        float2 acc = make_float2(0.f, 0.f);
-        for (int j = 0; j <= pos; ++j) {
-            float2 k = kc, v = vc;
-            if (j < pos) {
-                const int64_t o = ((int64_t)__ldcg(src + r * T + j) * T + j) * A + h * 64 + c;
-                k = ldcg_bf2(L.Kc + o);
-                v = ldcg_bf2(L.Vc + o);
+        const int i = task / H, h = task - i * H, r = live[i];
+        const bf16* row = P.qkv + (int64_t)r * 3 * A + h * 64 + 16 * dq;
+        float q[16];
+        ld16_bf(q, row);
+        if (jg == 0) {      // KV append: this row owns position `pos`
+            const int64_t o = ((int64_t)r * T + pos) * A + h * 64 + 16 * dq;
+            *reinterpret_cast<uint4*>(L.Kc + o) = __ldcg(reinterpret_cast<const uint4*>(row + A));
+            *reinterpret_cast<uint4*>(L.Kc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row + A + 8));
+            *reinterpret_cast<uint4*>(L.Vc + o) = __ldcg(reinterpret_cast<const uint4*>(row + 2 * A));
+            *reinterpret_cast<uint4*>(L.Vc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row + 2 * A + 8));
+        }
+        float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        for (int j0 = 0; j0 <= pos; j0 += 8) {           // warp-uniform trip count: the shuffles below need every lane
+            const int j = j0 + jg;
+            const bool valid = j <= pos;
+            const bf16 *kp = row + A, *vp = row + 2 * A;
+            if (valid && j < pos) {
+                const int64_t o = ((int64_t)__ldcg(src + r * T + j) * T + j) * A + h * 64 + 16 * dq;
+                kp = L.Kc + o; vp = L.Vc + o;
             }
-            float sc = warp_sum(fmaf(q.x, k.x, q.y * k.y));
-            int di = j - pos + P.bias_off;
-            di = di < 0 ? 0 : (di >= P.n_delta ? P.n_delta - 1 : di);
-            sc += P.bias_dec[h * P.n_delta + di];
-            const float mn = fmaxf(m, sc);
-            const float scale = __expf(m - mn), p = __expf(sc - mn);
-            l = l * scale + p;
-            acc.x = fmaf(acc.x, scale, p * v.x);
-            acc.y = fmaf(acc.y, scale, p * v.y);
+            float k[16], v[16];
+            ld16_bf(k, kp);
+            ld16_bf(v, vp);
+            float sc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sc = fmaf(q[c], k[c], sc);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+            if (valid) {
+                int di = j - pos + P.bias_off;
+                di = di < 0 ? 0 : (di >= P.n_delta ? P.n_delta - 1 : di);
+                sc += P.bias_dec[h * P.n_delta + di];
+                const float mn = fmaxf(m, sc);
+                const float scale = __expf(m - mn), p = __expf(sc - mn);
+                l = l * scale + p;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = fmaf(acc[c], scale, p * v[c]);
+                m = mn;
+            }
+        }
+        // merge the 8 position groups (lanes differing in bits 2..4 hold the same dims)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o), ol = __shfl_xor_sync(0xffffffffu, l, o);
+            const float mn = fmaxf(m, om);
+            const float s0 = (m > -INFINITY) ? __expf(m - mn) : 0.f, s1 = (om > -INFINITY) ? __expf(om - mn) : 0.f;
+            l = l * s0 + ol * s1;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = acc[c] * s0 + __shfl_xor_sync(0xffffffffu, acc[c], o) * s1;
             m = mn;
         }
-        const float inv = 1.f / l;
-        st_bf2(P.ctx + (int64_t)r * A + h * 64 + c, acc.x * inv, acc.y * inv);
+        if (jg == 0) {
+            const float inv = 1.f / l;
+            bf16* out = P.ctx + (int64_t)r * A + h * 64 + 16 * dq;
+            uint4 w0, w1;
+            w0.x = pack_bf16(acc[0] * inv, acc[1] * inv); w0.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+            w0.z = pack_bf16(acc[4] * inv, acc[5] * inv); w0.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+            w1.x = pack_bf16(acc[8] * inv, acc[9] * inv); w1.y = pack_bf16(acc[10] * inv, acc[11] * inv);
+            w1.z = pack_bf16(acc[12] * inv, acc[13] * inv); w1.w = pack_bf16(acc[14] * inv, acc[15] * inv);
+            *reinterpret_cast<uint4*>(out) = w0;
+            *reinterpret_cast<uint4*>(out + 8) = w1;
+        }
     }
 }
 
@@ -453,6 +652,105 @@ __device__ void cross_attn_phase(const PdParams& P, const PdLayer& L, uint8_t* s
     }
 }
 
+// Cross-attention when every user has only a few distinct beams (the forced item prefix: ONE): a 32-row mma tile per
+// (user, head) would be 97 % padding and the phase is pure K | V streaming, so each (user, head, beam) is ONE WARP:
+// lane j owns keys j, j+32, ...; it holds the whole 64-dim query, dots it with its key rows (16-byte loads, all
+// independent), the warp softmaxes with shuffles, each lane accumulates p . V over its keys and a 62-shuffle
+// reduce-scatter leaves two output dims per lane.  Le <= 512.
+__device__ void cross_attn_light(const PdParams& P, const PdLayer& L) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int B = P.B, H = P.H, K = P.K, Le = P.Le, A = P.A;
+    const int per_user = H * K;       // task index space (b, i, h) with i < n_u[b] checked inside
+    for (int task = blockIdx.x * (PD_THREADS / 32) + warp; task < B * per_user; task += gridDim.x * (PD_THREADS / 32)) {
+        const int b = task / per_user, rem = task - b * per_user, i = rem / H, h = rem - i * H;
+        if (i >= __ldcg(P.n_u + b)) continue;
+        const int r = __ldcg(P.live_u + b * K + i);
+        float q[64];
+        {
+            const bf16* qp = P.cq + (int64_t)r * A + h * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { float t16[16]; ld16_bf(t16, qp + 16 * c);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) q[16 * c + e] = t16[e]; }
+        }
+        const bf16* kb = L.ck + (int64_t)b * Le * P.ckv_ld + h * 64;
+        const bf16* vb = L.cv + (int64_t)b * Le * P.ckv_ld + h * 64;
+        const int* mask = P.mask_e + (int64_t)b * Le;
+        constexpr int MAXJ = 16;                       // Le <= 512
+        float sc[MAXJ];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < MAXJ; ++jj) {
+            const int j = lane + 32 * jj;
+            sc[jj] = -INFINITY;
+            if (j < Le && mask[j] != 0) {
+                const uint4* kp = reinterpret_cast<const uint4*>(kb + (int64_t)j * P.ckv_ld);
+                float d = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 x = kp[c];
+                    const uint32_t u[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+                        d = fmaf(q[8 * c + 2 * e], kv.x, d);
+                        d = fmaf(q[8 * c + 2 * e + 1], kv.y, d);
+                    }
+                }
+                sc[jj] = d;
+                mx = fmaxf(mx, d);
+            }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MAXJ; ++jj) {
+            const float p = (sc[jj] > -INFINITY) ? __expf(sc[jj] - mx) : 0.f;
+            sc[jj] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        float acc[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MAXJ; ++jj) {
+            const int j = lane + 32 * jj;
+            if (j < Le && sc[jj] > 0.f) {
+                const float p = __bfloat162float(__float2bfloat16_rn(sc[jj] * inv));      // P is a bf16 operand of P.V in the tiled kernel
+                const uint4* vp = reinterpret_cast<const uint4*>(vb + (int64_t)j * P.ckv_ld);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 x = vp[c];
+                    const uint32_t u[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+                        acc[8 * c + 2 * e] = fmaf(p, vv.x, acc[8 * c + 2 * e]);
+                        acc[8 * c + 2 * e + 1] = fmaf(p, vv.y, acc[8 * c + 2 * e + 1]);
+                    }
+                }
+            }
+        }
+        // reduce-scatter over the 32 lanes: after the step with offset o a lane keeps the half of its values selected by bit o
+#pragma unroll
+        for (int o = 16, n = 64; o >= 1; o >>= 1, n >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                if (c < n / 2) {
+                    const float mine = up ? acc[c + n / 2] : acc[c], send = up ? acc[c] : acc[c + n / 2];
+                    acc[c] = mine + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+        }
+        // lane now holds dims: bit16 -> +32, bit8 -> +16, bit4 -> +8, bit2 -> +4, bit1 -> +2 ; two consecutive dims
+        const int d0 = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+        st_bf2(P.ctx + (int64_t)r * A + h * 64 + d0, acc[0], acc[1]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // per user: log-softmax normaliser from the LM-head partials, trie scoring + top-2K, HF beam bookkeeping, duplicate
 // detection, embedding of the next input token
@@ -471,7 +769,8 @@ __device__ __forceinline__ int pd_trie_child(const int* off, const int* tok, con
 
 struct UserSmem {
     float rowmax[PD_MAXK], logsum[PD_MAXK];
-    int s_off[PD_MAXK + 1], s_nd[PD_MAXK], s_rep[PD_MAXK];
+    int s_off[PD_MAXK + 1], s_nd[PD_MAXK], s_rep[PD_MAXK], s_cnt[PD_MAXK];
+    float s_rs[PD_MAXK];
     float s_sc[1024]; int s_fl[1024];
     float s_best[8]; int s_besti[8], s_bestf[8];
     int run_sel[PD_MAXK], fin_sel[PD_MAXK], s_cb[2 * PD_MAXK], s_ct[2 * PD_MAXK], s_fin[PD_MAXK], rep_new[PD_MAXK], node_new[PD_MAXK];
@@ -485,11 +784,11 @@ __device__ __forceinline__ void embed_row(const PdParams& P, int r, int tok, int
     const float* e = P.E + (int64_t)tok * P.d;
     const float* ln = P.layer[0].ln0;
     float ss = 0.f;
-    for (int c = 2 * lane; c < P.d; c += 64) {
-        const float2 v = *reinterpret_cast<const float2*>(e + c);
-        *reinterpret_cast<float2*>(P.y + (int64_t)r * P.d + c) = v;
-        st_bf2(P.y16 + (int64_t)r * P.d + c, v.x * ln[c], v.y * ln[c + 1]);
-        ss += v.x * v.x + v.y * v.y;
+    for (int c = 4 * lane; c < P.d; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(e + c), w = *reinterpret_cast<const float4*>(ln + c);
+        *reinterpret_cast<float4*>(P.y + (int64_t)r * P.d + c) = v;
+        *reinterpret_cast<uint2*>(P.y16 + (int64_t)r * P.d + c) = make_uint2(pack_bf16(v.x * w.x, v.y * w.y), pack_bf16(v.z * w.z, v.w * w.w));
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     ss = warp_sum(ss);
     const int n_sites = 3 * P.ND + 1;
@@ -525,13 +824,14 @@ __device__ void user_phase(const PdParams& P, UserSmem& S, int b, int cur, int c
     if (threadIdx.x < K) { S.s_nd[threadIdx.x] = __ldcg(node_in + b * K + threadIdx.x); S.s_rep[threadIdx.x] = __ldcg(rep_in + b * K + threadIdx.x); }
     __syncthreads();
     // ---- (2) score the trie children of every running beam, keep the best 2K (score desc, flat index asc)  [beam.cu topk]
+    if (threadIdx.x < K) {            // children per beam, in parallel (the trie offsets are two dependent-free global loads each)
+        const int nd = S.s_nd[threadIdx.x];
+        S.s_cnt[threadIdx.x] = nd >= 0 ? P.t_off[nd + 1] - P.t_off[nd] : 0;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int k = 0; k < K; ++k) {
-            S.s_off[k] = acc;
-            const int nd = S.s_nd[k];
-            if (nd >= 0) acc += P.t_off[nd + 1] - P.t_off[nd];
-        }
+        for (int k = 0; k < K; ++k) { S.s_off[k] = acc; acc += S.s_cnt[k]; }
         S.s_off[K] = acc;
     }
     __syncthreads();
@@ -541,23 +841,20 @@ __device__ void user_phase(const PdParams& P, UserSmem& S, int b, int cur, int c
     const bool in_smem = n <= 1024;
     float* vsc = in_smem ? S.s_sc : gsc;
     int* vfl = in_smem ? S.s_fl : gfl;
-    for (int k = 0; k < K; ++k) {
-        const int nd = S.s_nd[k];
-        if (nd < 0) continue;
-        const int rk = S.s_rep[k];                                 // the row that owns this beam's logits
-        const int e0 = P.t_off[nd], cnt = S.s_off[k + 1] - S.s_off[k], base = S.s_off[k];
-        const float rs = __ldcg(P.run_score[cur] + b * K + k), nrm = S.rowmax[rk], ls = S.logsum[rk];
-        const float* lrow = P.logits + (int64_t)(b * K + rk) * P.Vpad;
-        for (int e = threadIdx.x; e < cnt; e += PD_THREADS) {
-            const int tok = P.t_tok[e0 + e];
-            const int slot = base + e;
-            if (slot < P.scr_cap && tok >= 0 && tok < V) {
-                const float lp = (__ldcg(lrow + tok) - nrm) - ls;
-                vsc[slot] = lp + rs;
-                vfl[slot] = k * V + tok;
-            } else if (slot < P.scr_cap) {
-                vsc[slot] = -INFINITY; vfl[slot] = 0x7fffffff;
-            }
+    if (threadIdx.x < K) S.s_rs[threadIdx.x] = __ldcg(P.run_score[cur] + b * K + threadIdx.x);
+    __syncthreads();
+    // every candidate slot is one independent (trie token -> logit) load chain: all slots of the user in flight at once
+    for (int slot = threadIdx.x; slot < n; slot += PD_THREADS) {
+        int k = 0;
+        while (k + 1 < K && S.s_off[k + 1] <= slot) ++k;           // beam that owns the slot (K <= 32)
+        const int nd = S.s_nd[k], rk = S.s_rep[k];                 // rk: the row that owns this beam's logits
+        const int tok = P.t_tok[P.t_off[nd] + (slot - S.s_off[k])];
+        if (tok >= 0 && tok < V) {
+            const float lp = (__ldcg(P.logits + (int64_t)(b * K + rk) * P.Vpad + tok) - S.rowmax[rk]) - S.logsum[rk];
+            vsc[slot] = lp + S.s_rs[k];
+            vfl[slot] = k * V + tok;
+        } else {
+            vsc[slot] = -INFINITY; vfl[slot] = 0x7fffffff;
         }
     }
     for (int sel = threadIdx.x; sel < 2 * K; sel += PD_THREADS) { S.s_lp[sel] = -INFINITY; S.s_cb[sel] = 0; S.s_ct[sel] = 0; }
@@ -727,6 +1024,22 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
     const PdParams& P = *Pp;
     int* s_live = reinterpret_cast<int*>(smem);                       // [R] live rows of the current position
     uint8_t* work = smem + ((P.R * 4 + 127) & ~127);                  // GEMM ring / attention staging
+    // ---- tcgen05 pipeline of the heavy GEMM phases: ring (1024-aligned, SWIZZLE_128B), mbarriers, TMEM accumulators
+    __shared__ uint32_t s_tmem_base;
+    const uint32_t ring = (smem_u32(work) + 1023u) & ~1023u;
+    const uint32_t bars = ring + T_STAGES * T_STAGE_BYTES;
+    if (threadIdx.x == 32) {
+        for (int s2 = 0; s2 < T_STAGES; ++s2) { mbar_init(bars + 8u * s2, 1); mbar_init(bars + 8u * (T_STAGES + s2), 1); }
+        for (int s2 = 0; s2 < 2; ++s2) { mbar_init(bars + 8u * (2 * T_STAGES + s2), 1); mbar_init(bars + 8u * (2 * T_STAGES + 2 + s2), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 2) tmem_alloc(smem_u32(&s_tmem_base), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+    TcState tcs;
     unsigned bar_target = 0;
     const int B = P.B, K = P.K, R = P.R, T = P.T, d = P.d, A = P.A, ff = P.ff;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -745,6 +1058,15 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
     for (int b = blockIdx.x * (PD_THREADS / 32) + warp; b < B; b += gridDim.x * (PD_THREADS / 32)) embed_row(P, b * K, 0, lane);
     grid_barrier(P.bar, bar_target);
 
+    uint64_t t_last = pd_timer();
+    bool prof_heavy = false;
+    auto mark = [&](int kind) {     // CTA 0 attributes the time since the previous mark to `kind`
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const uint64_t now = pd_timer();
+            P.prof[(prof_heavy ? 16 : 0) + kind] += now - t_last;
+            t_last = now;
+        }
+    };
     int cur = 0;
     for (int step = 0; step < P.n_steps; ++step) {
         const int cur_len = step + 1, pos = step;
@@ -762,11 +1084,22 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
         }
         __syncthreads();
         const int n_live = s_nlive;
+        int max_nq = 0;
+        for (int b = 0; b < B; ++b) max_nq = max(max_nq, s_uoff[b + 1] - s_uoff[b]);
         const float inv_d = 1.f / (float)d;
         // <= 32 live rows (one distinct beam per user through the forced item prefix): weight-streaming variant
         const bool light = n_live <= 32 && !P.no_light;
         const int n_parts = light ? (P.V + L_TN - 1) / L_TN : P.n_ct_head;
-        auto run_gemm = [&](const GemmDesc& gd) { if (light) gemm_light(gd, s_live, n_live, work); else gemm_phase(gd, s_live, n_live, work); };
+        // heavy positions: every beam row through the tcgen05 tiles (rows that are not live compute values nobody reads);
+        // the mma.sync tile loop (gemm_phase) remains as the P5_DECODE_NO_TC=1 cross-check
+        auto run_gemm = [&](const GemmDesc& gd, int wmap, int amap) {
+            if (light) gemm_light(gd, s_live, n_live, work);
+            else if (P.no_tc) gemm_phase(gd, s_live, n_live, work);
+            else gemm_tc_phase(gd, P.tmaps + amap, P.tmaps + wmap, R, ring, bars, tmem_base, tcs);
+        };
+        const int TM_HEAD = TM_PER_LAYER * P.ND, TM_Y16 = TM_HEAD + 1, TM_CTX = TM_HEAD + 2, TM_H = TM_HEAD + 3;
+        prof_heavy = !light;
+        mark(PH_LIST);
 
         for (int l = 0; l < P.ND; ++l) {
             const PdLayer& L = P.layer[l];
@@ -779,47 +1112,62 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             // (a) q | k | v = RMSNorm(y) . Wqkv^T
             g = GemmDesc{P.y16, d, d, L.wqkv, 3 * A, 0, 1.f, ss0, inv_d, P.eps, 0, P.qkv, 3 * A, nullptr, nullptr, nullptr, nullptr, d,
                          nullptr, 0, nullptr, 0, 0};
-            run_gemm(g);
+            run_gemm(g, TM_PER_LAYER * l + TM_QKV, TM_Y16);
             grid_barrier(P.bar, bar_target);
+            mark(PH_QKV);
             // (b) self-attention over the cached positions (+ KV append)
             self_attn_phase(P, L, s_live, n_live, P.src[cur], pos);
             grid_barrier(P.bar, bar_target);
+            mark(PH_SA);
             // (c) y += ctx . Wo^T      -> y16 = bf16(y * ln1), rowss1
             g = GemmDesc{P.ctx, A, A, L.wo, d, 1, 1.f, nullptr, inv_d, P.eps, 0, nullptr, 0, P.y, P.y16, L.ln1, ss1, d, nullptr, 0, nullptr, 0, 0};
-            run_gemm(g);
+            run_gemm(g, TM_PER_LAYER * l + TM_O, TM_CTX);
             grid_barrier(P.bar, bar_target);
+            mark(PH_O);
             // (d) cross-attention query
             g = GemmDesc{P.y16, d, d, L.wcq, A, 0, 1.f, ss1, inv_d, P.eps, 0, P.cq, A, nullptr, nullptr, nullptr, nullptr, d, nullptr, 0, nullptr, 0, 0};
-            run_gemm(g);
+            run_gemm(g, TM_PER_LAYER * l + TM_CQ, TM_Y16);
             grid_barrier(P.bar, bar_target);
+            mark(PH_CQ);
             // (e) cross-attention over the user's encoder K | V (zero position bias + encoder padding mask)
-            if (P.Le <= 256) cross_attn_phase<4>(P, L, work); else cross_attn_phase<8>(P, L, work);
+            if (max_nq <= 4) cross_attn_light(P, L);
+            else if (P.Le <= 256) cross_attn_phase<4>(P, L, work);
+            else cross_attn_phase<8>(P, L, work);
             grid_barrier(P.bar, bar_target);
+            mark(PH_CA);
             // (f) y += ctx . Wco^T     -> y16 = bf16(y * ln2), rowss2
             g = GemmDesc{P.ctx, A, A, L.wco, d, 1, 1.f, nullptr, inv_d, P.eps, 0, nullptr, 0, P.y, P.y16, L.ln2, ss2, d, nullptr, 0, nullptr, 0, 0};
-            run_gemm(g);
+            run_gemm(g, TM_PER_LAYER * l + TM_CO, TM_CTX);
             grid_barrier(P.bar, bar_target);
+            mark(PH_CO);
             // (g) h = relu(RMSNorm(y) . Wi^T)
             g = GemmDesc{P.y16, d, d, L.wi, ff, 0, 1.f, ss2, inv_d, P.eps, 1, P.h, ff, nullptr, nullptr, nullptr, nullptr, d, nullptr, 0, nullptr, 0, 0};
-            run_gemm(g);
+            run_gemm(g, TM_PER_LAYER * l + TM_WI, TM_Y16);
             grid_barrier(P.bar, bar_target);
+            mark(PH_WI);
             // (h) y += h . Wo^T        -> y16 = bf16(y * ln0 of the next block / final norm), rowss of that site
             g = GemmDesc{P.h, ff, ff, L.wwo, d, 1, 1.f, nullptr, inv_d, P.eps, 0, nullptr, 0, P.y, P.y16, ln_after, ss_next, d, nullptr, 0, nullptr, 0, 0};
-            run_gemm(g);
+            run_gemm(g, TM_PER_LAYER * l + TM_WO, TM_H);
             grid_barrier(P.bar, bar_target);
+            mark(PH_WO);
         }
         // ---- tied LM head: logits = (RMSNorm(y) * d^-0.5) . E^T  (+ per-tile log-sum-exp partials)   (P5_T5.py:357-361)
         {
             GemmDesc g{P.y16, d, d, P.E16, P.V, 2, P.hs, P.rowss + (int64_t)(3 * P.ND) * R, inv_d, P.eps, 0, nullptr, 0, nullptr, nullptr,
                        nullptr, nullptr, d, P.logits, P.Vpad, P.lse_part, n_parts, P.V};
-            run_gemm(g);
+            run_gemm(g, TM_HEAD, TM_Y16);
         }
         grid_barrier(P.bar, bar_target);
+        mark(PH_LM);
         // ---- per user: normaliser, constrained top-2K, beam update, next input embedding
         for (int b = blockIdx.x; b < B; b += gridDim.x) user_phase(P, US, b, cur, cur_len, step, n_parts);
         grid_barrier(P.bar, bar_target);
+        mark(PH_USER);
         cur ^= 1;
     }
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
     // ---- finalize (HF:generation/utils.py:3380-3400): the n_ret best finished hypotheses per user, cropped length
     if (blockIdx.x == 0) {
         __shared__ int s_max;
@@ -842,6 +1190,7 @@ struct PersistWs {
     std::vector<void*> allocs;
     PdParams host;
     PdParams* dev = nullptr;
+    CUtensorMap* tmaps_dev = nullptr;
     int smem_bytes = 0, grid = 0;
 };
 PersistWs* g_pws = nullptr;
@@ -868,6 +1217,14 @@ int decode_last_launch(float* ms, double* bytes, int* steps) {
     if (bytes) *bytes = g_last_bytes;
     if (steps) *steps = g_last_steps;
     return 0;
+}
+
+// per-phase nanoseconds of the last launch as CTA 0 saw them: out[0..15] positions run by the light GEMM variant,
+// out[16..31] heavy positions; index = PdPhase (qkv, self-attn, o, cq, cross-attn, co, wi, wo, lm-head, user, list)
+int decode_phase_ns(unsigned long long* out32) {
+    if (!g_pws || !g_ev1) return 1;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return 2;
+    return cudaMemcpy(out32, g_pws->host.prof, 32 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 3;
 }
 
 bool decode_persistent_supported(const Engine* e, int B, int K, int max_len, int Le) {
@@ -909,10 +1266,12 @@ const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, co
         H.cur_tok = (int*)al((size_t)R * 4); H.unsat = (int*)al((size_t)B * 4); H.live_u = (int*)al((size_t)R * 4); H.n_u = (int*)al((size_t)B * 4);
         H.scr_score = (float*)al((size_t)B * cand_cap * 4); H.scr_flat = (int*)al((size_t)B * cand_cap * 4); H.scr_cap = cand_cap;
         H.bar = (unsigned*)al(256);
+        H.prof = (unsigned long long*)al(32 * 8);
         H.out_len = (int*)al(16);
         w->dev = (PdParams*)al(sizeof(PdParams));
+        w->tmaps_dev = (CUtensorMap*)al(sizeof(CUtensorMap) * (TM_PER_LAYER * ND + 4));
         // launch geometry: one CTA per SM, all co-resident (cooperative launch)
-        const int work = std::max(G_RING_BYTES, std::max(DCfg<8, PD_THREADS / 32>::TILE, PD_THREADS * 64 * 4) + PD_THREADS * 2 * 4);
+        const int work = std::max(std::max(G_RING_BYTES, T_RING_BYTES), std::max(DCfg<8, PD_THREADS / 32>::TILE, PD_THREADS * 64 * 4) + PD_THREADS * 2 * 4);
         w->smem_bytes = (int)round_up((int64_t)R * 4, 128) + work;
         P5_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w->smem_bytes));
         int sms = 0, per_sm = 0;
@@ -941,8 +1300,35 @@ const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, co
     H.bias_dec = e->bias_dec; H.n_delta = 2 * T - 1; H.bias_off = T - 1;
     H.t_off = t_off; H.t_tok = t_tok; H.t_node = t_node;
     H.out_seqs = seqs; H.out_scores = scores;
+    {   // tensor maps of the tcgen05 phases: K-major bf16, SWIZZLE_128B, boxes 64 (k) x 128 (A rows) / 64 (W rows)
+        std::vector<CUtensorMap> maps(TM_PER_LAYER * ND + 4);
+        auto mk = [&](const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+            const uint64_t dims[4] = {(uint64_t)K, (uint64_t)rows, 1, 1};
+            const uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)rows * ld * 2, (uint64_t)rows * ld * 2};
+            const uint32_t box[4] = {(uint32_t)T_KB, (uint32_t)box_rows, 1, 1};
+            return tmap_bf16_4d(ptr, dims, strides, box);
+        };
+        for (int l = 0; l < ND; ++l) {
+            const PdLayer& L = H.layer[l];
+            maps[TM_PER_LAYER * l + TM_QKV] = mk(L.wqkv, 3 * A, d, d, T_TN);
+            maps[TM_PER_LAYER * l + TM_O] = mk(L.wo, d, A, A, T_TN);
+            maps[TM_PER_LAYER * l + TM_CQ] = mk(L.wcq, A, d, d, T_TN);
+            maps[TM_PER_LAYER * l + TM_CO] = mk(L.wco, d, A, A, T_TN);
+            maps[TM_PER_LAYER * l + TM_WI] = mk(L.wi, ff, d, d, T_TN);
+            maps[TM_PER_LAYER * l + TM_WO] = mk(L.wwo, d, ff, ff, T_TN);
+        }
+        maps[TM_PER_LAYER * ND] = mk(H.E16, e->V, d, d, T_TN);
+        maps[TM_PER_LAYER * ND + 1] = mk(H.y16, R, d, d, T_TM);
+        maps[TM_PER_LAYER * ND + 2] = mk(H.ctx, R, A, A, T_TM);
+        maps[TM_PER_LAYER * ND + 3] = mk(H.h, R, ff, ff, T_TM);
+        P5_CUDA(cudaMemcpyAsync(w->tmaps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+        H.tmaps = w->tmaps_dev;
+        static const bool no_tc = getenv("P5_DECODE_NO_TC") != nullptr;
+        H.no_tc = (no_tc || d % 64 != 0) ? 1 : 0;
+    }
     P5_CUDA(cudaMemcpyAsync(w->dev, &H, sizeof(PdParams), cudaMemcpyHostToDevice, st));
     P5_CUDA(cudaMemsetAsync(H.bar, 0, 256, st));
+    P5_CUDA(cudaMemsetAsync(H.prof, 0, 32 * 8, st));
     const PdParams* dp = w->dev;
     void* args[] = {(void*)&dp};
     if (!g_ev0) { P5_CUDA(cudaEventCreate(&g_ev0)); P5_CUDA(cudaEventCreate(&g_ev1)); }

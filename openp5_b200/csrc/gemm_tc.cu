@@ -22,6 +22,8 @@
 #include <unordered_map>
 #include <vector>
 #include <mutex>
+#include <algorithm>
+#include <string>
 #include <string.h>
 #include <stdlib.h>
 
@@ -647,7 +649,7 @@ int sm_budget() {
 
 // ---- optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream around every
 //      tcgen05 GEMM launch, with the algorithmic FLOPs of the problem
-struct ProfRec { cudaEvent_t e0, e1; double flops; int bn; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int bn; int M, N, K, nb, flags, am, bm; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 void gemm_tc_prof_enable(bool on) {
@@ -674,6 +676,31 @@ std::string gemm_tc_prof_summary() {
              "\"flops\": %.6e}, \"bn64\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e}}",
              n[0], ms[0], fl[0], n[1], ms[1], fl[1], n[2], ms[2], fl[2]);
     return std::string(b);
+}
+// per-shape table of the profiled launches: "M N K batches flags a_major b_major bn : launches total_ms TFLOP/s" lines
+std::string gemm_tc_prof_shapes() {
+    cudaDeviceSynchronize();
+    struct Acc { long n = 0; double ms = 0, fl = 0; };
+    std::unordered_map<std::string, Acc> tab;
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
+        char k[128];
+        snprintf(k, sizeof(k), "%6d %6d %6d nb%-3d epi%-3d maj%d%d bn%d", r.M, r.N, r.K, r.nb, r.flags, r.am, r.bm, r.bn);
+        Acc& a = tab[k];
+        a.n += 1; a.ms += t; a.fl += r.flops;
+    }
+    std::vector<std::pair<double, std::string>> rows;
+    for (auto& kv : tab) {
+        char b[256];
+        snprintf(b, sizeof(b), "%s : %4ld x %8.2f us  %7.1f TFLOP/s  total %8.3f ms\n", kv.first.c_str(), kv.second.n, 1e3 * kv.second.ms / kv.second.n,
+                 kv.second.ms > 0 ? kv.second.fl / (kv.second.ms * 1e-3) / 1e12 : 0.0, kv.second.ms);
+        rows.push_back({-kv.second.ms, b});
+    }
+    std::sort(rows.begin(), rows.end());
+    std::string out;
+    for (auto& r : rows) out += r.second;
+    return out;
 }
 void gemm_tc_force_block_n(int bn) { g_force_block_n = bn; }
 
@@ -705,6 +732,8 @@ static void launch_tc(const GemmProblem& p, cudaStream_t stream) {
     if (g_prof_on) {
         cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
         rec.flops = 2.0 * p.M * p.N * (double)p.K * p.nb1 * p.nb2; rec.bn = BN;
+        rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.nb = p.nb1 * p.nb2; rec.flags = p.epi.flags | (p.epi.c_dtype == DT_F32 ? 64 : 0);
+        rec.am = p.A.major; rec.bm = p.B.major;
         cudaEventRecord(rec.e0, stream);
     }
     launch_k(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, P);

@@ -258,9 +258,42 @@ def gelu_new(x):
     return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
 
 
-def _attn_core(q, k, v, bias):
+class _EmuFusedAttn(torch.autograd.Function):
+    """bf16 emulation of the FUSED encoder self-attention (csrc/fattn.cu forward, csrc/fattn_bwd.cu backward, Le <= 256):
+    the backward recomputes the normalised P from the saved row statistic, takes delta_i = sum_c dO_ic O_ic from the
+    bf16-stored forward output (not from sum_j P_ij dP_ij), and feeds P and dS to the tensor cores as bf16."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, bias):
+        bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+        s = (q @ k.transpose(-1, -2) + bias).float()
+        m = s.max(dim=-1, keepdim=True)[0]
+        pu = torch.exp(s - m)
+        l = pu.sum(dim=-1, keepdim=True)
+        o = (bf(pu) @ v) / l
+        ctx.save_for_backward(q, k, v, s, m + torch.log(l), bf(o))
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+        q, k, v, s, lse, o_r = ctx.saved_tensors
+        p = torch.exp(s - lse)
+        dp = do @ v.transpose(-1, -2)
+        delta = (do * o_r).sum(dim=-1, keepdim=True)
+        ds = p * (dp - delta)
+        ds16 = bf(ds)
+        dv = bf(p).transpose(-1, -2) @ do
+        dq = ds16 @ k
+        dk = ds16.transpose(-1, -2) @ q
+        return dq, dk, dv, ds
+
+
+def _attn_core(q, k, v, bias, fused_bwd=False):
     """softmax(q k^T + bias) v on [.., H, L, d_kv] tensors: unscaled scores, fp32 softmax (HF:modeling_t5.py:308-334)"""
-    scores = q @ k.transpose(-1, -2) + bias
+    if _EMU and fused_bwd:
+        return _EmuFusedAttn.apply(q, k, v, bias.expand(q.shape[0], q.shape[1], q.shape[2], k.shape[2]))
+    scores = _rg(q @ k.transpose(-1, -2) + bias)      # emulation: the score gradient dS is a bf16 MMA operand in the backward
     if _EMU:
         # engine: fp32 scores and statistics; UN-normalised probabilities rounded to bf16 for the P.V product, the
         # fp32 row sum divides the fp32 accumulator afterwards (fattn.cu / dattn.cu)
@@ -271,7 +304,7 @@ def _attn_core(q, k, v, bias):
     return p @ v
 
 
-def attention(w, prefix, x_q, x_kv, bias, cfg: T5Cfg, trace=None):
+def attention(w, prefix, x_q, x_kv, bias, cfg: T5Cfg, trace=None, fused_bwd=False):
     """HF:models/t5/modeling_t5.py:253-344 (T5Attention.forward): NO 1/sqrt(d) scaling; softmax in fp32;
     `bias` already contains position bias + additive mask."""
     B, Lq, _ = x_q.shape
@@ -280,7 +313,7 @@ def attention(w, prefix, x_q, x_kv, bias, cfg: T5Cfg, trace=None):
     q = _ra(x_q @ _rw(w[prefix + ".q.weight"]).T).view(B, Lq, H, dk).transpose(1, 2)
     k = _ra(x_kv @ _rw(w[prefix + ".k.weight"]).T).view(B, Lk, H, dk).transpose(1, 2)
     v = _ra(x_kv @ _rw(w[prefix + ".v.weight"]).T).view(B, Lk, H, dk).transpose(1, 2)
-    ctx = _attn_core(q, k, v, bias)
+    ctx = _attn_core(q, k, v, bias, fused_bwd)
     ctx = _ra(ctx.transpose(1, 2).reshape(B, Lq, H * dk))
     if trace is not None:
         trace[prefix + ".ctx"] = ctx
@@ -315,7 +348,8 @@ def encode(w, cfg: T5Cfg, input_ids, whole_word_ids, attention_mask, trace=None)
     for i in range(cfg.num_layers):
         b = f"encoder.block.{i}.layer"
         n = rms_norm(x, w[b + ".0.layer_norm.weight"], cfg.ln_eps)
-        x = x + attention(w, b + ".0.SelfAttention", n, n, bias, cfg, trace)
+        # (emulation) the engine's fused tcgen05 attention backward covers encoder lengths up to 256 (padded to 8)
+        x = x + attention(w, b + ".0.SelfAttention", n, n, bias, cfg, trace, fused_bwd=((L + 7) // 8) * 8 <= 256)
         n = rms_norm(x, w[b + ".1.layer_norm.weight"], cfg.ln_eps)
         x = x + ffn(w, b + ".1.DenseReluDense", n, cfg)
         if trace is not None:
