@@ -157,7 +157,8 @@ struct GenWs {
 // decode_persist.cu: the whole search as one persistent cooperative kernel (bf16 mode)
 bool decode_persistent_supported(const Engine* e, int B, int K, int max_len, int Le);
 const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, const int* t_node, int root_child, int max_depth,
-                               int max_fanout, int B, int K, int Rret, int max_len, float length_penalty, int32_t* seqs, float* scores);
+                               int max_fanout, int B, int K, int Rret, int max_len, float length_penalty, int32_t* seqs, float* scores,
+                               const int* forced_host, int n_forced, int node_forced);
 void free_persist_ws();
 
 void free_gen_ws(GenWs* g) {
@@ -705,9 +706,18 @@ void generate(Engine* e, const int32_t* ids, const int32_t* mask, const int32_t*
     e->build_bias(false, T);   // decoder relative bias for positions 0..T-1: [H, 2T-1], offset T-1
     const int n_delta = 2 * T - 1, bias_off = T - 1;
     if (persist) {
+        // forced prefix: while the node reached so far has exactly one child (and it is not EOS) every beam of every user
+        // must take that token ("ML1M item_" ... of the reference's item strings): known before decoding starts
+        std::vector<int> forced;
+        int node_f = root_child;
+        while ((int)forced.size() < 31 && trie->h_off[node_f + 1] - trie->h_off[node_f] == 1 && trie->h_tok[trie->h_off[node_f]] != 1) {
+            forced.push_back(trie->h_tok[trie->h_off[node_f]]);
+            node_f = trie->h_node[trie->h_off[node_f]];
+        }
         // ONE cooperative launch runs every decode position (decode_persist.cu)
         const int* out_len_dev = generate_persistent(e, trie->d_off, trie->d_tok, trie->d_node, root_child, trie->max_depth,
-                                                     trie->max_fanout, B, K, Rret, max_len, length_penalty, seqs, scores);
+                                                     trie->max_fanout, B, K, Rret, max_len, length_penalty, seqs, scores,
+                                                     forced.data(), (int)forced.size(), node_f);
         if (out_len_host) {
             P5_CUDA(cudaMemcpyAsync(out_len_host, out_len_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
             P5_CUDA(cudaStreamSynchronize(st));

@@ -65,6 +65,7 @@ struct PdLayer {
 struct PdParams {
     int B, K, R, T, Le, d, A, H, ff, V, Vpad, ND;
     int n_steps, max_len, max_len_eff, n_ret, root_child, no_light;
+    int n_forced, node_forced, forced[32];     // forced item prefix (the trie has ONE child per node there): prefilled in one pass
     float eps, hs, length_penalty;
     PdLayer layer[PD_MAXL];
     const float* E;            // shared.weight fp32 [V, d] (embedding lookups)
@@ -83,6 +84,7 @@ struct PdParams {
     int *cur_tok, *unsat, *live_u, *n_u;
     float* scr_score; int* scr_flat; int scr_cap;
     const int *t_off, *t_tok, *t_node;
+    int* tile_cnt;             // arrival counters of the split-K residual tiles (zero between phases)
     const CUtensorMap* tmaps;  // [6 * ND + 1 + 3]: weights per layer, LM head, then A operands y16 / ctx / h
     int no_tc;
     unsigned* bar;
@@ -309,10 +311,18 @@ __device__ void gemm_phase(const GemmDesc& g, const int* __restrict__ live, int 
 // (release / acquire at gpu scope); the producer adds the generic -> async proxy fence before its first TMA read.
 // ------------------------------------------------------------------------------------------------------------
 __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const CUtensorMap* tmB, int rows, uint32_t ring, uint32_t bars,
-                              uint32_t tmem_base, TcState& st) {
+                              uint32_t tmem_base, TcState& st, int* __restrict__ tile_cnt, int* s_flag) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (rows + T_TM - 1) / T_TM, n_tiles = (g.N + T_TN - 1) / T_TN, k_blocks = g.K / T_KB;
     const int total = m_tiles * n_tiles;
+    // Residual phases (mode 1) have N = d_model: only a few dozen tiles for 148 SMs, each streaming the whole K extent
+    // through ONE SM's L2 port.  They are split along K into `splits` work units per tile: every unit adds its partial
+    // product into y with red.global; the unit that arrives last on the tile's counter finalises the rows of the tile
+    // (y16 = bf16(y * ln_next), row sums of squares).
+    int splits = 1;
+    if (g.mode == 1) { splits = (int)gridDim.x / total; splits = splits < 1 ? 1 : (splits > k_blocks ? k_blocks : splits); if (splits > 4) splits = 4; }
+    const int kbs = (k_blocks + splits - 1) / splits;
+    const int units = total * splits;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (T_STAGES + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * T_STAGES + s); };
@@ -320,9 +330,11 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int t = u / splits, sp = u - t * splits;
                 const int m_blk = t % m_tiles, n_blk = t / m_tiles;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int kb0 = sp * kbs, kb1 = min(k_blocks, kb0 + kbs);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(st.stage), st.phase ^ 1);
                     const uint32_t sa = ring + st.stage * T_STAGE_BYTES, sb = sa + T_A_BYTES;
                     mbar_expect_tx(full_bar(st.stage), T_STAGE_BYTES);
@@ -337,17 +349,20 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
         if (lane == 0) {
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_TN >> 3) << 17) | ((uint32_t)(T_TM >> 4) << 24);
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sp = u % splits;
+                const int kb0 = sp * kbs, kb1 = min(k_blocks, kb0 + kbs);
                 mbar_wait(tempty_bar(st.acc), st.acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(st.acc * T_TN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(st.stage), st.phase);
                     tc_fence_after();
                     const uint32_t sa = ring + st.stage * T_STAGE_BYTES, sb = sa + T_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < T_KB / 16; ++k)
-                        umma_bf16(tmem_d, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_d, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc,
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
                     umma_commit(empty_bar(st.stage));
                     if (++st.stage == T_STAGES) { st.stage = 0; st.phase ^= 1; }
                 }
@@ -358,7 +373,8 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
         __syncwarp();
     } else if (warp >= 4) {
         const int ew = warp & 3;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int t = u / splits;
             const int m_blk = t % m_tiles, n_blk = t / m_tiles;
             mbar_wait(tfull_bar(st.acc), st.acc_phase);
             tc_fence_after();
@@ -372,8 +388,9 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
             if (lane == 0) mbar_arrive(tempty_bar(st.acc));          // the accumulator may be overwritten
             if (++st.acc == 2) { st.acc = 0; st.acc_phase ^= 1; }
             const int r = m_blk * T_TM + ew * 32 + lane, col0 = n_blk * T_TN;
-            if (r >= rows) continue;
+            const bool row_ok = r < rows;
             if (g.mode == 0) {
+                if (!row_ok) continue;
                 const float sc = row_scale(g, r);
                 bf16* out = g.out16 + (int64_t)r * g.ldo + col0;
 #pragma unroll
@@ -385,7 +402,31 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
                         *reinterpret_cast<uint4*>(out + 8 * c) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 }
             } else if (g.mode == 1) {
-                float* yp = g.y + (int64_t)r * g.d + col0;
+                float* yp = g.y + (int64_t)(row_ok ? r : 0) * g.d + col0;
+                bool finalize = true;
+                if (splits > 1) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (col0 + 4 * c < g.N)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yp + 4 * c), "f"(__uint_as_float(rr[4 * c])),
+                                             "f"(__uint_as_float(rr[4 * c + 1])), "f"(__uint_as_float(rr[4 * c + 2])), "f"(__uint_as_float(rr[4 * c + 3])) : "memory");
+                    }
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");                 // the 4 epilogue warps: every partial of this unit is out
+                    if (warp == 4 && lane == 0) {
+                        const int old = atomicAdd(tile_cnt + t, 1);
+                        const int last = (old == splits - 1) ? 1 : 0;
+                        if (last) { tile_cnt[t] = 0; __threadfence(); }
+                        *s_flag = last;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    finalize = *s_flag != 0;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");                 // s_flag is rewritten by the next unit
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) rr[c] = 0u;                      // the finaliser adds nothing more
+                }
+                if (!finalize || !row_ok) continue;
                 bf16* y16 = g.y16 + (int64_t)r * g.d + col0;
                 float ss = 0.f;
 #pragma unroll
@@ -395,14 +436,17 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
                     const float4 l0 = *reinterpret_cast<const float4*>(g.ln_next + col0 + 8 * c), l1 = *reinterpret_cast<const float4*>(g.ln_next + col0 + 8 * c + 4);
                     a.x += __uint_as_float(rr[8 * c]); a.y += __uint_as_float(rr[8 * c + 1]); a.z += __uint_as_float(rr[8 * c + 2]); a.w += __uint_as_float(rr[8 * c + 3]);
                     b.x += __uint_as_float(rr[8 * c + 4]); b.y += __uint_as_float(rr[8 * c + 5]); b.z += __uint_as_float(rr[8 * c + 6]); b.w += __uint_as_float(rr[8 * c + 7]);
-                    *reinterpret_cast<float4*>(yp + 8 * c) = a;
-                    *reinterpret_cast<float4*>(yp + 8 * c + 4) = b;
+                    if (splits == 1) {
+                        *reinterpret_cast<float4*>(yp + 8 * c) = a;
+                        *reinterpret_cast<float4*>(yp + 8 * c + 4) = b;
+                    }
                     *reinterpret_cast<uint4*>(y16 + 8 * c) = make_uint4(pack_bf16(a.x * l0.x, a.y * l0.y), pack_bf16(a.z * l0.z, a.w * l0.w),
                                                                         pack_bf16(b.x * l1.x, b.y * l1.y), pack_bf16(b.z * l1.z, b.w * l1.w));
                     ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
                 }
                 atomicAdd(g.rowss_out + r, ss);
             } else {
+                if (!row_ok) continue;
                 const float sc = row_scale(g, r);
                 float* lp = g.logits + (int64_t)r * g.ldl + col0;
                 float m = -INFINITY;
@@ -631,6 +675,76 @@ __device__ void self_attn_phase(const PdParams& P, const PdLayer& L, const int* 
     }
 }
 
+// Self-attention of the PREFILL pass: the forced item prefix (positions 0 .. p of every user, known before decoding starts
+// because the trie has a single child per node there) is decoded in one pass like a training sequence.  Item (b, t) lives in
+// row b * K + t; its keys / values for positions j <= t are the k / v projections of the sibling rows b * K + j of the same
+// pass (causal), and its own k / v go to position t of the user's representative KV-cache row b * K.
+__device__ void self_attn_prefill(const PdParams& P, const PdLayer& L, int p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, jg = lane >> 2, dq = lane & 3;
+    const int A = P.A, T = P.T, H = P.H, K = P.K, n_items = P.B * (p + 1);
+    for (int task = blockIdx.x * (PD_THREADS / 32) + warp; task < n_items * H; task += gridDim.x * (PD_THREADS / 32)) {
+        const int it = task / H, h = task - it * H, b = it / (p + 1), t = it - b * (p + 1), r = b * K + t;
+        const bf16* row = P.qkv + (int64_t)r * 3 * A + h * 64 + 16 * dq;
+        float q[16];
+        ld16_bf(q, row);
+        if (jg == 0) {
+            const int64_t o = ((int64_t)(b * K) * T + t) * A + h * 64 + 16 * dq;
+            *reinterpret_cast<uint4*>(L.Kc + o) = __ldcg(reinterpret_cast<const uint4*>(row + A));
+            *reinterpret_cast<uint4*>(L.Kc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row + A + 8));
+            *reinterpret_cast<uint4*>(L.Vc + o) = __ldcg(reinterpret_cast<const uint4*>(row + 2 * A));
+            *reinterpret_cast<uint4*>(L.Vc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row + 2 * A + 8));
+        }
+        float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        for (int j0 = 0; j0 <= t; j0 += 8) {
+            const int j = j0 + jg;
+            const bool valid = j <= t;
+            const bf16* kv = P.qkv + (int64_t)(b * K + (valid ? j : t)) * 3 * A + h * 64 + 16 * dq;
+            float k[16], v[16];
+            ld16_bf(k, kv + A);
+            ld16_bf(v, kv + 2 * A);
+            float sc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sc = fmaf(q[c], k[c], sc);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+            if (valid) {
+                int di = j - t + P.bias_off;
+                di = di < 0 ? 0 : (di >= P.n_delta ? P.n_delta - 1 : di);
+                sc += P.bias_dec[h * P.n_delta + di];
+                const float mn = fmaxf(m, sc);
+                const float scale = __expf(m - mn), pr = __expf(sc - mn);
+                l = l * scale + pr;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = fmaf(acc[c], scale, pr * v[c]);
+                m = mn;
+            }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o), ol = __shfl_xor_sync(0xffffffffu, l, o);
+            const float mn = fmaxf(m, om);
+            const float s0 = (m > -INFINITY) ? __expf(m - mn) : 0.f, s1 = (om > -INFINITY) ? __expf(om - mn) : 0.f;
+            l = l * s0 + ol * s1;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = acc[c] * s0 + __shfl_xor_sync(0xffffffffu, acc[c], o) * s1;
+            m = mn;
+        }
+        if (jg == 0) {
+            const float inv = 1.f / l;
+            bf16* out = P.ctx + (int64_t)r * A + h * 64 + 16 * dq;
+            uint4 w0, w1;
+            w0.x = pack_bf16(acc[0] * inv, acc[1] * inv); w0.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+            w0.z = pack_bf16(acc[4] * inv, acc[5] * inv); w0.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+            w1.x = pack_bf16(acc[8] * inv, acc[9] * inv); w1.y = pack_bf16(acc[10] * inv, acc[11] * inv);
+            w1.z = pack_bf16(acc[12] * inv, acc[13] * inv); w1.w = pack_bf16(acc[14] * inv, acc[15] * inv);
+            *reinterpret_cast<uint4*>(out) = w0;
+            *reinterpret_cast<uint4*>(out + 8) = w1;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // cross-attention: CTA per (user, head); the user's live beams are the query rows against that user's K | V
 // ------------------------------------------------------------------------------------------------------------
@@ -652,102 +766,101 @@ __device__ void cross_attn_phase(const PdParams& P, const PdLayer& L, uint8_t* s
     }
 }
 
-// Cross-attention when every user has only a few distinct beams (the forced item prefix: ONE): a 32-row mma tile per
-// (user, head) would be 97 % padding and the phase is pure K | V streaming, so each (user, head, beam) is ONE WARP:
-// lane j owns keys j, j+32, ...; it holds the whole 64-dim query, dots it with its key rows (16-byte loads, all
-// independent), the warp softmaxes with shuffles, each lane accumulates p . V over its keys and a 62-shuffle
-// reduce-scatter leaves two output dims per lane.  Le <= 512.
-__device__ void cross_attn_light(const PdParams& P, const PdLayer& L) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Cross-attention when every user has only a few distinct beams (the forced item prefix: ONE).  A 32-row mma tile per
+// (user, head) would be 97 % padding and the phase is pure K | V streaming, so it is organised for memory parallelism:
+// CTA per (user, head), THREAD per key (Le <= 256).  Every thread loads its key row and its share of the value rows up
+// front (16-byte loads, all independent), dots the key with the query held in shared memory, the block softmaxes, and the
+// P.V product is reduced through shared memory (thread = (8-key group, 8-dim chunk)).  Up to 8 query rows per user reuse
+// the K / V registers.
+__device__ void cross_attn_light(const PdParams& P, const PdLayer& L, uint8_t* smem) {
     const int B = P.B, H = P.H, K = P.K, Le = P.Le, A = P.A;
-    const int per_user = H * K;       // task index space (b, i, h) with i < n_u[b] checked inside
-    for (int task = blockIdx.x * (PD_THREADS / 32) + warp; task < B * per_user; task += gridDim.x * (PD_THREADS / 32)) {
-        const int b = task / per_user, rem = task - b * per_user, i = rem / H, h = rem - i * H;
-        if (i >= __ldcg(P.n_u + b)) continue;
-        const int r = __ldcg(P.live_u + b * K + i);
-        float q[64];
-        {
-            const bf16* qp = P.cq + (int64_t)r * A + h * 64;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { float t16[16]; ld16_bf(t16, qp + 16 * c);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) q[16 * c + e] = t16[e]; }
-        }
+    float* s_q = reinterpret_cast<float*>(smem);                 // [8][64] queries
+    float* s_p = s_q + 8 * 64;                                   // [256] probabilities of the current query
+    float* s_red = s_p + 256;                                    // [32] block reductions
+    float* s_o = s_red + 32;                                     // [32 key groups][64 dims] partial outputs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 3, ch = tid & 7;                      // P.V mapping: keys 8 grp .. 8 grp + 7, dims 8 ch .. 8 ch + 7
+    for (int task = blockIdx.x; task < B * H; task += gridDim.x) {
+        const int b = task / H, h = task - b * H;
+        const int nq = __ldcg(P.n_u + b);
+        if (nq <= 0) continue;
+        __syncthreads();                                         // the previous task's shared arrays are no longer read
         const bf16* kb = L.ck + (int64_t)b * Le * P.ckv_ld + h * 64;
         const bf16* vb = L.cv + (int64_t)b * Le * P.ckv_ld + h * 64;
-        const int* mask = P.mask_e + (int64_t)b * Le;
-        constexpr int MAXJ = 16;                       // Le <= 512
-        float sc[MAXJ];
-        float mx = -INFINITY;
+        // ---- issue every global load first: key row `tid`, value chunk of the 8 keys of `grp`
+        const bool kvalid = tid < Le && P.mask_e[(int64_t)b * Le + tid] != 0;
+        uint4 kr[8];
 #pragma unroll
-        for (int jj = 0; jj < MAXJ; ++jj) {
-            const int j = lane + 32 * jj;
-            sc[jj] = -INFINITY;
-            if (j < Le && mask[j] != 0) {
-                const uint4* kp = reinterpret_cast<const uint4*>(kb + (int64_t)j * P.ckv_ld);
+        for (int c = 0; c < 8; ++c) kr[c] = kvalid ? reinterpret_cast<const uint4*>(kb + (int64_t)tid * P.ckv_ld)[c] : make_uint4(0, 0, 0, 0);
+        uint4 vr[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = 8 * grp + jj;
+            vr[jj] = j < Le ? reinterpret_cast<const uint4*>(vb + (int64_t)j * P.ckv_ld)[ch] : make_uint4(0, 0, 0, 0);
+        }
+        for (int e = tid; e < nq * 64; e += PD_THREADS) {
+            const int i = e >> 6, c = e & 63;
+            s_q[e] = __bfloat162float(P.cq[(int64_t)__ldcg(P.live_u + b * K + i) * A + h * 64 + c]);
+        }
+        __syncthreads();
+        for (int i = 0; i < nq; ++i) {
+            const int r = __ldcg(P.live_u + b * K + i);
+            float sc = -INFINITY;
+            if (kvalid) {
                 float d = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 x = kp[c];
-                    const uint32_t u[4] = {x.x, x.y, x.z, x.w};
+                    const uint32_t u[4] = {kr[c].x, kr[c].y, kr[c].z, kr[c].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
-                        d = fmaf(q[8 * c + 2 * e], kv.x, d);
-                        d = fmaf(q[8 * c + 2 * e + 1], kv.y, d);
+                        d = fmaf(s_q[i * 64 + 8 * c + 2 * e], kv.x, d);
+                        d = fmaf(s_q[i * 64 + 8 * c + 2 * e + 1], kv.y, d);
                     }
                 }
-                sc[jj] = d;
-                mx = fmaxf(mx, d);
+                sc = d;
             }
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
+            float mx = warp_max(sc);
+            if (lane == 0) s_red[warp] = mx;
+            __syncthreads();
+            mx = s_red[0];
 #pragma unroll
-        for (int jj = 0; jj < MAXJ; ++jj) {
-            const float p = (sc[jj] > -INFINITY) ? __expf(sc[jj] - mx) : 0.f;
-            sc[jj] = p;
-            sum += p;
-        }
-        sum = warp_sum(sum);
-        const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        float acc[64];
+            for (int w2 = 1; w2 < PD_THREADS / 32; ++w2) mx = fmaxf(mx, s_red[w2]);
+            const float p = (sc > -INFINITY) ? __expf(sc - mx) : 0.f;
+            float sum = warp_sum(p);
+            if (lane == 0) s_red[8 + warp] = sum;
+            __syncthreads();
+            sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+            for (int w2 = 0; w2 < PD_THREADS / 32; ++w2) sum += s_red[8 + w2];
+            const float inv = sum > 0.f ? 1.f / sum : 0.f;
+            s_p[tid] = __bfloat162float(__float2bfloat16_rn(p * inv));        // P is a bf16 operand of P.V in the tiled kernels
+            __syncthreads();
+            float acc[8];
 #pragma unroll
-        for (int jj = 0; jj < MAXJ; ++jj) {
-            const int j = lane + 32 * jj;
-            if (j < Le && sc[jj] > 0.f) {
-                const float p = __bfloat162float(__float2bfloat16_rn(sc[jj] * inv));      // P is a bf16 operand of P.V in the tiled kernel
-                const uint4* vp = reinterpret_cast<const uint4*>(vb + (int64_t)j * P.ckv_ld);
+            for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 x = vp[c];
-                    const uint32_t u[4] = {x.x, x.y, x.z, x.w};
+            for (int jj = 0; jj < 8; ++jj) {
+                const float pj = s_p[8 * grp + jj];
+                const uint32_t u[4] = {vr[jj].x, vr[jj].y, vr[jj].z, vr[jj].w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
-                        acc[8 * c + 2 * e] = fmaf(p, vv.x, acc[8 * c + 2 * e]);
-                        acc[8 * c + 2 * e + 1] = fmaf(p, vv.y, acc[8 * c + 2 * e + 1]);
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+                    acc[2 * e] = fmaf(pj, vv.x, acc[2 * e]);
+                    acc[2 * e + 1] = fmaf(pj, vv.y, acc[2 * e + 1]);
                 }
             }
-        }
-        // reduce-scatter over the 32 lanes: after the step with offset o a lane keeps the half of its values selected by bit o
 #pragma unroll
-        for (int o = 16, n = 64; o >= 1; o >>= 1, n >>= 1) {
-            const bool up = (lane & o) != 0;
+            for (int c = 0; c < 8; ++c) s_o[grp * 64 + 8 * ch + c] = acc[c];
+            __syncthreads();
+            if (tid < 64) {
+                float o = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                if (c < n / 2) {
-                    const float mine = up ? acc[c + n / 2] : acc[c], send = up ? acc[c] : acc[c + n / 2];
-                    acc[c] = mine + __shfl_xor_sync(0xffffffffu, send, o);
-                }
+                for (int g2 = 0; g2 < 32; ++g2) o += s_o[g2 * 64 + tid];
+                P.ctx[(int64_t)r * A + h * 64 + tid] = __float2bfloat16_rn(o);
             }
+            __syncthreads();
         }
-        // lane now holds dims: bit16 -> +32, bit8 -> +16, bit4 -> +8, bit2 -> +4, bit1 -> +2 ; two consecutive dims
-        const int d0 = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
-        st_bf2(P.ctx + (int64_t)r * A + h * 64 + d0, acc[0], acc[1]);
     }
 }
 
@@ -795,6 +908,58 @@ __device__ __forceinline__ void embed_row(const PdParams& P, int r, int tok, int
     for (int s = lane; s < n_sites; s += 32) P.rowss[(int64_t)s * P.R + r] = (s == 0) ? ss : 0.f;
 }
 
+// log-softmax normaliser of one row from the LM-head tile partials (warp): S.rowmax / S.logsum [slot]
+__device__ __forceinline__ void combine_lse(const PdParams& P, UserSmem& S, int r, int slot, int n_parts, int lane) {
+    const float2* part = P.lse_part + (int64_t)r * n_parts;
+    float m = -INFINITY, s = 0.f;
+    for (int c = lane; c < n_parts; c += 32) {
+        const float2 p = __ldcg(part + c);
+        if (p.x > m) { s = s * __expf(m - p.x) + p.y; m = p.x; }
+        else if (p.x > -INFINITY) s += p.y * __expf(p.x - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+        const float M = fmaxf(m, om);
+        s = (m > -INFINITY ? s * __expf(m - M) : 0.f) + (om > -INFINITY ? os * __expf(om - M) : 0.f);
+        m = M;
+    }
+    if (lane == 0) { S.rowmax[slot] = m; S.logsum[slot] = logf(s); }
+}
+
+// After the prefill pass: the beam state HF's loop has after the p forced positions.  Beam 0 carries the accumulated
+// log-probability of the forced tokens (added position by position in fp32, as the loop does); the K-1 other beams are the
+// "-1e9" duplicates of beam 0 (HF:generation/utils.py:3200-3215: -1e9 plus a log-probability rounds back to -1e9 in fp32);
+// every beam's trie node is the node after the prefix, its KV rows are the representative row b*K, and the logits of the
+// next position sit in row b*K + p.
+__device__ void prefill_user_init(const PdParams& P, UserSmem& S, int b, int cur, int p, int n_parts) {
+    const int K = P.K, T = P.T, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = warp; t <= p; t += PD_THREADS / 32) combine_lse(P, S, b * K + t, t, n_parts, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sc = 0.f;
+        for (int t = 0; t < p; ++t) {
+            const float lp = (__ldcg(P.logits + (int64_t)(b * K + t) * P.Vpad + P.forced[t]) - S.rowmax[t]) - S.logsum[t];
+            sc = lp + sc;
+        }
+        S.s_misc[0] = sc;
+        P.live_u[b * K] = b * K + p;
+        P.n_u[b] = 1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += PD_THREADS) {
+        const int r = b * K + k;
+        P.run_score[cur][r] = (k == 0) ? S.s_misc[0] : PD_NEG_BIG;
+        P.node[cur][r] = P.node_forced;
+        P.rep[cur][r] = p;
+    }
+    for (int idx = threadIdx.x; idx < K * T; idx += PD_THREADS) {
+        const int t = idx % T;
+        P.seq[cur][b * K * T + idx] = (t >= 1 && t <= p) ? P.forced[t - 1] : 0;
+    }
+    __syncthreads();
+}
+
 __device__ void user_phase(const PdParams& P, UserSmem& S, int b, int cur, int cur_len, int step, int n_parts) {
     const int K = P.K, T = P.T, V = P.V;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -805,21 +970,7 @@ __device__ void user_phase(const PdParams& P, UserSmem& S, int b, int cur, int c
     const int nq = __ldcg(P.n_u + b);
     for (int i = warp; i < nq; i += PD_THREADS / 32) {
         const int r = __ldcg(P.live_u + b * K + i);
-        const float2* part = P.lse_part + (int64_t)r * n_parts;
-        float m = -INFINITY, s = 0.f;
-        for (int c = lane; c < n_parts; c += 32) {
-            const float2 p = __ldcg(part + c);
-            if (p.x > m) { s = s * __expf(m - p.x) + p.y; m = p.x; }
-            else if (p.x > -INFINITY) s += p.y * __expf(p.x - m);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
-            const float M = fmaxf(m, om);
-            s = (m > -INFINITY ? s * __expf(m - M) : 0.f) + (om > -INFINITY ? os * __expf(om - M) : 0.f);
-            m = M;
-        }
-        if (lane == 0) { S.rowmax[r - b * K] = m; S.logsum[r - b * K] = logf(s); }
+        combine_lse(P, S, r, r - b * K, n_parts, lane);
     }
     if (threadIdx.x < K) { S.s_nd[threadIdx.x] = __ldcg(node_in + b * K + threadIdx.x); S.s_rep[threadIdx.x] = __ldcg(rep_in + b * K + threadIdx.x); }
     __syncthreads();
@@ -1026,6 +1177,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
     uint8_t* work = smem + ((P.R * 4 + 127) & ~127);                  // GEMM ring / attention staging
     // ---- tcgen05 pipeline of the heavy GEMM phases: ring (1024-aligned, SWIZZLE_128B), mbarriers, TMEM accumulators
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_tcflag;
     const uint32_t ring = (smem_u32(work) + 1023u) & ~1023u;
     const uint32_t bars = ring + T_STAGES * T_STAGE_BYTES;
     if (threadIdx.x == 32) {
@@ -1053,9 +1205,16 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
         P.run_score[0][r] = (k == 0) ? 0.f : PD_NEG_BIG;
         P.fin_score[0][r] = PD_NEG_BIG;
         P.is_fin[0][r] = 0; P.gen_len[0][r] = 0; P.cur_tok[r] = 0;
-        if (k == 0) { P.unsat[b] = 1; P.n_u[b] = 1; P.live_u[b * K] = r; }
+        if (k == 0) { P.unsat[b] = 1; P.n_u[b] = 1 + P.n_forced; }
+        if (k <= P.n_forced) P.live_u[r] = r;          // prefill: item (b, t) = row b*K + t, t = 0 .. n_forced
     }
-    for (int b = blockIdx.x * (PD_THREADS / 32) + warp; b < B; b += gridDim.x * (PD_THREADS / 32)) embed_row(P, b * K, 0, lane);
+    {   // decoder inputs: the start token, and (prefill) the forced prefix tokens as the inputs of positions 1 .. p
+        const int per = 1 + P.n_forced;
+        for (int e = blockIdx.x * (PD_THREADS / 32) + warp; e < B * per; e += gridDim.x * (PD_THREADS / 32)) {
+            const int b = e / per, t = e - b * per;
+            embed_row(P, b * K + t, t == 0 ? 0 : P.forced[t - 1], lane);
+        }
+    }
     grid_barrier(P.bar, bar_target);
 
     uint64_t t_last = pd_timer();
@@ -1068,7 +1227,12 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
         }
     };
     int cur = 0;
-    for (int step = 0; step < P.n_steps; ++step) {
+    const int n_forced = P.n_forced;
+    // iteration -1 (only with a forced prefix): the PREFILL pass over positions 0 .. p of every user; it produces the logits of
+    // position p, so the regular loop continues at position p + 1
+    for (int it = (n_forced > 0 ? -1 : 0); it < P.n_steps; it = (it < 0 ? n_forced + 1 : it + 1)) {
+        const bool prefill = it < 0;
+        const int step = prefill ? n_forced : it;
         const int cur_len = step + 1, pos = step;
         // ---- live rows of this position (every CTA builds the same list)
         if (threadIdx.x == 0) {
@@ -1095,7 +1259,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
         auto run_gemm = [&](const GemmDesc& gd, int wmap, int amap) {
             if (light) gemm_light(gd, s_live, n_live, work);
             else if (P.no_tc) gemm_phase(gd, s_live, n_live, work);
-            else gemm_tc_phase(gd, P.tmaps + amap, P.tmaps + wmap, R, ring, bars, tmem_base, tcs);
+            else gemm_tc_phase(gd, P.tmaps + amap, P.tmaps + wmap, R, ring, bars, tmem_base, tcs, P.tile_cnt, &s_tcflag);
         };
         const int TM_HEAD = TM_PER_LAYER * P.ND, TM_Y16 = TM_HEAD + 1, TM_CTX = TM_HEAD + 2, TM_H = TM_HEAD + 3;
         prof_heavy = !light;
@@ -1116,7 +1280,8 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             grid_barrier(P.bar, bar_target);
             mark(PH_QKV);
             // (b) self-attention over the cached positions (+ KV append)
-            self_attn_phase(P, L, s_live, n_live, P.src[cur], pos);
+            if (prefill) self_attn_prefill(P, L, n_forced);
+            else self_attn_phase(P, L, s_live, n_live, P.src[cur], pos);
             grid_barrier(P.bar, bar_target);
             mark(PH_SA);
             // (c) y += ctx . Wo^T      -> y16 = bf16(y * ln1), rowss1
@@ -1130,7 +1295,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             grid_barrier(P.bar, bar_target);
             mark(PH_CQ);
             // (e) cross-attention over the user's encoder K | V (zero position bias + encoder padding mask)
-            if (max_nq <= 4) cross_attn_light(P, L);
+            if (max_nq <= 8 && P.Le <= 256) cross_attn_light(P, L, work);
             else if (P.Le <= 256) cross_attn_phase<4>(P, L, work);
             else cross_attn_phase<8>(P, L, work);
             grid_barrier(P.bar, bar_target);
@@ -1160,7 +1325,10 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
         grid_barrier(P.bar, bar_target);
         mark(PH_LM);
         // ---- per user: normaliser, constrained top-2K, beam update, next input embedding
-        for (int b = blockIdx.x; b < B; b += gridDim.x) user_phase(P, US, b, cur, cur_len, step, n_parts);
+        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            if (prefill) prefill_user_init(P, US, b, cur, n_forced, n_parts);
+            user_phase(P, US, b, cur, cur_len, step, n_parts);
+        }
         grid_barrier(P.bar, bar_target);
         mark(PH_USER);
         cur ^= 1;
@@ -1236,7 +1404,8 @@ bool decode_persistent_supported(const Engine* e, int B, int K, int max_len, int
 
 // the search itself; the caller (beam.cu generate) has run the encoder, projected the cross K|V and built the decoder bias
 const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, const int* t_node, int root_child, int max_depth,
-                               int max_fanout, int B, int K, int Rret, int max_len, float length_penalty, int32_t* seqs, float* scores) {
+                               int max_fanout, int B, int K, int Rret, int max_len, float length_penalty, int32_t* seqs, float* scores,
+                               const int* forced_host, int n_forced, int node_forced) {
     cudaStream_t st = e->st;
     const int R = B * K, T = max_len, d = e->d, A = e->A, ff = e->ff, ND = e->ND, Vpad = e->Vpad;
     const int cand_cap = K * (max_fanout > 0 ? max_fanout : 1);
@@ -1267,6 +1436,7 @@ const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, co
         H.scr_score = (float*)al((size_t)B * cand_cap * 4); H.scr_flat = (int*)al((size_t)B * cand_cap * 4); H.scr_cap = cand_cap;
         H.bar = (unsigned*)al(256);
         H.prof = (unsigned long long*)al(32 * 8);
+        H.tile_cnt = (int*)al(1024 * 4);
         H.out_len = (int*)al(16);
         w->dev = (PdParams*)al(sizeof(PdParams));
         w->tmaps_dev = (CUtensorMap*)al(sizeof(CUtensorMap) * (TM_PER_LAYER * ND + 4));
@@ -1287,6 +1457,12 @@ const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, co
     H.eps = e->cfg.ln_eps; H.hs = 1.f / sqrtf((float)d); H.length_penalty = length_penalty;
     static const bool no_light = getenv("P5_DECODE_NO_LIGHT") != nullptr;
     H.no_light = no_light ? 1 : 0;
+    // forced item prefix (single-child trie nodes from the root): decoded in ONE prefill pass instead of one position at a
+    // time.  Needs the items (b, t) of a user to fit its K beam rows and the last position to stay in the regular loop.
+    static const bool no_prefill = getenv("P5_DECODE_NO_PREFILL") != nullptr;
+    if (no_prefill || n_forced + 1 > K || n_forced > 31 || n_forced + 1 > H.n_steps) n_forced = 0;
+    H.n_forced = n_forced; H.node_forced = n_forced > 0 ? node_forced : root_child;
+    for (int i = 0; i < 32; ++i) H.forced[i] = i < n_forced ? forced_host[i] : 0;
     for (int l = 0; l < ND; ++l) {
         const DecLayerOff& o = e->dec[l];
         PdLayer& L = H.layer[l];

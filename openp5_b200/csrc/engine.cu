@@ -138,7 +138,9 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     yd.resize(3 * ND + 1); rstd_d.resize(3 * ND + 1); nd.resize(3 * ND);
     for (auto& p : yd) p = dalloc_t<float>(Mdm * d);
     for (auto& p : rstd_d) p = dalloc_t<float>(Mdm);
-    for (auto& p : nd) p = dalloc(Mdm * d * e);
+    // the saved inputs of the decoder's linear layers are slabs with a constant per-layer stride (batched weight gradients)
+    nd_all = dalloc((size_t)3 * (ND > 0 ? ND : 1) * Mdm * d * e);
+    for (int i = 0; i < 3 * ND; ++i) nd[i] = poff(nd_all, (int64_t)i * Mdm * d, dt);
     dec_out = dalloc(Mdm * d * e);
     sqkv.resize(ND); sctx.resize(ND); cq.resize(ND); ckv.resize(ND); cctx.resize(ND); h_d.resize(ND);
     z_d.assign(ND, nullptr); slse.resize(ND); clse.resize(ND);
@@ -151,13 +153,26 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
         for (int i = 1; i < ND; ++i) batched_ckv = batched_ckv && (dec[i].ca.k - dec[0].ca.k == i * dec_layer_stride);
         if (batched_ckv) g_ckv_all = dalloc(Mem * ckv_ld * e);
     }
+    h_d_all = dalloc((size_t)(ND > 0 ? ND : 1) * Mdm * ff * e);
+    sctx_all = dalloc((size_t)(ND > 0 ? ND : 1) * Mdm * A * e);
+    cctx_all = dalloc((size_t)(ND > 0 ? ND : 1) * Mdm * A * e);
+    {
+        static const bool off = getenv("P5_NO_BATCHED_DWG") != nullptr;
+        batched_dwg = dt == DT_BF16 && ND > 2 && !gated && !off;
+        for (int i = 2; i < ND; ++i)      // layer 0 carries the relative-bias table between sa.o and ln0: strides are checked from layer 1 on
+            batched_dwg = batched_dwg && (dec[i].sa.q - dec[1].sa.q == (i - 1) * dec_layer_stride) && (dec[i].ff.wo - dec[0].ff.wo == i * dec_layer_stride);
+        if (batched_dwg) {
+            gdw_all = dalloc((size_t)ND * Mdm * d * e); gdc_all = dalloc((size_t)ND * Mdm * d * e); gds_all = dalloc((size_t)ND * Mdm * d * e);
+            gff_all = dalloc((size_t)ND * Mdm * ff * e); gcq_all = dalloc((size_t)ND * Mdm * A * e); gsq_all = dalloc((size_t)ND * Mdm * 3 * A * e);
+        }
+    }
     for (int i = 0; i < ND; ++i) {
         sqkv[i] = dalloc(Mdm * 3 * A * e);
-        sctx[i] = dalloc(Mdm * A * e);
+        sctx[i] = poff(sctx_all, (int64_t)i * Mdm * A, dt);
         cq[i] = dalloc(Mdm * A * e);
         ckv[i] = poff(ckv_all, (int64_t)i * 2 * A, dt);
-        cctx[i] = dalloc(Mdm * A * e);
-        h_d[i] = dalloc(Mdm * ff * e);
+        cctx[i] = poff(cctx_all, (int64_t)i * Mdm * A, dt);
+        h_d[i] = poff(h_d_all, (int64_t)i * Mdm * ff, dt);
         if (gated) z_d[i] = dalloc(Mdm * 2 * ff * e);
         slse[i] = dalloc_t<float>((int64_t)Bm * H * Ldm);
         clse[i] = dalloc_t<float>((int64_t)Bm * H * Ldm);
@@ -458,15 +473,18 @@ void Engine::ffn_fwd(const void* n, int64_t M, const FfnOff& w, void* z, void* h
 
 // in: dx_out = dL/dx_out (fp32).  out: dn_out (dt) = dL/dn; weight grads accumulated.
 void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void* n, const void* z, const void* h,
-                     void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer) {
-    // g_d = dropout-cast(dx_out) was already produced by the rmsnorm_bwd that computed dx_out
-    // every linear: dgrad first, then its wgrad (independent of the dgrad -> fills the dgrad's partial last wave)
+                     void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer, const void* gd, void* gff, bool skip_wgrad) {
+    // gd (default g_d) = dropout-cast(dx_out) was already produced by the rmsnorm_bwd that computed dx_out
+    // every linear: dgrad first, then its wgrad (independent of the dgrad -> fills the dgrad's partial last wave);
+    // skip_wgrad: the caller batches the weight gradients of all layers afterwards (gd / gff are then per-layer buffers)
+    if (!gd) gd = g_d;
+    if (!gff) gff = g_ff;
     if (!gated) {
         const DropCfg da = drop(kind_act, layer);
-        linear_dgrad(g_d, d, w.wo, d, ff, (int)M, g_ff, dt, ff, EPI_MULPOS, da.inv_keep, h, false);
-        linear_wgrad(g_d, d, h, ff, w.wo, d, ff, (int)M, 1.f, true);
-        linear_dgrad(g_ff, ff, w.wi, ff, d, (int)M, dn_out, dt, d, 0, 1.f, nullptr, false);
-        linear_wgrad(g_ff, ff, n, d, w.wi, ff, d, (int)M, 1.f, true);
+        linear_dgrad(gd, d, w.wo, d, ff, (int)M, gff, dt, ff, EPI_MULPOS, da.inv_keep, h, false);
+        if (!skip_wgrad) linear_wgrad(gd, d, h, ff, w.wo, d, ff, (int)M, 1.f, true);
+        linear_dgrad(gff, ff, w.wi, ff, d, (int)M, dn_out, dt, d, 0, 1.f, nullptr, false);
+        if (!skip_wgrad) linear_wgrad(gff, ff, n, d, w.wi, ff, d, (int)M, 1.f, true);
     } else {
         void* dh = poff(g_ff, (int64_t)M * 2 * ff, dt);   // g_ff = [dz (M x 2ff) | dh (M x ff)]
         linear_dgrad(g_d, d, w.wo, d, ff, (int)M, dh, dt, ff, 0, 1.f, nullptr, false);
@@ -741,6 +759,39 @@ void Engine::forward(const int32_t* ids, const int32_t* mask, const int32_t* ww,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// decoder weight gradients, batched over the layers: dW_l = dY_l^T . X_l for the six linear layers of a decoder block
+// (FFN wo / wi, cross-attention o / q, self-attention o / q|k|v).  One GEMM per weight type, batch dimension 2 = layer:
+// dY and X are read from the per-layer slabs (MN-major, in place), dW lands in the flat gradient buffer at the layer
+// stride.  The self-attention weights of layer 0 sit before the relative-bias table, so their stride to layer 1 differs:
+// layer 0 is its own launch.
+// ------------------------------------------------------------------------------------------------------------
+void Engine::decoder_wgrads_batched() {
+    const int64_t rs = (int64_t)Ldm * Bm;            // rows per layer slab
+    auto run = [&](const void* dY, int64_t wy, int64_t sy, const void* X, int64_t wx, int64_t sx, int64_t w_off, int N, int K, int l0, int nl) {
+        if (nl <= 0) return;
+        GemmProblem p;
+        p.indep_of_prev = true;
+        p.M = N; p.N = K; p.K = (int)Md; p.nb1 = 1; p.nb2 = nl;
+        p.prefer_bn = K > 128 ? 256 : (K > 64 ? 128 : 64);
+        p.A.ptr = poff(dY, (int64_t)l0 * sy, dt); p.A.dtype = dt; p.A.major = MAJOR_MN; p.A.ld = wy; p.A.bs2 = sy;
+        p.B.ptr = poff(X, (int64_t)l0 * sx, dt); p.B.dtype = dt; p.B.major = MAJOR_MN; p.B.ld = wx; p.B.bs2 = sx;
+        p.epi.C = G + w_off; p.epi.c_dtype = DT_F32; p.epi.ldc = K; p.epi.cs2 = dec_layer_stride; p.epi.alpha = 1.f;
+        p.epi.flags = EPI_ATOMIC;
+        gemm(p);
+    };
+    // FFN and cross-attention weights come after the relative-bias table of layer 0: one stride for all layers
+    run(gdw_all, d, rs * d, h_d_all, ff, rs * ff, dec[0].ff.wo, d, ff, 0, ND);
+    run(gff_all, ff, rs * ff, poff(nd_all, 2 * rs * d, dt), d, 3 * rs * d, dec[0].ff.wi, ff, d, 0, ND);
+    run(gdc_all, d, rs * d, cctx_all, A, rs * A, dec[0].ca.o, d, A, 0, ND);
+    run(gcq_all, A, rs * A, poff(nd_all, rs * d, dt), d, 3 * rs * d, dec[0].ca.q, A, d, 0, ND);
+    // self-attention weights: layer 0 alone, layers 1.. batched
+    run(gds_all, d, rs * d, sctx_all, A, rs * A, dec[0].sa.o, d, A, 0, 1);
+    run(gds_all, d, rs * d, sctx_all, A, rs * A, dec[1].sa.o, d, A, 1, ND - 1);
+    run(gsq_all, 3 * A, rs * 3 * A, nd_all, d, 3 * rs * d, dec[0].sa.q, 3 * A, d, 0, 1);
+    run(gsq_all, 3 * A, rs * 3 * A, nd_all, d, 3 * rs * d, dec[1].sa.q, 3 * A, d, 1, ND - 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // backward (consumes this->dloss = dL/dloss_tok)
 // ------------------------------------------------------------------------------------------------------------
 void Engine::backward() {
@@ -759,8 +810,14 @@ void Engine::backward() {
     linear_dgrad(dlogits, Vpad, off_shared, V, d, (int)Md, g_d2, dt, d, 0, hs, nullptr, false);
     linear_wgrad(dlogits, Vpad, dec_out, d, off_shared, V, d, (int)Md, hs, true);
     float* dy = dx_a;
+    // per-layer dY buffers when the decoder weight gradients are batched over the layers afterwards (decoder_wgrads_batched)
+    const bool bw = batched_dwg && dattn_supported(dec_self_args(*this, 0, DropCfg())) && dattn_supported(dec_cross_args(*this, 0, DropCfg()));
+    auto L_ = [&](void* slab, int l, int64_t width) -> void* { return poff(slab, (int64_t)l * Ldm * Bm * width, dt); };
+    auto gdw = [&](int l) -> void* { return bw ? L_(gdw_all, l, d) : g_d; };
+    auto gdc = [&](int l) -> void* { return bw ? L_(gdc_all, l, d) : g_d; };
+    auto gds = [&](int l) -> void* { return bw ? L_(gds_all, l, d) : g_d; };
     rmsnorm_bwd(g_d2, dt, yd[3 * ND], rstd_d[3 * ND], P + off_dec_final, nullptr, dy, G + off_dec_final, (int)Md, d,
-                drop(S_DEC_FINAL, 0), st, g_d, dt, drop(S_DEC_WO, ND - 1));
+                drop(S_DEC_FINAL, 0), st, ND > 0 ? gdw(ND - 1) : g_d, dt, drop(S_DEC_WO, ND - 1));
     P5_CUDA(cudaMemsetAsync(d_encout, 0, Mt * d * sizeof(float), st));
     P5_CUDA(cudaMemsetAsync(dbias_dec, 0, (size_t)H * (2 * Ld) * sizeof(float), st));
     DropCfg none;
@@ -768,23 +825,24 @@ void Engine::backward() {
     for (int l = ND - 1; l >= 0; --l) {
         const DecLayerOff& w = dec[l];
         float *y0 = yd[3 * l], *y1 = yd[3 * l + 1], *y2 = yd[3 * l + 2];
-        ffn_bwd(dy, Md, w.ff, nd[3 * l + 2], z_d[l], h_d[l], g_d2, S_DEC_ACT, S_DEC_WO, l);
-        rmsnorm_bwd(g_d2, dt, y2, rstd_d[3 * l + 2], P + w.ln2, dy, dy, G + w.ln2, (int)Md, d, none, st, g_d, dt,
+        ffn_bwd(dy, Md, w.ff, nd[3 * l + 2], z_d[l], h_d[l], g_d2, S_DEC_ACT, S_DEC_WO, l, gdw(l), bw ? L_(gff_all, l, ff) : nullptr, bw);
+        rmsnorm_bwd(g_d2, dt, y2, rstd_d[3 * l + 2], P + w.ln2, dy, dy, G + w.ln2, (int)Md, d, none, st, gdc(l), dt,
                     drop(S_DEC_CO, l));
-        // cross attention (g_d = dropout-cast(dy))
-        linear_dgrad(g_d, d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f, true);
+        // cross attention (gdc = dropout-cast(dy))
+        linear_dgrad(gdc(l), d, w.ca.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        if (!bw) linear_wgrad(g_d, d, cctx[l], A, w.ca.o, d, A, (int)Md, 1.f, true);
         void *gq, *gkv = nullptr;
         const AttnArgs ca = dec_cross_args(*this, l, drop(S_DEC_CP, l));
         const bool batch_kv = batched_ckv && dattn_supported(ca);     // dK|dV of all layers -> one wgrad / dgrad after the loop
         if (dattn_supported(ca)) {   // bf16: tensor-core kernel writes dQ and dK|dV as bf16 in place
             void* dk = batch_kv ? poff(g_ckv_all, (int64_t)l * 2 * A, dt) : g_ckv;
             const int64_t ldkv = batch_kv ? ckv_ld : 2 * A;
-            dattn_bwd(ca, g_ctx, A, (int64_t)Ld * A, clse[l], g_qkv, A, (int64_t)Ld * A, dk, poff(dk, A, dt), ldkv,
+            void* dq = bw ? L_(gcq_all, l, A) : g_qkv;
+            dattn_bwd(ca, g_ctx, A, (int64_t)Ld * A, clse[l], dq, A, (int64_t)Ld * A, dk, poff(dk, A, dt), ldkv,
                       (int64_t)Le * ldkv, nullptr, st);
             if (!batch_kv && packed && Mt > Mt_true)   // filler rows of dK|dV: zero gradient
                 P5_CUDA(cudaMemsetAsync(poff(g_ckv, Mt_true * 2 * A, dt), 0, (Mt - Mt_true) * 2 * A * dtype_size(dt), st));
-            gq = g_qkv;
+            gq = dq;
             gkv = g_ckv;
         } else {
             if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_ckv, 0, Mt * 2 * A * sizeof(float), st));
@@ -801,18 +859,19 @@ void Engine::backward() {
             next_gemm_indep = true;   // reads gq and W only: independent of the cross-K|V dgrad / wgrad before it
         }
         linear_dgrad(gq, A, w.ca.q, A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
-        linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f, true);
-        rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st, g_d, dt,
+        if (!bw) linear_wgrad(gq, A, nd[3 * l + 1], d, w.ca.q, A, d, (int)Md, 1.f, true);
+        rmsnorm_bwd(g_d2, dt, y1, rstd_d[3 * l + 1], P + w.ln1, dy, dy, G + w.ln1, (int)Md, d, none, st, gds(l), dt,
                     drop(S_DEC_SO, l));
-        // self attention (g_d = dropout-cast(dy))
-        linear_dgrad(g_d, d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
-        linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f, true);
+        // self attention (gds = dropout-cast(dy))
+        linear_dgrad(gds(l), d, w.sa.o, d, A, (int)Md, g_ctx, dt, A, 0, 1.f, nullptr, false);
+        if (!bw) linear_wgrad(g_d, d, sctx[l], A, w.sa.o, d, A, (int)Md, 1.f, true);
         void* gqkv;
         const AttnArgs sa = dec_self_args(*this, l, drop(S_DEC_SP, l));
         if (dattn_supported(sa)) {
-            dattn_bwd(sa, g_ctx, A, (int64_t)Ld * A, slse[l], g_qkv, 3 * A, (int64_t)Ld * 3 * A, poff(g_qkv, A, dt),
-                      poff(g_qkv, 2 * A, dt), 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
-            gqkv = g_qkv;
+            void* dq = bw ? L_(gsq_all, l, 3 * A) : g_qkv;
+            dattn_bwd(sa, g_ctx, A, (int64_t)Ld * A, slse[l], dq, 3 * A, (int64_t)Ld * 3 * A, poff(dq, A, dt),
+                      poff(dq, 2 * A, dt), 3 * A, (int64_t)Ld * 3 * A, dbias_dec, st);
+            gqkv = dq;
         } else {
             if (attn_bwd_needs_zero(Ld)) P5_CUDA(cudaMemsetAsync(f_qkv, 0, Md * 3 * A * sizeof(float), st));
             attn_simt_bwd(sa, sctx[l], g_ctx, dt, A, (int64_t)Ld * A, slse[l], f_qkv, 3 * A, (int64_t)Ld * 3 * A, f_qkv + A,
@@ -820,10 +879,11 @@ void Engine::backward() {
             gqkv = as_T(f_qkv, g_qkv, Md * 3 * A);
         }
         linear_dgrad(gqkv, 3 * A, w.sa.q, 3 * A, d, (int)Md, g_d2, dt, d, 0, 1.f, nullptr, false);
-        linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f, true);
-        rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st, l > 0 ? g_d : nullptr, dt,
+        if (!bw) linear_wgrad(gqkv, 3 * A, nd[3 * l], d, w.sa.q, 3 * A, d, (int)Md, 1.f, true);
+        rmsnorm_bwd(g_d2, dt, y0, rstd_d[3 * l], P + w.ln0, dy, dy, G + w.ln0, (int)Md, d, none, st, l > 0 ? gdw(l - 1) : nullptr, dt,
                     drop(S_DEC_WO, l > 0 ? l - 1 : 0));
     }
+    if (bw) decoder_wgrads_batched();
     if (batched_ckv && ND > 0 && dattn_supported(dec_cross_args(*this, 0, none))) {
         if (packed && Mt > Mt_true)   // filler rows of every layer's dK|dV: zero gradient
             P5_CUDA(cudaMemsetAsync(poff(g_ckv_all, Mt_true * ckv_ld, dt), 0, (Mt - Mt_true) * ckv_ld * dtype_size(dt), st));

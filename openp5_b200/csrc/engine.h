@@ -107,6 +107,14 @@ struct Engine {
     void *ckv_all = nullptr, *g_ckv_all = nullptr;
     int64_t ckv_ld = 0, dec_layer_stride = 0;
     bool batched_ckv = false;
+    // Decoder weight gradients of ALL layers as one batched GEMM per weight type (batch dimension = layer): the decoder has
+    // only B * Ld (= 512) tokens, so its 6 wgrads per layer are launch- and pipeline-fill-bound (~13 us each for < 1 us of
+    // tensor work, 72 launches per step); none of them is on the critical path of the backward.  Their operands (the
+    // incoming gradient dY of every linear and its saved input X) live in per-layer slabs with a constant stride.
+    bool batched_dwg = false;
+    void *gdw_all = nullptr, *gdc_all = nullptr, *gds_all = nullptr, *gff_all = nullptr, *gcq_all = nullptr, *gsq_all = nullptr;
+    void *nd_all = nullptr, *h_d_all = nullptr, *sctx_all = nullptr, *cctx_all = nullptr;
+    void decoder_wgrads_batched();
     void project_cross_kv_all(int64_t rows);
     // model.resize_token_embeddings(n) (main.py:193): rebuilds the flat buffers for the new vocabulary, keeps every other
     // tensor and the first min(V, n) embedding rows (and their Adam moments); new rows ~ N(0, 1) like HF's T5 init
@@ -179,7 +187,8 @@ struct Engine {
     void ffn_fwd(const void* n, int64_t M, const FfnOff& w, void* z, void* h, const float* x_resid, float* x_out,
                  uint32_t kind_act, uint32_t kind_wo, int layer);
     void ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void* n, const void* z, const void* h,
-                 void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer);
+                 void* dn_out, uint32_t kind_act, uint32_t kind_wo, int layer, const void* gd = nullptr, void* gff = nullptr,
+                 bool skip_wgrad = false);
 
     NoDecay no_decay(int64_t base) const;
     void grad_norm();

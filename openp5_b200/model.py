@@ -423,7 +423,9 @@ class P5B200:
         callback built from a Trie (gt.prefix_allowed_tokens_fn(trie)); the closure's trie is recovered and flattened
         to the device CSR form once and cached on the callable."""
         self._on_stream()
-        self._sync_params()
+        # an eval loop calls generate() batch after batch on unchanged weights (ref DistributedRunner.py:359-371): the bf16
+        # shadows are re-cast only when a parameter tensor's version moved or after load_state_dict / mark_params_changed
+        self._sync_params(fast_path=True)
         if trie is None:
             trie = self._trie_from_callback(prefix_allowed_tokens_fn)
         ids = _i32(input_ids, self.device)
