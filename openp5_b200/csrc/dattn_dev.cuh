@@ -10,6 +10,13 @@ namespace p5 {
 namespace {
 
 
+#ifdef P5_CA_STAMPS      // debugging aid of decode_persist.cu: where one (user, head) pair of the decode cross-attention spends its time
+__device__ unsigned long long g_ca_stamp[8];
+#define CA_STAMP(i) do { if (blockIdx.x == 0 && tid == 0 && bar_id == 2) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_ca_stamp[i] = t_; } } while (0)
+#else
+#define CA_STAMP(i)
+#endif
+
 struct DAttnDev {
     int B, H, Lq, Lk;
     const bf16 *q, *k, *v;
@@ -130,15 +137,25 @@ template <int NT, int NW> struct DCfg {
 // One (batch b, head h) pair on NW warps: up to 32 query rows (the beams of a user at a decode step) against that user's
 // keys.  `qrows` (optional): the i-th query / output row lives at absolute row qrows[i] of q / O (row stride q_ld / ld_o,
 // no batch stride) — the persistent decode kernel passes the user's live beam rows; null = rows b*bs + i*ld.
-template <int NT, int NW>
+// `tid` / `bar_id`: the NW warps may be a SUB-GROUP of the CTA (two (user, head) pairs side by side in the persistent decode
+// kernel): tid = thread index inside the group, bar_id = the named barrier the group synchronises on (0 = the whole CTA).
+// KSMEM: the K rows go through shared memory too (cp.async, every row of the pair in flight at once; the tile follows the
+// V region and the softmax scratch) instead of eight dependent rounds of register loads — for K | V that come from HBM.
+template <int NT, int NW, bool KSMEM = false>
 __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __restrict__ O, int64_t ld_o, int64_t bs_o, int b, int h,
-                                                 uint8_t* smem, const int* qrows = nullptr) {
+                                                 uint8_t* smem, const int* qrows = nullptr, int tid = -1, int bar_id = 0) {
+    if (tid < 0) tid = threadIdx.x;
+    auto group_sync = [&]() {
+        if (bar_id == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(NW * 32) : "memory");
+    };
+    CA_STAMP(0);
     using C = DCfg<NT, NW>;
     constexpr int PART = NW * 32 * 64 * 4;
     constexpr int REGION = C::TILE > PART ? C::TILE : PART;
     uint8_t* Vs = smem;
     float* red = reinterpret_cast<float*>(smem + REGION);            // [2][NW][32]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int Lk = a.kv_len ? a.kv_len[b] : a.Lk;
     const int64_t k_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.k_ld : (int64_t)b * a.k_bs;
     const int64_t v_boff = a.kv_off ? (int64_t)a.kv_off[b] * a.v_ld : (int64_t)b * a.v_bs;
@@ -146,8 +163,27 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
     const int key0 = warp * kpw, ntw = kpw >> 3;
     const bf16* kb = a.k + k_boff + h * 64;
     const bf16* vb = a.v + v_boff + h * 64;
+    uint8_t* Ks = smem + REGION + 2 * NW * 32 * 4 + 128;
+    if (KSMEM) {
+        stage_rows(Ks, warp * C::KW, kb, a.k_ld, key0, kpw, Lk, lane);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
     stage_rows(Vs, warp * C::KW, vb, a.v_ld, key0, kpw, Lk, lane);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
 
+    // validity of this lane's 2 NT key columns (length + padding mask), read once and early: the score loop below touches
+    // every column 4 times and used to go back to the mask in global memory for each of them
+    uint32_t kbits = 0;
+    {
+        const int* km = a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = key0 + 8 * nt + 2 * t + e;
+                if (nt < ntw && j < Lk && (!km || km[j] != 0)) kbits |= 1u << (2 * nt + e);
+            }
+    }
     uint32_t q[2][2][8];
     const bf16* qb = a.q + (qrows ? 0 : (int64_t)b * a.q_bs) + h * 64 + 16 * t;
 #pragma unroll
@@ -157,6 +193,12 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
             const int r = 16 * mt + 8 * hi + g;
             ld_row16(q[mt][hi], qb + (int64_t)((qrows && r < a.Lq) ? qrows[r] : r) * a.q_ld, r < a.Lq);
         }
+    CA_STAMP(1);
+    if (KSMEM) {
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncwarp();
+    }
+    CA_STAMP(2);
     float s[2][NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -165,7 +207,13 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
         if (nt < ntw) {
             const int j = key0 + 8 * nt + g;
             uint32_t kr[8];
-            ld_row16(kr, kb + (int64_t)j * a.k_ld + 16 * t, j < Lk);
+            if (KSMEM) {
+                const int lr = warp * C::KW + 8 * nt + g;
+                const uint4 x = *reinterpret_cast<const uint4*>(Ks + swz(lr, 2 * t)), y = *reinterpret_cast<const uint4*>(Ks + swz(lr, 2 * t + 1));
+                kr[0] = x.x; kr[1] = x.y; kr[2] = x.z; kr[3] = x.w; kr[4] = y.x; kr[5] = y.y; kr[6] = y.z; kr[7] = y.w;
+            } else {
+                ld_row16(kr, kb + (int64_t)j * a.k_ld + 16 * t, j < Lk);
+            }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -174,6 +222,7 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
                              kr[2 * k4 + 1]);
         }
     }
+    CA_STAMP(3);
     ScoreCtx sc{a.Lq, Lk, a.Lk, a.causal, a.bias_off, a.n_delta, a.bias_rel ? a.bias_rel + h * a.n_delta : nullptr,
                 a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr};
     float mx[2][2], sum[2][2];
@@ -186,7 +235,8 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
             for (int e = 0; e < 4; ++e) {
                 const int r = 16 * mt + g + 8 * (e >> 1), j = key0 + 8 * nt + 2 * t + (e & 1);
                 float v = -FLT_MAX;
-                if (nt < ntw && score_valid(sc, r, j)) v = s[mt][nt][e] + (sc.bias ? sc.bias[bias_index(sc, r, j)] : 0.f);
+                if (((kbits >> (2 * nt + (e & 1))) & 1u) && r < sc.Lq && (!sc.causal || j <= r))
+                    v = s[mt][nt][e] + (sc.bias ? sc.bias[bias_index(sc, r, j)] : 0.f);
                 s[mt][nt][e] = v;
                 mx[mt][e >> 1] = fmaxf(mx[mt][e >> 1], v);
             }
@@ -199,7 +249,7 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
     if (t == 0)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) { red[warp * 32 + 16 * mt + g] = mx[mt][0]; red[warp * 32 + 16 * mt + g + 8] = mx[mt][1]; }
-    __syncthreads();
+    group_sync();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -226,7 +276,7 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
         }
         if (t == 0) { red2[warp * 32 + 16 * mt + g] = sum[mt][0]; red2[warp * 32 + 16 * mt + g + 8] = sum[mt][1]; }
     }
-    __syncthreads();
+    group_sync();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         float tot[2] = {0.f, 0.f};
@@ -236,8 +286,10 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { s[mt][nt][0] *= inv0; s[mt][nt][1] *= inv0; s[mt][nt][2] *= inv1; s[mt][nt][3] *= inv1; }
     }
+    CA_STAMP(4);
     cp_async_wait_all();
     __syncwarp();
+    CA_STAMP(5);
     float o[2][8][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -245,7 +297,8 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
         for (int c = 0; c < 8; ++c) o[mt][c][0] = o[mt][c][1] = o[mt][c][2] = o[mt][c][3] = 0.f;
         pv_tiles<NT>(o[mt], s[mt], Vs, warp * C::KW, ntw, lane);
     }
-    __syncthreads();                       // every warp is done with its V rows: reuse the region for the partial sums
+    CA_STAMP(6);
+    group_sync();                       // every warp is done with its V rows: reuse the region for the partial sums
     float* part = reinterpret_cast<float*>(smem);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -254,8 +307,8 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
             *reinterpret_cast<float2*>(part + (warp * 32 + 16 * mt + g) * 64 + 8 * c + 2 * t) = make_float2(o[mt][c][0], o[mt][c][1]);
             *reinterpret_cast<float2*>(part + (warp * 32 + 16 * mt + g + 8) * 64 + 8 * c + 2 * t) = make_float2(o[mt][c][2], o[mt][c][3]);
         }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * 8; e += NW * 32) {      // (row, 8-column chunk)
+    group_sync();
+    for (int e = tid; e < 32 * 8; e += NW * 32) {      // (row, 8-column chunk)
         const int r = e >> 3, c8 = (e & 7) * 8;
         if (r >= a.Lq) continue;
         float v[8];
@@ -268,6 +321,7 @@ __device__ __forceinline__ void dattn_fwd32_body(const DAttnDev& a, bf16* __rest
         uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         *reinterpret_cast<uint4*>(O + (qrows ? (int64_t)qrows[r] * ld_o : (int64_t)b * bs_o + (int64_t)r * ld_o) + h * 64 + c8) = pk;
     }
+    CA_STAMP(7);
 }
 
 

@@ -23,6 +23,7 @@
 // bf16 operands / fp32 accumulation and statistics, like the precision=1 engine path; the fp32 and bf16x3 parity modes
 // keep the per-position kernels of beam.cu.
 #include "engine.h"
+// #define P5_CA_STAMPS     // sub-phase timers of the two attention phases (tools/decode_phases.py with P5_DECODE_PROF_FINE=1)
 #include "dattn_dev.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -64,7 +65,7 @@ struct PdLayer {
 
 struct PdParams {
     int B, K, R, T, Le, d, A, H, ff, V, Vpad, ND;
-    int n_steps, max_len, max_len_eff, n_ret, root_child, no_light;
+    int n_steps, max_len, max_len_eff, n_ret, root_child, no_light, no_prefetch, prof_fine;
     int n_forced, node_forced, forced[32];     // forced item prefix (the trie has ONE child per node there): prefilled in one pass
     float eps, hs, length_penalty;
     PdLayer layer[PD_MAXL];
@@ -330,6 +331,7 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring was attention staging (generic proxy) a phase ago
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int t = u / splits, sp = u - t * splits;
                 const int m_blk = t % m_tiles, n_blk = t / m_tiles;
@@ -605,73 +607,111 @@ __device__ __forceinline__ void ld16_bf(float (&f)[16], const bf16* p) {      //
 // longer prefixes loop in blocks of 8 with an online softmax per lane, merged across the groups with shuffles at the end.
 __device__ void self_attn_phase(const PdParams& P, const PdLayer& L, const int* __restrict__ live, int n_live, const int* __restrict__ src,
                                 int pos) {
+    // Two (row, head) tasks per warp and iteration: their index -> K | V load chains are independent, so the second one rides
+    // in the latency shadow of the first (the phase is a handful of dependent L2 round trips per task, not bandwidth).
+    constexpr int U = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, jg = lane >> 2, dq = lane & 3;
-    const int A = P.A, T = P.T, H = P.H;
-    for (int task = blockIdx.x * (PD_THREADS / 32) + warp; task < n_live * H; task += gridDim.x * (PD_THREADS / 32)) {
-        const int i = task / H, h = task - i * H, r = live[i];
-        const bf16* row = P.qkv + (int64_t)r * 3 * A + h * 64 + 16 * dq;
-        float q[16];
-        ld16_bf(q, row);
-        if (jg == 0) {      // KV append: this row owns position `pos`
-            const int64_t o = ((int64_t)r * T + pos) * A + h * 64 + 16 * dq;
-            *reinterpret_cast<uint4*>(L.Kc + o) = __ldcg(reinterpret_cast<const uint4*>(row + A));
-            *reinterpret_cast<uint4*>(L.Kc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row + A + 8));
-            *reinterpret_cast<uint4*>(L.Vc + o) = __ldcg(reinterpret_cast<const uint4*>(row + 2 * A));
-            *reinterpret_cast<uint4*>(L.Vc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row + 2 * A + 8));
-        }
-        float m = -INFINITY, l = 0.f, acc[16];
+    const int A = P.A, T = P.T, H = P.H, n_tasks = n_live * H, n_warps = gridDim.x * (PD_THREADS / 32);
+    for (int task0 = blockIdx.x * (PD_THREADS / 32) + warp; task0 < n_tasks; task0 += U * n_warps) {
+#ifdef P5_CA_STAMPS
+        const bool stamp = blockIdx.x == 0 && threadIdx.x == 0 && P.prof_fine;
+        uint64_t ts0 = 0, ts1 = 0;
+        if (stamp) ts0 = pd_timer();
+#endif
+        int r[U], h[U];
+        bool has[U];
+        const bf16* row[U];
+        float q[U][16], m[U], l[U], acc[U][16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int task = task0 + u * n_warps;
+            has[u] = task < n_tasks;                               // warp-uniform
+            const int tk = has[u] ? task : task0;
+            const int i = tk / H;
+            h[u] = tk - i * H; r[u] = live[i];
+            row[u] = P.qkv + (int64_t)r[u] * 3 * A + h[u] * 64 + 16 * dq;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ld16_bf(q[u], row[u]);
+            if (jg == 0 && has[u]) {      // KV append: this row owns position `pos`
+                const int64_t o = ((int64_t)r[u] * T + pos) * A + h[u] * 64 + 16 * dq;
+                *reinterpret_cast<uint4*>(L.Kc + o) = __ldcg(reinterpret_cast<const uint4*>(row[u] + A));
+                *reinterpret_cast<uint4*>(L.Kc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row[u] + A + 8));
+                *reinterpret_cast<uint4*>(L.Vc + o) = __ldcg(reinterpret_cast<const uint4*>(row[u] + 2 * A));
+                *reinterpret_cast<uint4*>(L.Vc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row[u] + 2 * A + 8));
+            }
+            m[u] = -INFINITY; l[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[u][c] = 0.f;
+        }
         for (int j0 = 0; j0 <= pos; j0 += 8) {           // warp-uniform trip count: the shuffles below need every lane
             const int j = j0 + jg;
             const bool valid = j <= pos;
-            const bf16 *kp = row + A, *vp = row + 2 * A;
-            if (valid && j < pos) {
-                const int64_t o = ((int64_t)__ldcg(src + r * T + j) * T + j) * A + h * 64 + 16 * dq;
-                kp = L.Kc + o; vp = L.Vc + o;
+            const bf16 *kp[U], *vp[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                kp[u] = row[u] + A; vp[u] = row[u] + 2 * A;
+                if (valid && j < pos) {
+                    const int64_t o = ((int64_t)__ldcg(src + r[u] * T + j) * T + j) * A + h[u] * 64 + 16 * dq;
+                    kp[u] = L.Kc + o; vp[u] = L.Vc + o;
+                }
             }
-            float k[16], v[16];
-            ld16_bf(k, kp);
-            ld16_bf(v, vp);
-            float sc = 0.f;
+            float k[U][16], v[U][16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) sc = fmaf(q[c], k[c], sc);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-            if (valid) {
-                int di = j - pos + P.bias_off;
-                di = di < 0 ? 0 : (di >= P.n_delta ? P.n_delta - 1 : di);
-                sc += P.bias_dec[h * P.n_delta + di];
-                const float mn = fmaxf(m, sc);
-                const float scale = __expf(m - mn), p = __expf(sc - mn);
-                l = l * scale + p;
+            for (int u = 0; u < U; ++u) { ld16_bf(k[u], kp[u]); ld16_bf(v[u], vp[u]); }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] = fmaf(acc[c], scale, p * v[c]);
-                m = mn;
+            for (int u = 0; u < U; ++u) {
+                float sc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) sc = fmaf(q[u][c], k[u][c], sc);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                if (valid) {
+                    int di = j - pos + P.bias_off;
+                    di = di < 0 ? 0 : (di >= P.n_delta ? P.n_delta - 1 : di);
+                    sc += P.bias_dec[h[u] * P.n_delta + di];
+                    const float mn = fmaxf(m[u], sc);
+                    const float scale = __expf(m[u] - mn), p = __expf(sc - mn);
+                    l[u] = l[u] * scale + p;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[u][c] = fmaf(acc[u][c], scale, p * v[u][c]);
+                    m[u] = mn;
+                }
             }
         }
-        // merge the 8 position groups (lanes differing in bits 2..4 hold the same dims)
+#ifdef P5_CA_STAMPS
+        if (stamp) { ts1 = pd_timer(); P.prof[28] += ts1 - ts0; }
+#endif
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            const float om = __shfl_xor_sync(0xffffffffu, m, o), ol = __shfl_xor_sync(0xffffffffu, l, o);
-            const float mn = fmaxf(m, om);
-            const float s0 = (m > -INFINITY) ? __expf(m - mn) : 0.f, s1 = (om > -INFINITY) ? __expf(om - mn) : 0.f;
-            l = l * s0 + ol * s1;
+        for (int u = 0; u < U; ++u) {
+            // merge the 8 position groups (lanes differing in bits 2..4 hold the same dims)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = acc[c] * s0 + __shfl_xor_sync(0xffffffffu, acc[c], o) * s1;
-            m = mn;
+            for (int o = 4; o < 32; o <<= 1) {
+                const float om = __shfl_xor_sync(0xffffffffu, m[u], o), ol = __shfl_xor_sync(0xffffffffu, l[u], o);
+                const float mn = fmaxf(m[u], om);
+                const float s0 = (m[u] > -INFINITY) ? __expf(m[u] - mn) : 0.f, s1 = (om > -INFINITY) ? __expf(om - mn) : 0.f;
+                l[u] = l[u] * s0 + ol * s1;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[u][c] = acc[u][c] * s0 + __shfl_xor_sync(0xffffffffu, acc[u][c], o) * s1;
+                m[u] = mn;
+            }
+            if (jg == 0 && has[u]) {
+                const float inv = 1.f / l[u];
+                const float* a = acc[u];
+                bf16* out = P.ctx + (int64_t)r[u] * A + h[u] * 64 + 16 * dq;
+                uint4 w0, w1;
+                w0.x = pack_bf16(a[0] * inv, a[1] * inv); w0.y = pack_bf16(a[2] * inv, a[3] * inv);
+                w0.z = pack_bf16(a[4] * inv, a[5] * inv); w0.w = pack_bf16(a[6] * inv, a[7] * inv);
+                w1.x = pack_bf16(a[8] * inv, a[9] * inv); w1.y = pack_bf16(a[10] * inv, a[11] * inv);
+                w1.z = pack_bf16(a[12] * inv, a[13] * inv); w1.w = pack_bf16(a[14] * inv, a[15] * inv);
+                *reinterpret_cast<uint4*>(out) = w0;
+                *reinterpret_cast<uint4*>(out + 8) = w1;
+            }
         }
-        if (jg == 0) {
-            const float inv = 1.f / l;
-            bf16* out = P.ctx + (int64_t)r * A + h * 64 + 16 * dq;
-            uint4 w0, w1;
-            w0.x = pack_bf16(acc[0] * inv, acc[1] * inv); w0.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-            w0.z = pack_bf16(acc[4] * inv, acc[5] * inv); w0.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-            w1.x = pack_bf16(acc[8] * inv, acc[9] * inv); w1.y = pack_bf16(acc[10] * inv, acc[11] * inv);
-            w1.z = pack_bf16(acc[12] * inv, acc[13] * inv); w1.w = pack_bf16(acc[14] * inv, acc[15] * inv);
-            *reinterpret_cast<uint4*>(out) = w0;
-            *reinterpret_cast<uint4*>(out + 8) = w1;
-        }
+#ifdef P5_CA_STAMPS
+        if (stamp) P.prof[30] += pd_timer() - ts1;
+#endif
     }
 }
 
@@ -763,6 +803,28 @@ __device__ void cross_attn_phase(const PdParams& P, const PdLayer& L, uint8_t* s
         a.kv_off = nullptr; a.kv_len = nullptr;
         __syncthreads();                 // the previous task's partial sums / staged V rows are no longer read
         dattn_fwd32_body<NT, PD_THREADS / 32>(a, P.ctx, P.A, 0, b, h, smem, P.live_u + b * K);
+    }
+}
+
+// Le <= 256: TWO (user, head) pairs per CTA, four warps each, on their own named barrier and shared-memory half: the
+// B * H = 240 pairs of the BASELINE eval shape then fit the 148 CTAs in one round instead of two.
+__device__ void cross_attn_phase_x2(const PdParams& P, const PdLayer& L, uint8_t* smem) {
+    const int B = P.B, H = P.H, K = P.K;
+    const int grp = threadIdx.x >> 7, tid = threadIdx.x & 127;
+    constexpr int HALF = DCfg<8, 4>::TILE > 4 * 32 * 64 * 4 ? DCfg<8, 4>::TILE : 4 * 32 * 64 * 4;       // V rows | partial sums
+    uint8_t* my = smem + grp * (HALF + 4 * 32 * 2 * 4 + 128 + DCfg<8, 4>::TILE);                         // ... | softmax scratch | K rows
+    for (int task = 2 * blockIdx.x + grp; task < B * H; task += 2 * gridDim.x) {
+        const int b = task / H, h = task - b * H;
+        const int nq = __ldcg(P.n_u + b);
+        if (nq <= 0) continue;           // uniform per 4-warp group
+        DAttnDev a;
+        a.B = B; a.H = H; a.Lq = nq; a.Lk = P.Le;
+        a.q = P.cq; a.k = L.ck; a.v = L.cv;
+        a.q_ld = P.A; a.q_bs = 0; a.k_ld = P.ckv_ld; a.k_bs = (int64_t)P.Le * P.ckv_ld; a.v_ld = P.ckv_ld; a.v_bs = a.k_bs;
+        a.bias_rel = nullptr; a.bias_off = 0; a.n_delta = 0; a.key_mask = P.mask_e; a.causal = 0;
+        a.kv_off = nullptr; a.kv_len = nullptr;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");     // this group's previous pair is done with its half
+        dattn_fwd32_body<8, 4, true>(a, P.ctx, P.A, 0, b, h, my, P.live_u + b * K, tid, 2 + grp);
     }
 }
 
@@ -1165,6 +1227,20 @@ __device__ void user_phase(const PdParams& P, UserSmem& S, int b, int cur, int c
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Optional (P5_DECODE_PREFETCH=1) L2 prefetch of the users' cross K | V of a layer, requested four phases ahead by a warp that
+// has no role in the GEMM phase; each CTA asks for its 1 / gridDim share of the encoder rows.  (Prefetching the weights of
+// the next phases the same way was measured in round 2: no phase got shorter, the issuing phase got longer.)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ void prefetch_cross_kv(const PdParams& P, const PdLayer& L) {          // K | V of one layer: 2A contiguous bf16 per encoder row
+    const int rows = P.B * P.Le;
+    for (int r = blockIdx.x + gridDim.x * (threadIdx.x & 31); r < rows; r += gridDim.x * 32)
+        if (__ldg(P.mask_e + r)) l2_prefetch(L.ck + (int64_t)r * P.ckv_ld, (uint32_t)(2 * P.A * 2));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const PdParams* __restrict__ Pp) {
@@ -1226,6 +1302,11 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             t_last = now;
         }
     };
+    // heavy positions only: CTA 0's own work time of the two attention phases (slots 27 / 29), its wait in the grid barrier
+    // behind them (28 / 30), and one back-to-back barrier per position as the cost of a bare barrier (31)
+    auto mark_sub = [&](int slot) {
+        if (prof_heavy && blockIdx.x == 0 && threadIdx.x == 0) { const uint64_t now = pd_timer(); P.prof[slot] += now - t_last; }
+    };
     int cur = 0;
     const int n_forced = P.n_forced;
     // iteration -1 (only with a forced prefix): the PREFILL pass over positions 0 .. p of every user; it produces the logits of
@@ -1273,6 +1354,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             float* ss_next = ss2 + R;                                   // site 3 (l + 1): next layer's ln0, or the final norm
             const float* ln_after = (l + 1 < P.ND) ? P.layer[l + 1].ln0 : P.ln_final;
             GemmDesc g;
+            if ((threadIdx.x >> 5) == 2 && !P.no_prefetch) prefetch_cross_kv(P, L);     // needed four phases from here
             // (a) q | k | v = RMSNorm(y) . Wqkv^T
             g = GemmDesc{P.y16, d, d, L.wqkv, 3 * A, 0, 1.f, ss0, inv_d, P.eps, 0, P.qkv, 3 * A, nullptr, nullptr, nullptr, nullptr, d,
                          nullptr, 0, nullptr, 0, 0};
@@ -1282,6 +1364,8 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             // (b) self-attention over the cached positions (+ KV append)
             if (prefill) self_attn_prefill(P, L, n_forced);
             else self_attn_phase(P, L, s_live, n_live, P.src[cur], pos);
+            __syncthreads();
+            mark_sub(29);
             grid_barrier(P.bar, bar_target);
             mark(PH_SA);
             // (c) y += ctx . Wo^T      -> y16 = bf16(y * ln1), rowss1
@@ -1296,8 +1380,14 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
             mark(PH_CQ);
             // (e) cross-attention over the user's encoder K | V (zero position bias + encoder padding mask)
             if (max_nq <= 8 && P.Le <= 256) cross_attn_light(P, L, work);
-            else if (P.Le <= 256) cross_attn_phase<4>(P, L, work);
+            else if (P.Le <= 256) cross_attn_phase_x2(P, L, work);
             else cross_attn_phase<8>(P, L, work);
+            __syncthreads();
+            mark_sub(27);
+#ifdef P5_CA_STAMPS
+            if (prof_heavy && blockIdx.x == 0 && threadIdx.x == 0)
+                for (int i = 0; i < 5; ++i) { const int a0[5] = {0, 2, 3, 5, 6}, a1[5] = {2, 3, 5, 6, 7}; P.prof[11 + i] += g_ca_stamp[a1[i]] - g_ca_stamp[a0[i]]; }
+#endif
             grid_barrier(P.bar, bar_target);
             mark(PH_CA);
             // (f) y += ctx . Wco^T     -> y16 = bf16(y * ln2), rowss2
@@ -1331,6 +1421,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_persistent_kernel(const 
         }
         grid_barrier(P.bar, bar_target);
         mark(PH_USER);
+        if (P.prof_fine) { grid_barrier(P.bar, bar_target); mark_sub(31); mark(PH_LIST); }
         cur ^= 1;
     }
     tc_fence_before();
@@ -1457,6 +1548,10 @@ const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, co
     H.eps = e->cfg.ln_eps; H.hs = 1.f / sqrtf((float)d); H.length_penalty = length_penalty;
     static const bool no_light = getenv("P5_DECODE_NO_LIGHT") != nullptr;
     H.no_light = no_light ? 1 : 0;
+    static const bool want_prefetch = getenv("P5_DECODE_PREFETCH") != nullptr;
+    H.no_prefetch = want_prefetch ? 0 : 1;      // measured r02: requesting the next phases' bytes ahead does not shorten them
+    static const bool prof_fine = getenv("P5_DECODE_PROF_FINE") != nullptr;
+    H.prof_fine = prof_fine ? 1 : 0;
     // forced item prefix (single-child trie nodes from the root): decoded in ONE prefill pass instead of one position at a
     // time.  Needs the items (b, t) of a user to fit its K beam rows and the last position to stay in the regular loop.
     static const bool no_prefill = getenv("P5_DECODE_NO_PREFILL") != nullptr;

@@ -39,3 +39,8 @@ for off, tag in ((0, "light positions"), (16, "heavy positions")):
     print("%s: %.1f us total" % (tag, tot / 1e3))
     for i, n in enumerate(names):
         print("   %-11s %9.1f us" % (n, arr[off + i] / 1e3))
+if os.environ.get("P5_DECODE_PROF_FINE"):
+    print("fine (heavy, CTA 0): cross_attn work %.1f us, self_attn work %.1f us, bare barrier %.1f us total over %d positions" % (
+        arr[27] / 1e3, arr[29] / 1e3, arr[31] / 1e3, st.value))
+    print("cross-attention pair (CTA 0, group 0): issue+K arrive %.1f, S %.1f, softmax %.1f, V wait+PV %.1f, reduce+write %.1f us" % tuple(arr[11 + i] / 1e3 for i in range(5)))
+    print("self-attention (CTA 0, warp 0): loads+scores %.1f, merge+store %.1f us" % (arr[28] / 1e3, arr[30] / 1e3))
