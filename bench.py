@@ -448,15 +448,22 @@ def run_b200(args):
         if _lib.load().p5_decode_last_launch(C.byref(dms), C.byref(dby), C.byref(dst)) == 0 and dms.value > 0:
             pk_hbm = peaks()["hbm"]
             gbs = dby.value / (dms.value * 1e-3) / 1e9
+            etraffic = None
+            try:   # DRAM bytes of ONE captured launch (ncu --set full, tools/collect_profiles_r02.sh)
+                tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_decode_traffic.json")))
+                etraffic = {"dram_bytes_per_launch": tj["dram_bytes"], "source": tj.get("source")}
+            except Exception:  # noqa
+                pass
             eval_roof = {"bound": "hbm", "kernel": "p5::decode_persistent_kernel (one cooperative launch per generate(): every decode "
                                                    "position, grid barriers between phases)",
-                         "achieved": gbs, "peak": pk_hbm, "unit": "GB/s", "frac": gbs / pk_hbm, "traffic": None,
+                         "achieved": gbs, "peak": pk_hbm, "unit": "GB/s", "frac": gbs / pk_hbm, "traffic": etraffic,
                          "launch_ms": dms.value, "positions": dst.value, "algorithmic_bytes_per_launch": dby.value,
                          "share_of_batch": dms.value / ev_ms,
                          "peak_source": peaks()["source"] + " — of measured",
                          "measured": "CUDA events on the launch stream around the persistent launch of the last timed batch; algorithmic "
-                                     "bytes = positions x (decoder-block weights used per position + tied LM head, bf16) + every "
-                                     "user's cross K|V once per position (DESIGN.md §3)"}
+                                     "bytes = decoder passes x (decoder-block weights + tied LM head, bf16, + every user's cross K|V "
+                                     "once); passes = positions - forced-prefix length (the prefix is decoded in ONE prefill pass) "
+                                     "(DESIGN.md §3)"}
         # end to end: pinned host inputs -> generate -> sequences and scores back on the host, every batch
         barrier()
         e0.record()
@@ -514,9 +521,9 @@ def run_b200(args):
         achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12 if dom["ms"] > 0 else 0.0
         traffic = None
         try:   # DRAM bytes of ONE captured launch of that kernel (ncu --set full, tools/collect_profiles.sh)
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")))
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_gemm_traffic.json")))
             traffic = {"dram_bytes_per_launch": tj["dram_bytes"], "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes"),
-                       "captured_launch": tj.get("launch"), "source": "profiles/r01_gemm_ncu_full_summary.txt"}
+                       "captured_launch": tj.get("launch"), "source": "profiles/r02_gemm_ncu_full_summary.txt"}
         except Exception:  # noqa
             pass
         roofline = {

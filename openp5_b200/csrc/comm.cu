@@ -78,10 +78,11 @@ void comm_init(Engine* e, const void* id128, int rank, int world) {
     CommState* c = new CommState();
     nccl_uid_t id;
     memcpy(&id, id128, 128);
-    // The all-reduce runs UNDER the backward's persistent tcgen05 kernels: give it a fixed, small number of CTAs and
-    // take exactly those SMs out of the persistent grids (common.cuh sm_budget), instead of letting NCCL's default
-    // (up to 32 CTAs) evict GEMM CTAs at random.  P5_COMM_CTAS overrides; an NCCL_MAX_CTAS set by the user wins.
-    int ctas = 8;
+    // The all-reduce runs UNDER the backward's persistent tcgen05 kernels.  P5_COMM_CTAS=n gives it a fixed number of CTAs
+    // and takes exactly those SMs out of the persistent grids (common.cuh sm_budget) instead of letting NCCL's default
+    // evict GEMM CTAs at random; an NCCL_MAX_CTAS set by the user wins.  Measured at N=2 (profiles/r02_scale_n2.txt):
+    // 0 (NCCL default, no reservation) 17.46 ms/step, 8: 17.55, 16: 17.82 -> default 0.
+    int ctas = 0;
     if (const char* ev = getenv("P5_COMM_CTAS")) ctas = atoi(ev);
     if (ctas > 0 && world > 1) {
         char b[16];

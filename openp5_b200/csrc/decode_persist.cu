@@ -1609,8 +1609,11 @@ const int* generate_persistent(Engine* e, const int* t_off, const int* t_tok, co
     ++g_launches;
     // algorithmic bytes of the launch: per position the decoder-block weights it multiplies with and the
     // tied LM head once (bf16), plus every user's cross K|V once (bf16)
+    // (a PASS is one trip through the decoder: the prefill covers positions 0 .. n_forced in one, so the weights stream
+    // n_steps - n_forced times, not n_steps times)
     g_last_steps = H.n_steps;
-    g_last_bytes = (double)H.n_steps * (2.0 * ((double)ND * ((double)3 * A * d + 3.0 * (double)A * d + 2.0 * (double)ff * d) + (double)e->V * d) +
+    const int passes = H.n_forced > 0 ? H.n_steps - H.n_forced : H.n_steps;
+    g_last_bytes = (double)passes * (2.0 * ((double)ND * ((double)3 * A * d + 3.0 * (double)A * d + 2.0 * (double)ff * d) + (double)e->V * d) +
                                         2.0 * (double)B * e->Le * ND * 2.0 * A);
     return H.out_len;      // device: 1 + longest returned hypothesis
 }

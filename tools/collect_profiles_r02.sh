@@ -16,4 +16,8 @@ for K in "gemm_tc_kernel:gemm" "fattn_fwd_kernel:fattn_fwd" "fattn_bwd_kernel:fa
 done
 # eval: the persistent decode kernel (one launch = the whole beam search of a batch)
 timeout 600 $NCU --set full --import-source on -k regex:decode_persistent_kernel -c 1 -o gpurun_out/${TAG}_decode_persistent python tools/profile_step.py eval > gpurun_out/${TAG}_ncu_decode.log 2>&1
+# summarise on the box (gpurun_out/ comes back only while it stays under 64 MiB) and keep the two reports worth reading at source level
+P5_PROF_DIR=gpurun_out/profiles_${TAG} python tools/summarise_profiles.py ${TAG}
 ls -la gpurun_out/*.ncu-rep | tail -20
+for f in gpurun_out/${TAG}_*.ncu-rep; do case "$f" in *_gemm.ncu-rep|*_decode_persistent.ncu-rep) ;; *) rm -f "$f";; esac; done
+du -sh gpurun_out
