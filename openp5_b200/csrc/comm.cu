@@ -81,7 +81,9 @@ void comm_init(Engine* e, const void* id128, int rank, int world) {
     // The all-reduce runs UNDER the backward's persistent tcgen05 kernels.  P5_COMM_CTAS=n gives it a fixed number of CTAs
     // and takes exactly those SMs out of the persistent grids (common.cuh sm_budget) instead of letting NCCL's default
     // evict GEMM CTAs at random; an NCCL_MAX_CTAS set by the user wins.  Measured at N=2 (profiles/r02_scale_n2.txt):
-    // 0 (NCCL default, no reservation) 17.46 ms/step, 8: 17.55, 16: 17.82 -> default 0.
+    // 0 (NCCL default, no reservation) 17.46 ms/step, 8: 17.55, 16: 17.82 -> default 0.  Also measured and dropped: bf16
+    // gradients on the wire (cast -> ncclAllReduce(bf16) -> cast back on the comm stream): 17.27 ms/step against 17.12 with
+    // fp32 on the same box — at N = 2 the two extra passes over the 892 MB buffer cost more than the halved NVLink bytes save.
     int ctas = 0;
     if (const char* ev = getenv("P5_COMM_CTAS")) ctas = atoi(ev);
     if (ctas > 0 && world > 1) {

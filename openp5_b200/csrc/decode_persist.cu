@@ -319,7 +319,8 @@ __device__ void gemm_tc_phase(const GemmDesc& g, const CUtensorMap* tmA, const C
     // Residual phases (mode 1) have N = d_model: only a few dozen tiles for 148 SMs, each streaming the whole K extent
     // through ONE SM's L2 port.  They are split along K into `splits` work units per tile: every unit adds its partial
     // product into y with red.global; the unit that arrives last on the tile's counter finalises the rows of the tile
-    // (y16 = bf16(y * ln_next), row sums of squares).
+    // (y16 = bf16(y * ln_next), row sums of squares).  Measured r02 on the K = d_model phases (12 k-blocks): 11.8 us split
+    // by 3 against 13.2 us unsplit; the unsplit non-residual phase of the same shape (cross-q) takes 8.4 us.
     int splits = 1;
     if (g.mode == 1) { splits = (int)gridDim.x / total; splits = splits < 1 ? 1 : (splits > k_blocks ? k_blocks : splits); if (splits > 4) splits = 4; }
     const int kbs = (k_blocks + splits - 1) / splits;
@@ -634,13 +635,6 @@ __device__ void self_attn_phase(const PdParams& P, const PdLayer& L, const int* 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ld16_bf(q[u], row[u]);
-            if (jg == 0 && has[u]) {      // KV append: this row owns position `pos`
-                const int64_t o = ((int64_t)r[u] * T + pos) * A + h[u] * 64 + 16 * dq;
-                *reinterpret_cast<uint4*>(L.Kc + o) = __ldcg(reinterpret_cast<const uint4*>(row[u] + A));
-                *reinterpret_cast<uint4*>(L.Kc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row[u] + A + 8));
-                *reinterpret_cast<uint4*>(L.Vc + o) = __ldcg(reinterpret_cast<const uint4*>(row[u] + 2 * A));
-                *reinterpret_cast<uint4*>(L.Vc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row[u] + 2 * A + 8));
-            }
             m[u] = -INFINITY; l[u] = 0.f;
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[u][c] = 0.f;
@@ -695,6 +689,14 @@ __device__ void self_attn_phase(const PdParams& P, const PdLayer& L, const int* 
 #pragma unroll
                 for (int c = 0; c < 16; ++c) acc[u][c] = acc[u][c] * s0 + __shfl_xor_sync(0xffffffffu, acc[u][c], o) * s1;
                 m[u] = mn;
+            }
+            if (jg == 1 && has[u]) {      // KV append: this row owns position `pos` (after the loop: the cache loads above
+                                          // must not queue behind these stores)
+                const int64_t o = ((int64_t)r[u] * T + pos) * A + h[u] * 64 + 16 * dq;
+                *reinterpret_cast<uint4*>(L.Kc + o) = __ldcg(reinterpret_cast<const uint4*>(row[u] + A));
+                *reinterpret_cast<uint4*>(L.Kc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row[u] + A + 8));
+                *reinterpret_cast<uint4*>(L.Vc + o) = __ldcg(reinterpret_cast<const uint4*>(row[u] + 2 * A));
+                *reinterpret_cast<uint4*>(L.Vc + o + 8) = __ldcg(reinterpret_cast<const uint4*>(row[u] + 2 * A + 8));
             }
             if (jg == 0 && has[u]) {
                 const float inv = 1.f / l[u];

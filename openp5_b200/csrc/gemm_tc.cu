@@ -8,8 +8,10 @@
 //   warp 0   : TMA producer      cp.async.bulk.tensor.4d -> 128B-swizzled smem ring (STAGES deep)
 //   warp 1   : MMA issuer        one lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16
 //   warp 2   : TMEM allocator    2 accumulator stages x BLOCK_N fp32 columns
-//   warps 4-7: epilogue          tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> fused epilogue (one
-//                                compile-time variant per flag set, operands prefetched 32 rows ahead) -> coalesced stores
+//   warps 4-11: epilogue         two warps per TMEM lane quarter, each owning half of the tile's columns (one warp per
+//                                scheduler cannot hide its own ALU / LDS latencies; the K = 768 shapes were epilogue-bound):
+//                                tcgen05.ld 32x32b -> registers -> per-warp swizzled smem transpose -> fused epilogue (one
+//                                compile-time variant per flag set, operands prefetched 16 row pairs ahead) -> row-segment stores
 // Two mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue).  Tile widths 64 / 128 / 192 / 256;
 // an opt-in CTA-pair variant (cta_group::2, cluster of two, 256 x 256 tile per pair); batch operands may be broadcast;
 // programmatic dependent launch with the wait at the start or (for GEMMs independent of their predecessor) at the end.
@@ -32,7 +34,8 @@ namespace p5 {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
 static constexpr int UMMA_K = 16;
-static constexpr int GEMM_THREADS = 256;
+static constexpr int EPI_WARPS = 8;          // two warps per TMEM lane quarter: each takes half of the tile's columns
+static constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 // ------------------------------------------------------------------------------------------
@@ -56,8 +59,8 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = CTA2 ? 6 : ((BLOCK_N >= 192) ? 4 : (BLOCK_N == 128 ? 6 : 8));
     static constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);   // power of two >= 2 accumulators
-    static constexpr int EPI_STRIDE = 66;                       // floats per staged row (64 + 2 pad: conflict-free 8-byte accesses)
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_STRIDE * 4;   // one 32x64 fp32 tile per epilogue warp
+    static constexpr int EPI_STRIDE = 32;                       // floats per staged row: 32 columns, column pairs XOR-swizzled by the row
+    static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_STRIDE * 4;   // one 32x32 fp32 tile per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
@@ -231,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
+            mbar_init(tempty_bar(s), (CTA2 ? 2 : 1) * EPI_WARPS);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -335,7 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp & 3;  // TMEM lane quarter owned by this warp
+        const int ew = warp & 3;            // TMEM lane quarter owned by this warp
+        const int half = (warp - 4) >> 2;   // which half of the tile's 32-column chunks
+        constexpr int NCH = BLOCK_N / 64;   // 32-column chunks per warp
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long t = unit; t < total_tiles; t += unit_stride) {
@@ -350,87 +355,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = row < P.M;
             const int64_t row_off = (int64_t)b1 * P.epi.cs1 + (int64_t)b2 * P.epi.cs2 + (int64_t)row * P.epi.ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            auto release_acc = [&]() {      // all TMEM reads of this warp are done: hand the accumulator back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CTA2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
+            };
             if constexpr (EPI != -2) {
-                // TMEM -> registers (thread = row) -> per-warp smem tile -> registers (lane = column pair) -> global:
-                // every global access of the fused epilogue (aux / residual / C) is a contiguous row segment
-                float* tile = epi_stage + ew * (32 * Cfg::EPI_STRIDE);
+                // TMEM -> registers (thread = row) -> per-warp smem tile -> registers (half-warp = 16 column pairs of a row,
+                // two rows per step) -> global: every access of the fused epilogue (aux / residual / C) is a row segment
+                float* tile = epi_stage + (warp - 4) * (32 * Cfg::EPI_STRIDE);
                 const int64_t boff = (int64_t)b1 * P.epi.cs1 + (int64_t)b2 * P.epi.cs2;
                 const int row0 = m_blk * BLOCK_M + ew * 32;
+                const int cp = lane & 15, rpar = lane >> 4;
                 // inputs of the fused epilogue (ReLU-mask operand, fp32 residual, fp32 accumulate target) are PREFETCHED
-                // into registers for all 32 rows of a chunk before the TMEM load: 32 independent 128-byte loads in
-                // flight per warp instead of one dependent load per row (4 epilogue warps cannot hide DRAM latency)
+                // into registers for all 32 rows of a chunk before the TMEM load: independent loads in flight instead of
+                // one dependent load per row
                 constexpr int F = EPI >= 0 ? (EPI & 63) : 0;
                 constexpr bool PF_AUX = (F & EPI_MULPOS) != 0, PF_RES = (F & EPI_ADD_RESID) != 0, PF_ACC = (F & EPI_ACCUM) != 0;
                 constexpr bool PF = PF_AUX || PF_RES || PF_ACC;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 64; ++c) {
-                    const int col = n_blk * BLOCK_N + c * 64 + 2 * lane;
+                for (int c = 0; c < NCH; ++c) {
+                    const int cc = half * NCH + c;
+                    const int col = n_blk * BLOCK_N + cc * 32 + 2 * cp;
                     const bool col_ok = col < P.N, two = col + 1 < P.N;
                     const int nrows = min(32, P.M - row0);
-                    const int64_t idx0 = boff + (int64_t)row0 * P.epi.ldc + col;
+                    const int64_t idx0 = boff + (int64_t)(row0 + rpar) * P.epi.ldc + col;    // this lane's first row
                     // fast path (every specialised epilogue): whole column pair in range and 4/8-byte aligned -> hoisted
                     // address arithmetic, straight-line fully unrolled row loop
                     // (full 32-row tiles only, so that the unrolled row loop is branch-free and the rows interleave)
                     const bool fast = (EPI >= 0) && col_ok && two && nrows == 32 && (((idx0 | P.epi.ldc) & 1) == 0) &&
                                       (!PF_AUX || P.epi.aux_dtype == DT_BF16);
-                    uint32_t pa[PF_AUX ? 32 : 1];
-                    float2 pr[PF_RES ? 32 : 1], pc[PF_ACC ? 32 : 1];
+                    uint32_t pa[PF_AUX ? 16 : 1];
+                    float2 pr[PF_RES ? 16 : 1], pc[PF_ACC ? 16 : 1];
                     if (PF && fast) {
 #pragma unroll
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int64_t idx = idx0 + (int64_t)rr * P.epi.ldc;
+                        for (int rr = 0; rr < 16; ++rr) {
+                            const int64_t idx = idx0 + (int64_t)(2 * rr) * P.epi.ldc;
                             if constexpr (PF_AUX) pa[rr] = *reinterpret_cast<const uint32_t*>((const bf16*)P.epi.aux + idx);
                             if constexpr (PF_RES) pr[rr] = *reinterpret_cast<const float2*>(P.epi.resid + idx);
                             if constexpr (PF_ACC) pc[rr] = *reinterpret_cast<const float2*>((const float*)P.epi.C + idx);
                         }
                     }
-                    uint32_t r[64];
+                    uint32_t r[32];
                     if (!(P.dbg & 4)) {
-                        tmem_ld32(taddr + c * 64, r);
-                        tmem_ld32(taddr + c * 64 + 32, r + 32);
+                        tmem_ld32(taddr + cc * 32, r);
                         tmem_ld_wait();
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) r[j] = j;
+                        for (int j = 0; j < 32; ++j) r[j] = j;
                     }
-                    if (c == BLOCK_N / 64 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { if (CTA2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
-                    }
+                    if (c == NCH - 1) release_acc();
                     if (P.dbg & 2) {
                         uint32_t x = 0;
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) x ^= r[j];
+                        for (int j = 0; j < 32; ++j) x ^= r[j];
                         if (x == 0x12345u) P.epi.alpha == 0.f ? (void)0 : (void)atomicAdd((int*)P.epi.C, 1);
                         continue;
                     }
+                    // staged row `lane`: column pair j lives at float2 slot j ^ (lane & 15) (conflict-free both ways)
                     float* myrow = tile + lane * Cfg::EPI_STRIDE;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        *reinterpret_cast<float2*>(myrow + 2 * j) = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    for (int j = 0; j < 16; ++j)
+                        *reinterpret_cast<float2*>(myrow + 2 * (j ^ cp)) = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                     __syncwarp();
                     if (col_ok) {
                         if (P.dbg & 1) {
                             float acc2 = 0.f;
-                            for (int rr = 0; rr < nrows; ++rr) {
-                                const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
+                            for (int rr = 0; rr < 16; ++rr) {
+                                const int R = 2 * rr + rpar;
+                                const float2 v = *reinterpret_cast<const float2*>(tile + R * Cfg::EPI_STRIDE + 2 * (cp ^ (R & 15)));
                                 acc2 += v.x + v.y;
                             }
                             if (acc2 == 1.2345e30f) ((float*)P.epi.C)[0] = acc2;
                         } else if (fast) {
                             const GemmEpilogue& e = P.epi;
                             const float alpha = e.alpha;
-                            const float* trow = tile + 2 * lane;
                             const int64_t ldc = e.ldc;
                             char* cptr = (char*)e.C + idx0 * ((EPI & EPI_OUT_F32) ? 4 : 2);
-                            const int64_t cstep = ldc * ((EPI & EPI_OUT_F32) ? 4 : 2);
+                            const int64_t cstep = 2 * ldc * ((EPI & EPI_OUT_F32) ? 4 : 2);
                             const uint64_t seed = e.seed;
                             const uint32_t site = e.site, thr = e.drop_thr;
                             const float inv_keep = e.inv_keep;
 #pragma unroll
-                            for (int rr = 0; rr < 32; ++rr) {
-                                const float2 v = *reinterpret_cast<const float2*>(trow + rr * Cfg::EPI_STRIDE);
+                            for (int rr = 0; rr < 16; ++rr) {
+                                const int R = 2 * rr + rpar;
+                                const float2 v = *reinterpret_cast<const float2*>(tile + R * Cfg::EPI_STRIDE + 2 * (cp ^ (R & 15)));
                                 float v0 = v.x * alpha, v1 = v.y * alpha;
                                 if constexpr ((F & EPI_RELU) != 0) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                                 if constexpr (PF_AUX) {
@@ -439,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                                 if constexpr ((F & EPI_DROPOUT) != 0) {
                                     bool k0, k1;   // idx is even on the fast path: one hash for the pair
-                                    drop_keep2(seed, site, (uint64_t)(idx0 + (int64_t)rr * ldc), thr, k0, k1);
+                                    drop_keep2(seed, site, (uint64_t)(idx0 + (int64_t)(2 * rr) * ldc), thr, k0, k1);
                                     v0 = k0 ? v0 * inv_keep : 0.f;
                                     v1 = k1 ? v1 * inv_keep : 0.f;
                                 }
@@ -455,9 +464,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         } else {
 #pragma unroll 4
-                            for (int rr = 0; rr < nrows; ++rr) {
-                                const float2 v = *reinterpret_cast<const float2*>(tile + rr * Cfg::EPI_STRIDE + 2 * lane);
-                                epi_store2<EPI>(P.epi, v.x, v.y, boff + (int64_t)(row0 + rr) * P.epi.ldc + col, two);
+                            for (int rr = 0; rr < 16; ++rr) {
+                                const int R = 2 * rr + rpar;
+                                if (R >= nrows) continue;
+                                const float2 v = *reinterpret_cast<const float2*>(tile + R * Cfg::EPI_STRIDE + 2 * (cp ^ (R & 15)));
+                                epi_store2<EPI>(P.epi, v.x, v.y, boff + (int64_t)(row0 + R) * P.epi.ldc + col, two);
                             }
                         }
                     }
@@ -467,17 +478,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 continue;
             }
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
+                const int cc = half * NCH + c;
                 uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
+                tmem_ld32(taddr + cc * 32, r);
                 tmem_ld_wait();
-                if (c == BLOCK_N / 32 - 1) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { if (CTA2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
-                }
-                const int col0 = n_blk * BLOCK_N + c * 32;
+                if (c == NCH - 1) release_acc();
+                const int col0 = n_blk * BLOCK_N + cc * 32;
                 if (row_ok && col0 < P.N) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
