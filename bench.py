@@ -385,6 +385,8 @@ def run_b200(args):
         clocks.window(t_w0, t_w1)
         clk = clocks.stop()
     final_loss = float(loss.item())
+    free_b, total_b = torch.cuda.mem_get_info()      # device memory in use after the timed steps (engine buffers + torch)
+    hbm_used_gb = (total_b - free_b) / 1e9
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -600,6 +602,7 @@ def run_b200(args):
             "gpu_reference": gpu_ref,
             "eval": eval_out,
             "final_loss": final_loss,
+            "hbm_used_gb": round(hbm_used_gb, 2),
             "dp_replica_max_rel_diff": dp_diff,
         }
         print(json.dumps(out), flush=True)

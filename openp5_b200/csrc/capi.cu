@@ -136,6 +136,11 @@ int p5_backward(p5_handle h, const float* dloss_tok) {
     e->backward();
     P5_API_END
 }
+// P5_NO_EARLY_NORM=1: the gradient norm is one pass over the whole buffer after the backward (A/B switch)
+static bool early_norm_enabled() {
+    static const bool on = getenv("P5_NO_EARLY_NORM") == nullptr;
+    return on;
+}
 int p5_train_fwd_bwd(p5_handle h, const int32_t* input_ids, const int32_t* attention_mask,
                      const int32_t* whole_word_ids, const int32_t* labels, const int32_t* labels_mask, int B, int Le,
                      int Ld, float* loss_out, uint64_t seed) {
@@ -147,8 +152,10 @@ int p5_train_fwd_bwd(p5_handle h, const int32_t* input_ids, const int32_t* atten
     runner_loss_fwd_bwd(e->loss_tok, e->lmask, B, Ld, e->loss_scalar, e->dloss, e->st);
     if (loss_out) P5_CUDA(cudaMemcpyAsync(loss_out, e->loss_scalar, 4, cudaMemcpyDeviceToDevice, e->st));
     e->overlap_comm = e->world > 1 && e->nccl_comm != nullptr;
+    e->early_norm = early_norm_enabled();
     e->backward();
     e->overlap_comm = false;
+    e->early_norm = false;
     P5_API_END
 }
 int p5_grad_norm(p5_handle h, float* out) {
@@ -163,7 +170,7 @@ int p5_grad_scale(p5_handle h, float s) {
     Engine* e = E(h);
     e->join_optimizer();
     scale_f32(e->G, e->n_flat, s, e->st);
-    e->norm_valid = false;
+    e->invalidate_norm();
     P5_API_END
 }
 int p5_zero_grad(p5_handle h) {

@@ -115,6 +115,11 @@ void comm_allreduce_range(Engine* e, int64_t off, int64_t n) {
     c->pending_done.push_back({off, off + n});
 }
 
+cudaStream_t comm_stream(Engine* e) {
+    CommState* c = (CommState*)e->nccl_comm;
+    return c ? c->stream : nullptr;
+}
+
 // finish: reduce every range not yet handed over, then make the main stream wait for the side stream
 void comm_allreduce_grads(Engine* e) {
     CommState* c = (CommState*)e->nccl_comm;
@@ -130,7 +135,10 @@ void comm_allreduce_grads(Engine* e) {
         if (r.second > cur) cur = r.second;
     }
     if (cur < e->n_flat) todo.push_back({cur, e->n_flat});
-    for (auto& r : todo) comm_allreduce_range(e, r.first, r.second - r.first);
+    for (auto& r : todo) {
+        comm_allreduce_range(e, r.first, r.second - r.first);
+        if (r.second > e->early_lo) e->early_norm_ready = false;   // a range whose early sum of squares was taken changes
+    }
     c->pending_done.clear();
     P5_CUDA(cudaEventRecord(c->done, c->stream));
     P5_CUDA(cudaStreamWaitEvent(e->st, c->done, 0));

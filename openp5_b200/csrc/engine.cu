@@ -16,6 +16,7 @@
 namespace p5 {
 
 void comm_allreduce_range(Engine* e, int64_t off, int64_t n);   // comm.cu (no-op without a communicator)
+cudaStream_t comm_stream(Engine* e);                              // comm.cu: the all-reduce side stream (null without a communicator)
 
 static inline void* poff(const void* p, int64_t elems, int dt) {
     return (void*)((const char*)p + elems * (int64_t)dtype_size(dt));
@@ -121,20 +122,16 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     enc_out = dalloc(Mem * d * e);
     qkv_e.resize(NE); ctx_e.resize(NE); h_e.resize(NE); z_e.assign(NE, nullptr); P_e.assign(NE, nullptr);
     lse_e.assign(NE, nullptr); p_unnorm.assign(NE, false); p_fbwd.assign(NE, false);
-    const int64_t SS = (int64_t)Bm * H * Lem * Lem;
     for (int i = 0; i < NE; ++i) {
         qkv_e[i] = dalloc(Mem * 3 * A * e);
         ctx_e[i] = dalloc(Mem * A * e);
         h_e[i] = dalloc(Mem * ff * e);
         if (gated) z_e[i] = dalloc(Mem * 2 * ff * e);
-        if (tc_attn) P_e[i] = dalloc(SS * e);
         lse_e[i] = dalloc_t<float>((int64_t)Bm * H * Lem);   // fp32 mode: LSE; bf16 mode: 1 / row sum of the fused kernel
     }
-    if (tc_attn) {
-        S_scr = dalloc_t<float>(SS);
-        Pd_scr = dalloc(SS * e);
-        dS_scr = dalloc(SS * e);
-    }
+    // the L^2-sized buffers of the materialised attention paths (P per layer, fp32 scores, Pd, dS) are allocated on first
+    // use (ensure_attn_scratch): with the fused forward + backward (Le <= 512) they are never touched, and at T5-large /
+    // Le = 512 / B = 64 they would take 15 GB
     yd.resize(3 * ND + 1); rstd_d.resize(3 * ND + 1); nd.resize(3 * ND);
     for (auto& p : yd) p = dalloc_t<float>(Mdm * d);
     for (auto& p : rstd_d) p = dalloc_t<float>(Mdm);
@@ -192,7 +189,7 @@ Engine::Engine(const P5Config& c, int dev, cudaStream_t stream) : cfg(c), device
     const int Ldb = Ldm > 256 ? Ldm : 256;   // generate() builds the decoder table for max_length <= 256 positions
     bias_dec = dalloc_t<float>((int64_t)H * (2 * Ldb)); dbias_dec = dalloc_t<float>((int64_t)H * (2 * Ldb));
     lut_enc = dalloc_t<int>(2 * Lem); lut_dec = dalloc_t<int>(2 * Ldb);
-    norm_partial = dalloc_t<float>(1024); norm_out = dalloc_t<float>(4);
+    norm_partial = dalloc_t<float>(1024); norm_out = dalloc_t<float>(4); norm_early = dalloc_t<float>(EARLY_SLOTS);
     lens_d = dalloc_t<int>(Bm + 1); offs_d = dalloc_t<int>(Bm + 1);
     ids_p = dalloc_t<int>(Mem); ww_p = dalloc_t<int>(Mem);
     qkv_pad = dalloc(Mem * 3 * A * e); ctx_pad = dalloc(Mem * A * e); dqkv_pad = dalloc(Mem * 3 * A * e);
@@ -210,6 +207,9 @@ Engine::~Engine() {
     for (auto e : ev_opt) cudaEventDestroy(e);
     if (ev_opt_start) cudaEventDestroy(ev_opt_start);
     if (st_opt) cudaStreamDestroy(st_opt);
+    if (st_norm) { cudaStreamSynchronize(st_norm); cudaStreamDestroy(st_norm); }
+    if (ev_norm_fork) cudaEventDestroy(ev_norm_fork);
+    if (ev_norm_join) cudaEventDestroy(ev_norm_join);
     if (gen) free_gen_ws(gen);
     free_persist_ws();
     gemm_x3_release();
@@ -500,15 +500,25 @@ void Engine::ffn_bwd(const float* dx_out, int64_t M, const FfnOff& w, const void
 // ------------------------------------------------------------------------------------------------------------
 // The attention kernels that work on the padded [B, Le] geometry (batched GEMMs of the backward, the SIMT kernels of
 // the parity mode) see packed activations through padded scratch copies: unpack -> kernel -> pack.
+void Engine::ensure_attn_scratch() {
+    if (S_scr || dt != DT_BF16) return;
+    const int64_t SS = (int64_t)Bm * H * Lem * Lem;
+    const size_t e = esz();
+    for (int i = 0; i < NE; ++i) P_e[i] = dalloc(SS * e);
+    S_scr = dalloc_t<float>(SS);
+    Pd_scr = dalloc(SS * e);
+    dS_scr = dalloc(SS * e);
+}
+
 void Engine::enc_attention_fwd(int l) {
     const int64_t SS1 = (int64_t)Le * Le;
     static int fused = -1;
     if (fused < 0) { const char* e = getenv("P5_ATTN"); fused = (e && strcmp(e, "unfused") == 0) ? 0 : 1; }
     const DropCfg dc = drop(S_ENC_P, l);
     if (dt == DT_BF16 && (fused || packed)) {
-        // Le <= 256: the fused backward recomputes P from the row statistic, nothing of size L^2 is saved
-        static const bool no_fbwd = getenv("P5_NO_FATTN_BWD") != nullptr;
-        const bool fbwd = Le <= 256 && !no_fbwd;
+        // the fused backward (Le <= 512) recomputes P from the row statistic, nothing of size L^2 is saved
+        const bool fbwd = fattn_bwd_supported(Le);
+        if (!fbwd) ensure_attn_scratch();
         const bool ok = fattn_fwd(qkv_e[l], 3 * A, A, B, H, Le, bias_enc, mask_e, fbwd ? nullptr : P_e[l],
                                   fbwd ? nullptr : lse_e[l], fbwd ? lse_e[l] : nullptr, ctx_e[l], A, dc, st,
                                   packed ? offs_d : nullptr, packed ? lens_d : nullptr, Mt);
@@ -524,6 +534,7 @@ void Engine::enc_attention_fwd(int l) {
         qkv = qkv_pad; ctx = ctx_pad;
     }
     if (dt == DT_BF16) {
+        ensure_attn_scratch();
         GemmProblem p;   // S = Q K^T   (unscaled, HF:modeling_t5.py:308)
         p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;
         p.A.ptr = qkv; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = 3 * A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * 3 * A;
@@ -573,6 +584,7 @@ void Engine::enc_attention_bwd(int l, const void* dctx_in, void* dqkv_out) {
         dqkv = dt == DT_F32 ? (void*)f_qkv_pad : dqkv_pad;
     }
     if (dt == DT_BF16) {
+        ensure_attn_scratch();
         GemmProblem p;   // dPd = dctx V^T
         p.M = Le; p.N = Le; p.K = 64; p.nb1 = H; p.nb2 = B;
         p.A.ptr = dctx; p.A.dtype = dt; p.A.major = MAJOR_K; p.A.ld = A; p.A.bs1 = 64; p.A.bs2 = (int64_t)Le * A;
@@ -798,7 +810,8 @@ void Engine::backward() {
     P5_CHECK(have_fwd, "p5_backward called without a preceding p5_forward");
     P5_CUDA(cudaSetDevice(device));
     join_optimizer();
-    norm_valid = false;
+    invalidate_norm();
+    early_np = 0; early_cov = 0; early_lo = n_flat;
     const float hs = 1.f / sqrtf((float)d);
     auto as_T = [&](float* src, void* dst, int64_t n) -> void* {
         if (dt == DT_F32) return (void*)src;
@@ -923,7 +936,7 @@ void Engine::backward() {
     embed_bwd(dy, dec_ids, nullptr, G + off_shared, nullptr, (int)Md, d, V, cfg.whole_word_rows, drop(S_EMB_D, 0), st);
     relbias_scatter_grad(dbias_dec, lut_dec, G + off_dec_rel, H, 2 * Ld - 1, st);
     // every decoder gradient is final: hand the range to NCCL while the encoder backward runs
-    if (overlap_comm && ND > 0) comm_allreduce_range(this, dec[0].sa.q, n_flat - dec[0].sa.q);
+    if (ND > 0) range_final(dec[0].sa.q, n_flat - dec[0].sa.q);
 
     // ---- encoder
     float* dx = dx_a;
@@ -945,14 +958,42 @@ void Engine::backward() {
         rmsnorm_bwd(g_d2, dt, x_in, rstd_e[2 * l], P + w.ln0, dx, dx, G + w.ln0, (int)Mt, d, none, st, l > 0 ? g_d : nullptr, dt,
                     drop(S_ENC_WO, l > 0 ? l - 1 : 0));
         // block l >= 1 is final (block 0 also holds the shared relative bias, reduced with the embeddings at the end)
-        if (overlap_comm && l >= 1) {
+        if (l >= 1) {
             const int64_t hi = (l + 1 < NE) ? enc[l + 1].sa.q : (ND > 0 ? dec[0].sa.q : n_flat);
-            comm_allreduce_range(this, w.sa.q, hi - w.sa.q);
+            range_final(w.sa.q, hi - w.sa.q);
         }
     }
     embed_bwd(dx, packed ? ids_p : ids_e, packed ? ww_p : ww_e, G + off_shared, G + off_ww, (int)Mt, d, V, cfg.whole_word_rows,
               drop(S_EMB_E, 0), st);
     relbias_scatter_grad(dbias_enc, lut_enc, G + off_enc_rel, H, 2 * Le - 1, st);
+    if (early_norm && early_cov > 0 && early_lo + early_cov == n_flat) {     // the early ranges tile [early_lo, n_flat)
+        P5_CUDA(cudaEventRecord(ev_norm_join, overlap_comm ? comm_stream(this) : st_norm));
+        early_norm_ready = true;
+    }
+}
+
+// A gradient range [off, off + n) of the flat buffer has received its last contribution of this backward pass.
+void Engine::range_final(int64_t off, int64_t n) {
+    if (overlap_comm) comm_allreduce_range(this, off, n);
+    if (!early_norm || n <= 0) return;
+    if (!ev_norm_join) {
+        P5_CUDA(cudaStreamCreateWithFlags(&st_norm, cudaStreamNonBlocking));
+        P5_CUDA(cudaEventCreateWithFlags(&ev_norm_fork, cudaEventDisableTiming));
+        P5_CUDA(cudaEventCreateWithFlags(&ev_norm_join, cudaEventDisableTiming));
+    }
+    cudaStream_t s = overlap_comm ? comm_stream(this) : st_norm;     // data parallel: ordered after the range's all-reduce
+    P5_CHECK(s != nullptr, "range_final: no side stream");
+    if (!overlap_comm) {
+        P5_CUDA(cudaEventRecord(ev_norm_fork, st));
+        P5_CUDA(cudaStreamWaitEvent(s, ev_norm_fork, 0));
+    }
+    int64_t nb = n / 65536;
+    nb = nb < 16 ? 16 : (nb > 512 ? 512 : nb);
+    if (early_np + nb > EARLY_SLOTS - 256) return;     // out of slots: coverage stays incomplete and grad_norm() takes the full pass
+    sumsq_partial(G + off, n, norm_early + early_np, (int)nb, s);
+    early_np += (int)nb;
+    early_cov += n;
+    if (off < early_lo) early_lo = off;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -971,13 +1012,22 @@ NoDecay Engine::no_decay(int64_t base) const {
 
 void Engine::grad_norm() {
     join_optimizer();
-    sumsq_norm(G, n_flat, norm_partial, norm_out, st);
+    if (early_norm_ready) {
+        // [early_lo, n_flat) was summed under the backward; the head of the buffer (embeddings + encoder block 0) is left
+        P5_CUDA(cudaStreamWaitEvent(st, ev_norm_join, 0));
+        int np = early_np;
+        if (early_lo > 0) { sumsq_partial(G, early_lo, norm_early + np, 256, st); np += 256; }
+        sumsq_final(norm_early, np, norm_out, st);
+        early_norm_ready = false;
+    } else {
+        sumsq_norm(G, n_flat, norm_partial, norm_out, st);
+    }
     norm_valid = true;
 }
 void Engine::zero_grad() {
     join_optimizer();
     P5_CUDA(cudaMemsetAsync(G, 0, n_flat * sizeof(float), st));
-    norm_valid = false;
+    invalidate_norm();
 }
 void Engine::wait_opt(int r) {
     if (opt_pending) P5_CUDA(cudaStreamWaitEvent(st, ev_opt[r], 0));
@@ -1017,7 +1067,7 @@ void Engine::adamw_async(float lr, float b1, float b2, float eps, float wd, int 
     }
     opt_pending = true;
     shadow_stale = false;
-    norm_valid = false;
+    invalidate_norm();
 }
 void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, float clip, bool zero_grad_after) {
     join_optimizer();
@@ -1025,7 +1075,7 @@ void Engine::adamw(float lr, float b1, float b2, float eps, float wd, int step, 
     adamw_flat(P, G, M1, V2, P16, n_flat, lr, b1, b2, eps, wd, step, clip, clip > 0.f ? norm_out : nullptr, 1.f, st,
                zero_grad_after, no_decay(0));
     shadow_stale = false;
-    if (zero_grad_after) norm_valid = false;
+    if (zero_grad_after) invalidate_norm();
 }
 
 }  // namespace p5

@@ -134,6 +134,20 @@ struct Engine {
     // optimiser scratch
     float *norm_partial = nullptr, *norm_out = nullptr;
     bool norm_valid = false;
+    // Early gradient norm (fused train step, p5_train_fwd_bwd): the sum of squares of a gradient range is taken on a side
+    // stream as soon as the backward has finished the range (after its all-reduce when data parallel), under the rest of
+    // the backward; grad_norm() then only has the last range (embeddings + encoder block 0) left instead of a pass over
+    // the whole 0.9 GB buffer between the backward and AdamW.
+    bool early_norm = false;           // set around backward() by the fused train step
+    bool early_norm_ready = false;     // the partials cover [early_lo, n_flat) of the CURRENT gradient buffer
+    int64_t early_lo = 0, early_cov = 0;
+    int early_np = 0;                  // block partials written so far
+    static constexpr int EARLY_SLOTS = 4096;
+    float* norm_early = nullptr;       // [EARLY_SLOTS]
+    cudaStream_t st_norm = nullptr;
+    cudaEvent_t ev_norm_fork = nullptr, ev_norm_join = nullptr;
+    void range_final(int64_t off, int64_t n);   // the gradient range is complete: all-reduce (data parallel) + early sum of squares
+    void invalidate_norm() { norm_valid = false; early_norm_ready = false; }
     // comm
     void* nccl_comm = nullptr;
     int world = 1, rank = 0;
@@ -182,6 +196,7 @@ struct Engine {
     void forward(const int32_t* ids, const int32_t* mask, const int32_t* ww, const int32_t* labels, int B, int Le,
                  int Ld, bool training, uint64_t seed);
     void backward();   // consumes this->dloss
+    void ensure_attn_scratch();   // L^2-sized buffers of the materialised attention paths, allocated on first use
     void enc_attention_fwd(int l);
     void enc_attention_bwd(int l, const void* dctx, void* dqkv);
     void ffn_fwd(const void* n, int64_t M, const FfnOff& w, void* z, void* h, const float* x_resid, float* x_out,

@@ -7,9 +7,13 @@
 // (265 us at T5-base B=64 Le=256) and makes the forward's P_save write unnecessary (P is recomputed from the row
 // statistic lse2 = m2 + log2(l) that the forward stores: 4 B per row instead of 2 B per score).
 //
-// One persistent CTA per SM walks (batch, head) pairs (sequence length <= 256: two 128-row query tiles, two 128-key
-// blocks).  Q, K, V, dO of the pair are TMA-loaded once into 128B-swizzled smem (128 KB) and serve as K-major AND
-// MN-major UMMA operands in place (the same bytes are A of S = Q K^T and B of dK = dS^T Q).
+// One persistent CTA per SM walks (batch, head) pairs.  Sequence length <= 256 (BIG = false): two 128-row query tiles,
+// two 128-key blocks; Q, K, V, dO of the pair are TMA-loaded once into 128B-swizzled smem (128 KB) and serve as K-major
+// AND MN-major UMMA operands in place (the same bytes are A of S = Q K^T and B of dK = dS^T Q).
+// 256 < length <= 512 (BIG = true, T5-large / Yelp configs): tensor memory holds dQ of only two query tiles next to
+// S, dPd, dV_j, dK_j, so a pair is processed as up to two UNITS of two query tiles each; a unit keeps its Q / dO tiles
+// resident and streams the key blocks K_j, V_j through a two-slot ring; the second unit of a pair adds its dK / dV
+// contribution onto the bf16 rows the first unit wrote (same CTA, same thread, so plain read-modify-write).
 //   warp 0    : TMA producer
 //   warp 1    : MMA issuer.  per (key block j, query tile i):  S = Q_i K_j^T, dPd = dO_i V_j^T  (128x128x64 each)
 //               then dV_j += Pd^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j  (128x64x128 each, Pd / dS read from smem)
@@ -64,6 +68,7 @@ struct FbParams {
     DropCfg drop;
 };
 
+template <bool BIG>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -83,6 +88,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                    tmem_holder = bar + 128;
     auto bm_full = [&](int i) { return bar + 96 + 8 * i; };      // two table buffers: warp 3 works one pair ahead
     auto bm_empty = [&](int i) { return bar + 112 + 8 * i; };
+    auto kv_full = [&](int i) { return bar + 144 + 8 * i; };     // BIG: two-slot ring of (K_j, V_j) key blocks
+    auto kv_empty = [&](int i) { return bar + 160 + 8 * i; };
+    constexpr int MASK_FLOATS = (BIG ? 4 : 2) * KB;              // key-mask table of one pair
     volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,6 +104,8 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(pds_full, 4 * NWG); mbar_init(pds_free, 1);
         mbar_init(dvk_full, 1); mbar_init(dvk_free, 4 * NWG);
         mbar_init(dq_full, 1); mbar_init(dq_free, 4 * NWG);
+        if constexpr (BIG)
+            for (int i = 0; i < 2; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_empty(i), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -115,20 +125,42 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ========================= TMA producer =========================
         if (lane == 0) {
             uint32_t ph = 0;
+            [[maybe_unused]] uint32_t kvc = 0;      // BIG: key blocks loaded so far (slot = kvc & 1, phase = (kvc >> 1) & 1)
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int b = pair / P.H, h = pair % P.H;
                 const int len = P.lens ? P.lens[b] : L;
                 const int row0 = P.offs ? P.offs[b] : 0, bc = P.offs ? 0 : b;
                 const int nt = (len + QT - 1) / QT;
-                mbar_wait(ld_empty, ph ^ 1);
-                mbar_expect_tx(ld_full, (uint32_t)(4 * nt * QT * 128));
-                for (int t = 0; t < nt; ++t) {
-                    tma_load_4d(sQ + t * (QT * 128), &tmQ, ld_full, 0, row0 + t * QT, h, bc);
-                    tma_load_4d(sdO + t * (QT * 128), &tmdO, ld_full, 0, row0 + t * QT, h, bc);
-                    tma_load_4d(sK + t * (KB * 128), &tmK, ld_full, 0, row0 + t * KB, h, bc);
-                    tma_load_4d(sV + t * (KB * 128), &tmV, ld_full, 0, row0 + t * KB, h, bc);
+                if constexpr (!BIG) {
+                    mbar_wait(ld_empty, ph ^ 1);
+                    mbar_expect_tx(ld_full, (uint32_t)(4 * nt * QT * 128));
+                    for (int t = 0; t < nt; ++t) {
+                        tma_load_4d(sQ + t * (QT * 128), &tmQ, ld_full, 0, row0 + t * QT, h, bc);
+                        tma_load_4d(sdO + t * (QT * 128), &tmdO, ld_full, 0, row0 + t * QT, h, bc);
+                        tma_load_4d(sK + t * (KB * 128), &tmK, ld_full, 0, row0 + t * KB, h, bc);
+                        tma_load_4d(sV + t * (KB * 128), &tmV, ld_full, 0, row0 + t * KB, h, bc);
+                    }
+                    ph ^= 1;
+                } else {
+                    for (int i0 = 0; i0 < nt; i0 += 2) {          // unit = two query tiles of the pair
+                        const int ni = min(2, nt - i0);
+                        mbar_wait(ld_empty, ph ^ 1);
+                        mbar_expect_tx(ld_full, (uint32_t)(2 * ni * QT * 128));
+                        for (int t = 0; t < ni; ++t) {
+                            tma_load_4d(sQ + t * (QT * 128), &tmQ, ld_full, 0, row0 + (i0 + t) * QT, h, bc);
+                            tma_load_4d(sdO + t * (QT * 128), &tmdO, ld_full, 0, row0 + (i0 + t) * QT, h, bc);
+                        }
+                        ph ^= 1;
+                        for (int j = 0; j < nt; ++j) {            // every key block of the pair streams past the unit
+                            const uint32_t slot = kvc & 1u;
+                            mbar_wait(kv_empty(slot), ((kvc >> 1) & 1u) ^ 1u);
+                            mbar_expect_tx(kv_full(slot), (uint32_t)(2 * KB * 128));
+                            tma_load_4d(sK + slot * (KB * 128), &tmK, kv_full(slot), 0, row0 + j * KB, h, bc);
+                            tma_load_4d(sV + slot * (KB * 128), &tmV, kv_full(slot), 0, row0 + j * KB, h, bc);
+                            ++kvc;
+                        }
+                    }
                 }
-                ph ^= 1;
             }
         }
         __syncwarp();
@@ -140,53 +172,73 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t idesc_g = f32bf16 | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // MN x MN
             const uint32_t idesc_q = f32bf16 | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);              // K x MN
             uint32_t ld_ph = 0, sdpf_ph = 0, pdsf_ph = 0, dvkf_ph = 0, dqf_ph = 0;
+            // BIG: key blocks whose S / dPd MMAs have been started (kv_i) and whose last MMA has been issued (kv_u); block n
+            // of the stream sits in ring slot n & 1 (the producer's kvc counts the same sequence)
+            [[maybe_unused]] uint32_t kv_i = 0, kv_u = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int len = P.lens ? P.lens[pair / P.H] : L;
-                const int nt = (len + QT - 1) / QT, T = nt * nt;
-                mbar_wait(ld_full, ld_ph);
-                ld_ph ^= 1;
-                tc_fence_after();
-                auto issue_sdp = [&](int t) {
-                    const int j = t / nt, i = t % nt;
-                    mbar_wait(sdp_free, sdpf_ph ^ 1);       // the softmax warps have read the previous S / dPd out of TMEM
-                    sdpf_ph ^= 1;
+                const int nt = (len + QT - 1) / QT;
+                // unit = the query tiles [i0, i0 + ni) of the pair against all nt key blocks (one unit when !BIG)
+                for (int i0 = 0; i0 < (BIG ? nt : 1); i0 += 2) {
+                    const int ni = BIG ? min(2, nt - i0) : nt, T = nt * ni;
+                    mbar_wait(ld_full, ld_ph);
+                    ld_ph ^= 1;
                     tc_fence_after();
+                    auto issue_sdp = [&](int t) {
+                        const int j = t / ni, i = t % ni;
+                        uint32_t ks = (uint32_t)j;              // smem tile of K_j / V_j
+                        if constexpr (BIG) {
+                            ks = kv_i & 1u;
+                            if (i == 0) mbar_wait(kv_full(ks), (kv_i >> 1) & 1u);      // K_j, V_j have landed
+                        }
+                        mbar_wait(sdp_free, sdpf_ph ^ 1);       // the softmax warps have read the previous S / dPd out of TMEM
+                        sdpf_ph ^= 1;
+                        tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tS, make_smem_desc(sQ + i * (QT * 128) + k * 32, 16, 1024),
-                                  make_smem_desc(sK + j * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tS, make_smem_desc(sQ + i * (QT * 128) + k * 32, 16, 1024),
+                                      make_smem_desc(sK + ks * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tdP, make_smem_desc(sdO + i * (QT * 128) + k * 32, 16, 1024),
-                                  make_smem_desc(sV + j * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
-                    umma_commit(sdp_full);
-                };
-                issue_sdp(0);
-                for (int t = 0; t < T; ++t) {
-                    const int j = t / nt, i = t % nt;
-                    if (t + 1 < T) issue_sdp(t + 1);
-                    mbar_wait(pds_full, pdsf_ph);           // Pd / dS tiles of (j, i) are in smem
-                    pdsf_ph ^= 1;
-                    if (i == 0) { mbar_wait(dvk_free, dvkf_ph ^ 1); dvkf_ph ^= 1; }      // previous dV / dK read out
-                    if (t == 0) { mbar_wait(dq_free, dqf_ph ^ 1); dqf_ph ^= 1; }         // previous pair's dQ read out
-                    tc_fence_after();
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tdP, make_smem_desc(sdO + i * (QT * 128) + k * 32, 16, 1024),
+                                      make_smem_desc(sV + ks * (KB * 128) + k * 32, 16, 1024), idesc_s, k != 0);
+                        umma_commit(sdp_full);
+                        if constexpr (BIG) { if (i == ni - 1) ++kv_i; }
+                    };
+                    issue_sdp(0);
+                    for (int t = 0; t < T; ++t) {
+                        const int j = t / ni, i = t % ni;
+                        if (t + 1 < T) issue_sdp(t + 1);
+                        mbar_wait(pds_full, pdsf_ph);           // Pd / dS tiles of (j, i) are in smem
+                        pdsf_ph ^= 1;
+                        if (i == 0) { mbar_wait(dvk_free, dvkf_ph ^ 1); dvkf_ph ^= 1; }      // previous dV / dK read out
+                        if (t == 0) { mbar_wait(dq_free, dqf_ph ^ 1); dqf_ph ^= 1; }         // previous unit's dQ read out
+                        tc_fence_after();
+                        const uint32_t ks = BIG ? (kv_u & 1u) : (uint32_t)j;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)       // dV_j += Pd^T dO_i : A = Pd tile MN-major (k = query row), B = dO_i MN-major
-                        umma_bf16(tdV, make_smem_desc(sPd + k * 2048, 16384, 1024),
-                                  make_smem_desc(sdO + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
+                        for (int k = 0; k < 8; ++k)       // dV_j += Pd^T dO_i : A = Pd tile MN-major (k = query row), B = dO_i MN-major
+                            umma_bf16(tdV, make_smem_desc(sPd + k * 2048, 16384, 1024),
+                                      make_smem_desc(sdO + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)       // dK_j += dS^T Q_i
-                        umma_bf16(tdK, make_smem_desc(sdS + k * 2048, 16384, 1024),
-                                  make_smem_desc(sQ + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
+                        for (int k = 0; k < 8; ++k)       // dK_j += dS^T Q_i
+                            umma_bf16(tdK, make_smem_desc(sdS + k * 2048, 16384, 1024),
+                                      make_smem_desc(sQ + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)       // dQ_i += dS K_j : A = dS tile K-major (k = key), B = K_j MN-major
-                        umma_bf16(tdQ(i), make_smem_desc(sdS + (k >> 2) * (QT * 128) + (k & 3) * 32, 16, 1024),
-                                  make_smem_desc(sK + j * (KB * 128) + k * 2048, 8192, 1024), idesc_q, (j | k) != 0);
-                    umma_commit(pds_free);
-                    if (i == nt - 1) umma_commit(dvk_full);
+                        for (int k = 0; k < 8; ++k)       // dQ_i += dS K_j : A = dS tile K-major (k = key), B = K_j MN-major
+                            umma_bf16(tdQ(i), make_smem_desc(sdS + (k >> 2) * (QT * 128) + (k & 3) * 32, 16, 1024),
+                                      make_smem_desc(sK + ks * (KB * 128) + k * 2048, 8192, 1024), idesc_q, (j | k) != 0);
+                        umma_commit(pds_free);
+                        if (i == ni - 1) {
+                            umma_commit(dvk_full);
+                            if constexpr (BIG) {          // every MMA that reads K_j / V_j has been issued: the slot is
+                                umma_commit(kv_empty(kv_u & 1u));   // refilled once they retire
+                                ++kv_u;
+                            }
+                        }
+                    }
+                    umma_commit(dq_full);
+                    umma_commit(ld_empty);
                 }
-                umma_commit(dq_full);
-                umma_commit(ld_empty);
             }
         }
         __syncwarp();
@@ -205,8 +257,11 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int len = P.lens ? P.lens[b] : L;
             const int nt = (len + KB - 1) / KB;
             const int64_t row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * L;
+            // BIG: one table buffer (shared memory), rebuilt per unit = two query tiles starting at tile u0
+            for (int u0 = 0; u0 < (BIG ? nt : 1); u0 += 2) {
+            const int nu = BIG ? min(2, nt - u0) : nt;
             float* bias_b = bias_s + buf * 4 * cs;
-            float* mask_b = mask_s + buf * 2 * KB;
+            float* mask_b = mask_s + buf * MASK_FLOATS;
             float* rows_b = rows_s + buf * 4 * QT;
             mbar_wait(bm_empty(buf), ((bm_ph >> buf) & 1u) ^ 1u);
 #pragma unroll 4
@@ -220,8 +275,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 mask_b[j] = (j < len && (!P.key_mask || P.key_mask[b * L + j] != 0)) ? 0.f : -INFINITY;
             // one row per lane (128 contiguous bytes of O and of dO each): 8 independent 16-byte loads in flight per
             // tensor and lane, 32 rows per step -> the whole pair costs a handful of memory round trips
-            for (int i0 = 0; i0 < nt * QT; i0 += 32) {
-                const int gi = i0 + lane;
+            for (int i0 = 0; i0 < nu * QT; i0 += 32) {
+                const int li = i0 + lane;              // row inside the unit
+                const int gi = u0 * QT + li;           // query position
                 float part = 0.f, lse_v = INFINITY;
                 if (gi < len) {
                     const uint4* po = reinterpret_cast<const uint4*>(P.ctx + (row0 + gi) * P.ld_ctx + h * 64);
@@ -239,13 +295,14 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                     bf_lo(o[q].w) * bf_lo(g[q].w) + bf_hi(o[q].w) * bf_hi(g[q].w);
                     }
                 }
-                rows_b[gi] = part;
-                rows_b[2 * QT + gi] = lse_v;
+                rows_b[li] = part;
+                rows_b[2 * QT + li] = lse_v;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bm_full(buf));
             bm_ph ^= 1u << buf;
-            buf ^= 1;
+            if constexpr (!BIG) buf ^= 1;
+            }
         }
     } else if (warp >= 4) {
         // ========================= softmax warps =========================
@@ -265,16 +322,19 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int len = P.lens ? P.lens[b] : L;
             const int nt = (len + QT - 1) / QT;
             const int64_t row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * L;
+            // unit = the query tiles [u0, u0 + nu) of the pair against all nt key blocks (one unit when !BIG)
+            for (int u0 = 0; u0 < (BIG ? nt : 1); u0 += 2) {
+            const int nu = BIG ? min(2, nt - u0) : nt;
             const float* bias_b = bias_s + buf * 4 * cs;
-            const float* mask_b = mask_s + buf * 2 * KB;
+            const float* mask_b = mask_s + buf * MASK_FLOATS;
             const float* rows_b = rows_s + buf * 4 * QT;
             mbar_wait(bm_full(buf), (bm_ph >> buf) & 1u);
             bm_ph ^= 1u << buf;
             const float delta0 = rows_b[r], delta1 = rows_b[QT + r], lse0 = rows_b[2 * QT + r], lse1 = rows_b[3 * QT + r];
 
             for (int j = 0; j < nt; ++j) {
-                for (int i = 0; i < nt; ++i) {
-                    const int gi = i * QT + r;
+                for (int i = 0; i < nu; ++i) {
+                    const int gi = (u0 + i) * QT + r;
                     const bool row_ok = gi < len;
                     const int j0 = j * KB + wg * 32;
                     const int o = (row_ok ? (L - 1 - gi) : 0) + j0;
@@ -284,7 +344,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     const uint32_t pair0 = (uint32_t)((uint64_t)((((int64_t)b * P.H + h) * L + gi) * L + j0) >> 1);
                     const float my_lse = i ? lse1 : lse0, my_delta = i ? delta1 : delta0;
                     // diagonal index of (row of lane 0, column j0): entry + (t - lane) is the bias slot of element (lane, t)
-                    const int diag0 = (j0 - (i * QT + sw * 32)) + (L - 1);
+                    const int diag0 = (j0 - ((u0 + i) * QT + sw * 32)) + (L - 1);
                     float dacc[2] = {0.f, 0.f};
                     mbar_wait(sdp_full, sdp_ph);
                     sdp_ph ^= 1;
@@ -381,8 +441,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         }
                         __syncwarp();
                     }
-                    if (i == nt - 1) {
+                    if (i == nu - 1) {
                         // ---- dV_j, dK_j complete: rows = keys of block j, this warpgroup writes 16 of the 64 columns
+                        //      (BIG: complete over this unit's query tiles; the pair's second unit adds onto the first's rows)
                         mbar_wait(dvk_full, dvk_ph);
                         dvk_ph ^= 1;
                         tc_fence_after();
@@ -396,6 +457,23 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         const int gj = j * KB + r;
                         if (gj < len) {
                             bf16* dst = P.dqkv + (row0 + gj) * P.ld_dqkv + h * 64 + wg * 16;
+                            if constexpr (BIG) {
+                                if (u0 > 0) {      // written by this very thread while it processed the pair's first unit
+#pragma unroll
+                                    for (int q = 0; q < 2; ++q) {
+                                        const uint4 pa = *reinterpret_cast<const uint4*>(dst + 2 * P.A + 8 * q);
+                                        const uint4 pc = *reinterpret_cast<const uint4*>(dst + P.A + 8 * q);
+                                        const uint32_t pav[4] = {pa.x, pa.y, pa.z, pa.w}, pcv[4] = {pc.x, pc.y, pc.z, pc.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            v[8 * q + 2 * e] = __float_as_uint(__uint_as_float(v[8 * q + 2 * e]) + bf_lo(pav[e]));
+                                            v[8 * q + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * q + 2 * e + 1]) + bf_hi(pav[e]));
+                                            w[8 * q + 2 * e] = __float_as_uint(__uint_as_float(w[8 * q + 2 * e]) + bf_lo(pcv[e]));
+                                            w[8 * q + 2 * e + 1] = __float_as_uint(__uint_as_float(w[8 * q + 2 * e + 1]) + bf_hi(pcv[e]));
+                                        }
+                                    }
+                                }
+                            }
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
                                 uint4 a, c;
@@ -414,15 +492,15 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     }
                 }
             }
-            // ---- dQ tiles of the pair
+            // ---- dQ tiles of the unit
             mbar_wait(dq_full, dq_ph);
             dq_ph ^= 1;
             tc_fence_after();
-            for (int i = 0; i < nt; ++i) {
+            for (int i = 0; i < nu; ++i) {
                 uint32_t v[16];
                 tmem_ld16(tdQ(i) + lane_off + wg * 16, v);
                 tmem_ld_wait();
-                const int gi = i * QT + r;
+                const int gi = (u0 + i) * QT + r;
                 if (gi < len) {
                     bf16* dst = P.dqkv + (row0 + gi) * P.ld_dqkv + h * 64 + wg * 16;
 #pragma unroll
@@ -439,8 +517,8 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(dq_free); mbar_arrive(bm_empty(buf)); }
-            buf ^= 1;
-            // ---- relative-bias gradient of this pair -> global, table cleared for the next pair
+            if constexpr (!BIG) buf ^= 1;
+            // ---- relative-bias gradient of this unit -> global, table cleared for the next one
             if (P.dbias_rel) {
                 asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
                 for (int e = st_tid; e < n_delta; e += NWG * 128) {
@@ -448,6 +526,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     if (v != 0.f) { atomicAdd(P.dbias_rel + h * n_delta + e, v); sdb[e] = 0.f; }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+            }
             }
         }
     }
@@ -462,12 +541,18 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace
 
+// the fused backward covers this encoder length (the forward then saves row statistics instead of probabilities)
+bool fattn_bwd_supported(int L) {
+    static const bool off = getenv("P5_NO_FATTN_BWD") != nullptr;
+    static const bool no_big = getenv("P5_NO_FATTN_BWD_BIG") != nullptr;     // 256 < L <= 512 back on the materialised path
+    return !off && L % 8 == 0 && L <= (no_big ? 256 : 512);
+}
+
 bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
                const float* row_lse2, const void* ctx, int64_t ld_ctx, const void* dctx, int64_t ld_dctx, void* dqkv,
                int64_t ld_dqkv, float* dbias_rel, DropCfg drop, cudaStream_t st, const int* offs, const int* lens,
                int64_t packed_rows) {
-    static const bool off = getenv("P5_NO_FATTN_BWD") != nullptr;
-    if (off || L > 256 || L % 8 != 0 || ld_qkv % 8 != 0 || ld_ctx % 8 != 0 || ld_dctx % 8 != 0 || ld_dqkv % 8 != 0 || !row_lse2)
+    if (!fattn_bwd_supported(L) || ld_qkv % 8 != 0 || ld_ctx % 8 != 0 || ld_dctx % 8 != 0 || ld_dqkv % 8 != 0 || !row_lse2)
         return false;
     static int num_sms = 0;
     if (!num_sms) {
@@ -475,14 +560,17 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
         P5_CUDA(cudaGetDevice(&dev));
         P5_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    const bool big = L > 256;
     FbParams P;
     P.B = B; P.H = H; P.L = L;
     const uint32_t tile = QT * 128;                      // 16 KB: 128 rows x 64 bf16
+    // big: sQ / sdO hold the unit's two query tiles, sK / sV are the two slots of the key-block ring
     P.sQ = 0; P.sdO = 2 * tile; P.sK = 4 * tile; P.sV = 6 * tile; P.sPd = 8 * tile; P.sdS = 10 * tile;
     P.sBias = 12 * tile;
     P.bias_cs = (uint32_t)(((2 * L + 4 + 31) & ~31) + 8);
-    P.sMask = P.sBias + 2 * (uint32_t)round_up(4 * P.bias_cs * 4, 16);     // two table buffers
-    P.sStat = P.sMask + 2 * 2 * KB * 4;
+    const uint32_t ntbl = big ? 1 : 2;                   // table buffers (bias copies + key mask): one is all that fits at L > 256
+    P.sMask = P.sBias + ntbl * (uint32_t)round_up(4 * P.bias_cs * 4, 16);
+    P.sStat = P.sMask + ntbl * (big ? 4 : 2) * KB * 4;
     P.sDb = P.sStat + 2 * 4 * QT * 4;
     P.sScr = P.sDb + (uint32_t)round_up(2 * L * 4, 16);
     P.sBar = P.sScr + NWG * 4 * 32 * 4;
@@ -492,10 +580,11 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.ctx = (const bf16*)ctx; P.dctx = (const bf16*)dctx; P.ld_ctx = ld_ctx; P.ld_dctx = ld_dctx;
     P.dqkv = (bf16*)dqkv; P.ld_dqkv = ld_dqkv; P.A = A; P.dbias_rel = dbias_rel;
     P.offs = offs; P.lens = lens; P.drop = drop;
-    static size_t max_set = 0;
-    if (smem > max_set) {
-        P5_CUDA(cudaFuncSetAttribute(fattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        max_set = smem;
+    static size_t max_set[2] = {0, 0};
+    if (smem > max_set[big]) {
+        if (big) P5_CUDA(cudaFuncSetAttribute(fattn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else P5_CUDA(cudaFuncSetAttribute(fattn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set[big] = smem;
     }
     const uint64_t rows = (uint64_t)(offs ? packed_rows : L);
     const uint64_t dims[4] = {64, rows, (uint64_t)H, (uint64_t)(offs ? 1 : B)};
@@ -510,7 +599,8 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     const int n_pairs = B * H;
     const int budget = sm_budget() < num_sms ? sm_budget() : num_sms;     // leaves SMs to a concurrent NCCL all-reduce (common.cuh)
     const int grid = n_pairs < budget ? n_pairs : budget;
-    launch_k(fattn_bwd_kernel, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
+    if (big) launch_k(fattn_bwd_kernel<true>, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
+    else launch_k(fattn_bwd_kernel<false>, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
     P5_CUDA(cudaGetLastError());
     ++g_launches;
     return true;

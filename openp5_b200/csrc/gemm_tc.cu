@@ -818,6 +818,20 @@ void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     P5_CHECK(gemm_tc_supported(p, true), "gemm_tc: unsupported problem");
     if (!g_num_sms) g_num_sms = sm_budget();
     int bn = g_force_block_n ? g_force_block_n : p.prefer_bn;
+    // P5_TILE_MODEL=1: one cost model over all four tile widths instead of the case analysis below:
+    // time ~ rounds(bn) x (bytes a CTA pulls per k-block ~ 128 + bn, plus a fixed part); ties go to the wider tile.
+    // It differs from the case analysis for M ~ 4-5 k rows (the eval encoder: N = 768 in ONE round of 192-wide tiles
+    // instead of two rounds of 128-wide ones) and for the decoder's M = 512 x N = 3072 (one round of 128-wide tiles).
+    static const int tile_model = [] { const char* e = getenv("P5_TILE_MODEL"); return e ? atoi(e) : 0; }();
+    if (!bn && tile_model && !p.tail_filled) {
+        const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
+        double best = 0;
+        for (int cand : {256, 192, 128, 64}) {
+            if (cand > 64 && p.N <= cand / 2) continue;          // more than half of the tile would be padding
+            const double c = (double)cdiv(mt * cdiv(p.N, cand), g_num_sms) * (128 + cand + 24);
+            if (!bn || c < best * 0.97) { bn = cand; best = c; }
+        }
+    }
     if (!bn) {
         const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
         // largest tile that still gives every SM a tile; narrow outputs use a narrow tile

@@ -121,9 +121,11 @@ void softmax_bwd(const float* dPd, const void* P, void* dS, void* Pd_out, int dt
 bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
                void* P_save, float* row_scale, float* row_lse2, void* ctx, int64_t ld_ctx, DropCfg drop, cudaStream_t st,
                const int* offs = nullptr, const int* lens = nullptr, int64_t packed_rows = 0);
-// fused tcgen05 backward of the same attention (fattn_bwd.cu), L <= 256: recomputes P from row_lse2 (= m2 + log2 l,
+// fused tcgen05 backward of the same attention (fattn_bwd.cu), L <= 512: recomputes P from row_lse2 (= m2 + log2 l,
 // written by fattn_fwd; P_save / row_scale may then be null), writes dQ | dK | dV as bf16 into dqkv (rows as qkv) and
 // accumulates d(bias_rel).  Returns false when the shape is unsupported (caller falls back to the GEMM chain).
+// fattn_bwd_supported(L): the encoder length is covered, i.e. the forward should save row_lse2 instead of P_save.
+bool fattn_bwd_supported(int L);
 bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, const float* bias_rel, const int* key_mask,
                const float* row_lse2, const void* ctx, int64_t ld_ctx, const void* dctx, int64_t ld_dctx, void* dqkv,
                int64_t ld_dqkv, float* dbias_rel, DropCfg drop, cudaStream_t st, const int* offs = nullptr,
@@ -132,6 +134,9 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
 
 // ---- optimiser (optim.cu) ---------------------------------------------------------------------------------------
 void sumsq_norm(const float* g, int64_t n, float* partial /*>=1024 floats*/, float* out_norm, cudaStream_t st);
+// the two halves of sumsq_norm: per-block sums of squares of a range (nblocks floats), sqrt of the sum of np partials
+void sumsq_partial(const float* g, int64_t n, float* partial, int nblocks, cudaStream_t st);
+void sumsq_final(const float* partial, int np, float* out_norm, cudaStream_t st);
 void scale_f32(float* g, int64_t n, float s, cudaStream_t st);
 // element ranges [lo, hi) (relative to the pointers passed to adamw_flat) that take weight_decay = 0: the reference's
 // no_decay group (SingleRunner.py:186-205, names containing "bias" -> the two relative_attention_bias tables)

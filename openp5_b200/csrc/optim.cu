@@ -37,12 +37,18 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restric
     f = block_sum(f, sh);
     if (threadIdx.x == 0) out[0] = sqrtf(f);
 }
-void sumsq_norm(const float* g, int64_t n, float* partial, float* out_norm, cudaStream_t st) {
-    const int np = 1024;
-    launch_k(sumsq_partial_kernel, np, 256, 0, st, g, n, partial);
+void sumsq_partial(const float* g, int64_t n, float* partial, int nblocks, cudaStream_t st) {
+    launch_k(sumsq_partial_kernel, nblocks, 256, 0, st, g, n, partial);
     LAUNCHED();
+}
+void sumsq_final(const float* partial, int np, float* out_norm, cudaStream_t st) {
     launch_k(sumsq_final_kernel, 1, 256, 0, st, partial, np, out_norm);
     LAUNCHED();
+}
+void sumsq_norm(const float* g, int64_t n, float* partial, float* out_norm, cudaStream_t st) {
+    const int np = 1024;
+    sumsq_partial(g, n, partial, np, st);
+    sumsq_final(partial, np, out_norm, st);
 }
 
 __global__ void scale_kernel(float* __restrict__ g, int64_t n, float s) {

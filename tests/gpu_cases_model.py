@@ -33,7 +33,10 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          # data-parallel semantics on one GPU: mean of two shards' gradients == concatenated-batch oracle gradient
          "dpaccum_fp32_small", "dpaccum_bf16_small",
          # optimiser-state checkpoint / resume, no-decay parameter groups
-         "resume_fp32_tiny", "resume_bf16_small", "varlen_bf16_small"]
+         "resume_fp32_tiny", "resume_bf16_small", "varlen_bf16_small",
+         # fused attention backward at 256 < Le <= 512 (two-query-tile units, streamed key blocks): more sequences with
+         # 3 and 4 tiles, and the dropout cross-check against the materialised GEMM chain
+         "bwd_bf16_small_le512_b6_packed", "xcheck_fbwd_dropout_small_le512", "xcheck_fbwd_dropout_small_le512_packed"]
 
 
 def setup(case):
@@ -67,6 +70,8 @@ def setup(case):
         Ld = 12          # second half of the 16-row query tile of the decoder attention kernels
     if "_b1" in case:
         B = 1
+    if "_b6" in case:
+        B = 6
     if "le8" in case:
         Le = 8
     if "gated" in case:
