@@ -91,6 +91,17 @@ __host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint32_t s
     const uint32_t k1 = mix32(k0 ^ 0x85ebca6bU);
     return mix32((uint32_t)idx ^ k0) + k1;
 }
+// The two halves of drop_hash for kernels that hash inside a hot loop: the key once per kernel (the compiler otherwise
+// re-derives it on the uniform datapath in every iteration: ~7 issue slots per hash), the counter round per pair.
+struct DropKey { uint32_t k0, k1; };
+__host__ __device__ __forceinline__ DropKey drop_key(uint64_t seed, uint32_t site) {
+    const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+    DropKey k;
+    k.k0 = mix32(mix32(s0 ^ 0x9e3779b9U) + 0x9e3779b9U * (site + 1u) + s1);
+    k.k1 = mix32(k.k0 ^ 0x85ebca6bU);
+    return k;
+}
+__host__ __device__ __forceinline__ uint32_t drop_hash_k(DropKey k, uint32_t pair_idx) { return mix32(pair_idx ^ k.k0) + k.k1; }
 // One 32-bit hash serves an aligned PAIR of elements (2k, 2k+1): the low 16 bits decide the even element, the high
 // 16 bits the odd one (keep iff bits >= thr16, thr16 = round(p * 2^16)).  Kernels that own both elements of a pair
 // (GEMM epilogue, softmax, dropout-cast) hash once per pair; element-wise kernels call drop_keep and get the same mask.

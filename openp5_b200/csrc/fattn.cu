@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 #include <float.h>
+#include <type_traits>
 
 namespace p5 {
 extern int g_launches;
@@ -59,6 +60,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// DROP: dropout on the probabilities; SAVEP: the un-normalised probabilities are written for the materialised backward
+template <bool DROP, bool SAVEP>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaParams P) {
@@ -215,6 +218,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             float* mask_s = mask_all + buf * (P.nkb * KB);
             mbar_wait(bm_empty(buf), ((bm_ph >> buf) & 1u) ^ 1u);
             // entries past n_delta are only touched for padded keys (masked with -inf): keep them finite
+            // (unrolled: four global loads in flight per lane — the table of a CTA's first pair is on the critical path)
+#pragma unroll 4
             for (int e = lane; e < Lq + nkb * KB + 4; e += 32) {
                 const float v = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] * LOG2E : 0.f;
 #pragma unroll
@@ -236,7 +241,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t lane_off = (uint32_t)(sw * 32) << 16;
         uint32_t sf_ph = 0, pe_ph = 0, of_ph = 0, bm_ph = 0;   // phase bits per buffer
         int sb = 0, pb = 0, buf = 0;
-        const uint32_t t16 = P.drop.thr >> 16;
+        const uint32_t thr_hi = P.drop.thr & 0xffff0000u;    // keep iff the element's 16-bit field >= thr16, compared in place
+        const DropKey dkey = drop_key(P.drop.seed, P.drop.site);   // once per kernel, not per hash
         const int cs = (int)P.bias_cs;
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
@@ -264,24 +270,30 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         const float4* b4 = reinterpret_cast<const float4*>(bias_s + (o & 3) * cs + (o & ~3));
                         const float4* m4 = reinterpret_cast<const float4*>(mask_s + j0);
                         const bool full = (j0 + 32 <= len) && !P.key_mask;       // warp-uniform
-                        float cm = -INFINITY;
+                        // two straight-line copies (FULL: no key-mask loads / adds) instead of predicated-off instructions
+                        auto slice_max = [&](auto full_c) {
+                            constexpr bool FULL = decltype(full_c)::value;
+                            float cm = -INFINITY;
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time keeps the register count down
-                            uint32_t v[16];
-                            tmem_ld16(tS(sb) + lane_off + wg * 32 + hf * 16, v);
-                            tmem_ld_wait();
+                            for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time keeps the register count down
+                                uint32_t v[16];
+                                tmem_ld16(tS(sb) + lane_off + wg * 32 + hf * 16, v);
+                                tmem_ld_wait();
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 bb = b4[4 * hf + q];
-                                float x0 = fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x), x1 = fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y);
-                                float x2 = fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z), x3 = fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w);
-                                if (!full) {
-                                    const float4 mm = m4[4 * hf + q];
-                                    x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 bb = b4[4 * hf + q];
+                                    float x0 = fmaf(__uint_as_float(v[4 * q]), LOG2E, bb.x), x1 = fmaf(__uint_as_float(v[4 * q + 1]), LOG2E, bb.y);
+                                    float x2 = fmaf(__uint_as_float(v[4 * q + 2]), LOG2E, bb.z), x3 = fmaf(__uint_as_float(v[4 * q + 3]), LOG2E, bb.w);
+                                    if constexpr (!FULL) {
+                                        const float4 mm = m4[4 * hf + q];
+                                        x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                    }
+                                    cm = fmaxf(cm, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
                                 }
-                                cm = fmaxf(cm, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
                             }
-                        }
+                            return cm;
+                        };
+                        const float cm = full ? slice_max(std::true_type{}) : slice_max(std::false_type{});
                         m2 = fmaxf(m2, cm);
                     }
                     tc_fence_before();
@@ -312,61 +324,73 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         const uint32_t pair0 = (uint32_t)((uint64_t)(grow + j0) >> 1);
                         mbar_wait(p_empty(pb), ((pe_ph >> pb) & 1u) ^ 1u);   // the MMA that read this P buffer has retired
                         pe_ph ^= 1u << pb;
+                        auto slice_p = [&](auto full_c) {
+                            constexpr bool FULL = decltype(full_c)::value;
+                            float ls = 0.f;
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time keeps the register count down
-                            uint32_t v[16];
-                            tmem_ld16(tS(sb) + lane_off + wg * 32 + hf * 16, v);
-                            tmem_ld_wait();
+                            for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time keeps the register count down
+                                uint32_t v[16];
+                                tmem_ld16(tS(sb) + lane_off + wg * 32 + hf * 16, v);
+                                tmem_ld_wait();
 #pragma unroll
-                            for (int q2 = 0; q2 < 2; ++q2) {     // 8 keys per step: one 16-byte store each way
-                                const int q = 2 * hf + q2;
-                                float pr[8];
+                                for (int q2 = 0; q2 < 2; ++q2) {     // 8 keys per step: one 16-byte store each way
+                                    const int q = 2 * hf + q2;
+                                    float pr[8];
 #pragma unroll
-                                for (int u = 0; u < 2; ++u) {
-                                    const float4 bb = b4[2 * q + u];
-                                    float x0 = fmaf(__uint_as_float(v[8 * q2 + 4 * u]), LOG2E, bb.x);
-                                    float x1 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 1]), LOG2E, bb.y);
-                                    float x2 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 2]), LOG2E, bb.z);
-                                    float x3 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 3]), LOG2E, bb.w);
-                                    if (!full) {
-                                        const float4 mm = m4[2 * q + u];
-                                        x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                    for (int u = 0; u < 2; ++u) {
+                                        const float4 bb = b4[2 * q + u];
+                                        float x0 = fmaf(__uint_as_float(v[8 * q2 + 4 * u]), LOG2E, bb.x);
+                                        float x1 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 1]), LOG2E, bb.y);
+                                        float x2 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 2]), LOG2E, bb.z);
+                                        float x3 = fmaf(__uint_as_float(v[8 * q2 + 4 * u + 3]), LOG2E, bb.w);
+                                        if constexpr (!FULL) {
+                                            const float4 mm = m4[2 * q + u];
+                                            x0 += mm.x; x1 += mm.y; x2 += mm.z; x3 += mm.w;
+                                        }
+                                        pr[4 * u] = ex2_approx(x0 - m2); pr[4 * u + 1] = ex2_approx(x1 - m2);
+                                        pr[4 * u + 2] = ex2_approx(x2 - m2); pr[4 * u + 3] = ex2_approx(x3 - m2);
                                     }
-                                    pr[4 * u] = ex2_approx(x0 - m2); pr[4 * u + 1] = ex2_approx(x1 - m2);
-                                    pr[4 * u + 2] = ex2_approx(x2 - m2); pr[4 * u + 3] = ex2_approx(x3 - m2);
-                                }
-                                l += ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
-                                uint32_t pk[4], pd[4];
+                                    ls += ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+                                    uint32_t pd[4];
+                                    if constexpr (DROP) {
+                                        // the 1 / (1 - p) factor is applied to O once per row (inv_l below), not per probability
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) pk[u] = pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
-                                if (P.drop.thr) {
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + u));
-                                        pd[u] = pack_bf16x2((hsh & 0xffffu) >= t16 ? pr[2 * u] * P.drop.inv_keep : 0.f,
-                                                            (hsh >> 16) >= t16 ? pr[2 * u + 1] * P.drop.inv_keep : 0.f);
+                                        for (int u = 0; u < 4; ++u) {
+                                            const uint32_t hsh = drop_hash_k(dkey, pair0 + 4 * q + u);
+                                            pd[u] = pack_bf16x2((hsh << 16) >= thr_hi ? pr[2 * u] : 0.f, hsh >= thr_hi ? pr[2 * u + 1] : 0.f);
+                                        }
                                     }
-                                } else {
+                                    if constexpr (SAVEP || !DROP) {
+                                        uint32_t pk[4];
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) pd[u] = pk[u];
-                                }
-                                // global P_save (un-normalised, un-dropped; the backward multiplies by row_scale)
-                                if (row_ok && P.P_save) {
-                                    const int j = j0 + 8 * q;
-                                    if (j + 8 <= Lk) {
-                                        *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                    } else {
+                                        for (int u = 0; u < 4; ++u) pk[u] = pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
+                                        if constexpr (!DROP) {
 #pragma unroll
-                                        for (int t = 0; t < 4; ++t)
-                                            if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[t];
+                                            for (int u = 0; u < 4; ++u) pd[u] = pk[u];
+                                        }
+                                        // global P_save (un-normalised, un-dropped; the backward multiplies by row_scale)
+                                        if constexpr (SAVEP) {
+                                            if (row_ok) {
+                                                const int j = j0 + 8 * q;
+                                                if (j + 8 <= Lk) {
+                                                    *reinterpret_cast<uint4*>(P.P_save + grow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                                } else {
+#pragma unroll
+                                                    for (int t = 0; t < 4; ++t)
+                                                        if (j + 2 * t < Lk) *reinterpret_cast<uint32_t*>(P.P_save + grow + j + 2 * t) = pk[t];
+                                                }
+                                            }
+                                        }
                                     }
+                                    // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
+                                    const uint32_t addr = p_chunk + (uint32_t)((((wg & 1) * 4 + q) ^ (r & 7)) << 4);
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[0]), "r"(pd[1]), "r"(pd[2]),
+                                                 "r"(pd[3]) : "memory");
                                 }
-                                // smem A tile, K-major SWIZZLE_128B: [128 rows][128 B] per 64-key chunk, 16-byte units XOR (row & 7)
-                                const uint32_t addr = p_chunk + (uint32_t)((((wg & 1) * 4 + q) ^ (r & 7)) << 4);
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pd[0]), "r"(pd[1]), "r"(pd[2]),
-                                             "r"(pd[3]) : "memory");
                             }
-                        }
+                            return ls;
+                        };
+                        l += full ? slice_p(std::true_type{}) : slice_p(std::false_type{});
                     }
                     // S buffer free; P tile complete: make the generic-proxy smem writes visible to the tensor core
                     tc_fence_before();
@@ -385,6 +409,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const float inv_l = l > 0.f ? 1.f / l : 0.f;
                 if (wg == 0 && row_ok && P.row_scale) P.row_scale[((int64_t)b * P.H + h) * Lq + i] = inv_l;
                 if (wg == 1 && row_ok && P.row_lse2) P.row_lse2[((int64_t)b * P.H + h) * Lq + i] = m2 + __log2f(l);
+                const float o_scale = DROP ? inv_l * P.drop.inv_keep : inv_l;     // dropout's 1 / (1 - p), once per row
                 // ---------------- O -> ctx (this warpgroup writes 16 of the 64 head columns)
                 mbar_wait(o_full, of_ph);
                 of_ph ^= 1;
@@ -401,10 +426,10 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             uint4 w;
-                            w.x = pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l);
-                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
-                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
-                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
+                            w.x = pack_bf16x2(__uint_as_float(o[8 * q]) * o_scale, __uint_as_float(o[8 * q + 1]) * o_scale);
+                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * o_scale, __uint_as_float(o[8 * q + 3]) * o_scale);
+                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * o_scale, __uint_as_float(o[8 * q + 5]) * o_scale);
+                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * o_scale, __uint_as_float(o[8 * q + 7]) * o_scale);
                             *reinterpret_cast<uint4*>(dst + 8 * q) = w;
                         }
                     }
@@ -458,10 +483,15 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.bias_rel = bias_rel; P.key_mask = offs ? nullptr : key_mask; P.P_save = (bf16*)P_save; P.row_scale = row_scale; P.row_lse2 = row_lse2; P.ctx = (bf16*)ctx; P.ld_ctx = ld_ctx;
     P.offs = offs; P.lens = lens;
     P.drop = drop;
-    static size_t max_set = 0;
-    if (smem > max_set) {
-        P5_CUDA(cudaFuncSetAttribute(fattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        max_set = smem;
+    // compile-time variants: dropout on / off, probabilities saved (materialised backward) or not
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FaParams);
+    static const KernelFn variants[4] = {fattn_fwd_kernel<false, false>, fattn_fwd_kernel<false, true>,
+                                         fattn_fwd_kernel<true, false>, fattn_fwd_kernel<true, true>};
+    const int vi = (drop.thr ? 2 : 0) + (P_save ? 1 : 0);
+    static size_t max_set[4] = {0, 0, 0, 0};
+    if (smem > max_set[vi]) {
+        P5_CUDA(cudaFuncSetAttribute(variants[vi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set[vi] = smem;
     }
     // 4-D views (c, pos, h, b): row stride ld_qkv, head stride 64 elements, batch stride L*ld_qkv
     // padded: (c, pos, h, b) with batch stride L*ld.  packed: one [packed_rows, .] matrix, batch dim 1 (TMA zero-fills
@@ -476,7 +506,7 @@ bool fattn_fwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     const int n_pairs = B * H;
     const int budget = sm_budget() < num_sms ? sm_budget() : num_sms;     // leaves SMs to a concurrent NCCL all-reduce (common.cuh)
     const int grid = n_pairs < budget ? n_pairs : budget;
-    launch_k(fattn_fwd_kernel, grid, FA_THREADS, smem, st, tmQ, tmK, tmV, P);
+    launch_k(variants[vi], grid, FA_THREADS, smem, st, tmQ, tmK, tmV, P);
     P5_CUDA(cudaGetLastError());
     ++g_launches;
     return true;

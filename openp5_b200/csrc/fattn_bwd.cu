@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 #include <float.h>
+#include <type_traits>
 
 namespace p5 {
 extern int g_launches;
@@ -68,7 +69,7 @@ struct FbParams {
     DropCfg drop;
 };
 
-template <bool BIG>
+template <bool BIG, bool DROP>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -99,7 +100,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO); }
     if (warp == 1 && lane == 0) {
         mbar_init(ld_full, 1); mbar_init(ld_empty, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bm_full(i), 1); mbar_init(bm_empty(i), 4 * NWG); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bm_full(i), 2); mbar_init(bm_empty(i), 4 * NWG); }   // bm_full: warps 2 and 3
         mbar_init(sdp_full, 1); mbar_init(sdp_free, 4 * NWG);
         mbar_init(pds_full, 4 * NWG); mbar_init(pds_free, 1);
         mbar_init(dvk_full, 1); mbar_init(dvk_free, 4 * NWG);
@@ -242,8 +243,11 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
         }
         __syncwarp();
-    } else if (warp == 3) {
+    } else if (warp == 2 || warp == 3) {
         // ========================= per-pair tables, one pair AHEAD of the softmax warps (double buffered) ==========
+        // warp 3: bias copies + key mask; warp 2 (idle once tensor memory is allocated): the delta / lse rows.  Both are
+        // chains of global-load round trips; split over two warps the tables of a CTA's FIRST pair (which nothing hides)
+        // arrive in half the time.
         //  * bias (log2 domain, four shifted copies for LDS.128) and key mask: see fattn.cu
         //  * rows_s[0][i] = delta_i = sum_c dO_ic O_ic, rows_s[1][i] = lse2_i (+inf for rows past the sequence end, so
         //    that P = 2^(x - lse2) is an exact 0 there without a select).  The global-load latency is off the softmax
@@ -264,6 +268,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             float* mask_b = mask_s + buf * MASK_FLOATS;
             float* rows_b = rows_s + buf * 4 * QT;
             mbar_wait(bm_empty(buf), ((bm_ph >> buf) & 1u) ^ 1u);
+            if (warp == 3) {
 #pragma unroll 4
             for (int e = lane; e < L + nt * KB + 4; e += 32) {
                 const float v = (P.bias_rel && e < n_delta) ? P.bias_rel[h * n_delta + e] * LOG2E_F : 0.f;
@@ -273,6 +278,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             for (int j = lane; j < nt * KB; j += 32)
                 mask_b[j] = (j < len && (!P.key_mask || P.key_mask[b * L + j] != 0)) ? 0.f : -INFINITY;
+            } else {
             // one row per lane (128 contiguous bytes of O and of dO each): 8 independent 16-byte loads in flight per
             // tensor and lane, 32 rows per step -> the whole pair costs a handful of memory round trips
             for (int i0 = 0; i0 < nu * QT; i0 += 32) {
@@ -298,6 +304,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 rows_b[li] = part;
                 rows_b[2 * QT + li] = lse_v;
             }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bm_full(buf));
             bm_ph ^= 1u << buf;
@@ -314,6 +321,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t bm_ph = 0, sdp_ph = 0, pdsf_ph = 0, dvk_ph = 0, dq_ph = 0;
         const uint32_t thr_hi = P.drop.thr & 0xffff0000u;       // keep iff 16-bit field >= thr16, compared in place
         const float ik = P.drop.inv_keep;
+        const DropKey dkey = drop_key(P.drop.seed, P.drop.site);   // once per kernel, not per hash
         const int cs = (int)P.bias_cs;
         const int n_delta = 2 * L - 1;
         int buf = 0;
@@ -349,6 +357,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     mbar_wait(sdp_full, sdp_ph);
                     sdp_ph ^= 1;
                     tc_fence_after();
+                    // two straight-line copies of the block (FULL: no key-mask loads / adds) instead of predicated-off instructions
+                    auto block = [&](auto full_c) {
+                    constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         uint32_t vs[16], vd[16];
@@ -373,7 +384,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                 x[1] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u + 1]), LOG2E_F, bb.y);
                                 x[2] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u + 2]), LOG2E_F, bb.z);
                                 x[3] = fmaf(__uint_as_float(vs[8 * q2 + 4 * u + 3]), LOG2E_F, bb.w);
-                                if (!full) {
+                                if constexpr (!FULL) {
                                     const float4 mm = m4[2 * q + u];
                                     x[0] += mm.x; x[1] += mm.y; x[2] += mm.z; x[3] += mm.w;
                                 }
@@ -382,8 +393,8 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                     const float p0 = ex2_approx(x[2 * e2] - my_lse), p1 = ex2_approx(x[2 * e2 + 1] - my_lse);
                                     const float g0 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2]), g1 = __uint_as_float(vd[8 * q2 + 4 * u + 2 * e2 + 1]);
                                     float m0 = 1.f, m1 = 1.f;          // dropout multiplier: 1 / keep or 0
-                                    if (P.drop.thr) {
-                                        const uint32_t hsh = drop_hash(P.drop.seed, P.drop.site, (uint64_t)(pair0 + 4 * q + 2 * u + e2));
+                                    if constexpr (DROP) {
+                                        const uint32_t hsh = drop_hash_k(dkey, pair0 + 4 * q + 2 * u + e2);
                                         m0 = (hsh << 16) >= thr_hi ? ik : 0.f;
                                         m1 = hsh >= thr_hi ? ik : 0.f;
                                     }
@@ -424,6 +435,8 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                          "r"(pk[q2][6]), "r"(pk[q2][7]) : "memory");
                         }
                     }
+                    };
+                    if (full) block(std::true_type{}); else block(std::false_type{});
                     // Pd / dS tiles complete: make the generic-proxy smem writes visible to the tensor core
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -580,11 +593,15 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     P.ctx = (const bf16*)ctx; P.dctx = (const bf16*)dctx; P.ld_ctx = ld_ctx; P.ld_dctx = ld_dctx;
     P.dqkv = (bf16*)dqkv; P.ld_dqkv = ld_dqkv; P.A = A; P.dbias_rel = dbias_rel;
     P.offs = offs; P.lens = lens; P.drop = drop;
-    static size_t max_set[2] = {0, 0};
-    if (smem > max_set[big]) {
-        if (big) P5_CUDA(cudaFuncSetAttribute(fattn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else P5_CUDA(cudaFuncSetAttribute(fattn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        max_set[big] = smem;
+    // compile-time variants: {Le <= 256, 256 < Le <= 512} x {dropout off, on}
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FbParams);
+    static const KernelFn variants[4] = {fattn_bwd_kernel<false, false>, fattn_bwd_kernel<false, true>,
+                                         fattn_bwd_kernel<true, false>, fattn_bwd_kernel<true, true>};
+    const int vi = (big ? 2 : 0) + (drop.thr ? 1 : 0);
+    static size_t max_set[4] = {0, 0, 0, 0};
+    if (smem > max_set[vi]) {
+        P5_CUDA(cudaFuncSetAttribute(variants[vi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set[vi] = smem;
     }
     const uint64_t rows = (uint64_t)(offs ? packed_rows : L);
     const uint64_t dims[4] = {64, rows, (uint64_t)H, (uint64_t)(offs ? 1 : B)};
@@ -599,8 +616,7 @@ bool fattn_bwd(const void* qkv, int64_t ld_qkv, int A, int B, int H, int L, cons
     const int n_pairs = B * H;
     const int budget = sm_budget() < num_sms ? sm_budget() : num_sms;     // leaves SMs to a concurrent NCCL all-reduce (common.cuh)
     const int grid = n_pairs < budget ? n_pairs : budget;
-    if (big) launch_k(fattn_bwd_kernel<true>, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
-    else launch_k(fattn_bwd_kernel<false>, grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
+    launch_k(variants[vi], grid, FB_THREADS, smem, st, tmQ, tmK, tmV, tmdO, P);
     P5_CUDA(cudaGetLastError());
     ++g_launches;
     return true;
