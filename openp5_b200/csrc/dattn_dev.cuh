@@ -87,20 +87,27 @@ __device__ __forceinline__ int bias_index(const ScoreCtx& c, int r, int j) {
 }
 
 // S (or dPd) tiles of this warp: acc[nt] += A(rows of the query block, fragments lo/hi) . B(rows key0 + 8 nt + g)^T
+// The B fragments of up to four tiles are loaded BEFORE the first mma (predicated loads, no branch): the kernel is a
+// chain of global-load round trips, and with one load -> mma dependency per tile the loads were not in flight together.
 template <int NT, bool LQ16>
 __device__ __forceinline__ void qk_tiles(float (&acc)[NT][4], const uint32_t (&alo)[8], const uint32_t (&ahi)[8], const bf16* kbase,
                                          int64_t ld, int key0, int ntw, int Lk, int g, int t) {
+    constexpr int G = NT < 4 ? NT : 4;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        if (nt < ntw) {
-            const int j = key0 + 8 * nt + g;
-            uint32_t kr[8];
-            ld_row16(kr, kbase + (int64_t)j * ld + 16 * t, j < Lk);
+    for (int n0 = 0; n0 < NT; n0 += G) {
+        uint32_t kr[G][8];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const int j = key0 + 8 * (n0 + u) + g;
+            ld_row16(kr[u], kbase + (int64_t)j * ld + 16 * t, (n0 + u) < ntw && j < Lk);   // zeros outside the warp's keys
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            acc[n0 + u][0] = acc[n0 + u][1] = acc[n0 + u][2] = acc[n0 + u][3] = 0.f;
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                mma16816(acc[nt], alo[2 * s], LQ16 ? ahi[2 * s] : 0u, alo[2 * s + 1], LQ16 ? ahi[2 * s + 1] : 0u, kr[2 * s],
-                         kr[2 * s + 1]);
+                mma16816(acc[n0 + u], alo[2 * s], LQ16 ? ahi[2 * s] : 0u, alo[2 * s + 1], LQ16 ? ahi[2 * s + 1] : 0u, kr[u][2 * s],
+                         kr[u][2 * s + 1]);
         }
     }
 }

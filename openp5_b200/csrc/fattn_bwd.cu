@@ -224,13 +224,15 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         for (int k = 0; k < 8; ++k)       // dK_j += dS^T Q_i
                             umma_bf16(tdK, make_smem_desc(sdS + k * 2048, 16384, 1024),
                                       make_smem_desc(sQ + i * (QT * 128) + k * 2048, 8192, 1024), idesc_g, (i | k) != 0);
+                        // dV_j / dK_j are complete with the MMAs above: signal the softmax warps (which wait for them before the
+                        // read-out) without the dQ MMAs in between
+                        if (i == ni - 1) umma_commit(dvk_full);
 #pragma unroll
                         for (int k = 0; k < 8; ++k)       // dQ_i += dS K_j : A = dS tile K-major (k = key), B = K_j MN-major
                             umma_bf16(tdQ(i), make_smem_desc(sdS + (k >> 2) * (QT * 128) + (k & 3) * 32, 16, 1024),
                                       make_smem_desc(sK + ks * (KB * 128) + k * 2048, 8192, 1024), idesc_q, (j | k) != 0);
                         umma_commit(pds_free);
                         if (i == ni - 1) {
-                            umma_commit(dvk_full);
                             if constexpr (BIG) {          // every MMA that reads K_j / V_j has been issued: the slot is
                                 umma_commit(kv_empty(kv_u & 1u));   // refilled once they retire
                                 ++kv_u;
@@ -325,11 +327,24 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int cs = (int)P.bias_cs;
         const int n_delta = 2 * L - 1;
         int buf = 0;
+        // sequence length / first row of the NEXT pair are fetched one pair ahead (a global-load round trip otherwise opens
+        // every pair of every softmax warp)
+        int len_nx = L;
+        int64_t row0_nx = 0;
+        auto fetch_geom = [&](int pr) {
+            if (pr < n_pairs) {
+                const int bb = pr / P.H;
+                len_nx = P.lens ? P.lens[bb] : L;
+                row0_nx = P.offs ? (int64_t)P.offs[bb] : (int64_t)bb * L;
+            }
+        };
+        fetch_geom((int)blockIdx.x);
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int b = pair / P.H, h = pair % P.H;
-            const int len = P.lens ? P.lens[b] : L;
+            const int len = len_nx;
             const int nt = (len + QT - 1) / QT;
-            const int64_t row0 = P.offs ? (int64_t)P.offs[b] : (int64_t)b * L;
+            const int64_t row0 = row0_nx;
+            fetch_geom(pair + (int)gridDim.x);
             // unit = the query tiles [u0, u0 + nu) of the pair against all nt key blocks (one unit when !BIG)
             for (int u0 = 0; u0 < (BIG ? nt : 1); u0 += 2) {
             const int nu = BIG ? min(2, nt - u0) : nt;

@@ -7,7 +7,8 @@ O=gpurun_out
 CASES="bwd_bf16_base_le256 bwd_bf16_base_le256_packed bwd_bf16_small_le512 bwd_bf16_small_le512_packed bwd_bf16_large_le512_packed \
 bwd_bf16_small_le512_b6_packed xcheck_fbwd_dropout_small xcheck_fbwd_dropout_base_le256_packed xcheck_fbwd_dropout_base_le256 \
 xcheck_fbwd_dropout_small_le512 xcheck_fbwd_dropout_small_le512_packed dropout_bf16_small bwd_bf16_small bwd_bf16_small_packed \
-bwd_bf16_tiny bwd_bf16_tiny_b1 bwd_bf16_tiny_le8 bwd_bf16_c2full_packed bwd_bf16_c2full"
+bwd_bf16_tiny bwd_bf16_tiny_b1 bwd_bf16_tiny_le8 bwd_bf16_c2full_packed bwd_bf16_c2full xcheck_dattn_dropout_small \
+xcheck_dattn_dropout_base_le256_packed bwd_bf16_small_ld12 gen_bf16_tiny gen_bf16_c5full gen_bf16_v32600 bwd_bf16_gated_small"
 timeout 900 python tests/gpu_cases_model.py $CASES > $O/ab2_cases.log 2>&1
 tail -1 $O/ab2_cases.log
 grep -v '"ok": true' $O/ab2_cases.log | head -20
