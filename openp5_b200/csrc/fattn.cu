@@ -74,6 +74,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float* statm_s = reinterpret_cast<float*>(gbase + P.sStat);    // [NWG][128] row max per warpgroup (log2 domain)
     float* statl_s = statm_s + NWG * QT;                           // [NWG][128] row sum per warpgroup
     // barriers (8 bytes each)
+    const uint32_t kv_full = bar, kv_empty = bar + 8;
     auto q_full = [&](int i) { return bar + 16 + 8 * i; };
     auto q_empty = [&](int i) { return bar + 32 + 8 * i; };
     auto s_full = [&](int i) { return bar + 48 + 8 * i; };     // NSB score buffers in TMEM (deeper MMA prefetch)
@@ -83,10 +84,6 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t o_full = bar + 128, o_empty = bar + 136;
     auto bm_full = [&](int i) { return bar + 144 + 8 * i; };     // table buffers: the table warp works one pair ahead
     auto bm_empty = [&](int i) { return bar + 160 + 8 * i; };
-    // K / V of a pair arrive and are released PER 128-key block: the next pair's block 0 is loaded while the last query
-    // tile still works on block 1, so no load latency opens a pair
-    auto kvb_full = [&](int i) { return bar + 184 + 8 * i; };
-    auto kvb_empty = [&](int i) { return bar + 216 + 8 * i; };
     const uint32_t tmem_holder = bar + 176;
     volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(gbase + P.sBar + 176);
 
@@ -96,7 +93,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(kvb_full(i), 1); mbar_init(kvb_empty(i), 1); }
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1);
             mbar_init(p_full(i), 4 * NWG); mbar_init(p_empty(i), 1);
@@ -120,7 +117,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 0) {
         // ========================= TMA producer =========================
         if (lane == 0) {
-            uint32_t kve_ph = 0, q_ph = 0;   // phase bits, one per buffer (register-resident: no dynamically indexed arrays)
+            uint32_t kv_ph = 0, q_ph = 0;   // phase bits, one per buffer (register-resident: no dynamically indexed arrays)
             int qb = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int b = pair / P.H, h = pair % P.H;
@@ -129,25 +126,20 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int len = P.lens ? P.lens[b] : Lk;
                 const int row0 = P.offs ? P.offs[b] : 0, bc = P.offs ? 0 : b;
                 const int nkb = (len + KB - 1) / KB, nqt = (len + QT - 1) / QT;
-                auto load_q = [&](int qt) {
+                mbar_wait(kv_empty, kv_ph ^ 1);
+                mbar_expect_tx(kv_full, (uint32_t)(2 * nkb * KB * 128));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_4d(sK + kb * (KB * 128), &tmK, kv_full, 0, row0 + kb * KB, h, bc);
+                    tma_load_4d(sV + kb * (KB * 128), &tmV, kv_full, 0, row0 + kb * KB, h, bc);
+                }
+                kv_ph ^= 1;
+                for (int qt = 0; qt < nqt; ++qt) {
                     mbar_wait(q_empty(qb), ((q_ph >> qb) & 1u) ^ 1u);
                     mbar_expect_tx(q_full(qb), QT * 128);
                     tma_load_4d(sQ + qb * (QT * 128), &tmQ, q_full(qb), 0, row0 + qt * QT, h, bc);
                     q_ph ^= 1u << qb;
                     qb = (qb + 1) % P.nq_buf;
-                };
-                // key block kb, then query tile kb: block 0 and tile 0 (all the first MMA needs) are never queued behind the
-                // wait for block 1, which the previous pair releases last
-                int qt = 0;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(kvb_empty(kb), ((kve_ph >> kb) & 1u) ^ 1u);
-                    kve_ph ^= 1u << kb;
-                    mbar_expect_tx(kvb_full(kb), (uint32_t)(2 * KB * 128));
-                    tma_load_4d(sK + kb * (KB * 128), &tmK, kvb_full(kb), 0, row0 + kb * KB, h, bc);
-                    tma_load_4d(sV + kb * (KB * 128), &tmV, kvb_full(kb), 0, row0 + kb * KB, h, bc);
-                    if (qt < nqt) load_q(qt++);
                 }
-                while (qt < nqt) load_q(qt++);
             }
         }
         __syncwarp();
@@ -158,7 +150,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                                      ((uint32_t)(128 >> 4) << 24);
-            uint32_t kvf_ph = 0, q_ph = 0, se_ph = 0, pf_ph = 0, oe_ph = 0;   // phase bits per buffer
+            uint32_t kv_ph = 0, q_ph = 0, se_ph = 0, pf_ph = 0, oe_ph = 0;   // phase bits per buffer
             int qb = 0, sb = 0, pb = 0;
             auto issue_s = [&](int kb, uint32_t q_addr) {
                 mbar_wait(s_empty(sb), ((se_ph >> sb) & 1u) ^ 1u);
@@ -174,19 +166,15 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const int len = P.lens ? P.lens[pair / P.H] : Lk;
                 const int nkb = (len + KB - 1) / KB, nqt = (len + QT - 1) / QT;
+                mbar_wait(kv_full, kv_ph);
+                kv_ph ^= 1;
                 for (int qt = 0; qt < nqt; ++qt) {
                     mbar_wait(q_full(qb), (q_ph >> qb) & 1u);
                     q_ph ^= 1u << qb;
                     tc_fence_after();
                     const uint32_t q_addr = sQ + qb * (QT * 128);
-                    // pass 1: statistics (the first tile of a pair is the first to touch each key block: wait for its K / V)
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        if (qt == 0) {
-                            mbar_wait(kvb_full(kb), (kvf_ph >> kb) & 1u);
-                            kvf_ph ^= 1u << kb;
-                        }
-                        issue_s(kb, q_addr);
-                    }
+                    // pass 1: statistics
+                    for (int kb = 0; kb < nkb; ++kb) issue_s(kb, q_addr);
                     // pass 2: probabilities and O
                     mbar_wait(o_empty, oe_ph ^ 1);     // the previous tile's O has been read out
                     oe_ph ^= 1;
@@ -204,14 +192,12 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             umma_bf16(tO, da, db, idesc_o, (kb | k) != 0);
                         }
                         umma_commit(p_empty(pb));
-                        // last tile of the pair: every MMA that reads K / V block kb has been issued (S of block kb went out
-                        // before P V of block kb - 1) -> the block may be refilled once they retire
-                        if (qt == nqt - 1) umma_commit(kvb_empty(kb));
                         pb = (pb + 1 == P.np_buf) ? 0 : pb + 1;
                     }
                     umma_commit(o_full);
                     qb = (qb + 1) % P.nq_buf;
                 }
+                umma_commit(kv_empty);   // K/V of this pair may be overwritten once every MMA above has retired
             }
         }
         __syncwarp();
