@@ -229,10 +229,10 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
     pdl_wait();   // programmatic dependent launch: everything above the wait overlaps the previous kernel
     pdl_launch_dependents();
     constexpr int d = NV * 128;
-    __shared__ float sdw[d];
+    __shared__ __align__(16) float sdw[8][d];     // per-warp dw partials (summed once at the end; shared fp32 atomics are CAS loops)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = threadIdx.x; c < d; c += 256) sdw[c] = 0.f;
-    __syncthreads();
+    const DropKey dkey = drop_key(drop.seed, drop.site);     // once per kernel, not per element
+    const uint32_t thr_hi = drop.thr & 0xffff0000u;
     float acc[NV][4];     // the norm weight (3 KB) is re-read from L1 per row instead of pinning NV*4 registers
 #pragma unroll
     for (int k = 0; k < NV; ++k)
@@ -257,11 +257,17 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
             const int c = 4 * (lane + 32 * k);
             float wk[4];
             ldv<4>(w + c, wk);
+            if (drop.thr) {     // one hash per aligned pair of elements (base + c is a multiple of 4): same mask as drop_keep
+#pragma unroll
+                for (int j2 = 0; j2 < 2; ++j2) {
+                    const uint32_t hsh = drop_hash_k(dkey, (uint32_t)((uint64_t)(base + c + 2 * j2) >> 1));
+                    gv[k][2 * j2] = (hsh << 16) >= thr_hi ? gv[k][2 * j2] * drop.inv_keep : 0.f;
+                    gv[k][2 * j2 + 1] = hsh >= thr_hi ? gv[k][2 * j2 + 1] * drop.inv_keep : 0.f;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float g = gv[k][j];
-                if (drop.thr) g = drop_keep(drop.seed, drop.site, (uint64_t)(base + c + j), drop.thr) ? g * drop.inv_keep : 0.f;
-                gv[k][j] = g;
+                const float g = gv[k][j];
                 xv[k][j] *= r;                  // xhat
                 dot += g * wk[j] * xv[k][j];
                 acc[k][j] += g * xv[k][j];
@@ -293,11 +299,12 @@ rmsnorm_bwd_vec_kernel(const T* __restrict__ dn, const float* __restrict__ x, co
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(&sdw[4 * (lane + 32 * k) + j], acc[k][j]);
+        *reinterpret_cast<float4*>(&sdw[warp][4 * (lane + 32 * k)]) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += 256) {
-        const float v = sdw[c];
+        float v = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) v += sdw[w8][c];
         if (v != 0.f) atomicAdd(dw + c, v);
     }
 }
