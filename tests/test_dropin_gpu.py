@@ -160,4 +160,8 @@ def test_batch_stager_delivers_the_collator_batches(built_lib):
         r = B200Runner(m, None, _Loader(train[:12]), None, m.device, _args(valid_select=0, stage_batches=stage))
         r.train()
         losses.append(r.last_train_loss)
-    assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[0]), losses
+    # Not bitwise: the fp32 weight-gradient reductions use atomics whose order varies from run to run, and twelve AdamW steps
+    # amplify that noise — the final loss of EITHER loop lands in one of two clusters 4.5e-5 apart (3.06021 / 3.06035, within
+    # a cluster 2e-6; tools/flaky_check.py repeats both loops).  A staging error (wrong batch, wrong order, stale slot) moves
+    # the loss in the second digit.
+    assert abs(losses[0] - losses[1]) <= 2e-4 * abs(losses[0]), losses
