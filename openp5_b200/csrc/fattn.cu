@@ -13,11 +13,14 @@
 //   warps 4-19: softmax, four warpgroups.  thread = (query row, 32 of the 128 key columns of a block); four warps per
 //               scheduler hide the ALU / MUFU / LDS latencies of the softmax arithmetic.  Log2 domain throughout:
 //               pass 1: row max only (FFMA + FMNMX per score; the four column slices are combined through smem);
-//               pass 2: p~ = 2^(s2 - m2) UN-normalised (FFMA + EX2), row sum, dropout -> bf16 -> swizzled smem A tile;
-//               O is scaled by 1 / l when it is read out of TMEM.
+//               pass 2: p~ = 2^(s2 - m2) UN-normalised (FFMA + EX2), row sum, dropout mask -> bf16 -> swizzled smem A
+//               tile; O is scaled by 1 / l (and by dropout's 1 / (1 - p)) when it is read out of TMEM.
+//               The hot loops are compile-time variants (dropout on / off, probabilities saved or not, full or partial
+//               key slice): a profile of the runtime-flag form showed a third of its issue slots going to the dropout
+//               key re-derived per iteration and to predicated-off key-mask instructions.
 // Two passes over the key blocks (QK^T is recomputed: K = 64, cheap) avoid rescaling the O accumulator in TMEM.  For the
-// backward the kernel stores either lse2 = m2 + log2(l) per row (Le <= 256: fattn_bwd recomputes P, nothing of size
-// L^2 is written) or the un-normalised P plus 1 / l (materialised backward for 256 < Le <= 512).
+// backward the kernel stores lse2 = m2 + log2(l) per row (fattn_bwd recomputes P, nothing of size L^2 is written), or —
+// only when the fused backward is switched off — the un-normalised P plus 1 / l for the materialised GEMM chain.
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 #include <float.h>
