@@ -195,6 +195,9 @@ typedef struct {
 } P5GemmDesc;
 int p5_op_gemm(const P5GemmDesc* d, void* cuda_stream);
 int p5_launch_count(void);   /* kernels launched by this library since load */
+/* tile width (64 / 128 / 192 / 256) the tcgen05 GEMM picks for an M x N output (x batches) on `sms` SMs: host arithmetic
+   only, no device needed (tests/test_cabi_cpu.py); 0 on invalid arguments */
+int p5_gemm_tile_width(int M, int N, int batches, int sms);
 /* per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg): enable, run steps, read a JSON summary
  * {"bn256": {"launches", "ms", "flops"}, "bn128": ..., "bn64": ...} (algorithmic FLOPs = 2*M*N*K per launch) */
 int p5_prof_enable(int on);

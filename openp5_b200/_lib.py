@@ -51,7 +51,7 @@ DECLARED_SYMBOLS = [
     "p5_zero_grad", "p5_adamw_step", "p5_adamw_step_zero_grad", "p5_adamw_step_zero_grad_async", "p5_optimizer_join", "p5_eval_metrics", "p5_comm_unique_id", "p5_comm_init", "p5_allreduce_grads",
     "p5_trie_build", "p5_trie_free", "p5_trie_stats", "p5_trie_get", "p5_generate", "p5_op_gemm",
     "p5_launch_count", "p5_prof_enable", "p5_prof_summary", "p5_prof_shapes", "p5_eval_metrics_filtered", "p5_opt_state_info",
-    "p5_decode_last_launch", "p5_decode_phase_ns", "p5_cooccurrence", "p5_submatrix",
+    "p5_decode_last_launch", "p5_decode_phase_ns", "p5_cooccurrence", "p5_submatrix", "p5_gemm_tile_width",
 ]
 
 _lib = None

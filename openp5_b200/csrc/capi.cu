@@ -55,6 +55,7 @@ extern "C" {
 const char* p5_last_error(void) { return g_last_error.c_str(); }
 int p5_version(void) { return 100; }
 int p5_launch_count(void) { return p5::g_launches + gemm_tc_launch_count(); }
+int p5_gemm_tile_width(int M, int N, int batches, int sms) { return (M > 0 && N > 0 && batches > 0 && sms > 0) ? gemm_tc_tile_width(M, N, batches, sms) : 0; }
 
 int p5_create(const P5Config* cfg, int device, void* cuda_stream, p5_handle* out) {
     P5_API_BEGIN

@@ -266,5 +266,6 @@ bool gemm_tc_supported(const GemmProblem& p, bool allow_mn_major);
 void gemm_tc(const GemmProblem& p, cudaStream_t stream);
 void gemm_tc_clear_cache();
 int  gemm_tc_launch_count();
+int  gemm_tc_tile_width(int M, int N, int batches, int sms);   // the tile-width cost model (host arithmetic only)
 
 }  // namespace p5

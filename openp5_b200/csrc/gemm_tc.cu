@@ -814,6 +814,21 @@ static void launch_bn(int bn, const GemmProblem& p, cudaStream_t stream) {
     else launch_tc<64, EPI>(p, stream);
 }
 
+// tile width (64 / 128 / 192 / 256) of an M x N output (x batches) on `sms` persistent CTAs: the candidate with the lowest
+// rounds(bn) x (128 + bn + 24); a narrower tile has to be 3 % better to displace a wider one.  Pure host arithmetic
+// (p5_gemm_tile_width exposes it to the CPU tests).
+int gemm_tc_tile_width(int M, int N, int batches, int sms) {
+    const long long mt = cdiv(M, BLOCK_M) * (long long)batches;
+    int bn = 0;
+    double best = 0;
+    for (int cand : {256, 192, 128, 64}) {
+        if (cand > 64 && N <= cand / 2) continue;          // more than half of the tile would be padding
+        const double c = (double)cdiv(mt * cdiv(N, cand), sms) * (128 + cand + 24);
+        if (!bn || c < best * 0.97) { bn = cand; best = c; }
+    }
+    return bn;
+}
+
 void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     P5_CHECK(gemm_tc_supported(p, true), "gemm_tc: unsupported problem");
     if (!g_num_sms) g_num_sms = sm_budget();
@@ -824,15 +839,7 @@ void gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     // decoder's M = 512 x N = 3072 (one round of 128-wide tiles).  Measured on one B200: eval batch 7.54 -> 7.41 ms, train
     // step 15.95 -> 15.92 ms.
     static const int tile_model = [] { const char* e = getenv("P5_TILE_MODEL"); return e ? atoi(e) : 1; }();
-    if (!bn && tile_model && !p.tail_filled) {
-        const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
-        double best = 0;
-        for (int cand : {256, 192, 128, 64}) {
-            if (cand > 64 && p.N <= cand / 2) continue;          // more than half of the tile would be padding
-            const double c = (double)cdiv(mt * cdiv(p.N, cand), g_num_sms) * (128 + cand + 24);
-            if (!bn || c < best * 0.97) { bn = cand; best = c; }
-        }
-    }
+    if (!bn && tile_model && !p.tail_filled) bn = gemm_tc_tile_width(p.M, p.N, p.nb1 * p.nb2, g_num_sms);
     if (!bn) {
         const long long mt = cdiv(p.M, BLOCK_M) * (long long)p.nb1 * p.nb2;
         // largest tile that still gives every SM a tile; narrow outputs use a narrow tile

@@ -77,3 +77,21 @@ def test_sass_contains_blackwell_instructions(built_lib):
     assert "UTCHMMA.2CTA" in out and "UTMALDG.4D.2CTA" in out, "cta_group::2 GEMM variant missing from SASS"
     assert "HMMA.16816.F32.BF16" in out and "LDSM" in out, "mma.sync / ldmatrix decoder attention missing from SASS"
     assert "ACQBULK" in out and "PREEXIT" in out, "programmatic dependent launch (griddepcontrol) missing from SASS"
+
+
+def test_gemm_tile_width_model(built_lib):
+    """the tile-width cost model of the tcgen05 GEMM (gemm_tc.cu::gemm_tc_tile_width; host arithmetic, no device): the
+    decisions DESIGN.md §8 / profiles/r02_session2_ab.txt describe, on 148 SMs"""
+    tw = built_lib.p5_gemm_tile_width
+    tw.restype = C.c_int
+    tw.argtypes = [C.c_int] * 4
+    # T5-base train step, 12800 packed rows: N = 768 in 2.7 waves of 192-wide tiles instead of 2.03 waves of 256-wide ones
+    assert tw(12800, 768, 1, 148) == 192
+    assert tw(12800, 2304, 1, 148) == 256 and tw(12800, 3072, 1, 148) == 256
+    # eval encoder (20 users, ~3.9 k packed rows): N = 768 in ONE round of 192-wide tiles
+    assert tw(3900, 768, 1, 148) == 192 and tw(3900, 2304, 1, 148) == 256
+    # decoder rows of a train step (M = 512): every SM gets at most one tile; N = 3072 fits one round of 128-wide tiles
+    assert tw(512, 768, 1, 148) == 64 and tw(512, 2304, 1, 148) == 64 and tw(512, 3072, 1, 148) == 128
+    assert tw(512, 32100, 1, 148) == 256           # LM head: many column tiles, wide tile
+    assert tw(400, 64, 1, 148) == 64               # narrow outputs never take a tile that is mostly padding
+    assert tw(0, 768, 1, 148) == 0 and tw(128, 768, 1, 0) == 0
