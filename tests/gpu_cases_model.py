@@ -36,7 +36,8 @@ CASES = ["fwd_fp32_tiny", "bwd_fp32_tiny", "fwd_bf16_tiny", "bwd_bf16_tiny", "fu
          "resume_fp32_tiny", "resume_bf16_small", "varlen_bf16_small",
          # fused attention backward at 256 < Le <= 512 (two-query-tile units, streamed key blocks): more sequences with
          # 3 and 4 tiles, and the dropout cross-check against the materialised GEMM chain
-         "bwd_bf16_small_le512_b6_packed", "xcheck_fbwd_dropout_small_le512", "xcheck_fbwd_dropout_small_le512_packed"]
+         "bwd_bf16_small_le512_b6_packed", "xcheck_fbwd_dropout_small_le512", "xcheck_fbwd_dropout_small_le512_packed",
+         "bwd_bf16_small_le512_b6_short_packed", "xcheck_fbwd_dropout_small_le512_b6_short_packed"]
 
 
 def setup(case):
@@ -90,6 +91,18 @@ def setup(case):
     else:
         items = po.synth_items(n_items, seed=3)
     batch = po.synth_batch(B, Le, Ld, cfg.vocab_size, items, seed=5)
+    if "_short" in case:
+        # sequences of 1, 2 and 3 query tiles next to a full one in the same Le = 512 batch (synth_batch never goes below
+        # Le / 2): the 256 < Le <= 512 attention backward with one unit of one / two tiles and with two units
+        ids, attn, ww, labels, oattn = batch
+        for b, n in enumerate([Le, 100, 200, 40, 300, 129][:B]):
+            ids[b, n:] = 0
+            ids[b, n - 1] = 1
+        attn = (ids != 0).long()
+        ww = ww * attn
+        for b, n in enumerate([Le, 100, 200, 40, 300, 129][:B]):
+            ww[b, n - 1] = 0
+        batch = (ids, attn, ww, labels, oattn)
     return po, cfg, w, items, batch
 
 
