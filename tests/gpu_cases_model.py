@@ -343,8 +343,11 @@ def run_case(case):
         res["ref_losses"], res["resumed_losses"] = ref_losses, l12 + l34
         res["worst_param_rel"] = worst
         res["opt_step"] = m2._opt_step
-        res["ok"] = (m2._opt_step == 4 and worst < (2e-3 if prec == "bf16" else 1e-6) and
-                     all(abs(x - y) <= (2e-3 if prec == "bf16" else 1e-6) * abs(x) for x, y in zip(ref_losses, l12 + l34)))
+        # fp32: the two runs differ by the order of the fp32 gradient atomics only (measured 6.6e-7 .. 9.4e-7 on the parameters
+        # after four steps, varying from run to run); a lost moment / step counter / parameter shows up at 1e-3 and above
+        tol = 2e-3 if prec == "bf16" else 1e-5
+        res["ok"] = (m2._opt_step == 4 and worst < tol and
+                     all(abs(x - y) <= tol * abs(x) for x, y in zip(ref_losses, l12 + l34)))
     elif case.startswith("varlen"):
         # pad-to-longest batches change Le from step to step (Collator.py:12): every geometry goes through fresh tensor
         # maps; the bounded tensor-map cache (gemm_tc.cu) must keep results independent of what was cached before
